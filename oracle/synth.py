@@ -1,0 +1,101 @@
+"""Deterministic synthetic weights / inputs shared by the golden generator, the tests and bench.py.
+
+TEST INFRASTRUCTURE ONLY.  There is no network for checkpoints, so every parity number is taken on
+seeded random weights.  Each tensor is drawn from its own generator keyed by (seed, crc32(key)) so
+the values do not depend on module construction order, and every class of parameter the
+reference's default init leaves degenerate (zero fragment tables, zero biases, unit LayerNorm,
+BN running stats (0,1) -- SURVEY.md section 0-8) is randomised.
+"""
+import zlib
+
+import torch
+
+
+def _gen(seed, key):
+    return torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31))
+
+
+def fill_like(key, shape, seed, dtype=torch.float32):
+    g = _gen(seed, key)
+    n = torch.randn(tuple(shape), generator=g, dtype=torch.float32)
+    leaf = key.rsplit(".", 1)[-1]
+    if "position_bias_table" in key:
+        t = 0.2 * n
+    elif leaf == "running_var":
+        t = 0.5 + torch.rand(tuple(shape), generator=g)
+    elif leaf == "running_mean":
+        t = 0.1 * n
+    elif leaf == "num_batches_tracked":
+        return torch.zeros(tuple(shape), dtype=torch.int64)
+    elif leaf == "bias":
+        t = 0.1 * n
+    elif leaf == "weight" and len(shape) == 1:          # LayerNorm / BatchNorm scale
+        t = 1.0 + 0.2 * n
+    elif leaf == "weight":                              # Linear / Conv: variance-preserving-ish
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        t = n * (1.0 / fan_in) ** 0.5
+    else:
+        t = 0.1 * n
+    return t.to(dtype)
+
+
+def synth_state_dict(shapes, seed):
+    """shapes: {key: shape or (shape, 'int64-buffer-value')}.  Returns {key: tensor}."""
+    return {k: fill_like(k, s, seed) for k, s in shapes.items()}
+
+
+def swin_shapes(prefix="", embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24),
+                window=(8, 7, 7), frag_biases=(True, True, True, False), patch=(2, 4, 4), in_chans=3):
+    """Float parameter shapes of SwinTransformer3D (reference swin_backbone.py:760-842); the int64
+    `relative_position_index` buffer is derived, not random, and is rebuilt by whoever needs it."""
+    nb = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
+    s = {prefix + "patch_embed.proj.weight": (embed_dim, in_chans) + tuple(patch),
+         prefix + "patch_embed.proj.bias": (embed_dim,),
+         prefix + "patch_embed.norm.weight": (embed_dim,),
+         prefix + "patch_embed.norm.bias": (embed_dim,)}
+    for i, depth in enumerate(depths):
+        C = embed_dim * 2 ** i
+        for j in range(depth):
+            b = f"{prefix}layers.{i}.blocks.{j}."
+            s[b + "norm1.weight"] = (C,)
+            s[b + "norm1.bias"] = (C,)
+            s[b + "attn.relative_position_bias_table"] = (nb, num_heads[i])
+            if frag_biases[i]:
+                s[b + "attn.fragment_position_bias_table"] = (nb, num_heads[i])
+            s[b + "attn.qkv.weight"] = (3 * C, C)
+            s[b + "attn.qkv.bias"] = (3 * C,)
+            s[b + "attn.proj.weight"] = (C, C)
+            s[b + "attn.proj.bias"] = (C,)
+            s[b + "norm2.weight"] = (C,)
+            s[b + "norm2.bias"] = (C,)
+            s[b + "mlp.fc1.weight"] = (4 * C, C)
+            s[b + "mlp.fc1.bias"] = (4 * C,)
+            s[b + "mlp.fc2.weight"] = (C, 4 * C)
+            s[b + "mlp.fc2.bias"] = (C,)
+        if i < len(depths) - 1:
+            b = f"{prefix}layers.{i}.downsample."
+            s[b + "reduction.weight"] = (2 * C, 4 * C)
+            s[b + "norm.weight"] = (4 * C,)
+            s[b + "norm.bias"] = (4 * C,)
+    Cf = embed_dim * 2 ** (len(depths) - 1)
+    s[prefix + "norm.weight"] = (Cf,)
+    s[prefix + "norm.bias"] = (Cf,)
+    return s
+
+
+def vqa_head_shapes(prefix="", in_channels=768, hidden=64):
+    return {prefix + "fc_hid.weight": (hidden, in_channels, 1, 1, 1), prefix + "fc_hid.bias": (hidden,),
+            prefix + "fc_last.weight": (1, hidden, 1, 1, 1), prefix + "fc_last.bias": (1,)}
+
+
+def swin_network_state_dict(seed, key="swin_tiny_grpb", **kw):
+    shapes = dict(swin_shapes(prefix=f"{key}_backbone.", **kw))
+    shapes.update(vqa_head_shapes(prefix=f"{key}_head."))
+    return synth_state_dict(shapes, seed)
+
+
+def clip_input(shape, seed):
+    """Synthetic normalised frames, [B,3,T,H,W] fp32 ~ N(0,1) (ImageNet-normalised scale)."""
+    return torch.randn(tuple(shape), generator=torch.Generator().manual_seed(seed))

@@ -1,0 +1,52 @@
+"""The CPU oracle (oracle/swin3d.py) must reproduce the vectors the REAL reference produced
+(tools/make_golden.py, run where /root/reference is importable).  Tolerance: the oracle is an fp32
+restatement with a different gather order, so allow fp32 round-off only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import swin3d, synth
+
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "swin_*.npz")))
+
+
+def _load(path):
+    g = np.load(path)
+    shape = tuple(int(v) for v in g["shape"])
+    fb = [bool(b) for b in g["frag_biases"]]
+    sd = synth.synth_state_dict(synth.swin_shapes(frag_biases=fb), int(g["wseed"]))
+    sd.update(synth.synth_state_dict(synth.vqa_head_shapes(), int(g["wseed"])))
+    x = synth.clip_input(shape, int(g["xseed"]))
+    return g, shape, fb, sd, x
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_oracle_matches_reference_golden(path):
+    g, shape, fb, sd, x = _load(path)
+    if shape[2] > 32 and os.environ.get("KVQ_SLOW_TESTS") != "1":
+        pytest.skip("96-frame case takes ~1 min on CPU; set KVQ_SLOW_TESTS=1")
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    feat = swin3d.swin3d_forward(sd, x, frag_biases=fb)
+    score = swin3d.vqa_head(sd, feat).numpy()
+    assert list(feat.shape) == [int(v) for v in g["feat_shape"]]
+    st = int(g["feat_stride"])
+    fs = feat[:, ::st].numpy() if st > 1 else feat.numpy()
+    assert fs.shape == g["feat"].shape
+    assert float(np.abs(g["feat"]).mean()) > 0.1          # the fixture is not degenerate
+    np.testing.assert_allclose(fs, g["feat"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(score, g["score"], rtol=0, atol=1e-5)
+
+
+def test_state_dict_key_fixture_matches_synth_shapes():
+    import json
+    with open(os.path.join(GOLDEN, "state_dict_keys.json")) as f:
+        spec = json.load(f)
+    ours = synth.swin_shapes()
+    ref = {k: v[0] for k, v in spec["SwinTransformer3D"].items() if "relative_position_index" not in k}
+    assert set(ours) == set(ref)
+    for k, shp in ours.items():
+        assert list(shp) == ref[k], k
