@@ -1,0 +1,126 @@
+/*
+ * kvq_b200.h -- C ABI of the B200 (sm_100a) hot path for the KVQ / KSVQE video-quality forward.
+ *
+ * The reference (lixinustc/KVQ-Challenge-CVPR-NTIRE2024) is pure PyTorch and has no FFI; the functions below are
+ * the entry points a binding for the path  fragment frames -> SwinTransformer3D (GRPB) -> VQAHead -> score  calls
+ * instead of the ATen/cuDNN ops behind the reference modules.  Each one cites the reference code it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (weights, activations, workspace); 16-byte aligned
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden synchronisation,
+ *     no allocation, graph-capturable
+ *   - return value 0 = ok, negative = error (see KVQ_ERR_*); kvq_last_error_string() describes the last failure
+ *     on the calling thread
+ *   - fp16 tensors are IEEE binary16; "packed" weights are produced once by the kvq_pack_* helpers
+ */
+#ifndef KVQ_B200_H_
+#define KVQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVQ_OK 0
+#define KVQ_ERR_BAD_SHAPE (-1)
+#define KVQ_ERR_MISALIGNED (-2)
+#define KVQ_ERR_ARCH (-3)
+#define KVQ_ERR_CUDA (-4)
+#define KVQ_ERR_WORKSPACE (-5)
+#define KVQ_ERR_DRIVER (-6)
+
+#define KVQ_MAX_STAGES 4
+
+/* Architecture of SwinTransformer3D (models/backbones/swin_backbone.py:760-842) + VQAHead (models/head.py:33-58). */
+typedef struct KvqSwinConfig {
+  int32_t embed_dim;                  /* 96 */
+  int32_t num_stages;                 /* 4 */
+  int32_t depths[KVQ_MAX_STAGES];     /* 2,2,6,2 */
+  int32_t num_heads[KVQ_MAX_STAGES];  /* 3,6,12,24 (head_dim must be 32) */
+  int32_t window[3];                  /* 8,7,7 */
+  int32_t frag_bias[KVQ_MAX_STAGES];  /* 1,1,1,0: stage owns a fragment_position_bias_table (GRPB) */
+  int32_t head_hidden;                /* 64; 0 = backbone only */
+  float ln_eps;                       /* 1e-5 */
+} KvqSwinConfig;
+
+/*
+ * Weight pointer table for kvq_swin3d_forward, in this order (f16 = packed by kvq_cast_f16, f32 = as in the
+ * reference state_dict):
+ *   [0] patch_embed.proj.weight  f16 [C0, 96]   (flattened [C0,3,2,4,4])
+ *   [1] patch_embed.proj.bias    f32 [C0]
+ *   [2] patch_embed.norm.weight  f32 [C0]
+ *   [3] patch_embed.norm.bias    f32 [C0]
+ *   then for every stage s, for every block j of the stage, 13 entries:
+ *     norm1.weight, norm1.bias (f32 [C]); attn.qkv.weight (f16 [3C, C]); attn.qkv.bias (f32 [3C]);
+ *     packed bias table (f32 [heads][kvq_attn_table_len][2], from kvq_pack_bias_table);
+ *     attn.proj.weight (f16 [C, C]); attn.proj.bias (f32 [C]); norm2.weight, norm2.bias (f32 [C]);
+ *     mlp.fc1.weight (f16 [4C, C]); mlp.fc1.bias (f32 [4C]); mlp.fc2.weight (f16 [C, 4C]); mlp.fc2.bias (f32 [C])
+ *   followed, for every stage but the last, by 3 entries:
+ *     downsample.norm.weight, downsample.norm.bias (f32 [4C]); downsample.reduction.weight (f16 [2C, 4C])
+ *   then  norm.weight, norm.bias (f32 [Cf])
+ *   then (head_hidden > 0)  fc_hid.weight (f16 [hidden, Cf]); fc_hid.bias (f32 [hidden]);
+ *                           fc_last.weight (f32 [hidden]); fc_last.bias (f32 [1])
+ */
+int kvq_swin3d_num_weights(const KvqSwinConfig* cfg);
+
+/* Bytes of caller-owned scratch kvq_swin3d_forward needs for a [B,3,T,H,W] batch. */
+size_t kvq_swin3d_workspace_bytes(const KvqSwinConfig* cfg, int B, int T, int H, int W);
+
+/*
+ * Whole hot path: replaces VQA_Network.forward for one Swin key (models/model.py:93-121) =
+ * SwinTransformer3D.forward (swin_backbone.py:1044-1080) + VQAHead.forward (head.py:60-68).
+ *   x         f32 [B,3,T,H,W]   (batch['technical'])
+ *   feat_out  f32 [B,Cf,D,Hf,Wf] or NULL  (the backbone's return value)
+ *   score_out f32 [B] or NULL             (head output, mean over D,H,W)
+ */
+int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const float* x, int B,
+                       int T, int H, int W, float* feat_out, float* score_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- weight packing (once per load_state_dict) ---- */
+int kvq_cast_f16(const float* in, void* out_f16, size_t n, void* stream);
+/* entries per head of a packed bias table for base window (wd,wh,ww) */
+int kvq_attn_table_len(int wd, int wh, int ww);
+/* relative_position_bias_table / fragment_position_bias_table [L, heads] (frag may be NULL) -> packed table
+ * (swin_backbone.py:202-243, :291-309) */
+int kvq_pack_bias_table(const float* rel, const float* frag, float* out, int wd, int wh, int ww, int heads,
+                        void* stream);
+
+/* ---- single operators (unit-testable pieces of the path) ---- */
+/* out = A[M,K] * W[N,K]^T + bias, optional exact-erf GELU; fp16 in/out, fp32 accumulate (nn.Linear, Mlp :64-89) */
+int kvq_linear_f16(const void* a_f16, const void* w_f16, const float* bias, void* out_f16, int M, int N, int K,
+                   int gelu, void* stream);
+/* out_f32[M,N] = resid + A*W^T + bias (resid / bias may be NULL; resid may alias out) */
+int kvq_linear_resid_f32(const void* a_f16, const void* w_f16, const float* bias, const float* resid, float* out,
+                         int M, int N, int K, void* stream);
+/* norm1 + cyclic shift + window_partition (swin_backbone.py:416-449): x f32 [B,D,H,W,C] -> f16 [B*nW*N, C] */
+int kvq_ln_window(const float* x, void* out_f16, const float* gamma, const float* beta, float eps, int B, int D,
+                  int H, int W, int C, const int32_t window[3], const int32_t shift[3], void* stream);
+/* rows of the window-ordered matrix for a geometry: B*nW*N */
+int64_t kvq_window_rows(int B, int D, int H, int W, const int32_t window[3], const int32_t shift[3]);
+/* scratch bytes for kvq_window_attention */
+size_t kvq_window_attention_workspace_bytes(int B, int D, int H, int W, int C, const int32_t window[3],
+                                            const int32_t shift[3]);
+/* WindowAttention3D.forward up to (not including) proj (swin_backbone.py:245-322) on window-ordered rows:
+ * xw f16 [B*nW*N, C] -> out f16 [B*nW*N, C] */
+int kvq_window_attention(const void* xw_f16, const void* qkv_w_f16, const float* qkv_b, const float* packed_table,
+                         void* out_f16, int B, int D, int H, int W, int C, int heads, const int32_t window[3],
+                         const int32_t shift[3], void* workspace, size_t workspace_bytes, int debug_variant,
+                         void* stream);
+/* Grid mini-patch sampling (datasets/fusion_datasets.py:22-121) fused with (v - mean)/std (:1017-1020):
+ * frames u8 [B,T,3,Hs,Ws] -> out f32 [B,3,T,fh*fs,fw*fs]; offsets i32 [B,2,fh,fw,T/aligned] (h then w) */
+int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
+                           int fragments_h, int fragments_w, int fsize, int aligned, const float mean[3],
+                           const float std[3], void* stream);
+
+const char* kvq_last_error_string(void);
+/* library / build identification, e.g. "kvq_b200 sm_100a" */
+const char* kvq_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVQ_B200_H_ */

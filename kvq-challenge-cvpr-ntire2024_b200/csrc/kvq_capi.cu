@@ -1,0 +1,334 @@
+// C-ABI entry points (include/kvq_b200.h) and the host-side orchestration of the Swin3D-GRPB + VQAHead forward.
+// Everything is enqueued on the caller's stream; the library allocates nothing.
+#include <algorithm>
+#include <vector>
+
+#include "../../include/kvq_b200.h"
+#include "kvq_common.cuh"
+#include "kvq_kernels.cuh"
+
+using namespace kvq;
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct StageDims {
+  int D, H, W, C, heads;
+};
+
+struct Plan {
+  int D0, H0, W0;
+  StageDims st[KVQ_MAX_STAGES];
+  size_t x_bytes, x2_bytes, a16_bytes, img_bytes, hid_bytes, rs_bytes;
+  size_t total;
+};
+
+int validate_cfg(const KvqSwinConfig* cfg) {
+  KVQ_REQUIRE(cfg != nullptr, KVQ_ERR_BAD_SHAPE, "config is NULL");
+  KVQ_REQUIRE(cfg->num_stages >= 1 && cfg->num_stages <= KVQ_MAX_STAGES, KVQ_ERR_BAD_SHAPE, "num_stages=%d",
+              cfg->num_stages);
+  KVQ_REQUIRE(cfg->embed_dim == 96, KVQ_ERR_BAD_SHAPE,
+              "embed_dim=%d: the fused patch-embed LayerNorm epilogue is built for 96 channels", cfg->embed_dim);
+  for (int s = 0; s < cfg->num_stages; ++s) {
+    const int C = cfg->embed_dim << s;
+    KVQ_REQUIRE(cfg->depths[s] >= 1, KVQ_ERR_BAD_SHAPE, "depths[%d]=%d", s, cfg->depths[s]);
+    KVQ_REQUIRE(cfg->num_heads[s] * 32 == C, KVQ_ERR_BAD_SHAPE, "stage %d: heads=%d x 32 != C=%d", s,
+                cfg->num_heads[s], C);
+  }
+  KVQ_REQUIRE(cfg->window[0] >= 1 && cfg->window[0] <= 8 && cfg->window[1] >= 1 && cfg->window[1] <= 7 &&
+                  cfg->window[2] >= 1 && cfg->window[2] <= 7,
+              KVQ_ERR_BAD_SHAPE, "window (%d,%d,%d) exceeds (8,7,7)", cfg->window[0], cfg->window[1], cfg->window[2]);
+  KVQ_REQUIRE(cfg->head_hidden == 0 || cfg->head_hidden == 64, KVQ_ERR_BAD_SHAPE, "head_hidden=%d (0 or 64)",
+              cfg->head_hidden);
+  return KVQ_OK;
+}
+
+int make_plan(const KvqSwinConfig* cfg, int B, int T, int H, int W, Plan* pl) {
+  KVQ_REQUIRE(B >= 1 && T >= 1 && H >= 1 && W >= 1, KVQ_ERR_BAD_SHAPE, "empty input %dx3x%dx%dx%d", B, T, H, W);
+  pl->D0 = (T + 1) / 2;
+  pl->H0 = (H + 3) / 4;
+  pl->W0 = (W + 3) / 4;
+  int D = pl->D0, Hh = pl->H0, Ww = pl->W0;
+  size_t max_a16 = 0, max_img = 0, max_hid = 0, max_x2 = 0;
+  const int zero[3] = {0, 0, 0};
+  for (int s = 0; s < cfg->num_stages; ++s) {
+    const int C = cfg->embed_dim << s;
+    pl->st[s] = {D, Hh, Ww, C, cfg->num_heads[s]};
+    const WinGeom g = make_geom(D, Hh, Ww, cfg->window, zero);  // padded sizes do not depend on the shift
+    const size_t rows_w = static_cast<size_t>(B) * g.nW * g.N;
+    const size_t rows = static_cast<size_t>(B) * g.tokens;
+    KVQ_REQUIRE(rows_w < (1ull << 31), KVQ_ERR_BAD_SHAPE, "stage %d has %zu window rows (int32 overflow)", s, rows_w);
+    max_a16 = std::max(max_a16, rows_w * C * 2);
+    max_img = std::max(max_img, static_cast<size_t>(B) * g.nW * cfg->num_heads[s] * ATT_UNIT_BYTES);
+    max_hid = std::max(max_hid, rows * 4 * C * 2);
+    if (s + 1 < cfg->num_stages) {
+      const int H2 = (Hh + 1) / 2, W2 = (Ww + 1) / 2;
+      const size_t rows2 = static_cast<size_t>(B) * D * H2 * W2;
+      max_a16 = std::max(max_a16, rows2 * 4 * C * 2);
+      max_x2 = std::max(max_x2, rows2 * 2 * C * 4);
+      Hh = H2;
+      Ww = W2;
+    }
+  }
+  const size_t rows0 = static_cast<size_t>(B) * pl->D0 * pl->H0 * pl->W0;
+  pl->x_bytes = align_up(rows0 * cfg->embed_dim * 4, 256);
+  pl->x2_bytes = align_up(std::max<size_t>(max_x2, 256), 256);
+  pl->a16_bytes = align_up(std::max(max_a16, rows0 * 96 * 2) + 128 * 3072 * 2, 256);  // + slack for TMA tile overhang
+  pl->img_bytes = align_up(max_img, 256);
+  pl->hid_bytes = align_up(max_hid + 128 * 3072 * 2, 256);
+  const StageDims& last = pl->st[cfg->num_stages - 1];
+  pl->rs_bytes = align_up(static_cast<size_t>(B) * last.D * last.H * last.W * 4, 256);
+  pl->total = pl->x_bytes + pl->x2_bytes + pl->a16_bytes + pl->img_bytes + pl->hid_bytes + pl->rs_bytes;
+  return KVQ_OK;
+}
+
+int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, const float* packed_tab, __half* out,
+                  __half* img, int B, int C, int heads, const WinGeom& g, const int32_t base_win[3], int variant,
+                  cudaStream_t st) {
+  const int rows_w = B * g.nW * g.N;
+  GemmParams gp{};
+  gp.M = rows_w; gp.N = 3 * C; gp.K = C;
+  gp.bias = qkv_b;
+  gp.geom = g;
+  gp.img = img;
+  gp.C = C;
+  gp.heads = heads;
+  gp.qscale = 0.17677669529663687f;  // head_dim^-0.5 with head_dim = 32 (:191)
+  int rc = launch_gemm(EPI_QKV_IMG, xw, C, qkv_w, C, gp, st);
+  if (rc != 0) return rc;
+  AttnParams ap{};
+  ap.img = img;
+  ap.out = out;
+  ap.packed_tab = packed_tab;
+  ap.B = B; ap.C = C; ap.heads = heads;
+  ap.shifted = (g.sd | g.sh | g.sw) != 0;
+  ap.geom = g;
+  ap.base_wd = base_win[0]; ap.base_wh = base_win[1]; ap.base_ww = base_win[2];
+  ap.variant = variant;
+  return launch_window_attn(ap, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
+                           int fragments_h, int fragments_w, int fsize, int aligned, const float mean[3],
+                           const float std[3], void* stream) {
+  KVQ_REQUIRE(frames && offsets && out && mean && std, KVQ_ERR_BAD_SHAPE, "fragment_gather: NULL argument");
+  return launch_fragment_gather_u8(frames, offsets, out, B, T, Hs, Ws, fragments_h, fragments_w, fsize, aligned, mean,
+                                   std, static_cast<cudaStream_t>(stream));
+}
+
+const char* kvq_last_error_string(void) { return kvq::last_error(); }
+
+const char* kvq_build_info(void) { return "kvq_b200 sm_100a tcgen05/TMEM/TMA fp16-operand fp32-accumulate"; }
+
+int kvq_swin3d_num_weights(const KvqSwinConfig* cfg) {
+  if (validate_cfg(cfg) != 0) return KVQ_ERR_BAD_SHAPE;
+  int n = 4;
+  for (int s = 0; s < cfg->num_stages; ++s) n += 13 * cfg->depths[s];
+  n += 3 * (cfg->num_stages - 1);
+  n += 2;
+  if (cfg->head_hidden > 0) n += 4;
+  return n;
+}
+
+size_t kvq_swin3d_workspace_bytes(const KvqSwinConfig* cfg, int B, int T, int H, int W) {
+  Plan pl;
+  if (validate_cfg(cfg) != 0 || make_plan(cfg, B, T, H, W, &pl) != 0) return 0;
+  return pl.total;
+}
+
+int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const float* x, int B,
+                       int T, int H, int W, float* feat_out, float* score_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  int rc = validate_cfg(cfg);
+  if (rc != 0) return rc;
+  Plan pl;
+  rc = make_plan(cfg, B, T, H, W, &pl);
+  if (rc != 0) return rc;
+  KVQ_REQUIRE(num_weights == kvq_swin3d_num_weights(cfg), KVQ_ERR_BAD_SHAPE, "expected %d weight pointers, got %d",
+              kvq_swin3d_num_weights(cfg), num_weights);
+  for (int i = 0; i < num_weights; ++i)
+    KVQ_REQUIRE(weights[i] != nullptr && (reinterpret_cast<uintptr_t>(weights[i]) & 15) == 0, KVQ_ERR_MISALIGNED,
+                "weight %d is NULL or not 16 B aligned", i);
+  KVQ_REQUIRE(workspace != nullptr && workspace_bytes >= pl.total, KVQ_ERR_WORKSPACE,
+              "workspace %zu B < required %zu B", workspace_bytes, pl.total);
+  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+              KVQ_ERR_MISALIGNED, "workspace must be 256 B aligned, x 16 B aligned");
+  KVQ_REQUIRE(score_out == nullptr || cfg->head_hidden > 0, KVQ_ERR_BAD_SHAPE, "score requested but head_hidden == 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* xa = reinterpret_cast<float*>(ws); ws += pl.x_bytes;
+  float* xb = reinterpret_cast<float*>(ws); ws += pl.x2_bytes;
+  __half* a16 = reinterpret_cast<__half*>(ws); ws += pl.a16_bytes;
+  __half* img = reinterpret_cast<__half*>(ws); ws += pl.img_bytes;
+  __half* hid = reinterpret_cast<__half*>(ws); ws += pl.hid_bytes;
+  float* rowscore = reinterpret_cast<float*>(ws);
+
+  int wi = 0;
+  auto WH = [&]() { return static_cast<const __half*>(weights[wi++]); };
+  auto WF = [&]() { return static_cast<const float*>(weights[wi++]); };
+  const float eps = cfg->ln_eps;
+
+  // ---- PatchEmbed3D: im2col -> GEMM (K = 96) with bias + LayerNorm epilogue ----
+  {
+    rc = launch_patch_im2col(x, a16, B, T, H, W, st);
+    if (rc != 0) return rc;
+    GemmParams gp{};
+    gp.M = B * pl.D0 * pl.H0 * pl.W0; gp.N = 96; gp.K = 96;
+    const __half* w = WH();
+    gp.bias = WF(); gp.gamma = WF(); gp.beta = WF(); gp.eps = eps;
+    gp.out = xa; gp.ldo = 96;
+    rc = launch_gemm(EPI_LN_F32, a16, 96, w, 96, gp, st);
+    if (rc != 0) return rc;
+  }
+
+  float* xcur = xa;
+  float* xnext = xb;
+  const int shift_full[3] = {cfg->window[0] / 2, cfg->window[1] / 2, cfg->window[2] / 2};
+  const int shift_none[3] = {0, 0, 0};
+  for (int s = 0; s < cfg->num_stages; ++s) {
+    const StageDims& sd = pl.st[s];
+    const int C = sd.C, M = B * sd.D * sd.H * sd.W;
+    for (int j = 0; j < cfg->depths[s]; ++j) {
+      const WinGeom g = make_geom(sd.D, sd.H, sd.W, cfg->window, (j & 1) ? shift_full : shift_none);
+      const float* n1g = WF(); const float* n1b = WF();
+      const __half* qkv_w = WH(); const float* qkv_b = WF(); const float* tab = WF();
+      const __half* proj_w = WH(); const float* proj_b = WF();
+      const float* n2g = WF(); const float* n2b = WF();
+      const __half* fc1_w = WH(); const float* fc1_b = WF();
+      const __half* fc2_w = WH(); const float* fc2_b = WF();
+
+      // forward_part1 (:407-488)
+      rc = launch_ln_window(xcur, a16, n1g, n1b, eps, B, C, g, st);
+      if (rc != 0) return rc;
+      rc = run_attention(a16, qkv_w, qkv_b, tab, a16, img, B, C, sd.heads, g, cfg->window, 0, st);
+      if (rc != 0) return rc;
+      {
+        GemmParams gp{};
+        gp.M = B * g.nW * g.N; gp.N = C; gp.K = C;
+        gp.bias = proj_b; gp.out = xcur; gp.ldo = C; gp.resid = xcur; gp.remap = 1; gp.geom = g;
+        rc = launch_gemm(EPI_RESID_F32, a16, C, proj_w, C, gp, st);
+        if (rc != 0) return rc;
+      }
+      // forward_part2 (:490-491)
+      rc = launch_ln_rows(xcur, a16, nullptr, n2g, n2b, eps, M, C, sd.D * sd.H * sd.W, st);
+      if (rc != 0) return rc;
+      {
+        GemmParams gp{};
+        gp.M = M; gp.N = 4 * C; gp.K = C;
+        gp.bias = fc1_b; gp.out = hid; gp.ldo = 4 * C;
+        rc = launch_gemm(EPI_GELU_F16, a16, C, fc1_w, C, gp, st);
+        if (rc != 0) return rc;
+      }
+      {
+        GemmParams gp{};
+        gp.M = M; gp.N = C; gp.K = 4 * C;
+        gp.bias = fc2_b; gp.out = xcur; gp.ldo = C; gp.resid = xcur;
+        rc = launch_gemm(EPI_RESID_F32, hid, 4 * C, fc2_w, 4 * C, gp, st);
+        if (rc != 0) return rc;
+      }
+    }
+    if (s + 1 < cfg->num_stages) {  // PatchMerging (:533-555)
+      const float* ng = WF(); const float* nb = WF(); const __half* red_w = WH();
+      rc = launch_ln_merge(xcur, a16, ng, nb, eps, B, sd.D, sd.H, sd.W, C, st);
+      if (rc != 0) return rc;
+      GemmParams gp{};
+      gp.M = B * sd.D * ((sd.H + 1) / 2) * ((sd.W + 1) / 2); gp.N = 2 * C; gp.K = 4 * C;
+      gp.out = xnext; gp.ldo = 2 * C;
+      rc = launch_gemm(EPI_RESID_F32, a16, 4 * C, red_w, 4 * C, gp, st);
+      if (rc != 0) return rc;
+      std::swap(xcur, xnext);
+      // after the first merge the big buffer is free: keep ping-ponging between the two (xa always fits)
+    }
+  }
+
+  // ---- final norm (:1066-1080) [+ VQAHead (head.py:60-68)] ----
+  {
+    const StageDims& sd = pl.st[cfg->num_stages - 1];
+    const int tokens = sd.D * sd.H * sd.W, M = B * tokens;
+    const float* ng = WF(); const float* nb = WF();
+    rc = launch_ln_rows(xcur, cfg->head_hidden > 0 ? a16 : nullptr, feat_out, ng, nb, eps, M, sd.C, tokens, st);
+    if (rc != 0) return rc;
+    if (cfg->head_hidden > 0 && score_out != nullptr) {
+      const __half* w1 = WH(); const float* b1 = WF(); const float* w2 = WF(); const float* b2 = WF();
+      GemmParams gp{};
+      gp.M = M; gp.N = cfg->head_hidden; gp.K = sd.C;
+      gp.bias = b1; gp.w2 = w2; gp.b2ptr = b2; gp.rowscore = rowscore;
+      rc = launch_gemm(EPI_HEAD, a16, sd.C, w1, sd.C, gp, st);
+      if (rc != 0) return rc;
+      rc = launch_row_mean(rowscore, score_out, B, tokens, st);
+      if (rc != 0) return rc;
+    }
+  }
+  return KVQ_OK;
+}
+
+int kvq_cast_f16(const float* in, void* out_f16, size_t n, void* stream) {
+  return launch_cast_f16(in, static_cast<__half*>(out_f16), n, static_cast<cudaStream_t>(stream));
+}
+
+int kvq_attn_table_len(int wd, int wh, int ww) { return attn_table_len(wd, wh, ww); }
+
+int kvq_pack_bias_table(const float* rel, const float* frag, float* out, int wd, int wh, int ww, int heads,
+                        void* stream) {
+  KVQ_REQUIRE(rel != nullptr && out != nullptr && heads > 0, KVQ_ERR_BAD_SHAPE, "pack_bias_table: NULL argument");
+  return launch_pack_bias(rel, frag, out, wd, wh, ww, heads, static_cast<cudaStream_t>(stream));
+}
+
+int kvq_linear_f16(const void* a_f16, const void* w_f16, const float* bias, void* out_f16, int M, int N, int K,
+                   int gelu, void* stream) {
+  GemmParams gp{};
+  gp.M = M; gp.N = N; gp.K = K;
+  gp.bias = bias; gp.out = out_f16; gp.ldo = N;
+  return launch_gemm(gelu ? EPI_GELU_F16 : EPI_STORE_F16, static_cast<const __half*>(a_f16), K,
+                     static_cast<const __half*>(w_f16), K, gp, static_cast<cudaStream_t>(stream));
+}
+
+int kvq_linear_resid_f32(const void* a_f16, const void* w_f16, const float* bias, const float* resid, float* out,
+                         int M, int N, int K, void* stream) {
+  GemmParams gp{};
+  gp.M = M; gp.N = N; gp.K = K;
+  gp.bias = bias; gp.out = out; gp.ldo = N; gp.resid = resid;
+  return launch_gemm(EPI_RESID_F32, static_cast<const __half*>(a_f16), K, static_cast<const __half*>(w_f16), K, gp,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int64_t kvq_window_rows(int B, int D, int H, int W, const int32_t window[3], const int32_t shift[3]) {
+  const WinGeom g = make_geom(D, H, W, window, shift);
+  return static_cast<int64_t>(B) * g.nW * g.N;
+}
+
+int kvq_ln_window(const float* x, void* out_f16, const float* gamma, const float* beta, float eps, int B, int D,
+                  int H, int W, int C, const int32_t window[3], const int32_t shift[3], void* stream) {
+  const WinGeom g = make_geom(D, H, W, window, shift);
+  return launch_ln_window(x, static_cast<__half*>(out_f16), gamma, beta, eps, B, C, g,
+                          static_cast<cudaStream_t>(stream));
+}
+
+size_t kvq_window_attention_workspace_bytes(int B, int D, int H, int W, int C, const int32_t window[3],
+                                            const int32_t shift[3]) {
+  const WinGeom g = make_geom(D, H, W, window, shift);
+  return static_cast<size_t>(B) * g.nW * (C / 32) * ATT_UNIT_BYTES;
+}
+
+int kvq_window_attention(const void* xw_f16, const void* qkv_w_f16, const float* qkv_b, const float* packed_table,
+                         void* out_f16, int B, int D, int H, int W, int C, int heads, const int32_t window[3],
+                         const int32_t shift[3], void* workspace, size_t workspace_bytes, int debug_variant,
+                         void* stream) {
+  KVQ_REQUIRE(window[0] <= 8 && window[1] <= 7 && window[2] <= 7, KVQ_ERR_BAD_SHAPE, "window exceeds (8,7,7)");
+  KVQ_REQUIRE(heads * 32 == C, KVQ_ERR_BAD_SHAPE, "heads=%d x 32 != C=%d", heads, C);
+  const WinGeom g = make_geom(D, H, W, window, shift);
+  const size_t need = static_cast<size_t>(B) * g.nW * heads * ATT_UNIT_BYTES;
+  KVQ_REQUIRE(workspace != nullptr && workspace_bytes >= need, KVQ_ERR_WORKSPACE, "workspace %zu B < required %zu B",
+              workspace_bytes, need);
+  return run_attention(static_cast<const __half*>(xw_f16), static_cast<const __half*>(qkv_w_f16), qkv_b,
+                       packed_table, static_cast<__half*>(out_f16), static_cast<__half*>(workspace), B, C, heads, g,
+                       window, debug_variant, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,376 @@
+// Persistent warp-specialised tcgen05 GEMM for every Linear / 1x1x1-conv / patch-embed contraction on the
+// Swin3D path:   D[M,N] = A[M,K] * B[N,K]^T,  fp16 operands (TMA, 128 B swizzle), fp32 accumulators in TMEM,
+// double-buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d -> 4-stage smem ring, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 per instruction)
+//   warps 2..5  : epilogue: tcgen05.ld 32x32b (thread = output row) -> fused bias / GELU / residual /
+//                 LayerNorm / attention-image scatter / head reduction -> vectorised global stores
+//
+// The epilogues replace, per reference call site (swin_backbone.py unless noted):
+//   EPI_QKV_IMG   WindowAttention3D.forward :253-261  (qkv Linear + bias, q*scale, head split, window layout)
+//   EPI_RESID_F32 :322-324 + :472-488 + :509 (proj + window_reverse + un-roll + crop + shortcut),
+//                 Mlp.fc2 + residual :490-491, PatchMerging.reduction :554
+//   EPI_GELU_F16  Mlp.fc1 + GELU(erf) :64-89
+//   EPI_LN_F32    PatchEmbed3D proj bias + LayerNorm :715-733
+//   EPI_HEAD      VQAHead fc_hid + GELU + fc_last (models/head.py:60-68)
+#include "kvq_common.cuh"
+#include "kvq_kernels.cuh"
+
+namespace kvq {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 halfs = one 128 B swizzle row
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg<BN>::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = p.N / BN;
+  const int tiles = num_m * num_n;
+  const int nkb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg<BN>::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], ph ^ 1);
+          uint8_t* sA = smem + stage * Cfg<BN>::STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          mbar_expect_tx(&full[stage], Cfg<BN>::STAGE_BYTES);
+          tma_load_2d(sA, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+      int stage = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], ph);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * Cfg<BN>::STAGE_BYTES);
+          const uint64_t da = umma_smem_desc(sA, 16, 1024, UMMA_SW_128);
+          const uint64_t db = umma_smem_desc(sA + A_BYTES, 16, 1024, UMMA_SW_128);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advancing 16 halfs (32 B) inside the 128 B swizzle row = +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quadrant this warp may touch
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      mbar_wait(&tfull[as], aph);
+      __syncwarp();
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const int nbase = n_blk * BN;
+
+      if constexpr (EPI == EPI_GELU_F16 || EPI == EPI_STORE_F16) {
+        __half* orow = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + nbase;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c0, r);
+          tmem_wait_ld();
+          uint32_t h[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+            if (p.bias != nullptr) {
+              v0 += __ldg(p.bias + nbase + c0 + j);
+              v1 += __ldg(p.bias + nbase + c0 + j + 1);
+            }
+            if constexpr (EPI == EPI_GELU_F16) {
+              v0 = gelu_erf(v0);
+              v1 = gelu_erf(v1);
+            }
+            h[j >> 1] = pack_half2(v0, v1);
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st_global_v4(orow + c0 + 8 * j, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          }
+        }
+      } else if constexpr (EPI == EPI_RESID_F32) {
+        long long orow_idx = row;
+        bool ok = row_ok;
+        if (p.remap) {
+          const int rows_in = p.geom.nW * p.geom.N;
+          const int b = row / rows_in;
+          const int src = win_row_to_src(p.geom, row - b * rows_in);
+          ok = ok && src >= 0;
+          orow_idx = static_cast<long long>(b) * p.geom.tokens + src;
+        }
+        float* orow = reinterpret_cast<float*>(p.out) + orow_idx * p.ldo + nbase;
+        const float* rrow = p.resid != nullptr ? p.resid + orow_idx * p.ldo + nbase : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c0, r);
+          tmem_wait_ld();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (p.bias != nullptr) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c0 + j));
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              }
+              if (rrow != nullptr) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow + c0 + j);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              *reinterpret_cast<float4*>(orow + c0 + j) = v;
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_QKV_IMG) {
+        const int ntok = p.geom.N;
+        const int win_g = row / ntok;
+        const int i = row - win_g * ntok;
+        const int slab = i / p.geom.SL;
+        const int kv_row = slab * ATT_SLAB + (i - slab * p.geom.SL);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c0, r);
+          tmem_wait_ld();
+          const int n0 = nbase + c0;
+          const int which = n0 / p.C;
+          const int head = (n0 - which * p.C) >> 5;
+          const float sc = which == 0 ? p.qscale : 1.0f;
+          uint32_t h[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float v0 = (__uint_as_float(r[j]) + __ldg(p.bias + n0 + j)) * sc;
+            const float v1 = (__uint_as_float(r[j + 1]) + __ldg(p.bias + n0 + j + 1)) * sc;
+            h[j >> 1] = pack_half2(v0, v1);
+          }
+          if (row_ok) {
+            const int rimg = which == 0 ? i : kv_row;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(p.img) +
+                           (static_cast<size_t>(win_g) * p.heads + head) * ATT_UNIT_BYTES +
+                           static_cast<size_t>(which) * ATT_IMG_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_global_v4(dst + att_img_offset(rimg, j), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          }
+        }
+      } else if constexpr (EPI == EPI_LN_F32) {
+        // whole output row lives in this thread's TMEM lane: exact two-pass LayerNorm, then a third read to write
+        float mean = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mean += __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
+        }
+        mean *= (1.0f / BN);
+        float var = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j) - mean;
+            var += d * d;
+          }
+        }
+        const float rstd = rsqrtf(var * (1.0f / BN) + p.eps);
+        float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c0, r);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v;
+              v.x = (__uint_as_float(r[j]) + __ldg(p.bias + c0 + j) - mean) * rstd * __ldg(p.gamma + c0 + j) + __ldg(p.beta + c0 + j);
+              v.y = (__uint_as_float(r[j + 1]) + __ldg(p.bias + c0 + j + 1) - mean) * rstd * __ldg(p.gamma + c0 + j + 1) + __ldg(p.beta + c0 + j + 1);
+              v.z = (__uint_as_float(r[j + 2]) + __ldg(p.bias + c0 + j + 2) - mean) * rstd * __ldg(p.gamma + c0 + j + 2) + __ldg(p.beta + c0 + j + 2);
+              v.w = (__uint_as_float(r[j + 3]) + __ldg(p.bias + c0 + j + 3) - mean) * rstd * __ldg(p.gamma + c0 + j + 3) + __ldg(p.beta + c0 + j + 3);
+              *reinterpret_cast<float4*>(orow + c0 + j) = v;
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_HEAD) {
+        float acc = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            acc += gelu_erf(__uint_as_float(r[j]) + __ldg(p.bias + c0 + j)) * __ldg(p.w2 + c0 + j);
+        }
+        if (row_ok) p.rowscore[row] = acc + __ldg(p.b2ptr);
+      }
+
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg<BN>::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI>
+int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    KVQ_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, A, p.M, p.K, static_cast<uint64_t>(lda) * 2, BM, BK, 2, 128);
+  if (rc != 0) return rc;
+  rc = make_tmap_2d(&tmB, B, p.N, p.K, static_cast<uint64_t>(ldb) * 2, BN, BK, 2, 128);
+  if (rc != 0) return rc;
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, p);
+  return check_cuda(cudaGetLastError(), "gemm_kernel launch");
+}
+
+template <int EPI>
+int launch_bn(const __half* A, int lda, const __half* B, int ldb, const GemmParams& p, cudaStream_t stream) {
+  if (p.N % 192 == 0) return launch_impl<192, EPI>(A, lda, B, ldb, p, stream);
+  if (p.N % 96 == 0) return launch_impl<96, EPI>(A, lda, B, ldb, p, stream);
+  if (p.N % 64 == 0) return launch_impl<64, EPI>(A, lda, B, ldb, p, stream);
+  set_error("gemm: N=%d is not a multiple of 64/96/192", p.N);
+  return KVQ_ERR_BAD_SHAPE;
+}
+
+}  // namespace
+
+int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
+                cudaStream_t stream) {
+  KVQ_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, KVQ_ERR_BAD_SHAPE, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
+  KVQ_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, KVQ_ERR_MISALIGNED,
+              "gemm: K=%d lda=%d ldb=%d must be multiples of 8 halfs (16 B TMA rows)", p.K, lda, ldb);
+  switch (epi) {
+    case EPI_GELU_F16:
+      KVQ_REQUIRE(p.ldo % 8 == 0, KVQ_ERR_MISALIGNED, "gemm: fp16 output stride %d not 16 B aligned", p.ldo);
+      return launch_bn<EPI_GELU_F16>(A, lda, B, ldb, p, stream);
+    case EPI_STORE_F16:
+      KVQ_REQUIRE(p.ldo % 8 == 0, KVQ_ERR_MISALIGNED, "gemm: fp16 output stride %d not 16 B aligned", p.ldo);
+      return launch_bn<EPI_STORE_F16>(A, lda, B, ldb, p, stream);
+    case EPI_RESID_F32:
+      KVQ_REQUIRE(p.ldo % 4 == 0, KVQ_ERR_MISALIGNED, "gemm: fp32 output stride %d not 16 B aligned", p.ldo);
+      return launch_bn<EPI_RESID_F32>(A, lda, B, ldb, p, stream);
+    case EPI_QKV_IMG:
+      KVQ_REQUIRE(p.N == 3 * p.C && p.C % 32 == 0 && p.bias != nullptr, KVQ_ERR_BAD_SHAPE,
+                  "gemm(qkv): N=%d C=%d (need N == 3C, C %% 32 == 0, bias)", p.N, p.C);
+      if (p.N % 192 == 0) return launch_impl<192, EPI_QKV_IMG>(A, lda, B, ldb, p, stream);
+      if (p.N % 96 == 0) return launch_impl<96, EPI_QKV_IMG>(A, lda, B, ldb, p, stream);
+      set_error("gemm(qkv): N=%d is not a multiple of 96", p.N);
+      return KVQ_ERR_BAD_SHAPE;
+    case EPI_LN_F32:
+      KVQ_REQUIRE(p.N == 96 && p.bias && p.gamma && p.beta, KVQ_ERR_BAD_SHAPE,
+                  "gemm(ln): the fused LayerNorm epilogue needs N == 96 (got %d) and bias/gamma/beta", p.N);
+      return launch_impl<96, EPI_LN_F32>(A, lda, B, ldb, p, stream);
+    case EPI_HEAD:
+      KVQ_REQUIRE(p.N == 64 && p.bias && p.w2 && p.rowscore, KVQ_ERR_BAD_SHAPE,
+                  "gemm(head): needs N == 64 hidden channels (got %d)", p.N);
+      return launch_impl<64, EPI_HEAD>(A, lda, B, ldb, p, stream);
+    default:
+      set_error("gemm: unknown epilogue %d", epi);
+      return KVQ_ERR_BAD_SHAPE;
+  }
+}
+
+}  // namespace kvq

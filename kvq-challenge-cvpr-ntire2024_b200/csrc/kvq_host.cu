@@ -1,0 +1,84 @@
+// Host-side plumbing shared by every entry point: last-error string, CUDA error capture, and the
+// driver-API tensor-map encoder (resolved through the runtime so the library does not link libcuda).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "kvq_common.cuh"
+
+namespace kvq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const char* last_error() { return g_err; }
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return KVQ_OK;
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return KVQ_ERR_CUDA;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                 uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  KVQ_REQUIRE(enc != nullptr, KVQ_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, KVQ_ERR_MISALIGNED, "TMA base %p not 16 B aligned", base);
+  KVQ_REQUIRE((row_stride_bytes & 15) == 0, KVQ_ERR_MISALIGNED, "TMA row stride %llu not a multiple of 16 B",
+              static_cast<unsigned long long>(row_stride_bytes));
+  KVQ_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols >= 1 && box_cols <= 256, KVQ_ERR_BAD_SHAPE,
+              "TMA box %ux%u out of range", box_rows, box_cols);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KVQ_REQUIRE(r == CUDA_SUCCESS, KVQ_ERR_DRIVER,
+              "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu stride=%llu box=%ux%u", static_cast<int>(r),
+              static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
+              static_cast<unsigned long long>(row_stride_bytes), box_rows, box_cols);
+  return KVQ_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace kvq

@@ -1,0 +1,163 @@
+// Internal (C++) interfaces between the host orchestration (kvq_swin.cu), the C-ABI shims (kvq_capi.cu)
+// and the kernels.  Nothing here crosses the shared-library boundary; include/kvq_b200.h does.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kvq {
+
+const char* last_error();
+int num_sms();
+
+// ----------------------------------------------------------------------------------------------
+// window geometry of one Swin block (reference: swin_backbone.py get_window_size :145-158,
+// window_partition :92-117, forward_part1 :407-488).  All token grids are [D,H,W] per clip.
+// ----------------------------------------------------------------------------------------------
+struct WinGeom {
+  int D, H, W;        // token grid of the stage
+  int Dp, Hp, Wp;     // padded up to window multiples
+  int wd, wh, ww;     // clamped window
+  int sd, sh, sw;     // clamped shift (0 on unshifted blocks)
+  int nwd, nwh, nww;  // windows per dim
+  int N;              // wd*wh*ww  tokens per window
+  int SL;             // wh*ww     tokens per temporal slab of a window
+  int nW;             // windows per clip
+  int tokens;         // D*H*W
+};
+
+static inline WinGeom make_geom(int D, int H, int W, const int base_win[3], const int shift[3]) {
+  WinGeom g;
+  g.D = D; g.H = H; g.W = W;
+  const int dims[3] = {D, H, W};
+  int w[3], s[3];
+  for (int i = 0; i < 3; ++i) {
+    if (dims[i] <= base_win[i]) { w[i] = dims[i]; s[i] = 0; } else { w[i] = base_win[i]; s[i] = shift[i]; }
+  }
+  g.wd = w[0]; g.wh = w[1]; g.ww = w[2];
+  g.sd = s[0]; g.sh = s[1]; g.sw = s[2];
+  g.Dp = (D + g.wd - 1) / g.wd * g.wd;
+  g.Hp = (H + g.wh - 1) / g.wh * g.wh;
+  g.Wp = (W + g.ww - 1) / g.ww * g.ww;
+  g.nwd = g.Dp / g.wd; g.nwh = g.Hp / g.wh; g.nww = g.Wp / g.ww;
+  g.N = g.wd * g.wh * g.ww;
+  g.SL = g.wh * g.ww;
+  g.nW = g.nwd * g.nwh * g.nww;
+  g.tokens = D * H * W;
+  return g;
+}
+
+// Window-order row r in [0, nW*N) of one clip  ->  flat original token index, or -1 for a padded slot.
+// shifted[p] = x[(p + s) mod size]  (torch.roll by -s, swin_backbone.py:430-435).
+__host__ __device__ __forceinline__ int win_row_to_src(const WinGeom& g, int r) {
+  const int win = r / g.N, i = r - win * g.N;
+  const int wdi = win / (g.nwh * g.nww), whi = (win / g.nww) % g.nwh, wwi = win % g.nww;
+  const int td = i / g.SL, th = (i / g.ww) % g.wh, tw = i % g.ww;
+  int od = wdi * g.wd + td + g.sd; if (od >= g.Dp) od -= g.Dp;
+  int oh = whi * g.wh + th + g.sh; if (oh >= g.Hp) oh -= g.Hp;
+  int ow = wwi * g.ww + tw + g.sw; if (ow >= g.Wp) ow -= g.Wp;
+  if (od >= g.D || oh >= g.H || ow >= g.W) return -1;
+  return (od * g.H + oh) * g.W + ow;
+}
+
+// ----------------------------------------------------------------------------------------------
+// attention operand images.  One (window, head) unit owns three 25 600 B images Q | K | V, each
+// 400 rows x 32 halfs in the UMMA no-swizzle core-matrix order
+//     byte(r, c) = (r/8)*512 + (c/8)*128 + (r%8)*16 + (c%8)*2
+// Q rows are tokens in window order i; K/V rows are slab-padded key slots  col(i) = (i/SL)*50 + i%SL
+// so that one temporal slab (<= 49 keys) starts every 50 columns of the logits tile.
+// ----------------------------------------------------------------------------------------------
+constexpr int ATT_ROWS = 400;
+constexpr int ATT_SLAB = 50;
+constexpr int ATT_HD = 32;
+constexpr int ATT_IMG_BYTES = ATT_ROWS * ATT_HD * 2;  // 25 600
+constexpr int ATT_UNIT_BYTES = 3 * ATT_IMG_BYTES;     // 76 800
+
+__host__ __device__ __forceinline__ int att_img_offset(int r, int chunk) {  // byte offset of a 16 B chunk
+  return (r >> 3) * 512 + chunk * 128 + (r & 7) * 16;
+}
+
+// ----------------------------------------------------------------------------------------------
+// GEMM  D[M,N] = A[M,K] * B[N,K]^T  (fp16 operands, fp32 accumulate in TMEM) + fused epilogues
+// ----------------------------------------------------------------------------------------------
+enum GemmEpilogue : int {
+  EPI_GELU_F16 = 0,  // out_h[m, n] = gelu(acc + bias[n])                         (Mlp.fc1 + act, :64-89)
+  EPI_RESID_F32 = 1, // out_f[row(m), n] = resid[row(m), n] + acc + bias[n]       (proj / fc2 / reduction)
+  EPI_QKV_IMG = 2,   // q*scale | k | v scattered into the attention operand images (WindowAttention3D :253-261)
+  EPI_LN_F32 = 3,    // out_f[m, :] = LayerNorm(acc + bias) * gamma + beta, N == BLOCK_N  (PatchEmbed3D :715-733)
+  EPI_HEAD = 4,      // rowscore[m] = sum_n gelu(acc + bias[n]) * w2[n] + b2      (VQAHead, head.py:60-68)
+  EPI_STORE_F16 = 5, // out_h[m, n] = acc + bias[n]
+};
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;    // [N] or nullptr
+  void* out;            // fp16 / fp32 matrix, row stride ldo elements
+  int ldo;
+  const float* resid;   // EPI_RESID_F32: nullptr = no residual; may alias out
+  // EPI_RESID_F32 row remap (proj): rows are window-ordered; rows_in = nW*N per clip, rows_out = tokens per clip
+  int remap;            // 0 = identity
+  WinGeom geom;
+  // EPI_QKV_IMG
+  __half* img;          // unit-major operand images
+  int C;                // channels (N == 3C)
+  int heads;
+  float qscale;
+  // EPI_LN_F32
+  const float* gamma;
+  const float* beta;
+  float eps;
+  // EPI_HEAD
+  const float* w2;
+  const float* b2ptr;   // device scalar
+  float* rowscore;
+};
+
+int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
+                cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
+// memory-bound row kernels
+// ----------------------------------------------------------------------------------------------
+// LN1 + cyclic shift + window partition: out[b*nW*N + r, :] = LN(x[b*tokens + src(r), :]) (zeros for padded slots)
+int launch_ln_window(const float* x, __half* out, const float* gamma, const float* beta, float eps, int B, int C,
+                     const WinGeom& g, cudaStream_t stream);
+// plain LN over rows: out[m, :] = LN(x[m, :]);  optionally also writes the fp32 result transposed into
+// feat[b, c, t] (channels-first, SwinTransformer3D.forward :1066-1080)
+int launch_ln_rows(const float* x, __half* out, float* feat_cf, const float* gamma, const float* beta, float eps,
+                   int M, int C, int tokens_per_clip, cudaStream_t stream);
+// PatchMerging gather + LN(4C) (:533-555): out[(b,d,h2,w2), 4C]
+int launch_ln_merge(const float* x, __half* out, const float* gamma, const float* beta, float eps, int B, int D,
+                    int H, int W, int C, cudaStream_t stream);
+// PatchEmbed3D im2col: x[B,3,T,H,W] fp32 -> A[B*D*Hs*Ws, 96] fp16, K index = c*32 + kt*16 + kh*4 + kw
+int launch_patch_im2col(const float* x, __half* out, int B, int T, int H, int W, cudaStream_t stream);
+// score[b] = mean_t rowscore[b*tokens + t]
+int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cudaStream_t stream);
+// Grid mini-patch sampling + normalisation (datasets/fusion_datasets.py:22-121, :1017-1020)
+int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
+                              int fh, int fw, int fs, int aligned, const float mean[3], const float stdv[3],
+                              cudaStream_t stream);
+// fp32 -> fp16 cast (weight packing)
+int launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
+// fused 3-D window attention
+// ----------------------------------------------------------------------------------------------
+struct AttnParams {
+  const __half* img;        // [units][Q|K|V] images
+  __half* out;              // [B*nW*N, C] window-order rows
+  const float* packed_tab;  // [heads][tab_len] float2 {t0, t1}: bias = t0 + fg*t1  (launch_pack_bias)
+  int B, C, heads;
+  int shifted;              // apply the SW-MSA region mask
+  WinGeom geom;
+  int base_wd, base_wh, base_ww;  // un-clamped window the bias tables are indexed with
+  int variant;              // debug: 1 swaps LBO/SBO of the MN-major V descriptor
+};
+// entries per head of the packed table for a base window (L rounded up to even)
+int attn_table_len(int bd, int bh, int bw);
+// rel/frag: [L, heads] fp32 (frag may be nullptr) -> out [heads][tab_len] float2
+int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, int bh, int bw, int heads,
+                     cudaStream_t stream);
+int launch_window_attn(const AttnParams& p, cudaStream_t stream);
+
+}  // namespace kvq

@@ -1,0 +1,318 @@
+// HBM-bound row kernels around the GEMMs: LayerNorm prologues (with the cyclic-shift / window-partition /
+// patch-merge gathers folded into the load), patch-embed im2col, head mean, fp32->fp16 weight packing and the
+// Grid-Mini-patch fragment gather.  One warp per output row, float4 loads / 8-byte fp16 stores, fp32 statistics.
+#include "kvq_common.cuh"
+#include "kvq_kernels.cuh"
+
+namespace kvq {
+
+namespace {
+
+constexpr int ROW_THREADS = 256;  // 8 rows per CTA
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// LayerNorm of a logical row made of SEG segments of C floats (SEG = 1: plain / window gather, SEG = 4: PatchMerging
+// concat).  src[s] < 0 means "zeros" for that segment.  MAXV = float4 chunks per lane.
+template <int MAXV>
+__device__ __forceinline__ void ln_row(const float* const* seg_ptr, int nseg, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, __half* __restrict__ out,
+                                       float* __restrict__ out_f32_cf, size_t cf_stride, int lane) {
+  const int chunks_per_seg = C >> 2;
+  const int chunks = chunks_per_seg * nseg;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int ch = lane + 32 * k;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch < chunks) {
+      const int sg = ch / chunks_per_seg;
+      const float* sp = seg_ptr[sg];
+      if (sp != nullptr) v[k] = __ldg(reinterpret_cast<const float4*>(sp) + (ch - sg * chunks_per_seg));
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  const float inv_n = 1.0f / static_cast<float>(4 * chunks);
+  const float mean = warp_sum(s) * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int ch = lane + 32 * k;
+    if (ch < chunks) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int ch = lane + 32 * k;
+    if (ch < chunks) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + ch);
+      const float y0 = (v[k].x - mean) * rstd * g.x + b.x;
+      const float y1 = (v[k].y - mean) * rstd * g.y + b.y;
+      const float y2 = (v[k].z - mean) * rstd * g.z + b.z;
+      const float y3 = (v[k].w - mean) * rstd * g.w + b.w;
+      if (out != nullptr) {
+        uint2 h;
+        h.x = pack_half2(y0, y1);
+        h.y = pack_half2(y2, y3);
+        *reinterpret_cast<uint2*>(out + 4 * ch) = h;
+      }
+      if (out_f32_cf != nullptr) {
+        out_f32_cf[static_cast<size_t>(4 * ch) * cf_stride] = y0;
+        out_f32_cf[static_cast<size_t>(4 * ch + 1) * cf_stride] = y1;
+        out_f32_cf[static_cast<size_t>(4 * ch + 2) * cf_stride] = y2;
+        out_f32_cf[static_cast<size_t>(4 * ch + 3) * cf_stride] = y3;
+      }
+    }
+  }
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_window_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, int rows, int C, WinGeom g) {
+  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int rows_in = g.nW * g.N;
+  const int b = row / rows_in;
+  const int src = win_row_to_src(g, row - b * rows_in);
+  __half* orow = out + static_cast<size_t>(row) * C;
+  if (src < 0) {  // padded slot: zeros AFTER the norm (swin_backbone.py:416-424)
+    for (int ch = lane; ch < (C >> 2); ch += 32) *reinterpret_cast<uint2*>(orow + 4 * ch) = make_uint2(0u, 0u);
+    return;
+  }
+  const float* sp = x + (static_cast<size_t>(b) * g.tokens + src) * C;
+  ln_row<MAXV>(&sp, 1, C, gamma, beta, eps, orow, nullptr, 0, lane);
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_rows_kernel(const float* __restrict__ x, __half* __restrict__ out, float* __restrict__ feat_cf,
+               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int C,
+               int tokens_per_clip) {
+  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sp = x + static_cast<size_t>(row) * C;
+  float* cf = nullptr;
+  if (feat_cf != nullptr) {
+    const int b = row / tokens_per_clip, t = row - b * tokens_per_clip;
+    cf = feat_cf + static_cast<size_t>(b) * C * tokens_per_clip + t;  // [B, C, tokens]
+  }
+  ln_row<MAXV>(&sp, 1, C, gamma, beta, eps, out != nullptr ? out + static_cast<size_t>(row) * C : nullptr, cf,
+               static_cast<size_t>(tokens_per_clip), lane);
+}
+
+// PatchMerging (:533-555): rows (b, d, h2, w2); channel order [x(2h,2w) | x(2h+1,2w) | x(2h,2w+1) | x(2h+1,2w+1)],
+// odd H/W zero-padded BEFORE the norm.
+template <int MAXV>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_merge_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, int rows, int D, int H, int W, int C) {
+  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+  const int w2 = row % W2;
+  const int h2 = (row / W2) % H2;
+  const int bd = row / (W2 * H2);  // b*D + d
+  const float* seg[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int hh = 2 * h2 + (s & 1), ww = 2 * w2 + (s >> 1);
+    seg[s] = (hh < H && ww < W) ? x + ((static_cast<size_t>(bd) * H + hh) * W + ww) * C : nullptr;
+  }
+  ln_row<MAXV>(seg, 4, C, gamma, beta, eps, out + static_cast<size_t>(row) * 4 * C, nullptr, 0, lane);
+}
+
+// PatchEmbed3D im2col (:715-731).  One thread per (output token, c, kt, kh): copies the 4 kw taps (16 B in, 8 B out).
+// Zero padding when T/H/W are not multiples of (2,4,4).
+__global__ void __launch_bounds__(256)
+patch_im2col_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int T, int H, int W, int D, int Hs,
+                    int Ws, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  // ws fastest so a warp reads 512 contiguous bytes of one input row; the 8 B stores merge in L2
+  const int ws = static_cast<int>(idx % Ws);
+  const int kq = static_cast<int>((idx / Ws) % 24);  // c*8 + kt*4 + kh
+  const long long bdh = idx / (static_cast<long long>(Ws) * 24);
+  const int hs = static_cast<int>(bdh % Hs);
+  const int d = static_cast<int>((bdh / Hs) % D);
+  const int b = static_cast<int>(bdh / (static_cast<long long>(Hs) * D));
+  const int c = kq >> 3, kt = (kq >> 2) & 1, kh = kq & 3;
+  const long long tok = ((static_cast<long long>(b) * D + d) * Hs + hs) * Ws + ws;
+  const int t = 2 * d + kt, h = 4 * hs + kh, w0 = 4 * ws;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (t < T && h < H) {
+    const float* src = x + (((static_cast<size_t>(b) * 3 + c) * T + t) * H + h) * W + w0;
+    if (w0 + 3 < W && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (w0 + k < W) v[k] = __ldg(src + k);
+    }
+  }
+  uint2 h2;
+  h2.x = pack_half2(v[0], v[1]);
+  h2.y = pack_half2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(out + tok * 96 + c * 32 + kt * 16 + kh * 4) = h2;
+}
+
+__global__ void __launch_bounds__(256)
+row_mean_kernel(const float* __restrict__ rowscore, float* __restrict__ score, int tokens) {
+  __shared__ float part[8];
+  const float* src = rowscore + static_cast<size_t>(blockIdx.x) * tokens;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < tokens; i += blockDim.x) s += src[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    score[blockIdx.x] = t / static_cast<float>(tokens);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+
+// Grid Mini-patch Sampling (get_spatial_fragments, fusion_datasets.py:22-121) + (v - mean) / std (:1017-1020).
+// One thread per 4 consecutive output pixels of one fragment row: 4 B in, 16 B out.
+__global__ void __launch_bounds__(256)
+fragment_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ offsets, float* __restrict__ out,
+                       int T, int Hs, int Ws, int fh, int fw, int fs, int aligned, float m0, float m1, float m2,
+                       float is0, float is1, float is2, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int OW = fw * fs, OH = fh * fs, OW4 = OW >> 2;
+  const int x4 = static_cast<int>(idx % OW4);
+  const int y = static_cast<int>((idx / OW4) % OH);
+  const int t = static_cast<int>((idx / (static_cast<long long>(OW4) * OH)) % T);
+  const int c = static_cast<int>((idx / (static_cast<long long>(OW4) * OH * T)) % 3);
+  const int b = static_cast<int>(idx / (static_cast<long long>(OW4) * OH * T * 3));
+  const int x = x4 * 4;
+  const int i = y / fs, dy = y - i * fs, j = x / fs, dx = x - j * fs;
+  const int nt = T / aligned, tc = t / aligned;
+  // hgrids / wgrids (:64-69): cell origin clamped so the patch stays inside the frame
+  int hg = (Hs / fh) * i; if (hg > Hs - fs) hg = Hs - fs;
+  int wg = (Ws / fw) * j; if (wg > Ws - fs) wg = Ws - fs;
+  const int32_t* off = offsets + static_cast<size_t>(b) * 2 * fh * fw * nt;
+  const int oh = off[(i * fw + j) * nt + tc];
+  const int ow = off[fh * fw * nt + (i * fw + j) * nt + tc];
+  const uint8_t* src = frames + (((static_cast<size_t>(b) * T + t) * 3 + c) * Hs + (hg + oh + dy)) * Ws + (wg + ow + dx);
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+  const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+  float4 v;
+  v.x = (static_cast<float>(src[0]) - mean) * istd;
+  v.y = (static_cast<float>(src[1]) - mean) * istd;
+  v.z = (static_cast<float>(src[2]) - mean) * istd;
+  v.w = (static_cast<float>(src[3]) - mean) * istd;
+  *reinterpret_cast<float4*>(out + (((static_cast<size_t>(b) * 3 + c) * T + t) * OH + y) * OW + x) = v;
+}
+
+template <typename F>
+int dispatch_maxv(int chunks, F&& f) {
+  if (chunks <= 32) return f(std::integral_constant<int, 1>{});
+  if (chunks <= 64) return f(std::integral_constant<int, 2>{});
+  if (chunks <= 96) return f(std::integral_constant<int, 3>{});
+  if (chunks <= 192) return f(std::integral_constant<int, 6>{});
+  if (chunks <= 384) return f(std::integral_constant<int, 12>{});
+  if (chunks <= 768) return f(std::integral_constant<int, 24>{});
+  set_error("LayerNorm row of %d floats is wider than this build supports (3072)", chunks * 4);
+  return KVQ_ERR_BAD_SHAPE;
+}
+
+}  // namespace
+
+int launch_ln_window(const float* x, __half* out, const float* gamma, const float* beta, float eps, int B, int C,
+                     const WinGeom& g, cudaStream_t stream) {
+  KVQ_REQUIRE(C % 4 == 0, KVQ_ERR_BAD_SHAPE, "ln_window: C=%d not a multiple of 4", C);
+  const long long rows = static_cast<long long>(B) * g.nW * g.N;
+  KVQ_REQUIRE(rows < (1ll << 31), KVQ_ERR_BAD_SHAPE, "ln_window: %lld rows overflow int32", rows);
+  const int grid = static_cast<int>((rows + 7) / 8);
+  return dispatch_maxv(C / 4, [&](auto mv) {
+    ln_window_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, gamma, beta, eps,
+                                                                             static_cast<int>(rows), C, g);
+    return check_cuda(cudaGetLastError(), "ln_window_kernel launch");
+  });
+}
+
+int launch_ln_rows(const float* x, __half* out, float* feat_cf, const float* gamma, const float* beta, float eps,
+                   int M, int C, int tokens_per_clip, cudaStream_t stream) {
+  KVQ_REQUIRE(C % 4 == 0 && M > 0, KVQ_ERR_BAD_SHAPE, "ln_rows: M=%d C=%d", M, C);
+  const int grid = (M + 7) / 8;
+  return dispatch_maxv(C / 4, [&](auto mv) {
+    ln_rows_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, feat_cf, gamma, beta, eps, M, C,
+                                                                           tokens_per_clip);
+    return check_cuda(cudaGetLastError(), "ln_rows_kernel launch");
+  });
+}
+
+int launch_ln_merge(const float* x, __half* out, const float* gamma, const float* beta, float eps, int B, int D,
+                    int H, int W, int C, cudaStream_t stream) {
+  KVQ_REQUIRE(C % 4 == 0, KVQ_ERR_BAD_SHAPE, "ln_merge: C=%d not a multiple of 4", C);
+  const long long rows = static_cast<long long>(B) * D * ((H + 1) / 2) * ((W + 1) / 2);
+  KVQ_REQUIRE(rows < (1ll << 31), KVQ_ERR_BAD_SHAPE, "ln_merge: %lld rows overflow int32", rows);
+  const int grid = static_cast<int>((rows + 7) / 8);
+  return dispatch_maxv(C, [&](auto mv) {
+    ln_merge_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, gamma, beta, eps,
+                                                                            static_cast<int>(rows), D, H, W, C);
+    return check_cuda(cudaGetLastError(), "ln_merge_kernel launch");
+  });
+}
+
+int launch_patch_im2col(const float* x, __half* out, int B, int T, int H, int W, cudaStream_t stream) {
+  const int D = (T + 1) / 2, Hs = (H + 3) / 4, Ws = (W + 3) / 4;
+  const long long total = static_cast<long long>(B) * D * Hs * Ws * 24;
+  const long long grid = (total + 255) / 256;
+  KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "im2col: grid too large");
+  patch_im2col_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(x, out, B, T, H, W, D, Hs, Ws, total);
+  return check_cuda(cudaGetLastError(), "patch_im2col_kernel launch");
+}
+
+int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cudaStream_t stream) {
+  row_mean_kernel<<<B, 256, 0, stream>>>(rowscore, score, tokens);
+  return check_cuda(cudaGetLastError(), "row_mean_kernel launch");
+}
+
+int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
+                              int fh, int fw, int fs, int aligned, const float mean[3], const float stdv[3],
+                              cudaStream_t stream) {
+  KVQ_REQUIRE(B > 0 && T > 0 && fh > 0 && fw > 0 && fs > 0 && fs % 4 == 0, KVQ_ERR_BAD_SHAPE,
+              "fragment_gather: bad geometry (fsize must be a multiple of 4)");
+  KVQ_REQUIRE(aligned > 0 && T % aligned == 0, KVQ_ERR_BAD_SHAPE,
+              "fragment_gather: T=%d is not a multiple of aligned=%d (fusion_datasets.py:59)", T, aligned);
+  KVQ_REQUIRE(Hs >= fh * fs && Ws >= fw * fs, KVQ_ERR_BAD_SHAPE,
+              "fragment_gather: %dx%d source is smaller than the %dx%d target; the bilinear upsample fallback "
+              "(fusion_datasets.py:43-50) is not on the B200 path", Hs, Ws, fh * fs, fw * fs);
+  const long long total = static_cast<long long>(B) * 3 * T * (fh * fs) * (fw * fs / 4);
+  const long long grid = (total + 255) / 256;
+  KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "fragment_gather: grid too large");
+  fragment_gather_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(
+      frames, offsets, out, T, Hs, Ws, fh, fw, fs, aligned, mean[0], mean[1], mean[2], 1.0f / stdv[0], 1.0f / stdv[1],
+      1.0f / stdv[2], total);
+  return check_cuda(cudaGetLastError(), "fragment_gather_kernel launch");
+}
+
+int launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
+  if (n == 0) return KVQ_OK;
+  cast_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, out, n);
+  return check_cuda(cudaGetLastError(), "cast_f16_kernel launch");
+}
+
+}  // namespace kvq

@@ -1,0 +1,80 @@
+"""ctypes binding of the C-ABI library (include/kvq_b200.h).  There is NO fallback: if libkvq_b200.so is missing
+or a call fails, a RuntimeError carrying kvq_last_error_string() is raised."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libkvq_b200.so")
+MAX_STAGES = 4
+
+
+class KvqSwinConfig(ctypes.Structure):
+    _fields_ = [("embed_dim", c_int32), ("num_stages", c_int32), ("depths", c_int32 * MAX_STAGES),
+                ("num_heads", c_int32 * MAX_STAGES), ("window", c_int32 * 3), ("frag_bias", c_int32 * MAX_STAGES),
+                ("head_hidden", c_int32), ("ln_eps", c_float)]
+
+
+_I3 = c_int32 * 3
+_F3 = c_float * 3
+
+# name -> (restype, argtypes); mirrors include/kvq_b200.h one to one
+PROTOTYPES = {
+    "kvq_swin3d_num_weights": (c_int, [POINTER(KvqSwinConfig)]),
+    "kvq_swin3d_workspace_bytes": (c_size_t, [POINTER(KvqSwinConfig), c_int, c_int, c_int, c_int]),
+    "kvq_swin3d_forward": (c_int, [POINTER(KvqSwinConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_cast_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_attn_table_len": (c_int, [c_int, c_int, c_int]),
+    "kvq_pack_bias_table": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "kvq_linear_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "kvq_linear_resid_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kvq_ln_window": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
+                              POINTER(c_int32), POINTER(c_int32), c_void_p]),
+    "kvq_window_rows": (c_int64, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32)]),
+    "kvq_window_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int32),
+                                                        POINTER(c_int32)]),
+    "kvq_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_void_p, c_size_t, c_int,
+                                     c_void_p]),
+    "kvq_fragment_gather_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, POINTER(c_float), POINTER(c_float), c_void_p]),
+    "kvq_last_error_string": (c_char_p, []),
+    "kvq_build_info": (c_char_p, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load libkvq_b200.so (built by `__graft_entry__.build()` / `make -C csrc`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"kvq_b200: native library not found at {LIB_PATH}; run `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (there is no CPU or PyTorch fallback for this path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)        # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().kvq_last_error_string().decode()
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"kvq_b200.{what} failed (code {rc}): {last_error()}")
+
+
+def i3(v):
+    return _I3(*[int(t) for t in v])
+
+
+def f3(v):
+    return _F3(*[float(t) for t in v])

@@ -1,0 +1,206 @@
+"""torch-tensor front ends of the C-ABI operators.  PyTorch only supplies device memory and the stream."""
+import ctypes
+
+import torch
+
+from . import lib as _l
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("kvq_b200 operators take CUDA tensors only (no CPU fallback exists)")
+        if t is not None and not t.is_contiguous():
+            raise RuntimeError("kvq_b200 operators take contiguous tensors")
+
+
+def cast_f16(t):
+    t = t.detach().float().contiguous()
+    _need_cuda(t)
+    out = torch.empty(t.shape, dtype=torch.float16, device=t.device)
+    _l.check(_l.load().kvq_cast_f16(_p(t), _p(out), t.numel(), _stream()), "cast_f16")
+    return out
+
+
+def attn_table_len(window):
+    return _l.load().kvq_attn_table_len(*[int(w) for w in window])
+
+
+def pack_bias_table(rel, frag, window, heads):
+    """[L, heads] fp32 tables -> packed [heads, tab_len, 2] fp32 ({frag, rel - frag} or {rel, 0})."""
+    rel = rel.detach().float().contiguous()
+    frag = frag.detach().float().contiguous() if frag is not None else None
+    _need_cuda(rel, frag)
+    out = torch.empty((heads, attn_table_len(window), 2), dtype=torch.float32, device=rel.device)
+    _l.check(_l.load().kvq_pack_bias_table(_p(rel), _p(frag), _p(out), int(window[0]), int(window[1]), int(window[2]),
+                                           heads, _stream()), "pack_bias_table")
+    return out
+
+
+def linear_f16(a, w, bias=None, gelu=False):
+    _need_cuda(a, w, bias)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float16, device=a.device)
+    _l.check(_l.load().kvq_linear_f16(_p(a), _p(w), _p(bias), _p(out), M, N, K, int(gelu), _stream()), "linear_f16")
+    return out
+
+
+def linear_resid_f32(a, w, bias=None, resid=None, out=None):
+    _need_cuda(a, w, bias, resid, out)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _l.check(_l.load().kvq_linear_resid_f32(_p(a), _p(w), _p(bias), _p(resid), _p(out), M, N, K, _stream()),
+             "linear_resid_f32")
+    return out
+
+
+def window_rows(B, D, H, W, window, shift):
+    return int(_l.load().kvq_window_rows(B, D, H, W, _l.i3(window), _l.i3(shift)))
+
+
+def ln_window(x, gamma, beta, window, shift, eps=1e-5):
+    """x f32 [B,D,H,W,C] -> f16 [B*nW*N, C]: norm1 + roll(-shift) + window_partition."""
+    _need_cuda(x, gamma, beta)
+    B, D, H, W, C = x.shape
+    rows = window_rows(B, D, H, W, window, shift)
+    out = torch.empty((rows, C), dtype=torch.float16, device=x.device)
+    _l.check(_l.load().kvq_ln_window(_p(x), _p(out), _p(gamma), _p(beta), eps, B, D, H, W, C, _l.i3(window),
+                                     _l.i3(shift), _stream()), "ln_window")
+    return out
+
+
+def window_attention(xw, qkv_w, qkv_b, packed_table, B, D, H, W, heads, window, shift, debug_variant=0):
+    """xw f16 [B*nW*N, C] (window order) -> attention output f16 [B*nW*N, C] (before proj)."""
+    _need_cuda(xw, qkv_w, qkv_b, packed_table)
+    C = xw.shape[1]
+    lib = _l.load()
+    nbytes = lib.kvq_window_attention_workspace_bytes(B, D, H, W, C, _l.i3(window), _l.i3(shift))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=xw.device)
+    out = torch.empty_like(xw)
+    _l.check(lib.kvq_window_attention(_p(xw), _p(qkv_w), _p(qkv_b), _p(packed_table), _p(out), B, D, H, W, C, heads,
+                                      _l.i3(window), _l.i3(shift), _p(ws), nbytes, debug_variant, _stream()),
+             "window_attention")
+    return out
+
+
+IMAGENET_MEAN = (123.675, 116.28, 103.53)
+IMAGENET_STD = (58.395, 57.12, 57.375)
+
+
+def fragment_gather_u8(frames, offsets, fragments_h=7, fragments_w=7, fsize=32, aligned=8, mean=IMAGENET_MEAN,
+                       std=IMAGENET_STD):
+    """frames u8 [B,T,3,Hs,Ws], offsets i32 [B,2,fh,fw,T//aligned] -> f32 [B,3,T,fh*fsize,fw*fsize] normalised."""
+    _need_cuda(frames, offsets)
+    if frames.dtype != torch.uint8 or offsets.dtype != torch.int32:
+        raise RuntimeError("fragment_gather_u8: frames must be uint8 and offsets int32")
+    B, T, _, Hs, Ws = frames.shape
+    out = torch.empty((B, 3, T, fragments_h * fsize, fragments_w * fsize), dtype=torch.float32, device=frames.device)
+    _l.check(_l.load().kvq_fragment_gather_u8(_p(frames), _p(offsets), _p(out), B, T, Hs, Ws, fragments_h, fragments_w,
+                                              fsize, aligned, _l.f3(mean), _l.f3(std), _stream()), "fragment_gather_u8")
+    return out
+
+
+class SwinWeights:
+    """Device-resident packed weights of SwinTransformer3D (+ VQAHead) in the order include/kvq_b200.h documents.
+
+    `sd` maps the REFERENCE state_dict names (swin_backbone.py:760-842; head.py:33-58) to tensors; `prefix` /
+    `head_prefix` select the sub-module (e.g. 'swin_tiny_grpb_backbone.' / 'swin_tiny_grpb_head.')."""
+
+    def __init__(self, sd, device, prefix="", head_prefix=None, embed_dim=96, depths=(2, 2, 6, 2),
+                 num_heads=(3, 6, 12, 24), window=(8, 7, 7), frag_biases=(True, True, True, False), eps=1e-5):
+        self.device = torch.device(device)
+        self.cfg = _l.KvqSwinConfig()
+        self.cfg.embed_dim = embed_dim
+        self.cfg.num_stages = len(depths)
+        for i, (d, h, f) in enumerate(zip(depths, num_heads, frag_biases)):
+            self.cfg.depths[i], self.cfg.num_heads[i], self.cfg.frag_bias[i] = int(d), int(h), int(bool(f))
+        for i in range(3):
+            self.cfg.window[i] = int(window[i])
+        self.cfg.ln_eps = eps
+        self.cfg.head_hidden = 0
+        self.depths, self.final_dim = tuple(depths), embed_dim * 2 ** (len(depths) - 1)
+
+        def f32(k):
+            return sd[k].detach().to(self.device, torch.float32).contiguous()
+
+        def f16(k, shape=None):
+            t = f32(k)
+            return cast_f16(t.reshape(shape) if shape is not None else t)
+
+        ts = [f16(prefix + "patch_embed.proj.weight", (embed_dim, -1)), f32(prefix + "patch_embed.proj.bias"),
+              f32(prefix + "patch_embed.norm.weight"), f32(prefix + "patch_embed.norm.bias")]
+        for s, depth in enumerate(depths):
+            for j in range(depth):
+                b = f"{prefix}layers.{s}.blocks.{j}."
+                frag = f32(b + "attn.fragment_position_bias_table") if frag_biases[s] else None
+                ts += [f32(b + "norm1.weight"), f32(b + "norm1.bias"), f16(b + "attn.qkv.weight"),
+                       f32(b + "attn.qkv.bias"),
+                       pack_bias_table(f32(b + "attn.relative_position_bias_table"), frag, window, num_heads[s]),
+                       f16(b + "attn.proj.weight"), f32(b + "attn.proj.bias"), f32(b + "norm2.weight"),
+                       f32(b + "norm2.bias"), f16(b + "mlp.fc1.weight"), f32(b + "mlp.fc1.bias"),
+                       f16(b + "mlp.fc2.weight"), f32(b + "mlp.fc2.bias")]
+        # per-stage downsample entries follow ALL blocks (header order): collect separately, then interleave
+        merged = ts[:4]
+        pos = 4
+        for s, depth in enumerate(depths):
+            merged += ts[pos:pos + 13 * depth]
+            pos += 13 * depth
+            if s < len(depths) - 1:
+                b = f"{prefix}layers.{s}.downsample."
+                merged += [f32(b + "norm.weight"), f32(b + "norm.bias"), f16(b + "reduction.weight")]
+        merged += [f32(prefix + "norm.weight"), f32(prefix + "norm.bias")]
+        if head_prefix is not None:
+            hid = sd[head_prefix + "fc_hid.weight"].shape[0]
+            self.cfg.head_hidden = int(hid)
+            merged += [f16(head_prefix + "fc_hid.weight", (hid, -1)), f32(head_prefix + "fc_hid.bias"),
+                       f32(head_prefix + "fc_last.weight").reshape(-1).contiguous(),
+                       f32(head_prefix + "fc_last.bias").reshape(-1).contiguous()]
+        self.tensors = merged
+        n = _l.load().kvq_swin3d_num_weights(ctypes.byref(self.cfg))
+        if n != len(merged):
+            raise RuntimeError(f"kvq_b200: weight table has {len(merged)} entries, library expects {n}: "
+                               f"{_l.last_error()}")
+        self.ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in merged])
+        self._ws = None
+
+    def workspace(self, B, T, H, W):
+        need = _l.load().kvq_swin3d_workspace_bytes(ctypes.byref(self.cfg), B, T, H, W)
+        if need == 0:
+            raise RuntimeError(f"kvq_b200: cannot plan a [{B},3,{T},{H},{W}] forward: {_l.last_error()}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws, need
+
+    def feat_shape(self, B, T, H, W):
+        D, h, w = (T + 1) // 2, (H + 3) // 4, (W + 3) // 4
+        for _ in range(len(self.depths) - 1):
+            h, w = (h + 1) // 2, (w + 1) // 2
+        return (B, self.final_dim, D, h, w)
+
+    def forward(self, x, want_feat=False, want_score=True, score_out=None):
+        """x f32 [B,3,T,H,W] on this device -> (feat [B,Cf,D,h,w] or None, score [B] or None)."""
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("kvq_b200: input clips must be float32 CUDA tensors (no CPU fallback exists)")
+        x = x.contiguous()
+        B, _, T, H, W = x.shape
+        ws, need = self.workspace(B, T, H, W)
+        feat = torch.empty(self.feat_shape(B, T, H, W), dtype=torch.float32, device=x.device) if want_feat else None
+        score = None
+        if want_score and self.cfg.head_hidden > 0:
+            score = score_out if score_out is not None else torch.empty(B, dtype=torch.float32, device=x.device)
+        rc = _l.load().kvq_swin3d_forward(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(x), B, T, H, W,
+                                          _p(feat), _p(score), _p(ws), ws.numel(), _stream())
+        _l.check(rc, "swin3d_forward")
+        return feat, score

@@ -1,0 +1,144 @@
+"""GPU parity tests of the individual C-ABI operators against the CPU oracle (oracle/swin3d.py) / fp32 torch.
+All calls go through libkvq_b200.so (ctypes).  Tolerances: operands are fp16 (11-bit significand), accumulation
+fp32, so a dot product of K terms carries ~K^0.5 * 2^-11 relative noise; bounds are stated per test."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+@pytest.mark.parametrize("M,N,K,gelu", [
+    (300, 96, 96, False),         # K tail (96 = 64 + 32 zero-filled by TMA), ragged M
+    (1000, 192, 384, True),       # BLOCK_N = 192, GELU epilogue
+    (256, 64, 768, False),        # BLOCK_N = 64
+    (128 * 160 + 5, 384, 96, True),   # more tiles than SMs: persistent loop + TMEM double buffering
+    (640, 96, 3072, False),       # long K: smem ring wraps many times
+    (130, 2304, 768, False),      # many N blocks
+])
+def test_linear_f16(M, N, K, gelu):
+    from kvq_b200 import ops
+    a = _rand((M, K), 1).half()
+    w = (_rand((N, K), 2) / math.sqrt(K)).half()
+    b = _rand((N,), 3, 0.1)
+    ref = a.float() @ w.float().t() + b
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    out = ops.linear_f16(a.to(_dev()), w.to(_dev()), b.to(_dev()), gelu=gelu).float().cpu()
+    # fp16 output rounding (2^-11 relative) dominates; |ref| is O(1)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < 6e-3, (out - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(777, 96, 384), (128 * 150, 192, 192), (500, 768, 1536)])
+def test_linear_resid_f32(M, N, K):
+    from kvq_b200 import ops
+    a = _rand((M, K), 4).half()
+    w = (_rand((N, K), 5) / math.sqrt(K)).half()
+    b = _rand((N,), 6, 0.1)
+    r = _rand((M, N), 7)
+    ref = r + a.float() @ w.float().t() + b
+    rd = r.to(_dev()).clone()
+    out = ops.linear_resid_f32(a.to(_dev()), w.to(_dev()), b.to(_dev()), resid=rd, out=rd)   # in place
+    assert (out.cpu() - ref).abs().max().item() < 2e-4          # fp32 accumulate, fp32 output
+    out2 = ops.linear_resid_f32(a.to(_dev()), w.to(_dev()), None, None)
+    assert (out2.cpu() - (ref - r - b)).abs().max().item() < 2e-4
+
+
+GEOMS = [
+    # (B, D, H, W, C, heads, shift, frag)
+    (2, 8, 14, 14, 96, 3, (0, 0, 0), True),       # 4 full windows, W-MSA, GRPB
+    (2, 16, 14, 14, 96, 3, (4, 3, 3), True),      # SW-MSA: wrap + region mask in all three dims
+    (1, 16, 7, 7, 192, 6, (4, 3, 3), False),      # spatial dims == window -> shift clamps to (4,0,0); no frag table
+    (1, 4, 10, 9, 96, 3, (4, 3, 3), True),        # D < window (clamped to 4), H/W padded to 14
+    (1, 8, 4, 4, 384, 12, (4, 3, 3), True),       # window clamped to (8,4,4): N = 128, slab of 16
+    (1, 16, 28, 28, 192, 6, (4, 3, 3), True),     # stage-1 geometry of a 224x224 clip
+]
+
+
+def _block_params(C, heads, frag, seed):
+    from oracle import synth
+    shapes = {"attn.qkv.weight": (3 * C, C), "attn.qkv.bias": (3 * C,),
+              "attn.relative_position_bias_table": (2535, heads), "norm1.weight": (C,), "norm1.bias": (C,)}
+    if frag:
+        shapes["attn.fragment_position_bias_table"] = (2535, heads)
+    return synth.synth_state_dict(shapes, seed)
+
+
+@pytest.mark.parametrize("geom", GEOMS, ids=[f"D{g[1]}H{g[2]}W{g[3]}C{g[4]}s{g[6][0]}{g[6][1]}{g[6][2]}" for g in GEOMS])
+def test_ln_window_and_attention(geom):
+    from kvq_b200 import ops
+    from oracle import swin3d
+    B, D, H, W, C, heads, shift, frag = geom
+    window = (8, 7, 7)
+    sd = _block_params(C, heads, frag, seed=31)
+    x = _rand((B, D, H, W, C), 32)
+
+    # oracle: LN -> pad -> shifted window gather -> attention
+    win, sh = swin3d.clamp_window((D, H, W), window, shift)
+    Dp, Hp, Wp = [math.ceil(a / b) * b for a, b in zip((D, H, W), win)]
+    tabs = swin3d.token_tables((Dp, Hp, Wp), win, sh)
+    xn = swin3d.layer_norm(x, sd["norm1.weight"], sd["norm1.bias"])
+    xn = torch.nn.functional.pad(xn, (0, 0, 0, Wp - W, 0, Hp - H, 0, Dp - D))
+    xw_ref = xn.reshape(B, Dp * Hp * Wp, C)[:, tabs["src"].reshape(-1)]
+
+    dev = _dev()
+    xw = ops.ln_window(x.to(dev), sd["norm1.weight"].to(dev), sd["norm1.bias"].to(dev), window, shift)
+    assert xw.shape == (B * tabs["nW"] * tabs["N"], C)
+    assert (xw.float().cpu().reshape(xw_ref.shape) - xw_ref).abs().max().item() < 4e-3   # fp16 rounding of O(4) values
+
+    # feed the oracle the SAME fp16-rounded rows so the comparison isolates the attention kernel
+    xw_in = xw.float().cpu().reshape(xw_ref.shape)
+    shifted = any(s > 0 for s in sh)
+    o_ref = swin3d.window_attention(xw_in, lambda n: sd[n], heads, tabs, frag, shifted)
+    tab = ops.pack_bias_table(sd["attn.relative_position_bias_table"].to(dev),
+                              sd["attn.fragment_position_bias_table"].to(dev) if frag else None, window, heads)
+    o = ops.window_attention(xw, ops.cast_f16(sd["attn.qkv.weight"].to(dev)), sd["attn.qkv.bias"].to(dev), tab,
+                             B, D, H, W, heads, window, shift)
+    o = o.float().cpu().reshape(o_ref.shape)
+    assert torch.isfinite(o).all()
+    err = (o - o_ref).abs().max().item()
+    # q,k,v and P are rounded to fp16 (rel 5e-4); logits O(5) -> softmax weights move by ~3e-3 relative; |o| O(1)
+    assert err < 1.5e-2, err
+    assert (o - o_ref).abs().mean().item() < 1.5e-3
+
+
+def test_fragment_gather_matches_reference_loop():
+    """get_spatial_fragments (fusion_datasets.py:22-121) restated as the slice-copy loop, then normalised."""
+    from kvq_b200 import ops
+    B, T, Hs, Ws, fh, fw, fs, al = 2, 16, 270, 300, 7, 7, 32, 8
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (B, T, 3, Hs, Ws), generator=g, dtype=torch.uint8)
+    hl, wl = Hs // fh, Ws // fw
+    offs = torch.stack([torch.stack([torch.randint(max(hl - fs, 1), (fh, fw, T // al), generator=g),
+                                     torch.randint(max(wl - fs, 1), (fh, fw, T // al), generator=g)])
+                        for _ in range(B)]).int()
+    if hl <= fs:
+        offs[:, 0] = 0
+    if wl <= fs:
+        offs[:, 1] = 0
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(3, 1, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD).view(3, 1, 1, 1)
+    ref = torch.zeros(B, 3, T, fh * fs, fw * fs)
+    for b in range(B):
+        video = frames[b].permute(1, 0, 2, 3).float()                      # [C,T,H,W] like the reference
+        hgrids = [min(Hs // fh * i, Hs - fs) for i in range(fh)]
+        wgrids = [min(Ws // fw * i, Ws - fs) for i in range(fw)]
+        for i, hs in enumerate(hgrids):
+            for j, ws in enumerate(wgrids):
+                for t in range(T // al):
+                    ho, wo = hs + int(offs[b, 0, i, j, t]), ws + int(offs[b, 1, i, j, t])
+                    ref[b, :, t * al:(t + 1) * al, i * fs:(i + 1) * fs, j * fs:(j + 1) * fs] = \
+                        video[:, t * al:(t + 1) * al, ho:ho + fs, wo:wo + fs]
+        ref[b] = (ref[b] - mean) / std
+    out = ops.fragment_gather_u8(frames.to(_dev()), offs.to(_dev()), fh, fw, fs, al).cpu()
+    assert (out - ref).abs().max().item() < 1e-5      # one fp32 multiply by 1/std vs a divide
