@@ -110,11 +110,26 @@ int kvq_window_attention(const void* xw_f16, const void* qkv_w_f16, const float*
                          void* out_f16, int B, int D, int H, int W, int C, int heads, const int32_t window[3],
                          const int32_t shift[3], void* workspace, size_t workspace_bytes, int debug_variant,
                          void* stream);
+/* VQAHead.forward (models/head.py:60-68) on a channels-first feature map: feat f32 [B,C,tokens] -> score f32 [B]
+ * (1x1x1 conv C->hidden, GELU(erf), hidden->1, mean over tokens).  w1 f16 [hidden,C]; b1,w2 f32 [hidden]; b2 f32 [1] */
+size_t kvq_vqa_head_workspace_bytes(int B, int C, int tokens);
+int kvq_vqa_head(const float* feat, const void* w1_f16, const float* b1, const float* w2, const float* b2,
+                 float* score_out, int B, int C, int tokens, int hidden, void* workspace, size_t workspace_bytes,
+                 void* stream);
 /* Grid mini-patch sampling (datasets/fusion_datasets.py:22-121) fused with (v - mean)/std (:1017-1020):
  * frames u8 [B,T,3,Hs,Ws] -> out f32 [B,3,T,fh*fs,fw*fs]; offsets i32 [B,2,fh,fw,T/aligned] (h then w) */
 int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
                            int fragments_h, int fragments_w, int fsize, int aligned, const float mean[3],
                            const float std[3], void* stream);
+
+/* ---- measurement hooks (bench.py): kernels launched so far by this process, and optional CUDA-event timing of
+ * every kernel of kvq_swin3d_forward grouped by (kind, stage).  Timing is OFF unless enabled. ---- */
+long long kvq_launch_count(void);
+void kvq_profile_enable(int on);
+int kvq_profile_num_categories(void);
+const char* kvq_profile_category_name(int category);
+/* synchronises on the last recorded event; returns the number of timed launches (or a negative error) */
+int kvq_profile_collect(float* ms_per_category, int* launches_per_category, int num_categories);
 
 const char* kvq_last_error_string(void);
 /* library / build identification, e.g. "kvq_b200 sm_100a" */

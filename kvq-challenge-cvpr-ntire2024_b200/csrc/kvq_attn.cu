@@ -320,6 +320,7 @@ int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, in
   const int Lp = attn_table_len(bd, bh, bw);
   const int n = heads * Lp;
   pack_bias_kernel<<<(n + 255) / 256, 256, 0, stream>>>(rel, frag, reinterpret_cast<float2*>(out), L, Lp, heads);
+  count_launch();
   return check_cuda(cudaGetLastError(), "pack_bias_kernel launch");
 }
 
@@ -346,6 +347,7 @@ int launch_window_attn(const AttnParams& p, cudaStream_t stream) {
   KVQ_REQUIRE(units > 0 && units < (1ll << 31), KVQ_ERR_BAD_SHAPE, "attn: %lld units", units);
   window_attn_kernel<<<static_cast<unsigned>(units), ATT_THREADS, smem, stream>>>(
       p, reinterpret_cast<const float2*>(p.packed_tab), tab_len, rpi_offset, p.variant);
+  count_launch();
   return check_cuda(cudaGetLastError(), "window_attn_kernel launch");
 }
 

@@ -85,7 +85,7 @@ int make_plan(const KvqSwinConfig* cfg, int B, int T, int H, int W, Plan* pl) {
 
 int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, const float* packed_tab, __half* out,
                   __half* img, int B, int C, int heads, const WinGeom& g, const int32_t base_win[3], int variant,
-                  cudaStream_t st) {
+                  cudaStream_t st, int stage = 0) {
   const int rows_w = B * g.nW * g.N;
   GemmParams gp{};
   gp.M = rows_w; gp.N = 3 * C; gp.K = C;
@@ -95,7 +95,11 @@ int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, con
   gp.C = C;
   gp.heads = heads;
   gp.qscale = 0.17677669529663687f;  // head_dim^-0.5 with head_dim = 32 (:191)
-  int rc = launch_gemm(EPI_QKV_IMG, xw, C, qkv_w, C, gp, st);
+  int rc;
+  {
+    ProfScope ps(PK_QKV_GEMM, stage, st);
+    rc = launch_gemm(EPI_QKV_IMG, xw, C, qkv_w, C, gp, st);
+  }
   if (rc != 0) return rc;
   AttnParams ap{};
   ap.img = img;
@@ -106,6 +110,7 @@ int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, con
   ap.geom = g;
   ap.base_wd = base_win[0]; ap.base_wh = base_win[1]; ap.base_ww = base_win[2];
   ap.variant = variant;
+  ProfScope ps(PK_ATTN, stage, st);
   return launch_window_attn(ap, st);
 }
 
@@ -119,6 +124,54 @@ int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float*
   KVQ_REQUIRE(frames && offsets && out && mean && std, KVQ_ERR_BAD_SHAPE, "fragment_gather: NULL argument");
   return launch_fragment_gather_u8(frames, offsets, out, B, T, Hs, Ws, fragments_h, fragments_w, fsize, aligned, mean,
                                    std, static_cast<cudaStream_t>(stream));
+}
+
+size_t kvq_vqa_head_workspace_bytes(int B, int C, int tokens) {
+  return align_up(static_cast<size_t>(B) * tokens * C * 2 + 128 * 3072 * 2, 256) +
+         align_up(static_cast<size_t>(B) * tokens * 4, 256);
+}
+
+int kvq_vqa_head(const float* feat, const void* w1_f16, const float* b1, const float* w2, const float* b2,
+                 float* score_out, int B, int C, int tokens, int hidden, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  KVQ_REQUIRE(feat && w1_f16 && b1 && w2 && b2 && score_out, KVQ_ERR_BAD_SHAPE, "vqa_head: NULL argument");
+  KVQ_REQUIRE(hidden == 64 && C % 8 == 0 && B > 0 && tokens > 0, KVQ_ERR_BAD_SHAPE,
+              "vqa_head: hidden=%d (64) C=%d (multiple of 8)", hidden, C);
+  const size_t need = kvq_vqa_head_workspace_bytes(B, C, tokens);
+  KVQ_REQUIRE(workspace != nullptr && workspace_bytes >= need, KVQ_ERR_WORKSPACE, "workspace %zu B < required %zu B",
+              workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __half* rows = static_cast<__half*>(workspace);
+  float* rowscore = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
+                                             align_up(static_cast<size_t>(B) * tokens * C * 2 + 128 * 3072 * 2, 256));
+  int rc = launch_cf_to_rows(feat, rows, B, C, tokens, st);
+  if (rc != 0) return rc;
+  GemmParams gp{};
+  gp.M = B * tokens; gp.N = hidden; gp.K = C;
+  gp.bias = b1; gp.w2 = w2; gp.b2ptr = b2; gp.rowscore = rowscore;
+  rc = launch_gemm(EPI_HEAD, rows, C, static_cast<const __half*>(w1_f16), C, gp, st);
+  if (rc != 0) return rc;
+  return launch_row_mean(rowscore, score_out, B, tokens, st);
+}
+
+long long kvq_launch_count(void) { return kvq::launch_count(); }
+
+void kvq_profile_enable(int on) { kvq::prof_set(on != 0); }
+
+int kvq_profile_num_categories(void) { return PK_COUNT * 4; }
+
+const char* kvq_profile_category_name(int cat) {
+  static const char* kinds[PK_COUNT] = {"embed_im2col", "embed_gemm", "ln_window", "qkv_gemm", "window_attn",
+                                        "proj_gemm", "ln_rows", "fc1_gemm", "fc2_gemm", "merge_ln", "merge_gemm",
+                                        "final_ln", "head"};
+  static thread_local char buf[48];
+  if (cat < 0 || cat >= PK_COUNT * 4) return "?";
+  snprintf(buf, sizeof(buf), "%s.s%d", kinds[cat / 4], cat % 4);
+  return buf;
+}
+
+int kvq_profile_collect(float* ms_per_category, int* launches_per_category, int num_categories) {
+  return kvq::prof_collect(ms_per_category, launches_per_category, num_categories);
 }
 
 const char* kvq_last_error_string(void) { return kvq::last_error(); }
@@ -176,14 +229,20 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
 
   // ---- PatchEmbed3D: im2col -> GEMM (K = 96) with bias + LayerNorm epilogue ----
   {
-    rc = launch_patch_im2col(x, a16, B, T, H, W, st);
+    {
+      ProfScope ps(PK_EMBED_IM2COL, 0, st);
+      rc = launch_patch_im2col(x, a16, B, T, H, W, st);
+    }
     if (rc != 0) return rc;
     GemmParams gp{};
     gp.M = B * pl.D0 * pl.H0 * pl.W0; gp.N = 96; gp.K = 96;
     const __half* w = WH();
     gp.bias = WF(); gp.gamma = WF(); gp.beta = WF(); gp.eps = eps;
     gp.out = xa; gp.ldo = 96;
-    rc = launch_gemm(EPI_LN_F32, a16, 96, w, 96, gp, st);
+    {
+      ProfScope ps(PK_EMBED_GEMM, 0, st);
+      rc = launch_gemm(EPI_LN_F32, a16, 96, w, 96, gp, st);
+    }
     if (rc != 0) return rc;
   }
 
@@ -204,24 +263,32 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
       const __half* fc2_w = WH(); const float* fc2_b = WF();
 
       // forward_part1 (:407-488)
-      rc = launch_ln_window(xcur, a16, n1g, n1b, eps, B, C, g, st);
+      {
+        ProfScope ps(PK_LN_WINDOW, s, st);
+        rc = launch_ln_window(xcur, a16, n1g, n1b, eps, B, C, g, st);
+      }
       if (rc != 0) return rc;
-      rc = run_attention(a16, qkv_w, qkv_b, tab, a16, img, B, C, sd.heads, g, cfg->window, 0, st);
+      rc = run_attention(a16, qkv_w, qkv_b, tab, a16, img, B, C, sd.heads, g, cfg->window, 0, st, s);
       if (rc != 0) return rc;
       {
         GemmParams gp{};
         gp.M = B * g.nW * g.N; gp.N = C; gp.K = C;
         gp.bias = proj_b; gp.out = xcur; gp.ldo = C; gp.resid = xcur; gp.remap = 1; gp.geom = g;
+        ProfScope ps(PK_PROJ_GEMM, s, st);
         rc = launch_gemm(EPI_RESID_F32, a16, C, proj_w, C, gp, st);
         if (rc != 0) return rc;
       }
       // forward_part2 (:490-491)
-      rc = launch_ln_rows(xcur, a16, nullptr, n2g, n2b, eps, M, C, sd.D * sd.H * sd.W, st);
+      {
+        ProfScope ps(PK_LN_ROWS, s, st);
+        rc = launch_ln_rows(xcur, a16, nullptr, n2g, n2b, eps, M, C, sd.D * sd.H * sd.W, st);
+      }
       if (rc != 0) return rc;
       {
         GemmParams gp{};
         gp.M = M; gp.N = 4 * C; gp.K = C;
         gp.bias = fc1_b; gp.out = hid; gp.ldo = 4 * C;
+        ProfScope ps(PK_FC1_GEMM, s, st);
         rc = launch_gemm(EPI_GELU_F16, a16, C, fc1_w, C, gp, st);
         if (rc != 0) return rc;
       }
@@ -229,14 +296,19 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
         GemmParams gp{};
         gp.M = M; gp.N = C; gp.K = 4 * C;
         gp.bias = fc2_b; gp.out = xcur; gp.ldo = C; gp.resid = xcur;
+        ProfScope ps(PK_FC2_GEMM, s, st);
         rc = launch_gemm(EPI_RESID_F32, hid, 4 * C, fc2_w, 4 * C, gp, st);
         if (rc != 0) return rc;
       }
     }
     if (s + 1 < cfg->num_stages) {  // PatchMerging (:533-555)
       const float* ng = WF(); const float* nb = WF(); const __half* red_w = WH();
-      rc = launch_ln_merge(xcur, a16, ng, nb, eps, B, sd.D, sd.H, sd.W, C, st);
+      {
+        ProfScope ps(PK_MERGE_LN, s, st);
+        rc = launch_ln_merge(xcur, a16, ng, nb, eps, B, sd.D, sd.H, sd.W, C, st);
+      }
       if (rc != 0) return rc;
+      ProfScope ps(PK_MERGE_GEMM, s, st);
       GemmParams gp{};
       gp.M = B * sd.D * ((sd.H + 1) / 2) * ((sd.W + 1) / 2); gp.N = 2 * C; gp.K = 4 * C;
       gp.out = xnext; gp.ldo = 2 * C;
@@ -252,13 +324,17 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
     const StageDims& sd = pl.st[cfg->num_stages - 1];
     const int tokens = sd.D * sd.H * sd.W, M = B * tokens;
     const float* ng = WF(); const float* nb = WF();
-    rc = launch_ln_rows(xcur, cfg->head_hidden > 0 ? a16 : nullptr, feat_out, ng, nb, eps, M, sd.C, tokens, st);
+    {
+      ProfScope ps(PK_FINAL_LN, cfg->num_stages - 1, st);
+      rc = launch_ln_rows(xcur, cfg->head_hidden > 0 ? a16 : nullptr, feat_out, ng, nb, eps, M, sd.C, tokens, st);
+    }
     if (rc != 0) return rc;
     if (cfg->head_hidden > 0 && score_out != nullptr) {
       const __half* w1 = WH(); const float* b1 = WF(); const float* w2 = WF(); const float* b2 = WF();
       GemmParams gp{};
       gp.M = M; gp.N = cfg->head_hidden; gp.K = sd.C;
       gp.bias = b1; gp.w2 = w2; gp.b2ptr = b2; gp.rowscore = rowscore;
+      ProfScope ps(PK_HEAD, cfg->num_stages - 1, st);
       rc = launch_gemm(EPI_HEAD, a16, sd.C, w1, sd.C, gp, st);
       if (rc != 0) return rc;
       rc = launch_row_mean(rowscore, score_out, B, tokens, st);

@@ -323,6 +323,7 @@ int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmPa
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, p);
+  count_launch();
   return check_cuda(cudaGetLastError(), "gemm_kernel launch");
 }
 

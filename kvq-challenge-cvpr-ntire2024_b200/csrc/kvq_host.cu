@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "kvq_common.cuh"
 
@@ -68,6 +69,56 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
               static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
               static_cast<unsigned long long>(row_stride_bytes), box_rows, box_cols);
   return KVQ_OK;
+}
+
+// ---- optional per-kernel-category device timing (bench.py's roofline leg) and a launch counter ----
+namespace {
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> cat;  // category of pair i (events 2i, 2i+1)
+  size_t used = 0;
+};
+ProfState g_prof;
+long long g_launches = 0;
+}  // namespace
+
+void count_launch() { ++g_launches; }
+long long launch_count() { return g_launches; }
+
+bool prof_enabled() { return g_prof.on; }
+
+void prof_set(bool on) {
+  g_prof.on = on;
+  g_prof.used = 0;
+  g_prof.cat.clear();
+}
+
+void prof_mark(int cat, bool begin, cudaStream_t st) {
+  if (!g_prof.on) return;
+  if (begin) g_prof.cat.push_back(cat);
+  if (g_prof.used >= g_prof.pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { g_prof.on = false; return; }
+    g_prof.pool.push_back(e);
+  }
+  cudaEventRecord(g_prof.pool[g_prof.used++], st);
+}
+
+int prof_collect(float* ms, int* launches, int ncat) {
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  const size_t pairs = g_prof.used / 2;
+  if (pairs == 0) return 0;
+  if (cudaEventSynchronize(g_prof.pool[g_prof.used - 1]) != cudaSuccess) return KVQ_ERR_CUDA;
+  for (size_t i = 0; i < pairs; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]) != cudaSuccess) return KVQ_ERR_CUDA;
+    const int c = g_prof.cat[i];
+    if (c >= 0 && c < ncat) { ms[c] += t; launches[c] += 1; }
+  }
+  g_prof.used = 0;
+  g_prof.cat.clear();
+  return static_cast<int>(pairs);
 }
 
 int num_sms() {

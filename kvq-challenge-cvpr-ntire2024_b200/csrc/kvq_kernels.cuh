@@ -9,6 +9,24 @@ namespace kvq {
 
 const char* last_error();
 int num_sms();
+void count_launch();
+long long launch_count();
+bool prof_enabled();
+void prof_set(bool on);
+void prof_mark(int cat, bool begin, cudaStream_t st);
+int prof_collect(float* ms, int* launches, int ncat);
+
+// timing categories: kind * 4 + stage
+enum ProfKind : int {
+  PK_EMBED_IM2COL = 0, PK_EMBED_GEMM, PK_LN_WINDOW, PK_QKV_GEMM, PK_ATTN, PK_PROJ_GEMM, PK_LN_ROWS, PK_FC1_GEMM,
+  PK_FC2_GEMM, PK_MERGE_LN, PK_MERGE_GEMM, PK_FINAL_LN, PK_HEAD, PK_COUNT
+};
+struct ProfScope {
+  int cat;
+  cudaStream_t st;
+  ProfScope(int kind, int stage, cudaStream_t s) : cat(kind * 4 + stage), st(s) { prof_mark(cat, true, st); }
+  ~ProfScope() { prof_mark(cat, false, st); }
+};
 
 // ----------------------------------------------------------------------------------------------
 // window geometry of one Swin block (reference: swin_backbone.py get_window_size :145-158,
@@ -137,6 +155,8 @@ int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cuda
 int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
                               int fh, int fw, int fs, int aligned, const float mean[3], const float stdv[3],
                               cudaStream_t stream);
+// fp32 [B, C, tokens] -> fp16 [B*tokens, C]
+int launch_cf_to_rows(const float* in, __half* out, int B, int C, int tokens, cudaStream_t stream);
 // fp32 -> fp16 cast (weight packing)
 int launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream);
 

@@ -225,6 +225,24 @@ fragment_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __rest
   *reinterpret_cast<float4*>(out + (((static_cast<size_t>(b) * 3 + c) * T + t) * OH + y) * OW + x) = v;
 }
 
+// channels-first fp32 [B, C, tokens] -> token rows fp16 [B*tokens, C] (input side of a stand-alone VQAHead)
+__global__ void __launch_bounds__(256)
+cf_to_rows_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int tokens) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, t = t0 + tx;
+    tile[k][tx] = (c < C && t < tokens) ? in[(static_cast<size_t>(b) * C + c) * tokens + t] : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int t = t0 + k, c = c0 + tx;
+    if (t < tokens && c < C) out[(static_cast<size_t>(b) * tokens + t) * C + c] = __float2half_rn(tile[tx][k]);
+  }
+}
+
 template <typename F>
 int dispatch_maxv(int chunks, F&& f) {
   if (chunks <= 32) return f(std::integral_constant<int, 1>{});
@@ -248,6 +266,7 @@ int launch_ln_window(const float* x, __half* out, const float* gamma, const floa
   return dispatch_maxv(C / 4, [&](auto mv) {
     ln_window_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, gamma, beta, eps,
                                                                              static_cast<int>(rows), C, g);
+    count_launch();
     return check_cuda(cudaGetLastError(), "ln_window_kernel launch");
   });
 }
@@ -259,6 +278,7 @@ int launch_ln_rows(const float* x, __half* out, float* feat_cf, const float* gam
   return dispatch_maxv(C / 4, [&](auto mv) {
     ln_rows_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, feat_cf, gamma, beta, eps, M, C,
                                                                            tokens_per_clip);
+    count_launch();
     return check_cuda(cudaGetLastError(), "ln_rows_kernel launch");
   });
 }
@@ -272,6 +292,7 @@ int launch_ln_merge(const float* x, __half* out, const float* gamma, const float
   return dispatch_maxv(C, [&](auto mv) {
     ln_merge_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, gamma, beta, eps,
                                                                             static_cast<int>(rows), D, H, W, C);
+    count_launch();
     return check_cuda(cudaGetLastError(), "ln_merge_kernel launch");
   });
 }
@@ -282,11 +303,13 @@ int launch_patch_im2col(const float* x, __half* out, int B, int T, int H, int W,
   const long long grid = (total + 255) / 256;
   KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "im2col: grid too large");
   patch_im2col_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(x, out, B, T, H, W, D, Hs, Ws, total);
+  count_launch();
   return check_cuda(cudaGetLastError(), "patch_im2col_kernel launch");
 }
 
 int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cudaStream_t stream) {
   row_mean_kernel<<<B, 256, 0, stream>>>(rowscore, score, tokens);
+  count_launch();
   return check_cuda(cudaGetLastError(), "row_mean_kernel launch");
 }
 
@@ -306,12 +329,21 @@ int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, flo
   fragment_gather_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(
       frames, offsets, out, T, Hs, Ws, fh, fw, fs, aligned, mean[0], mean[1], mean[2], 1.0f / stdv[0], 1.0f / stdv[1],
       1.0f / stdv[2], total);
+  count_launch();
   return check_cuda(cudaGetLastError(), "fragment_gather_kernel launch");
+}
+
+int launch_cf_to_rows(const float* in, __half* out, int B, int C, int tokens, cudaStream_t stream) {
+  dim3 grid((tokens + 31) / 32, (C + 31) / 32, B);
+  cf_to_rows_kernel<<<grid, 256, 0, stream>>>(in, out, C, tokens);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "cf_to_rows_kernel launch");
 }
 
 int launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
   if (n == 0) return KVQ_OK;
   cast_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, out, n);
+  count_launch();
   return check_cuda(cudaGetLastError(), "cast_f16_kernel launch");
 }
 

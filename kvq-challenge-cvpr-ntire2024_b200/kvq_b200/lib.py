@@ -37,8 +37,16 @@ PROTOTYPES = {
     "kvq_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_void_p, c_size_t, c_int,
                                      c_void_p]),
+    "kvq_vqa_head_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "kvq_vqa_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                             c_void_p, c_size_t, c_void_p]),
     "kvq_fragment_gather_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_int, POINTER(c_float), POINTER(c_float), c_void_p]),
+    "kvq_launch_count": (ctypes.c_longlong, []),
+    "kvq_profile_enable": (None, [c_int]),
+    "kvq_profile_num_categories": (c_int, []),
+    "kvq_profile_category_name": (c_char_p, [c_int]),
+    "kvq_profile_collect": (c_int, [POINTER(c_float), POINTER(c_int), c_int]),
     "kvq_last_error_string": (c_char_p, []),
     "kvq_build_info": (c_char_p, []),
 }

@@ -94,6 +94,22 @@ def window_attention(xw, qkv_w, qkv_b, packed_table, B, D, H, W, heads, window, 
     return out
 
 
+def vqa_head(feat, w1_f16, b1, w2, b2):
+    """feat f32 [B,C,D,H,W] -> score f32 [B,1]  (VQAHead.forward, head.py:60-68; dropout is identity in eval)."""
+    _need_cuda(feat, w1_f16, b1, w2, b2)
+    if feat.dtype != torch.float32:
+        raise RuntimeError("vqa_head: features must be float32")
+    B, C = feat.shape[:2]
+    tokens = feat[0, 0].numel()
+    lib = _l.load()
+    nbytes = lib.kvq_vqa_head_workspace_bytes(B, C, tokens)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
+    out = torch.empty(B, dtype=torch.float32, device=feat.device)
+    _l.check(lib.kvq_vqa_head(_p(feat), _p(w1_f16), _p(b1), _p(w2), _p(b2), _p(out), B, C, tokens, w1_f16.shape[0],
+                              _p(ws), nbytes, _stream()), "vqa_head")
+    return out.reshape(B, 1)
+
+
 IMAGENET_MEAN = (123.675, 116.28, 103.53)
 IMAGENET_STD = (58.395, 57.12, 57.375)
 

@@ -1,0 +1,34 @@
+"""VQAHead / simpleVQAHead with the reference's parameter names (models/head.py:10-68)."""
+import torch
+import torch.nn as nn
+
+from kvq_b200 import ops
+
+
+class VQAHead(nn.Module):
+    """1x1x1 Conv3d C->hidden, GELU, hidden->1, mean over (D,H,W)  (head.py:33-68).  Parameter containers only;
+    the arithmetic runs in libkvq_b200.so (fused into the backbone call by VQA_Network, or stand-alone here)."""
+
+    def __init__(self, in_channels=768, hidden_channels=64, num_class=1, dropout_ratio=0.5, pre_pool=False, **kwargs):
+        super().__init__()
+        if num_class != 1 or pre_pool or hidden_channels != 64:
+            raise NotImplementedError("kvq_b200: VQAHead is built for num_class=1, pre_pool=False, hidden_channels=64")
+        self.in_channels, self.hidden_channels = in_channels, hidden_channels
+        self.fc_hid = nn.Conv3d(in_channels, hidden_channels, (1, 1, 1))
+        self.fc_last = nn.Conv3d(hidden_channels, num_class, (1, 1, 1))
+        self._packed = None
+        self._key = None
+
+    def forward(self, x, rois=None):
+        if self.training:
+            raise RuntimeError("kvq_b200: inference path only (call .eval(); dropout is identity there)")
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or self._key != key:
+            with torch.cuda.device(x.device):
+                self._packed = (ops.cast_f16(self.fc_hid.weight.reshape(self.hidden_channels, -1)),
+                                self.fc_hid.bias.detach().float().contiguous(),
+                                self.fc_last.weight.detach().float().reshape(-1).contiguous(),
+                                self.fc_last.bias.detach().float().reshape(-1).contiguous())
+            self._key = key
+        with torch.cuda.device(x.device):
+            return ops.vqa_head(x.contiguous(), *self._packed)

@@ -1,0 +1,60 @@
+"""VQA_Network with the reference's constructor / forward contract (models/model.py:18-121).
+
+For Swin keys the backbone and head are fused into one libkvq_b200.so call; the module tree
+(`<key>_backbone`, `<key>_head`) and state_dict names are the reference's, so `load_state_dict` of a reference
+checkpoint (with or without the DataParallel `module.` prefix stripped by the caller) works unchanged."""
+from functools import reduce
+
+import torch
+import torch.nn as nn
+
+from .backbones.swin_backbone import SwinTransformer3D as VideoBackbone
+from .backbones.swin_backbone import swin_3d_small, swin_3d_tiny
+from .head import VQAHead
+
+__all__ = ["VQA_Network", "VideoBackbone", "VQAHead", "swin_3d_tiny", "swin_3d_small"]
+
+SWIN_KEYS = ("swin_tiny", "swin_tiny_grpb", "swin_tiny_grpb_m", "swin_small")
+
+
+class VQA_Network(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.key_names = []
+        self.multi = False
+        self.layer = -1
+        for key, hypers in config["model"]["args"].items():
+            if key == "swin_tiny":
+                backbone = swin_3d_tiny(**hypers.get("backbone", {}))
+            elif key == "swin_tiny_grpb":
+                backbone = VideoBackbone()                                                  # model.py:34-38
+            elif key == "swin_tiny_grpb_m":
+                backbone = VideoBackbone(window_size=(4, 4, 4), frag_biases=[0, 0, 0, 0])    # model.py:39-43
+            elif key == "swin_small":
+                backbone = swin_3d_small(**hypers.get("backbone", {}))
+            else:
+                raise NotImplementedError(
+                    f"kvq_b200: model key '{key}' is not on the B200 hot path yet (DESIGN.md, out-of-scope table)")
+            head = VQAHead(**hypers["head"])
+            self.key_names.append(key)
+            setattr(self, key + "_backbone", backbone)
+            setattr(self, key + "_head", head)
+
+    def forward(self, inputs, targets=None, inference=True, return_pooled_feats=False, reduce_scores=False,
+                pooled=False, clip_return=False, **kwargs):
+        if self.training:
+            raise RuntimeError("kvq_b200: inference path only -- call model.eval() (trainer.py:305)")
+        scores, feats = [], {}
+        for key in self.key_names:
+            backbone, head = getattr(self, key + "_backbone"), getattr(self, key + "_head")
+            x = inputs["technical"]
+            feat, score = backbone.forward_with_head(x, head, want_feat=return_pooled_feats)
+            scores.append(score)
+            if return_pooled_feats:
+                feats[key] = feat
+        if reduce_scores:
+            scores = reduce(lambda a, b: a + b, scores) if len(scores) > 1 else scores[0]
+        if return_pooled_feats:
+            return scores, feats
+        return scores
