@@ -94,7 +94,7 @@ int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, con
   gp.img = img;
   gp.C = C;
   gp.heads = heads;
-  gp.qscale = 0.17677669529663687f;  // head_dim^-0.5 with head_dim = 32 (:191)
+  gp.qscale = attn_qscale();  // head_dim^-0.5 (:191), folded with log2(e) for the exp2 softmax
   int rc;
   {
     ProfScope ps(PK_QKV_GEMM, stage, st);

@@ -233,6 +233,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               st_global_v4(dst + att_img_offset(rimg, j), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+            // the last token of a slab also zeroes the padded K/V key slots behind it (P is 0 there, but 0 * NaN
+            // from uninitialised workspace would poison PV); the last token of the window zeroes all the rest
+            if (which != 0 && (i - slab * p.geom.SL) == p.geom.SL - 1) {
+              const int end = (i == ntok - 1) ? ATT_ROWS : (slab + 1) * ATT_SLAB;
+              for (int rz = kv_row + 1; rz < end; ++rz) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st_global_v4(dst + att_img_offset(rz, j), 0u, 0u, 0u, 0u);
+              }
+            }
           }
         }
       } else if constexpr (EPI == EPI_LN_F32) {

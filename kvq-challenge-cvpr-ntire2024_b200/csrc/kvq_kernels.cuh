@@ -175,6 +175,8 @@ struct AttnParams {
 };
 // entries per head of the packed table for a base window (L rounded up to even)
 int attn_table_len(int bd, int bh, int bw);
+// q pre-scale the attention kernels expect from the QKV epilogue: head_dim^-0.5 * log2(e)
+float attn_qscale();
 // rel/frag: [L, heads] fp32 (frag may be nullptr) -> out [heads][tab_len] float2
 int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, int bh, int bw, int heads,
                      cudaStream_t stream);
