@@ -131,6 +131,9 @@ const char* kvq_profile_category_name(int category);
 /* synchronises on the last recorded event; returns the number of timed launches (or a negative error) */
 int kvq_profile_collect(float* ms_per_category, int* launches_per_category, int num_categories);
 
+/* debug builds (-DKVQ_TIMING) only: per-phase cycle counters of the fast attention kernel; returns 0 otherwise */
+int kvq_debug_attn_timers(unsigned long long* out16, int reset);
+
 const char* kvq_last_error_string(void);
 /* library / build identification, e.g. "kvq_b200 sm_100a" */
 const char* kvq_build_info(void);

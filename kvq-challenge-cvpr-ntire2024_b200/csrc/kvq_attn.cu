@@ -103,6 +103,19 @@ struct FastSmall {
 };
 static_assert(sizeof(FastSmall) <= 7168, "FastSmall overflows its slot");
 
+#ifdef KVQ_TIMING
+// debug build: per-phase cycle counters of the softmax warps (summed over warps' lane 0), read by kvq_debug_timers
+__device__ unsigned long long g_attn_timers[16];
+#define TMARK(slot)                                               \
+  do {                                                            \
+    const long long _now = clock64();                             \
+    if (lane == 0) tacc[slot] += _now - tprev;                    \
+    tprev = _now;                                                 \
+  } while (0)
+#else
+#define TMARK(slot) do {} while (0)
+#endif
+
 constexpr int FAST_SOFTMAX_THREADS = 256;
 constexpr int FAST_THREADS = FAST_SOFTMAX_THREADS + 32;   // + one control warp: bulk loads and tcgen05.mma issue
 
@@ -236,7 +249,12 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
     const int q = warp & 3, hs = warp >> 2;
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t n_s = 0, n_o = 0;
+#ifdef KVQ_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#endif
     mbar_wait(&sm.bar_tab, 0);
+    TMARK(0);  // table wait
 
     for (int unit = blockIdx.x; unit < units; unit += G) {
       const int win_g = unit / p.heads;
@@ -266,10 +284,12 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
       for (int t = 0; t < 4; ++t) {
         const bool tail = (t == 3);
         const int par = t & 1;
+        TMARK(7);  // unit prologue / previous arrive
         mbar_wait(&sm.bar_s, n_s & 1);
         ++n_s;
         __syncwarp();
         tc_fence_after();
+        TMARK(1);  // wait for S(t)
 
         // ---- this thread's query row and its constants ----
         const int ri = tail ? 384 + (lane & 7) : t * 128 + q * 32 + lane;
@@ -316,6 +336,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
           }
         }
         tmem_wait_st();
+        TMARK(2);  // pass 1
         float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         if (tail) {
           if (lane < 8) sm.tmax[warp][lane] = m;
@@ -323,6 +344,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
           sm.smax[par][hs][q * 32 + lane] = m;
         }
         named_bar_sync(1, FAST_SOFTMAX_THREADS);
+        TMARK(3);  // max exchange barrier
         if (tail) {
           m = sm.tmax[0][lane & 7];
 #pragma unroll
@@ -348,6 +370,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
           }
         }
 
+        TMARK(4);  // wait PV(t-1) + O epilogue
         // ---- pass 2: P = exp2(v - max) -> fp16 smem image; row sums ----
         float sum = 0.f;
         if (!tail) {
@@ -400,6 +423,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
           }
           if (lane < 8) sm.tsum[warp][lane] = sum;
         }
+        TMARK(5);  // pass 2
         // publish P(t) / release S(t) to the control warp
         fence_proxy_async_smem();
         tc_fence_before();
@@ -424,7 +448,14 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
         }
         tc_fence_before();
       }
+      TMARK(6);  // tail O wait + epilogue
     }
+#ifdef KVQ_TIMING
+    if (lane == 0) {
+      for (int k = 0; k < 8; ++k) atomicAdd(&g_attn_timers[k], static_cast<unsigned long long>(tacc[k]));
+      atomicAdd(&g_attn_timers[8], 1ull);
+    }
+#endif
   }
 
   tc_fence_before();
@@ -694,6 +725,20 @@ static int compact_len(int bd, int bh, int bw) {
 static bool is_fast_window(int bd, int bh, int bw) { return bd == 8 && bh == 7 && bw == 7; }
 
 // float2 entries per head in the packed buffer (compact layout, plus the fast layout for the (8,7,7) window)
+int debug_attn_timers(unsigned long long* out16, int reset) {
+#ifdef KVQ_TIMING
+  if (cudaMemcpyFromSymbol(out16, g_attn_timers, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_attn_timers, z, sizeof(z));
+  }
+  return 1;
+#else
+  (void)out16; (void)reset;
+  return 0;
+#endif
+}
+
 int attn_table_len(int bd, int bh, int bw) {
   return compact_len(bd, bh, bw) + (is_fast_window(bd, bh, bw) ? FAST_TAB_LEN : 0);
 }

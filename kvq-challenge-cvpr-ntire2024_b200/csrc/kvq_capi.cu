@@ -154,6 +154,8 @@ int kvq_vqa_head(const float* feat, const void* w1_f16, const float* b1, const f
   return launch_row_mean(rowscore, score_out, B, tokens, st);
 }
 
+int kvq_debug_attn_timers(unsigned long long* out16, int reset) { return kvq::debug_attn_timers(out16, reset); }
+
 long long kvq_launch_count(void) { return kvq::launch_count(); }
 
 void kvq_profile_enable(int on) { kvq::prof_set(on != 0); }

@@ -23,30 +23,55 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 halfs = one 128 B swizzle row
-constexpr int STAGES = 4;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_BYTES = BM * BK * 2;
 
+// Two CTAs are resident per SM (12 warps: 2 TMA, 2 MMA, 8 epilogue) so one CTA's epilogue overlaps the other's
+// MMAs; each CTA therefore gets <= 113 KB of shared memory and <= 256 TMEM columns.  Accumulators are
+// double-buffered inside a CTA only when two tiles fit 256 columns (BLOCK_N <= 128).
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (3 * STAGE_BYTES + 2048 <= 113 * 1024) ? 3 : 2;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int ACC_STAGES = (2 * BN <= 256) ? 2 : 1;
+  static constexpr int TMEM_NEED = ACC_STAGES * BN;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : 256;
+  static_assert(TMEM_NEED <= 256, "two resident CTAs must share the 512 TMEM columns");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (nn.GELU default, swin_backbone.py:72).  erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, below
+// fp32 round-off of the surrounding arithmetic), branch-free: 2 MUFU + ~10 FMA-pipe instructions.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = fast_exp2(-1.4426950408889634f * ax * ax);
+  return copysignf(fmaf(-p, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_as(x * 0.70710678118654752f), hx);
+}
 
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr int STAGES = Cfg<BN>::STAGES;
+  constexpr int ACC = Cfg<BN>::ACC_STAGES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg<BN>::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
@@ -125,8 +150,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
         umma_commit(&tfull[as]);
-        as ^= 1;
-        if (as == 0) aph ^= 1;
+        if (++as == ACC) { as = 0; aph ^= 1; }
       }
     }
   } else {
@@ -304,8 +328,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
-      as ^= 1;
-      if (as == 0) aph ^= 1;
+      if (++as == ACC) { as = 0; aph ^= 1; }
     }
   }
 
@@ -330,7 +353,7 @@ int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmPa
   rc = make_tmap_2d(&tmB, B, p.N, p.K, static_cast<uint64_t>(ldb) * 2, BN, BK, 2, 128);
   if (rc != 0) return rc;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
   gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "gemm_kernel launch");

@@ -180,6 +180,8 @@ float attn_qscale();
 // rel/frag: [L, heads] fp32 (frag may be nullptr) -> out [heads][tab_len] float2
 int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, int bh, int bw, int heads,
                      cudaStream_t stream);
+// debug builds (-DKVQ_TIMING) only: 1 + fills out16; production build returns 0
+int debug_attn_timers(unsigned long long* out16, int reset);
 int launch_window_attn(const AttnParams& p, cudaStream_t stream);
 
 }  // namespace kvq

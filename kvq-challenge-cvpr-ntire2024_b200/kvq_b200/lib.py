@@ -47,6 +47,7 @@ PROTOTYPES = {
     "kvq_profile_num_categories": (c_int, []),
     "kvq_profile_category_name": (c_char_p, [c_int]),
     "kvq_profile_collect": (c_int, [POINTER(c_float), POINTER(c_int), c_int]),
+    "kvq_debug_attn_timers": (c_int, [POINTER(ctypes.c_ulonglong), c_int]),
     "kvq_last_error_string": (c_char_p, []),
     "kvq_build_info": (c_char_p, []),
 }
