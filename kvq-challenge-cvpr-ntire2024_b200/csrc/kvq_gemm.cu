@@ -173,20 +173,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t r[32];
           tmem_ld_x32(taddr + c0, r);
+          float4 bv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            bv[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c0) + j)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
           tmem_wait_ld();
           uint32_t h[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
-            if (p.bias != nullptr) {
-              v0 += __ldg(p.bias + nbase + c0 + j);
-              v1 += __ldg(p.bias + nbase + c0 + j + 1);
-            }
+          for (int j = 0; j < 8; ++j) {
+            float v0 = __uint_as_float(r[4 * j]) + bv[j].x, v1 = __uint_as_float(r[4 * j + 1]) + bv[j].y;
+            float v2 = __uint_as_float(r[4 * j + 2]) + bv[j].z, v3 = __uint_as_float(r[4 * j + 3]) + bv[j].w;
             if constexpr (EPI == EPI_GELU_F16) {
-              v0 = gelu_erf(v0);
-              v1 = gelu_erf(v1);
+              v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
             }
-            h[j >> 1] = pack_half2(v0, v1);
+            h[2 * j] = pack_half2(v0, v1);
+            h[2 * j + 1] = pack_half2(v2, v3);
           }
           if (row_ok) {
 #pragma unroll
@@ -244,10 +246,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const float sc = which == 0 ? p.qscale : 1.0f;
           uint32_t h[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float v0 = (__uint_as_float(r[j]) + __ldg(p.bias + n0 + j)) * sc;
-            const float v1 = (__uint_as_float(r[j + 1]) + __ldg(p.bias + n0 + j + 1)) * sc;
-            h[j >> 1] = pack_half2(v0, v1);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+            h[2 * j] = pack_half2((__uint_as_float(r[4 * j]) + bb.x) * sc, (__uint_as_float(r[4 * j + 1]) + bb.y) * sc);
+            h[2 * j + 1] = pack_half2((__uint_as_float(r[4 * j + 2]) + bb.z) * sc, (__uint_as_float(r[4 * j + 3]) + bb.w) * sc);
           }
           if (row_ok) {
             const int rimg = which == 0 ? i : kv_row;

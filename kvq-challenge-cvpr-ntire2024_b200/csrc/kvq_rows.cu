@@ -8,7 +8,7 @@ namespace kvq {
 
 namespace {
 
-constexpr int ROW_THREADS = 256;  // 8 rows per CTA
+constexpr int ROW_THREADS = 256;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -16,19 +16,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// LayerNorm of a logical row made of SEG segments of C floats (SEG = 1: plain / window gather, SEG = 4: PatchMerging
-// concat).  src[s] < 0 means "zeros" for that segment.  MAXV = float4 chunks per lane.
-template <int MAXV>
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {   // sum over the LPR lanes that share a row
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// LayerNorm of a logical row made of `nseg` segments of C floats (1: plain / window gather, 4: PatchMerging concat);
+// seg_ptr[s] == nullptr means zeros.  LPR lanes cooperate on one row (a warp covers 32/LPR rows, so narrow rows
+// still keep >= 1.5 KB of loads in flight per warp); each lane owns MAXV float4 chunks: ch = sub + LPR*k.
+// fp32 two-pass statistics (mean, then centred variance) like nn.LayerNorm.
+template <int LPR, int MAXV>
 __device__ __forceinline__ void ln_row(const float* const* seg_ptr, int nseg, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, __half* __restrict__ out,
-                                       float* __restrict__ out_f32_cf, size_t cf_stride, int lane) {
+                                       float* __restrict__ out_f32_cf, size_t cf_stride, int sub) {
   const int chunks_per_seg = C >> 2;
   const int chunks = chunks_per_seg * nseg;
   float4 v[MAXV];
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
-    const int ch = lane + 32 * k;
+    const int ch = sub + LPR * k;
     v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ch < chunks) {
       const int sg = ch / chunks_per_seg;
@@ -38,20 +47,20 @@ __device__ __forceinline__ void ln_row(const float* const* seg_ptr, int nseg, in
     }
   }
   const float inv_n = 1.0f / static_cast<float>(4 * chunks);
-  const float mean = warp_sum(s) * inv_n;
+  const float mean = group_sum<LPR>(s) * inv_n;
   float q = 0.f;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
-    const int ch = lane + 32 * k;
+    const int ch = sub + LPR * k;
     if (ch < chunks) {
       const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
       q += (a * a + b * b) + (c * c + d * d);
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+  const float rstd = rsqrtf(group_sum<LPR>(q) * inv_n + eps);
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
-    const int ch = lane + 32 * k;
+    const int ch = sub + LPR * k;
     if (ch < chunks) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
       const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + ch);
@@ -75,52 +84,60 @@ __device__ __forceinline__ void ln_row(const float* const* seg_ptr, int nseg, in
   }
 }
 
-template <int MAXV>
+// All lanes of a warp must reach the shuffles: rows past the end are clamped to the last row and only skip stores.
+template <int LPR, int MAXV>
 __global__ void __launch_bounds__(ROW_THREADS)
 ln_window_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, int rows, int C, WinGeom g) {
-  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  int row = (blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
   const int rows_in = g.nW * g.N;
   const int b = row / rows_in;
   const int src = win_row_to_src(g, row - b * rows_in);
-  __half* orow = out + static_cast<size_t>(row) * C;
-  if (src < 0) {  // padded slot: zeros AFTER the norm (swin_backbone.py:416-424)
-    for (int ch = lane; ch < (C >> 2); ch += 32) *reinterpret_cast<uint2*>(orow + 4 * ch) = make_uint2(0u, 0u);
-    return;
+  __half* orow = live ? out + static_cast<size_t>(row) * C : nullptr;
+  const float* sp = x + (static_cast<size_t>(b) * g.tokens + (src < 0 ? 0 : src)) * C;
+  if (src < 0) {  // padded slot: zeros AFTER the norm (swin_backbone.py:416-424); still join the shuffles below
+    if (live)
+      for (int ch = sub; ch < (C >> 2); ch += LPR) *reinterpret_cast<uint2*>(orow + 4 * ch) = make_uint2(0u, 0u);
+    orow = nullptr;
   }
-  const float* sp = x + (static_cast<size_t>(b) * g.tokens + src) * C;
-  ln_row<MAXV>(&sp, 1, C, gamma, beta, eps, orow, nullptr, 0, lane);
+  ln_row<LPR, MAXV>(&sp, 1, C, gamma, beta, eps, orow, nullptr, 0, sub);
 }
 
-template <int MAXV>
+template <int LPR, int MAXV>
 __global__ void __launch_bounds__(ROW_THREADS)
 ln_rows_kernel(const float* __restrict__ x, __half* __restrict__ out, float* __restrict__ feat_cf,
                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int C,
                int tokens_per_clip) {
-  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  int row = (blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
   const float* sp = x + static_cast<size_t>(row) * C;
   float* cf = nullptr;
-  if (feat_cf != nullptr) {
+  if (feat_cf != nullptr && live) {
     const int b = row / tokens_per_clip, t = row - b * tokens_per_clip;
     cf = feat_cf + static_cast<size_t>(b) * C * tokens_per_clip + t;  // [B, C, tokens]
   }
-  ln_row<MAXV>(&sp, 1, C, gamma, beta, eps, out != nullptr ? out + static_cast<size_t>(row) * C : nullptr, cf,
-               static_cast<size_t>(tokens_per_clip), lane);
+  ln_row<LPR, MAXV>(&sp, 1, C, gamma, beta, eps, (out != nullptr && live) ? out + static_cast<size_t>(row) * C : nullptr,
+                    cf, static_cast<size_t>(tokens_per_clip), sub);
 }
 
 // PatchMerging (:533-555): rows (b, d, h2, w2); channel order [x(2h,2w) | x(2h+1,2w) | x(2h,2w+1) | x(2h+1,2w+1)],
 // odd H/W zero-padded BEFORE the norm.
-template <int MAXV>
+template <int LPR, int MAXV>
 __global__ void __launch_bounds__(ROW_THREADS)
 ln_merge_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int rows, int D, int H, int W, int C) {
-  const int row = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  int row = (blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
   const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
   const int w2 = row % W2;
   const int h2 = (row / W2) % H2;
@@ -131,7 +148,8 @@ ln_merge_kernel(const float* __restrict__ x, __half* __restrict__ out, const flo
     const int hh = 2 * h2 + (s & 1), ww = 2 * w2 + (s >> 1);
     seg[s] = (hh < H && ww < W) ? x + ((static_cast<size_t>(bd) * H + hh) * W + ww) * C : nullptr;
   }
-  ln_row<MAXV>(seg, 4, C, gamma, beta, eps, out + static_cast<size_t>(row) * 4 * C, nullptr, 0, lane);
+  ln_row<LPR, MAXV>(seg, 4, C, gamma, beta, eps, live ? out + static_cast<size_t>(row) * 4 * C : nullptr, nullptr, 0,
+                    sub);
 }
 
 // PatchEmbed3D im2col (:715-731).  One thread per (output token, c, kt, kh): copies the 4 kw taps (16 B in, 8 B out).
@@ -243,14 +261,15 @@ cf_to_rows_kernel(const float* __restrict__ in, __half* __restrict__ out, int C,
   }
 }
 
+// (lanes per row, chunks per lane) for a row of `chunks` float4s
 template <typename F>
-int dispatch_maxv(int chunks, F&& f) {
-  if (chunks <= 32) return f(std::integral_constant<int, 1>{});
-  if (chunks <= 64) return f(std::integral_constant<int, 2>{});
-  if (chunks <= 96) return f(std::integral_constant<int, 3>{});
-  if (chunks <= 192) return f(std::integral_constant<int, 6>{});
-  if (chunks <= 384) return f(std::integral_constant<int, 12>{});
-  if (chunks <= 768) return f(std::integral_constant<int, 24>{});
+int dispatch_ln(int chunks, F&& f) {
+  if (chunks <= 24) return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 3>{});
+  if (chunks <= 48) return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 3>{});
+  if (chunks <= 96) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 3>{});
+  if (chunks <= 192) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 6>{});
+  if (chunks <= 384) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 12>{});
+  if (chunks <= 768) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 24>{});
   set_error("LayerNorm row of %d floats is wider than this build supports (3072)", chunks * 4);
   return KVQ_ERR_BAD_SHAPE;
 }
@@ -262,10 +281,11 @@ int launch_ln_window(const float* x, __half* out, const float* gamma, const floa
   KVQ_REQUIRE(C % 4 == 0, KVQ_ERR_BAD_SHAPE, "ln_window: C=%d not a multiple of 4", C);
   const long long rows = static_cast<long long>(B) * g.nW * g.N;
   KVQ_REQUIRE(rows < (1ll << 31), KVQ_ERR_BAD_SHAPE, "ln_window: %lld rows overflow int32", rows);
-  const int grid = static_cast<int>((rows + 7) / 8);
-  return dispatch_maxv(C / 4, [&](auto mv) {
-    ln_window_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, gamma, beta, eps,
-                                                                             static_cast<int>(rows), C, g);
+  return dispatch_ln(C / 4, [&](auto lpr, auto mv) {
+    constexpr int RPC = (ROW_THREADS / 32) * (32 / decltype(lpr)::value);
+    const int grid = static_cast<int>((rows + RPC - 1) / RPC);
+    ln_window_kernel<decltype(lpr)::value, decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(
+        x, out, gamma, beta, eps, static_cast<int>(rows), C, g);
     count_launch();
     return check_cuda(cudaGetLastError(), "ln_window_kernel launch");
   });
@@ -274,10 +294,11 @@ int launch_ln_window(const float* x, __half* out, const float* gamma, const floa
 int launch_ln_rows(const float* x, __half* out, float* feat_cf, const float* gamma, const float* beta, float eps,
                    int M, int C, int tokens_per_clip, cudaStream_t stream) {
   KVQ_REQUIRE(C % 4 == 0 && M > 0, KVQ_ERR_BAD_SHAPE, "ln_rows: M=%d C=%d", M, C);
-  const int grid = (M + 7) / 8;
-  return dispatch_maxv(C / 4, [&](auto mv) {
-    ln_rows_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, feat_cf, gamma, beta, eps, M, C,
-                                                                           tokens_per_clip);
+  return dispatch_ln(C / 4, [&](auto lpr, auto mv) {
+    constexpr int RPC = (ROW_THREADS / 32) * (32 / decltype(lpr)::value);
+    const int grid = (M + RPC - 1) / RPC;
+    ln_rows_kernel<decltype(lpr)::value, decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(
+        x, out, feat_cf, gamma, beta, eps, M, C, tokens_per_clip);
     count_launch();
     return check_cuda(cudaGetLastError(), "ln_rows_kernel launch");
   });
@@ -288,10 +309,11 @@ int launch_ln_merge(const float* x, __half* out, const float* gamma, const float
   KVQ_REQUIRE(C % 4 == 0, KVQ_ERR_BAD_SHAPE, "ln_merge: C=%d not a multiple of 4", C);
   const long long rows = static_cast<long long>(B) * D * ((H + 1) / 2) * ((W + 1) / 2);
   KVQ_REQUIRE(rows < (1ll << 31), KVQ_ERR_BAD_SHAPE, "ln_merge: %lld rows overflow int32", rows);
-  const int grid = static_cast<int>((rows + 7) / 8);
-  return dispatch_maxv(C, [&](auto mv) {
-    ln_merge_kernel<decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(x, out, gamma, beta, eps,
-                                                                            static_cast<int>(rows), D, H, W, C);
+  return dispatch_ln(C, [&](auto lpr, auto mv) {
+    constexpr int RPC = (ROW_THREADS / 32) * (32 / decltype(lpr)::value);
+    const int grid = static_cast<int>((rows + RPC - 1) / RPC);
+    ln_merge_kernel<decltype(lpr)::value, decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(
+        x, out, gamma, beta, eps, static_cast<int>(rows), D, H, W, C);
     count_launch();
     return check_cuda(cudaGetLastError(), "ln_merge_kernel launch");
   });
