@@ -23,22 +23,25 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 halfs = one 128 B swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_WARPS = 8;
 constexpr int A_BYTES = BM * BK * 2;
+constexpr int STAGING_BYTES = EPI_WARPS * (32 * 36 * 4 + 32 * 8);   // per warp: 32x36 fp32 tile + 32 row offsets
 
-// Two CTAs are resident per SM (12 warps: 2 TMA, 2 MMA, 8 epilogue) so one CTA's epilogue overlaps the other's
-// MMAs; each CTA therefore gets <= 113 KB of shared memory and <= 256 TMEM columns.  Accumulators are
-// double-buffered inside a CTA only when two tiles fit 256 columns (BLOCK_N <= 128).
+// One CTA per SM: a deep TMA ring (the large-K GEMMs are latency-bound with fewer than 4 stages in flight) and
+// double-buffered accumulators so 8 epilogue warps drain tile t while the tensor pipe works on tile t+1.
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (3 * STAGE_BYTES + 2048 <= 113 * 1024) ? 3 : 2;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int ACC_STAGES = (2 * BN <= 256) ? 2 : 1;
+  static constexpr int STAGES = BN >= 192 ? 4 : 6;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int CW = (BN % 64 == 0) ? 32 : 16;       // TMEM columns per epilogue chunk
+  static constexpr int NCHUNK = BN / CW;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
   static constexpr int TMEM_NEED = ACC_STAGES * BN;
-  static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : 256;
-  static_assert(TMEM_NEED <= 256, "two resident CTAs must share the 512 TMEM columns");
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  static_assert(TMEM_NEED <= 512 && SMEM <= 227 * 1024, "tile configuration exceeds the SM");
 };
 
 // exact-erf GELU (nn.GELU default, swin_backbone.py:72).  erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, below
@@ -64,15 +67,24 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+template <int CW>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t* r) {
+  if constexpr (CW == 32) tmem_ld_x32(taddr, r);
+  else tmem_ld_x16(taddr, r);
+}
+
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   constexpr int STAGES = Cfg<BN>::STAGES;
   constexpr int ACC = Cfg<BN>::ACC_STAGES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg<BN>::STAGE_BYTES);
+  constexpr int CW = Cfg<BN>::CW;
+  constexpr int NCHUNK = Cfg<BN>::NCHUNK;
+  uint8_t* staging = smem + STAGES * Cfg<BN>::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -95,7 +107,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -154,14 +166,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int ew = warp - 2;        // 0..7
+    const int q = warp & 3;         // TMEM lane quadrant this warp may touch
+    const int half = ew >> 2;       // which interleaved set of column chunks this warp drains
+    // epilogues that need the whole output row in one thread run on the half-0 warps only
+    constexpr bool kWholeRow = (EPI == EPI_LN_F32 || EPI == EPI_HEAD);
+    const int c_begin = kWholeRow ? 0 : half;
+    const int c_step = kWholeRow ? 1 : 2;
+    const bool active = !kWholeRow || half == 0;
+    float* stile = reinterpret_cast<float*>(staging + ew * (32 * 36 * 4 + 32 * 8));
+    long long* srow = reinterpret_cast<long long*>(stile + 32 * 36);
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-      mbar_wait(&tfull[as], aph);
-      __syncwarp();
-      tc_fence_after();
+      if constexpr (EPI != EPI_RESID_F32) {   // (the residual epilogue prefetches x before it waits)
+        mbar_wait(&tfull[as], aph);
+        __syncwarp();
+        tc_fence_after();
+      }
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -170,18 +193,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if constexpr (EPI == EPI_GELU_F16 || EPI == EPI_STORE_F16) {
         __half* orow = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + nbase;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c0, r);
-          float4 bv[8];
+        for (int c = c_begin; c < NCHUNK; c += c_step) {
+          const int c0 = c * CW;
+          uint32_t r[CW];
+          tmem_ld_chunk<CW>(taddr + c0, r);
+          float4 bv[CW / 4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < CW / 4; ++j)
             bv[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c0) + j)
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
           tmem_wait_ld();
-          uint32_t h[16];
+          uint32_t h[CW / 2];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < CW / 4; ++j) {
             float v0 = __uint_as_float(r[4 * j]) + bv[j].x, v1 = __uint_as_float(r[4 * j + 1]) + bv[j].y;
             float v2 = __uint_as_float(r[4 * j + 2]) + bv[j].z, v3 = __uint_as_float(r[4 * j + 3]) + bv[j].w;
             if constexpr (EPI == EPI_GELU_F16) {
@@ -192,10 +216,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) st_global_v4(orow + c0 + 8 * j, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+            for (int j = 0; j < CW / 8; ++j) st_global_v4(orow + c0 + 8 * j, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
           }
         }
       } else if constexpr (EPI == EPI_RESID_F32) {
+        // Row-per-thread TMEM reads are transposed through a per-warp smem tile so that global traffic is
+        // row-contiguous: CW/4 lanes cover one output row (full 32 B sectors for the fp32 read-modify-write).
         long long orow_idx = row;
         bool ok = row_ok;
         if (p.remap) {
@@ -205,30 +231,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           ok = ok && src >= 0;
           orow_idx = static_cast<long long>(b) * p.geom.tokens + src;
         }
-        float* orow = reinterpret_cast<float*>(p.out) + orow_idx * p.ldo + nbase;
-        const float* rrow = p.resid != nullptr ? p.resid + orow_idx * p.ldo + nbase : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c0, r);
-          tmem_wait_ld();
-          if (ok) {
+        srow[lane] = ok ? orow_idx * p.ldo : -1;
+        constexpr int LPRW = CW / 4;          // lanes per row on the global side
+        constexpr int RPI = 32 / LPRW;        // rows per instruction
+        constexpr int MYCH = (NCHUNK + 1) / 2;  // chunks this warp drains
+        const int sub = lane % LPRW, rsel = lane / LPRW;
+        __syncwarp();
+        // prefetch the residual rows while the tensor pipe is still producing this tile: the HBM latency of the
+        // fp32 stream is hidden behind the accumulator wait instead of being paid once per chunk
+        float4 pre[MYCH][LPRW];
+        if (p.resid != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                     __uint_as_float(r[j + 3]));
-              if (p.bias != nullptr) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c0 + j));
-                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-              }
-              if (rrow != nullptr) {
-                const float4 rr = *reinterpret_cast<const float4*>(rrow + c0 + j);
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-              }
-              *reinterpret_cast<float4*>(orow + c0 + j) = v;
+          for (int ci = 0; ci < MYCH; ++ci) {
+            const int c0 = (c_begin + ci * c_step) * CW;
+#pragma unroll
+            for (int it = 0; it < LPRW; ++it) {
+              const long long off = srow[it * RPI + rsel];
+              pre[ci][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (off >= 0 && c0 < BN) pre[ci][it] = *reinterpret_cast<const float4*>(p.resid + off + nbase + c0 + 4 * sub);
             }
           }
         }
+        mbar_wait(&tfull[as], aph);
+        __syncwarp();
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < MYCH; ++ci) {
+          const int c0 = (c_begin + ci * c_step) * CW;
+          if (c0 >= BN) break;
+          uint32_t r[CW];
+          tmem_ld_chunk<CW>(taddr + c0, r);
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c0) + sub);
+          tmem_wait_ld();
+          __syncwarp();                       // previous chunk's readers are done with the tile
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j)
+            *reinterpret_cast<uint4*>(stile + lane * 36 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < LPRW; ++it) {
+            const int rr = it * RPI + rsel;
+            const long long off = srow[rr];
+            if (off >= 0) {
+              float4 v = *reinterpret_cast<const float4*>(stile + rr * 36 + 4 * sub);
+              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              if (p.resid != nullptr) {
+                v.x += pre[ci][it].x; v.y += pre[ci][it].y; v.z += pre[ci][it].z; v.w += pre[ci][it].w;
+              }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + nbase + c0 + 4 * sub) = v;
+            }
+          }
+        }
+        __syncwarp();                         // srow / tile are rewritten by the next tile
       } else if constexpr (EPI == EPI_QKV_IMG) {
         const int ntok = p.geom.N;
         const int win_g = row / ntok;
@@ -236,20 +291,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int slab = i / p.geom.SL;
         const int kv_row = slab * ATT_SLAB + (i - slab * p.geom.SL);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c0, r);
-          tmem_wait_ld();
+        for (int c = c_begin; c < NCHUNK; c += c_step) {
+          const int c0 = c * CW;
+          uint32_t r[CW];
+          tmem_ld_chunk<CW>(taddr + c0, r);
           const int n0 = nbase + c0;
           const int which = n0 / p.C;
-          const int head = (n0 - which * p.C) >> 5;
+          const int cin = n0 - which * p.C;       // channel inside q / k / v
+          const int head = cin >> 5;
+          const int kc0 = (cin & 31) >> 3;        // first 16-byte chunk of the head's 32 channels
           const float sc = which == 0 ? p.qscale : 1.0f;
-          uint32_t h[16];
+          float4 bv[CW / 4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-            h[2 * j] = pack_half2((__uint_as_float(r[4 * j]) + bb.x) * sc, (__uint_as_float(r[4 * j + 1]) + bb.y) * sc);
-            h[2 * j + 1] = pack_half2((__uint_as_float(r[4 * j + 2]) + bb.z) * sc, (__uint_as_float(r[4 * j + 3]) + bb.w) * sc);
+          for (int j = 0; j < CW / 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+          tmem_wait_ld();
+          uint32_t h[CW / 2];
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) {
+            h[2 * j] = pack_half2((__uint_as_float(r[4 * j]) + bv[j].x) * sc, (__uint_as_float(r[4 * j + 1]) + bv[j].y) * sc);
+            h[2 * j + 1] = pack_half2((__uint_as_float(r[4 * j + 2]) + bv[j].z) * sc, (__uint_as_float(r[4 * j + 3]) + bv[j].w) * sc);
           }
           if (row_ok) {
             const int rimg = which == 0 ? i : kv_row;
@@ -257,74 +317,81 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                            (static_cast<size_t>(win_g) * p.heads + head) * ATT_UNIT_BYTES +
                            static_cast<size_t>(which) * ATT_IMG_BYTES;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              st_global_v4(dst + att_img_offset(rimg, j), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+            for (int j = 0; j < CW / 8; ++j)
+              st_global_v4(dst + att_img_offset(rimg, kc0 + j), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
             // the last token of a slab also zeroes the padded K/V key slots behind it (P is 0 there, but 0 * NaN
             // from uninitialised workspace would poison PV); the last token of the window zeroes all the rest
             if (which != 0 && (i - slab * p.geom.SL) == p.geom.SL - 1) {
               const int end = (i == ntok - 1) ? ATT_ROWS : (slab + 1) * ATT_SLAB;
               for (int rz = kv_row + 1; rz < end; ++rz) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) st_global_v4(dst + att_img_offset(rz, j), 0u, 0u, 0u, 0u);
+                for (int j = 0; j < CW / 8; ++j) st_global_v4(dst + att_img_offset(rz, kc0 + j), 0u, 0u, 0u, 0u);
               }
             }
           }
         }
       } else if constexpr (EPI == EPI_LN_F32) {
         // whole output row lives in this thread's TMEM lane: exact two-pass LayerNorm, then a third read to write
-        float mean = 0.f;
+        if (active) {
+          float mean = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c0, r);
-          tmem_wait_ld();
+          for (int c0 = 0; c0 < BN; c0 += CW) {
+            uint32_t r[CW];
+            tmem_ld_chunk<CW>(taddr + c0, r);
+            tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mean += __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
-        }
-        mean *= (1.0f / BN);
-        float var = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c0, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j) - mean;
-            var += d * d;
+            for (int j = 0; j < CW; ++j) mean += __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
           }
-        }
-        const float rstd = rsqrtf(var * (1.0f / BN) + p.eps);
-        float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo;
+          mean *= (1.0f / BN);
+          float var = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c0, r);
-          tmem_wait_ld();
-          if (row_ok) {
+          for (int c0 = 0; c0 < BN; c0 += CW) {
+            uint32_t r[CW];
+            tmem_ld_chunk<CW>(taddr + c0, r);
+            tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              v.x = (__uint_as_float(r[j]) + __ldg(p.bias + c0 + j) - mean) * rstd * __ldg(p.gamma + c0 + j) + __ldg(p.beta + c0 + j);
-              v.y = (__uint_as_float(r[j + 1]) + __ldg(p.bias + c0 + j + 1) - mean) * rstd * __ldg(p.gamma + c0 + j + 1) + __ldg(p.beta + c0 + j + 1);
-              v.z = (__uint_as_float(r[j + 2]) + __ldg(p.bias + c0 + j + 2) - mean) * rstd * __ldg(p.gamma + c0 + j + 2) + __ldg(p.beta + c0 + j + 2);
-              v.w = (__uint_as_float(r[j + 3]) + __ldg(p.bias + c0 + j + 3) - mean) * rstd * __ldg(p.gamma + c0 + j + 3) + __ldg(p.beta + c0 + j + 3);
-              *reinterpret_cast<float4*>(orow + c0 + j) = v;
+            for (int j = 0; j < CW; ++j) {
+              const float d = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j) - mean;
+              var += d * d;
+            }
+          }
+          const float rstd = rsqrtf(var * (1.0f / BN) + p.eps);
+          float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += CW) {
+            uint32_t r[CW];
+            tmem_ld_chunk<CW>(taddr + c0, r);
+            tmem_wait_ld();
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < CW; j += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                const float4 gg = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + j));
+                const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + j));
+                float4 v;
+                v.x = (__uint_as_float(r[j]) + bb.x - mean) * rstd * gg.x + be.x;
+                v.y = (__uint_as_float(r[j + 1]) + bb.y - mean) * rstd * gg.y + be.y;
+                v.z = (__uint_as_float(r[j + 2]) + bb.z - mean) * rstd * gg.z + be.z;
+                v.w = (__uint_as_float(r[j + 3]) + bb.w - mean) * rstd * gg.w + be.w;
+                *reinterpret_cast<float4*>(orow + c0 + j) = v;
+              }
             }
           }
         }
       } else if constexpr (EPI == EPI_HEAD) {
-        float acc = 0.f;
+        if (active) {
+          float acc = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c0, r);
-          tmem_wait_ld();
+          for (int c0 = 0; c0 < BN; c0 += CW) {
+            uint32_t r[CW];
+            tmem_ld_chunk<CW>(taddr + c0, r);
+            tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            acc += gelu_erf(__uint_as_float(r[j]) + __ldg(p.bias + c0 + j)) * __ldg(p.w2 + c0 + j);
+            for (int j = 0; j < CW; ++j)
+              acc += gelu_erf(__uint_as_float(r[j]) + __ldg(p.bias + c0 + j)) * __ldg(p.w2 + c0 + j);
+          }
+          if (row_ok) p.rowscore[row] = acc + __ldg(p.b2ptr);
         }
-        if (row_ok) p.rowscore[row] = acc + __ldg(p.b2ptr);
       }
 
       tc_fence_before();
@@ -355,7 +422,7 @@ int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmPa
   rc = make_tmap_2d(&tmB, B, p.N, p.K, static_cast<uint64_t>(ldb) * 2, BN, BK, 2, 128);
   if (rc != 0) return rc;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
+  const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "gemm_kernel launch");
