@@ -72,6 +72,18 @@ __device__ __forceinline__ void store_o_row(__half* dst, const uint32_t* r, floa
   }
 }
 
+__device__ __forceinline__ void store_o_half(__half* dst, const uint32_t* r, float inv) {   // 16 channels
+#pragma unroll
+  for (int j = 0; j < 16; j += 8) {
+    uint4 o;
+    o.x = pack_half2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+    o.y = pack_half2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+    o.z = pack_half2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+    o.w = pack_half2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+    *reinterpret_cast<uint4*>(dst + j) = o;
+  }
+}
+
 // =====================================================================================================
 // fast path: window (8,7,7), N = 392
 // =====================================================================================================
@@ -119,24 +131,39 @@ __device__ unsigned long long g_attn_timers[16];
 constexpr int FAST_SOFTMAX_THREADS = 256;
 constexpr int FAST_THREADS = FAST_SOFTMAX_THREADS + 32;   // + one control warp: bulk loads and tcgen05.mma issue
 
-// pass 1 over one 50-column slab: v = s + t0[idx] + fg * t1[idx] (+ mask); running max; write back (pad = -inf)
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
+// pass 1 over one 50-column slab: v = s + t0[idx] + fg * t1[idx] (+ mask); running max; write back (pad = -inf).
+// The table gathers are software-pipelined one key row (7 entries) ahead of the arithmetic: with only two warps per
+// scheduler an LDS consumed a few instructions after issue stalls the in-order warp for most of its ~30 cycle latency.
 template <bool MASK>
-__device__ __forceinline__ void pass1_slab(uint32_t taddr, const float2* __restrict__ trow, const float (&Ah)[7],
+__device__ __forceinline__ void pass1_slab(uint32_t taddr, uint32_t trow_addr, const float (&Ah)[7],
                                            const float (&Aw)[7], float m00, float m01, float m10, float m11,
                                            float (&mx)[4]) {
   uint32_t r[50];
   tmem_ld_x32(taddr, r);
   tmem_ld_x16(taddr + 32, r + 32);
   tmem_ld_x2(taddr + 48, r + 48);
+  float2 e[2][7];
+#pragma unroll
+  for (int wj = 0; wj < 7; ++wj) e[0][wj] = lds_f2(trow_addr - 8u * wj);
   tmem_wait_ld();
 #pragma unroll
   for (int hj = 0; hj < 7; ++hj) {
+    if (hj < 6) {
+#pragma unroll
+      for (int wj = 0; wj < 7; ++wj) e[(hj + 1) & 1][wj] = lds_f2(trow_addr - 8u * ((hj + 1) * TS_H + wj));
+    }
 #pragma unroll
     for (int wj = 0; wj < 7; ++wj) {
       const int j = hj * 7 + wj;
-      const float2 e = trow[-(hj * TS_H + wj)];
+      const float2 ee = e[hj & 1][wj];
       const float fg = Ah[hj] + Aw[wj];
-      float v = fmaf(fg, e.y, __uint_as_float(r[j])) + e.x;
+      float v = fmaf(fg, ee.y, __uint_as_float(r[j])) + ee.x;
       if (MASK) v += (hj < 4) ? ((wj < 4) ? m00 : m01) : ((wj < 4) ? m10 : m11);
       mx[j & 3] = fmaxf(mx[j & 3], v);
       r[j] = __float_as_uint(v);
@@ -255,6 +282,30 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
 #endif
     mbar_wait(&sm.bar_tab, 0);
     TMARK(0);  // table wait
+    int prev_t = -1, prev_win_g = 0;   // tile whose O = P V is still waiting for its epilogue
+    auto o_epilogue = [&](int wg, int tp) {
+      if (tp < 3) {
+        uint32_t r[16];
+        tmem_ld_x16(taddr_row + TMEM_O_COL + 16 * hs, r);
+        tmem_wait_ld();
+        const int row = q * 32 + lane;
+        const float inv = 1.0f / (sm.ssum[tp & 1][0][row] + sm.ssum[tp & 1][1][row]);
+        __half* dst = p.out + (static_cast<size_t>(wg) * 392 + tp * 128 + row) * p.C + head * ATT_HD + 16 * hs;
+        store_o_half(dst, r, inv);
+      } else if (q == 0) {
+        uint32_t r[16];
+        tmem_ld_x16(taddr_row + TMEM_O_COL + 16 * hs, r);
+        tmem_wait_ld();
+        if (lane < 8) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w2 = 0; w2 < 8; ++w2) tot += sm.tsum[w2][lane];
+          __half* dst = p.out + (static_cast<size_t>(wg) * 392 + 384 + lane) * p.C + head * ATT_HD + 16 * hs;
+          store_o_half(dst, r, 1.0f / tot);
+        }
+      }
+      tc_fence_before();
+    };
 
     for (int unit = blockIdx.x; unit < units; unit += G) {
       const int win_g = unit / p.heads;
@@ -289,7 +340,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
         ++n_s;
         __syncwarp();
         tc_fence_after();
-        TMARK(1);  // wait for S(t)
+        if (t == 0) TMARK(6); else TMARK(1);  // wait for S(0) (includes the unit's operand load) / S(t>0)
 
         // ---- this thread's query row and its constants ----
         const int ri = tail ? 384 + (lane & 7) : t * 128 + q * 32 + lane;
@@ -313,7 +364,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
           rd_i = sm.rdm[d_i];
         }
         // table row pointer for key slab d:  idx = (d_i+7)*TS_D + (h_i+6)*TS_H + (w_i+6) - d*TS_D - (hj*TS_H + wj)
-        const float2* trow0 = stab + ((d_i + 7) * TS_D + (h_i + 6) * TS_H + (w_i + 6));
+        const uint32_t trow0 = smem_u32(stab) + 8u * static_cast<uint32_t>((d_i + 7) * TS_D + (h_i + 6) * TS_H + (w_i + 6));
 
         // ---- pass 1 ----
         const int slab0 = tail ? warp : hs * 4;
@@ -324,7 +375,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
           for (int s = 0; s < nslab; ++s) {
             const int d = slab0 + s;
             const float dm = (sm.rdm[d] != rd_i) ? MASK_L2 : 0.f;
-            pass1_slab<true>(taddr_row + d * ATT_SLAB, trow0 - d * TS_D, Ah, Aw, fminf(fminf(hlo, wlo), dm),
+            pass1_slab<true>(taddr_row + d * ATT_SLAB, trow0 - 8u * (d * TS_D), Ah, Aw, fminf(fminf(hlo, wlo), dm),
                              fminf(fminf(hlo, whi_m), dm), fminf(fminf(hhi, wlo), dm), fminf(fminf(hhi, whi_m), dm),
                              mx);
           }
@@ -332,7 +383,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
 #pragma unroll 1
           for (int s = 0; s < nslab; ++s) {
             const int d = slab0 + s;
-            pass1_slab<false>(taddr_row + d * ATT_SLAB, trow0 - d * TS_D, Ah, Aw, 0.f, 0.f, 0.f, 0.f, mx);
+            pass1_slab<false>(taddr_row + d * ATT_SLAB, trow0 - 8u * (d * TS_D), Ah, Aw, 0.f, 0.f, 0.f, 0.f, mx);
           }
         }
         tmem_wait_st();
@@ -353,23 +404,15 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
           m = fmaxf(sm.smax[par][0][q * 32 + lane], sm.smax[par][1][q * 32 + lane]);
         }
 
-        // ---- O epilogue of the previous tile (its PV finished long ago; must precede overwriting P) ----
-        if (t > 0) {
+        // ---- O epilogue of the previous tile -- of this unit or, for t == 0, the tail tile of the previous unit:
+        //      its PV finished long ago, and it must precede overwriting P.  The two column halves split O.
+        if (prev_t >= 0) {
           mbar_wait(&sm.bar_o, n_o & 1);
           ++n_o;
           __syncwarp();
           tc_fence_after();
-          if (hs == 0) {
-            uint32_t r[32];
-            tmem_ld_x32(taddr_row + TMEM_O_COL, r);
-            tmem_wait_ld();
-            const int row = q * 32 + lane;
-            const float inv = 1.0f / (sm.ssum[par ^ 1][0][row] + sm.ssum[par ^ 1][1][row]);
-            __half* dst = p.out + (static_cast<size_t>(win_g) * 392 + (t - 1) * 128 + row) * p.C + head * ATT_HD;
-            store_o_row(dst, r, inv);
-          }
+          o_epilogue(prev_win_g, prev_t);
         }
-
         TMARK(4);  // wait PV(t-1) + O epilogue
         // ---- pass 2: P = exp2(v - max) -> fp16 smem image; row sums ----
         float sum = 0.f;
@@ -429,26 +472,16 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.bar_p);
+        prev_t = t;
+        prev_win_g = win_g;
       }
-      // ---- tail O epilogue ----
+    }
+    if (prev_t >= 0) {   // the very last tile of this CTA
       mbar_wait(&sm.bar_o, n_o & 1);
       ++n_o;
       __syncwarp();
       tc_fence_after();
-      if (warp == 0) {
-        uint32_t r[32];
-        tmem_ld_x32(taddr_row + TMEM_O_COL, r);
-        tmem_wait_ld();
-        if (lane < 8) {
-          float s = 0.f;
-#pragma unroll
-          for (int w2 = 0; w2 < 8; ++w2) s += sm.tsum[w2][lane];
-          __half* dst = p.out + (static_cast<size_t>(win_g) * 392 + 384 + lane) * p.C + head * ATT_HD;
-          store_o_row(dst, r, 1.0f / s);
-        }
-        tc_fence_before();
-      }
-      TMARK(6);  // tail O wait + epilogue
+      o_epilogue(prev_win_g, prev_t);
     }
 #ifdef KVQ_TIMING
     if (lane == 0) {

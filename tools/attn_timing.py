@@ -14,7 +14,7 @@ import torch  # noqa: E402
 from kvq_b200 import ops  # noqa: E402
 from oracle import synth  # noqa: E402
 
-NAMES = ["table wait", "wait S(t)", "pass 1", "max barrier", "wait PV + O epilogue", "pass 2", "tail O", "prologue/arrive"]
+NAMES = ["table wait", "wait S(t>0)", "pass 1", "max barrier", "wait PV + O epilogue", "pass 2", "wait S(0) incl. load", "prologue/arrive"]
 
 
 def main():
