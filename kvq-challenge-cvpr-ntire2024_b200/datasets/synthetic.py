@@ -1,0 +1,40 @@
+"""Synthetic stand-in for ViewDecompositionDataset_KVQ (reference datasets/fusion_datasets.py:930-1050).
+
+Each item mimics what the reference loader yields for the `technical` view: raw uint8-valued frames are sampled
+into a fragment grid (Grid Mini-patch Sampling, :22-121) and normalised (:1017-1020); `num_clips` clips of
+`clip_len` frames are concatenated along T.  With `device='cuda'` the gather + normalisation run in the sm_100a
+fragment kernel; with the default `device=None` the item carries the raw frames and offsets and the Trainer runs the
+kernel after the H2D copy (the DataLoader workers stay CPU-only)."""
+import torch
+
+
+class SyntheticFragmentDataset(torch.utils.data.Dataset):
+    def __init__(self, opt, _unused=None):
+        self.opt = opt
+        st = opt["sample_types"]["technical"]
+        self.fh, self.fw = st.get("fragments_h", 7), st.get("fragments_w", 7)
+        self.fs = st.get("fsize_h", 32)
+        self.aligned = st.get("aligned", 8)
+        self.clip_len, self.num_clips = st.get("clip_len", 32), st.get("num_clips", 1)
+        self.src_h, self.src_w = opt.get("src_h", 448), opt.get("src_w", 448)
+        self.n = opt.get("num_videos", 4)
+        self.seed = opt.get("seed", 5)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed + i)
+        T = self.clip_len * self.num_clips
+        frames = torch.randint(0, 256, (T, 3, self.src_h, self.src_w), generator=g, dtype=torch.uint8)
+        hl, wl = self.src_h // self.fh, self.src_w // self.fw
+        nt = T // self.aligned
+        # reference draw order: rnd_h then rnd_w (fusion_datasets.py:87-98)
+        rnd_h = torch.randint(hl - self.fs, (self.fh, self.fw, nt), generator=g) if hl > self.fs else \
+            torch.zeros(self.fh, self.fw, nt, dtype=torch.int64)
+        rnd_w = torch.randint(wl - self.fs, (self.fh, self.fw, nt), generator=g) if wl > self.fs else \
+            torch.zeros(self.fh, self.fw, nt, dtype=torch.int64)
+        return {"frames": frames, "offsets": torch.stack([rnd_h, rnd_w]).int(),
+                "num_clips": {"technical": self.num_clips}, "video_name": f"synthetic_{i:04d}",
+                "fragment_opts": {"fragments_h": self.fh, "fragments_w": self.fw, "fsize": self.fs,
+                                  "aligned": self.aligned}}

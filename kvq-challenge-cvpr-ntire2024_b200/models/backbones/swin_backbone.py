@@ -168,17 +168,24 @@ class SwinTransformer3D(nn.Module):
             self._packed_key = key
         return self._packed
 
+    @staticmethod
+    def _require_cuda(x):
+        if not x.is_cuda:
+            raise RuntimeError("kvq_b200: input clips must be CUDA tensors -- this path has no CPU fallback")
+
     def forward(self, batch, multi=False, layer=-1, adaptive_window_size=False):
         """batch['technical'] f32 [B,3,T,H,W] -> [B, 8C, T/2, H/32, W/32]  (:1044-1080)."""
         if multi or layer > -1 or adaptive_window_size:
             raise NotImplementedError("kvq_b200: multi / layer / adaptive_window_size outputs are not on the B200 path")
         x = batch["technical"] if isinstance(batch, dict) else batch
+        self._require_cuda(x)
         with torch.cuda.device(x.device):
             feat, _ = self.packed().forward(x, want_feat=True, want_score=False)
         return feat
 
     def forward_with_head(self, x, head, want_feat=False):
         """Fused backbone + VQAHead: one C-ABI call, score [B,1] (+ features when asked)."""
+        self._require_cuda(x)
         with torch.cuda.device(x.device):
             feat, score = self.packed(head).forward(x, want_feat=want_feat, want_score=True)
         return feat, score.reshape(-1, 1)

@@ -22,6 +22,8 @@ class VQAHead(nn.Module):
     def forward(self, x, rois=None):
         if self.training:
             raise RuntimeError("kvq_b200: inference path only (call .eval(); dropout is identity there)")
+        if not x.is_cuda:
+            raise RuntimeError("kvq_b200: features must be CUDA tensors -- this path has no CPU fallback")
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed is None or self._key != key:
             with torch.cuda.device(x.device):

@@ -1,0 +1,107 @@
+"""Inference-side drop-in for the reference Trainer (trainer.py:36-74, :298-334).
+
+`test.py` in the reference calls `trainer.inferece()`, which `trainer.Trainer` never defines; the
+intended behaviour is `inferece_test`: per video -> reshape [b,c,T,h,w] into clips -> model(inputs=data,
+reduce_scores=True) -> mean over clips -> `output.txt` lines `video_name,score`.  This class provides `inferece`
+with those semantics on the B200 path.  One process drives ONE GPU; under torchrun the videos are sharded across
+ranks and rank 0 writes the file (the reference wraps the model in nn.DataParallel instead, trainer.py:61)."""
+import os
+
+import torch
+
+import datasets
+from kvq_b200 import ops, parallel
+from models import VQA_Network
+
+
+def split_clips(x, num_clips):
+    """[b,c,T,h,w] -> [b*num_clips, c, T/num_clips, h, w]  (trainer.py:308-319)."""
+    b, c, t, h, w = x.shape
+    return (x.reshape(b, c, num_clips, t // num_clips, h, w).permute(0, 2, 1, 3, 4, 5)
+            .reshape(b * num_clips, c, t // num_clips, h, w))
+
+
+def strip_module_prefix(state_dict):
+    """Checkpoints are saved from the DataParallel / DDP wrapper (trainer.py:223-230): keys carry `module.`."""
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+
+
+def score_video(model, data, key_list, device=None):
+    """Body of the inferece_test loop (trainer.py:306-329) for one loader item; returns the video's mean score."""
+    if "frames" in data and "technical" not in data:                    # raw frames: fragment kernel on the GPU
+        fo = data["fragment_opts"]
+        frames = data["frames"].to(device, non_blocking=True)
+        if frames.dim() == 4:
+            frames, offsets = frames[None], data["offsets"][None]
+        else:
+            offsets = data["offsets"]
+        g = lambda v: int(v[0]) if torch.is_tensor(v) else int(v)         # DataLoader collates ints into tensors
+        data["technical"] = ops.fragment_gather_u8(frames.contiguous(), offsets.to(device).int().contiguous(),
+                                                   g(fo["fragments_h"]), g(fo["fragments_w"]), g(fo["fsize"]),
+                                                   g(fo["aligned"]))
+    for key in key_list:
+        if key in data:
+            if device is not None:
+                data[key] = data[key].to(device)
+            nc = data["num_clips"][key]
+            data[key] = split_clips(data[key], int(nc[0]) if torch.is_tensor(nc) else int(nc)).contiguous()
+    with torch.no_grad():
+        pred = model(inputs=data, reduce_scores=True)
+        if isinstance(pred, tuple):            # KSVQE key returns (scores, dis_contra_loss)  (trainer.py:323-325)
+            pred = pred[0]
+    return pred.float().mean(0).reshape(-1)[0]
+
+
+class Trainer:
+    def __init__(self, args, config):
+        self.args, self.config = args, config
+        self.gpu_list = [int(i) for i in str(args.gpu_id).split(",")]
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        gpu = self.gpu_list[local % len(self.gpu_list)] if "LOCAL_RANK" in os.environ else self.gpu_list[0]
+        self.device = torch.device("cuda", gpu)
+        torch.cuda.set_device(self.device)
+        self.key_list = ["technical"] if any(k.startswith("swin") for k in config["model"]["args"]) \
+            else config["model"]["type"].split(",")
+        self.build_datasets()
+        self.build_models()
+
+    def build_datasets(self):
+        if "val" in self.config["data"]:
+            v = self.config["data"]["val"]
+            self.val_dataset = getattr(datasets, v["type"])(v["args"], None)
+
+    def build_models(self):
+        self.model = VQA_Network(self.config).to(self.device)
+        path = self.config.get("load_path")
+        if path is not None:
+            sd = torch.load(path, map_location="cpu")
+            sd = sd.get("state_dict", sd)
+            msg = self.model.load_state_dict(strip_module_prefix(sd), strict=False)
+            print("load", path, msg)
+        self.model.eval()
+
+    def inferece(self, output_path="output.txt"):
+        import torch.distributed as dist
+        ddp = dist.is_available() and dist.is_initialized()
+        world, rank = (dist.get_world_size(), dist.get_rank()) if ddp else (1, 0)
+        n = len(self.val_dataset)
+        lo, hi = parallel.shard_bounds(n, world, rank)
+        loader = torch.utils.data.DataLoader(torch.utils.data.Subset(self.val_dataset, range(lo, hi)), batch_size=1,
+                                             num_workers=self.config.get("num_workers", 0), pin_memory=True)
+        names, scores = [], []
+        for data in loader:
+            names.append(data["video_name"][0])
+            scores.append(score_video(self.model, data, self.key_list, self.device))
+        local = torch.stack(scores) if scores else torch.zeros(0, device=self.device)
+        allscores = parallel.all_gather_scores(local, n).cpu().tolist()
+        if ddp:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, names)
+            names = [x for part in gathered for x in part]
+        if rank == 0:
+            with open(output_path, "w") as f:
+                for name, s in zip(names, allscores):
+                    f.write(f"{name},{s}\n")
+        return list(zip(names, allscores))
+
+    inferece_test = inferece
