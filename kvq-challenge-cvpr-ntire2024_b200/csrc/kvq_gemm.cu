@@ -63,6 +63,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, erf_as(x * 0.70710678118654752f), hx);
 }
 
+// two GELUs per call on the packed fp32x2 pipe (same formula as gelu_erf)
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 z = fmul2(x, splat2(0.70710678118654752f));
+  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 den = ffma2(splat2(0.3275911f), az, splat2(1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  float2 p = ffma2(splat2(1.061405429f), t, splat2(-1.453152027f));
+  p = ffma2(p, t, splat2(1.421413741f));
+  p = ffma2(p, t, splat2(-0.284496736f));
+  p = ffma2(p, t, splat2(0.254829592f));
+  p = fmul2(p, t);
+  const float2 q = fmul2(fmul2(az, az), splat2(-1.4426950408889634f));
+  const float2 e = make_float2(fast_exp2(q.x), fast_exp2(q.y));
+  const float2 er = ffma2(make_float2(-p.x, -p.y), e, splat2(1.0f));          // erf(|z|)
+  const float2 hx = fmul2(x, splat2(0.5f));
+  return ffma2(hx, make_float2(copysignf(er.x, x.x), copysignf(er.y, x.y)), hx);
+}
+
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -178,6 +198,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     long long* srow = reinterpret_cast<long long*>(stile + 32 * 36);
     int as = 0;
     uint32_t aph = 0;
+    int bias_nblk = -1;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       if constexpr (EPI != EPI_RESID_F32) {   // (the residual epilogue prefetches x before it waits)
@@ -192,33 +213,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       if constexpr (EPI == EPI_GELU_F16 || EPI == EPI_STORE_F16) {
         __half* orow = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + nbase;
-#pragma unroll 1
-        for (int c = c_begin; c < NCHUNK; c += c_step) {
-          const int c0 = c * CW;
-          uint32_t r[CW];
-          tmem_ld_chunk<CW>(taddr + c0, r);
-          float4 bv[CW / 4];
+        constexpr int MYCH = (NCHUNK + 1) / 2;
+        // this warp's bias slice lives in its private smem tile; refreshed only when the CTA moves to another n-block
+        if (n_blk != bias_nblk) {
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < CW / 4; ++j)
-            bv[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c0) + j)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int ci = 0; ci < MYCH; ++ci) {
+            const int c0 = (c_begin + ci * c_step) * CW;
+            if (lane < CW && c0 < BN) stile[ci * CW + lane] = p.bias != nullptr ? __ldg(p.bias + nbase + c0 + lane) : 0.f;
+          }
+          bias_nblk = n_blk;
+          __syncwarp();
+        }
+        uint32_t r[2][CW];
+        tmem_ld_chunk<CW>(taddr + c_begin * CW, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < MYCH; ++ci) {
+          const int c0 = (c_begin + ci * c_step) * CW;
+          if (c0 >= BN) break;
           tmem_wait_ld();
+          if (ci + 1 < MYCH && c0 + c_step * CW < BN) tmem_ld_chunk<CW>(taddr + c0 + c_step * CW, r[(ci + 1) & 1]);
+          const uint32_t* rc = r[ci & 1];
           uint32_t h[CW / 2];
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) {
-            float v0 = __uint_as_float(r[4 * j]) + bv[j].x, v1 = __uint_as_float(r[4 * j + 1]) + bv[j].y;
-            float v2 = __uint_as_float(r[4 * j + 2]) + bv[j].z, v3 = __uint_as_float(r[4 * j + 3]) + bv[j].w;
+            const float4 bb = *reinterpret_cast<const float4*>(stile + ci * CW + 4 * j);
+            float2 v01 = fadd2(make_float2(__uint_as_float(rc[4 * j]), __uint_as_float(rc[4 * j + 1])), make_float2(bb.x, bb.y));
+            float2 v23 = fadd2(make_float2(__uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3])), make_float2(bb.z, bb.w));
             if constexpr (EPI == EPI_GELU_F16) {
-              v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+              v01 = gelu_erf2(v01);
+              v23 = gelu_erf2(v23);
             }
-            h[2 * j] = pack_half2(v0, v1);
-            h[2 * j + 1] = pack_half2(v2, v3);
+            h[2 * j] = pack_half2(v01.x, v01.y);
+            h[2 * j + 1] = pack_half2(v23.x, v23.y);
           }
-          if (row_ok) {
+          // transpose through the warp's smem tile (80 B row pitch: conflict-free both ways) so that every store
+          // instruction writes whole 32 B sectors: 32/SEGS rows x (CW*2) contiguous bytes instead of 32 x 16 B
+          constexpr int SEGS = CW / 8;                    // 16-byte segments per row chunk
+          uint8_t* st16 = reinterpret_cast<uint8_t*>(stile) + 512;
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < CW / 8; ++j) st_global_v4(orow + c0 + 8 * j, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          for (int j = 0; j < SEGS; ++j)
+            *reinterpret_cast<uint4*>(st16 + lane * 80 + j * 16) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          __syncwarp();
+          constexpr int RPI = 32 / SEGS;                  // rows per store instruction
+          const int seg = lane / RPI, rl = lane % RPI;
+#pragma unroll
+          for (int it = 0; it < SEGS; ++it) {
+            const int rr = it * RPI + rl;
+            const uint4 v = *reinterpret_cast<const uint4*>(st16 + rr * 80 + seg * 16);
+            const int grow = m_blk * BM + q * 32 + rr;
+            if (grow < p.M)
+              st_global_v4(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldo + nbase + c0 + 8 * seg,
+                           v.x, v.y, v.z, v.w);
           }
         }
+        (void)orow;
+        (void)row_ok;
       } else if constexpr (EPI == EPI_RESID_F32) {
         // Row-per-thread TMEM reads are transposed through a per-warp smem tile so that global traffic is
         // row-contiguous: CW/4 lanes cover one output row (full 32 B sectors for the fp32 read-modify-write).
