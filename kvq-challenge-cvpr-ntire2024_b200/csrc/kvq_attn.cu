@@ -419,16 +419,19 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
         if (!tail) {
           uint8_t* prow = sP + (q * 4 + (lane >> 3)) * P_SBO + (lane & 7) * 16;
           const int col0 = hs * 200;
+          const float2 negm2 = make_float2(-m, -m);
+          float2 sum2 = make_float2(0.f, 0.f);
           auto exp_chunk = [&](const uint32_t* r, int c_abs, int n) {
 #pragma unroll
             for (int j = 0; j < n; j += 8) {
               uint32_t h[4];
 #pragma unroll
               for (int k = 0; k < 8; k += 2) {
-                const float e0 = fast_exp2(__uint_as_float(r[j + k]) - m);
-                const float e1 = fast_exp2(__uint_as_float(r[j + k + 1]) - m);
-                sum += e0 + e1;
-                h[k >> 1] = pack_half2(e0, e1);
+                // packed fp32x2: one FADD2 for the two max subtractions, one for the two row-sum updates
+                const float2 d = fadd2(make_float2(__uint_as_float(r[j + k]), __uint_as_float(r[j + k + 1])), negm2);
+                const float2 e = make_float2(fast_exp2(d.x), fast_exp2(d.y));
+                sum2 = fadd2(sum2, e);
+                h[k >> 1] = pack_half2(e.x, e.y);
               }
               *reinterpret_cast<uint4*>(prow + ((c_abs + j) >> 3) * 128) = make_uint4(h[0], h[1], h[2], h[3]);
             }
@@ -446,6 +449,7 @@ window_attn_fast_kernel(const AttnParams p, const float2* __restrict__ tabs, int
             tmem_wait_ld();
             exp_chunk(r, col0 + 192, 8);
           }
+          sum = sum2.x + sum2.y;
           sm.ssum[par][hs][q * 32 + lane] = sum;
         } else {
           // tail: rows 0..7 of the P tile, this warp's slab of 50 columns (4-byte stores: slab starts are even)
