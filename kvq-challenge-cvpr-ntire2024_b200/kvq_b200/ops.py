@@ -1,9 +1,19 @@
 """torch-tensor front ends of the C-ABI operators.  PyTorch only supplies device memory and the stream."""
 import ctypes
+import os
 
 import torch
 
 from . import lib as _l
+
+
+# kernels launched through CUDA-graph replays (kvq_launch_count() only sees eager launches and captures)
+GRAPH_KERNEL_LAUNCHES = 0
+
+
+def kernel_launches():
+    """Total kernels of libkvq_b200.so launched by this process: eager launches + graph-replayed ones."""
+    return int(_l.load().kvq_launch_count()) + GRAPH_KERNEL_LAUNCHES
 
 
 def _stream():
@@ -189,6 +199,7 @@ class SwinWeights:
                                f"{_l.last_error()}")
         self.ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in merged])
         self._ws = None
+        self._graphs = {}
 
     def workspace(self, B, T, H, W):
         need = _l.load().kvq_swin3d_workspace_bytes(ctypes.byref(self.cfg), B, T, H, W)
@@ -196,6 +207,7 @@ class SwinWeights:
             raise RuntimeError(f"kvq_b200: cannot plan a [{B},3,{T},{H},{W}] forward: {_l.last_error()}")
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
+            self._graphs = {}                      # captured graphs point into the old workspace
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws, need
 
@@ -205,18 +217,50 @@ class SwinWeights:
             h, w = (h + 1) // 2, (w + 1) // 2
         return (B, self.final_dim, D, h, w)
 
-    def forward(self, x, want_feat=False, want_score=True, score_out=None):
-        """x f32 [B,3,T,H,W] on this device -> (feat [B,Cf,D,h,w] or None, score [B] or None)."""
+    def _launch(self, x, feat, score, ws):
+        B, _, T, H, W = x.shape
+        rc = _l.load().kvq_swin3d_forward(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(x), B, T, H, W,
+                                          _p(feat), _p(score), _p(ws), ws.numel(), _stream())
+        _l.check(rc, "swin3d_forward")
+
+    def forward(self, x, want_feat=False, want_score=True, score_out=None, graph=None):
+        """x f32 [B,3,T,H,W] on this device -> (feat [B,Cf,D,h,w] or None, score [B] or None).
+
+        graph=True (default: env KVQ_CUDA_GRAPH=1) replays the ~95 kernel launches of the forward from a CUDA graph
+        captured per (input buffer, shape): the library enqueues everything on the current stream, allocates nothing
+        and takes tensor maps by value, so the whole call is capturable.  Outputs of a graphed call live in buffers
+        owned by the graph and are overwritten by the next replay for the same input buffer."""
         if not x.is_cuda or x.dtype != torch.float32:
             raise RuntimeError("kvq_b200: input clips must be float32 CUDA tensors (no CPU fallback exists)")
         x = x.contiguous()
         B, _, T, H, W = x.shape
         ws, need = self.workspace(B, T, H, W)
+        has_score = want_score and self.cfg.head_hidden > 0
+        if graph is None:
+            graph = os.environ.get("KVQ_CUDA_GRAPH", "0") == "1"
+        if graph and score_out is None:
+            key = (x.data_ptr(), tuple(x.shape), bool(want_feat), has_score, ws.data_ptr())
+            entry = self._graphs.get(key)
+            if entry is None:
+                feat = torch.empty(self.feat_shape(B, T, H, W), dtype=torch.float32, device=x.device) if want_feat else None
+                score = torch.empty(B, dtype=torch.float32, device=x.device) if has_score else None
+                self._launch(x, feat, score, ws)                       # warm-up: one-time function attributes
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = _l.load().kvq_launch_count()
+                with torch.cuda.graph(g):
+                    self._launch(x, feat, score, ws)
+                nodes = int(_l.load().kvq_launch_count() - n0)          # kernels a replay launches
+                if len(self._graphs) >= 8:                               # bounded cache
+                    self._graphs.pop(next(iter(self._graphs)))
+                entry = self._graphs[key] = (g, feat, score, nodes)
+            entry[0].replay()
+            global GRAPH_KERNEL_LAUNCHES
+            GRAPH_KERNEL_LAUNCHES += entry[3]
+            return entry[1], entry[2]
         feat = torch.empty(self.feat_shape(B, T, H, W), dtype=torch.float32, device=x.device) if want_feat else None
         score = None
-        if want_score and self.cfg.head_hidden > 0:
+        if has_score:
             score = score_out if score_out is not None else torch.empty(B, dtype=torch.float32, device=x.device)
-        rc = _l.load().kvq_swin3d_forward(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(x), B, T, H, W,
-                                          _p(feat), _p(score), _p(ws), ws.numel(), _stream())
-        _l.check(rc, "swin3d_forward")
+        self._launch(x, feat, score, ws)
         return feat, score

@@ -183,11 +183,11 @@ class SwinTransformer3D(nn.Module):
             feat, _ = self.packed().forward(x, want_feat=True, want_score=False)
         return feat
 
-    def forward_with_head(self, x, head, want_feat=False):
+    def forward_with_head(self, x, head, want_feat=False, graph=None):
         """Fused backbone + VQAHead: one C-ABI call, score [B,1] (+ features when asked)."""
         self._require_cuda(x)
         with torch.cuda.device(x.device):
-            feat, score = self.packed(head).forward(x, want_feat=want_feat, want_score=True)
+            feat, score = self.packed(head).forward(x, want_feat=want_feat, want_score=True, graph=graph)
         return feat, score.reshape(-1, 1)
 
 

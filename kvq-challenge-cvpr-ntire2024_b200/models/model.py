@@ -24,6 +24,8 @@ class VQA_Network(nn.Module):
         self.key_names = []
         self.multi = False
         self.layer = -1
+        # None = follow env KVQ_CUDA_GRAPH; True = replay each (input buffer, shape) forward from a captured CUDA graph
+        self.use_cuda_graph = None
         for key, hypers in config["model"]["args"].items():
             if key == "swin_tiny":
                 backbone = swin_3d_tiny(**hypers.get("backbone", {}))
@@ -49,7 +51,7 @@ class VQA_Network(nn.Module):
         for key in self.key_names:
             backbone, head = getattr(self, key + "_backbone"), getattr(self, key + "_head")
             x = inputs["technical"]
-            feat, score = backbone.forward_with_head(x, head, want_feat=return_pooled_feats)
+            feat, score = backbone.forward_with_head(x, head, want_feat=return_pooled_feats, graph=self.use_cuda_graph)
             scores.append(score)
             if return_pooled_feats:
                 feats[key] = feat

@@ -103,3 +103,20 @@ def test_trainer_inferece_writes_reference_format(tmp_path):
         got = float(line.split(",")[1])
         assert abs(got - ref) <= 1e-3, (i, got, ref)
         assert abs(res[i][1] - got) < 1e-6
+
+
+def test_cuda_graph_replay_matches_eager():
+    from oracle import synth
+    dev = torch.device("cuda:0")
+    g, m = _golden_model(os.path.join(GOLDEN, "swin_t16_64x64.npz"), dev)
+    xa = synth.clip_input((3, 3, 16, 64, 64), 41).to(dev)
+    xb = synth.clip_input((3, 3, 16, 64, 64), 42).to(dev)
+    with torch.no_grad():
+        m.use_cuda_graph = False
+        ea, eb = m(inputs={"technical": xa}, reduce_scores=True).clone(), m(inputs={"technical": xb}, reduce_scores=True).clone()
+        m.use_cuda_graph = True
+        ga = m(inputs={"technical": xa}, reduce_scores=True).clone()       # capture + replay
+        gb = m(inputs={"technical": xb}, reduce_scores=True).clone()       # second buffer -> second graph
+        xa.copy_(xb)                                                       # same buffer, new contents -> replay
+        ga2 = m(inputs={"technical": xa}, reduce_scores=True).clone()
+    assert torch.equal(ga, ea) and torch.equal(gb, eb) and torch.equal(ga2, eb)
