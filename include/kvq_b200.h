@@ -96,6 +96,10 @@ int kvq_linear_f16(const void* a_f16, const void* w_f16, const float* bias, void
 /* out_f32[M,N] = resid + A*W^T + bias (resid / bias may be NULL; resid may alias out) */
 int kvq_linear_resid_f32(const void* a_f16, const void* w_f16, const float* bias, const float* resid, float* out,
                          int M, int N, int K, void* stream);
+/* x[M,C] += fc2(gelu(fc1(a) + b1)) + b2 with the [M,4C] hidden kept on chip (Mlp.forward + residual,
+ * swin_backbone.py:64-89, :490-491, :509).  a f16 [M,C]; w1 f16 [4C,C]; w2 f16 [C,4C]; built for C = 96, 192 */
+int kvq_mlp_fused(const void* a_f16, const void* w1_f16, const float* b1, const void* w2_f16, const float* b2, float* x,
+                  int M, int C, void* stream);
 /* norm1 + cyclic shift + window_partition (swin_backbone.py:416-449): x f32 [B,D,H,W,C] -> f16 [B*nW*N, C] */
 int kvq_ln_window(const float* x, void* out_f16, const float* gamma, const float* beta, float eps, int B, int D,
                   int H, int W, int C, const int32_t window[3], const int32_t shift[3], void* stream);

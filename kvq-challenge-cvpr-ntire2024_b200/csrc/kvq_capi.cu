@@ -1,6 +1,7 @@
 // C-ABI entry points (include/kvq_b200.h) and the host-side orchestration of the Swin3D-GRPB + VQAHead forward.
 // Everything is enqueued on the caller's stream; the library allocates nothing.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/kvq_b200.h"
@@ -165,7 +166,7 @@ int kvq_profile_num_categories(void) { return PK_COUNT * 4; }
 const char* kvq_profile_category_name(int cat) {
   static const char* kinds[PK_COUNT] = {"embed_im2col", "embed_gemm", "ln_window", "qkv_gemm", "window_attn",
                                         "proj_gemm", "ln_rows", "fc1_gemm", "fc2_gemm", "merge_ln", "merge_gemm",
-                                        "final_ln", "head"};
+                                        "final_ln", "head", "fused_mlp"};
   static thread_local char buf[48];
   if (cat < 0 || cat >= PK_COUNT * 4) return "?";
   snprintf(buf, sizeof(buf), "%s.s%d", kinds[cat / 4], cat % 4);
@@ -286,21 +287,28 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
         rc = launch_ln_rows(xcur, a16, nullptr, n2g, n2b, eps, M, C, sd.D * sd.H * sd.W, st);
       }
       if (rc != 0) return rc;
-      {
-        GemmParams gp{};
-        gp.M = M; gp.N = 4 * C; gp.K = C;
-        gp.bias = fc1_b; gp.out = hid; gp.ldo = 4 * C;
-        ProfScope ps(PK_FC1_GEMM, s, st);
-        rc = launch_gemm(EPI_GELU_F16, a16, C, fc1_w, C, gp, st);
+      static const bool fuse_mlp = []() { const char* e = getenv("KVQ_FUSED_MLP"); return e == nullptr || atoi(e) != 0; }();
+      if (fuse_mlp && fused_mlp_supported(C)) {
+        ProfScope ps(PK_FUSED_MLP, s, st);
+        rc = launch_fused_mlp(a16, fc1_w, fc1_b, fc2_w, fc2_b, xcur, M, C, st);
         if (rc != 0) return rc;
-      }
-      {
-        GemmParams gp{};
-        gp.M = M; gp.N = C; gp.K = 4 * C;
-        gp.bias = fc2_b; gp.out = xcur; gp.ldo = C; gp.resid = xcur;
-        ProfScope ps(PK_FC2_GEMM, s, st);
-        rc = launch_gemm(EPI_RESID_F32, hid, 4 * C, fc2_w, 4 * C, gp, st);
-        if (rc != 0) return rc;
+      } else {
+        {
+          GemmParams gp{};
+          gp.M = M; gp.N = 4 * C; gp.K = C;
+          gp.bias = fc1_b; gp.out = hid; gp.ldo = 4 * C;
+          ProfScope ps(PK_FC1_GEMM, s, st);
+          rc = launch_gemm(EPI_GELU_F16, a16, C, fc1_w, C, gp, st);
+          if (rc != 0) return rc;
+        }
+        {
+          GemmParams gp{};
+          gp.M = M; gp.N = C; gp.K = 4 * C;
+          gp.bias = fc2_b; gp.out = xcur; gp.ldo = C; gp.resid = xcur;
+          ProfScope ps(PK_FC2_GEMM, s, st);
+          rc = launch_gemm(EPI_RESID_F32, hid, 4 * C, fc2_w, 4 * C, gp, st);
+          if (rc != 0) return rc;
+        }
       }
     }
     if (s + 1 < cfg->num_stages) {  // PatchMerging (:533-555)
@@ -374,6 +382,12 @@ int kvq_linear_resid_f32(const void* a_f16, const void* w_f16, const float* bias
   gp.bias = bias; gp.out = out; gp.ldo = N; gp.resid = resid;
   return launch_gemm(EPI_RESID_F32, static_cast<const __half*>(a_f16), K, static_cast<const __half*>(w_f16), K, gp,
                      static_cast<cudaStream_t>(stream));
+}
+
+int kvq_mlp_fused(const void* a_f16, const void* w1_f16, const float* b1, const void* w2_f16, const float* b2, float* x,
+                  int M, int C, void* stream) {
+  return launch_fused_mlp(static_cast<const __half*>(a_f16), static_cast<const __half*>(w1_f16), b1,
+                          static_cast<const __half*>(w2_f16), b2, x, M, C, static_cast<cudaStream_t>(stream));
 }
 
 int64_t kvq_window_rows(int B, int D, int H, int W, const int32_t window[3], const int32_t shift[3]) {

@@ -19,7 +19,7 @@ int prof_collect(float* ms, int* launches, int ncat);
 // timing categories: kind * 4 + stage
 enum ProfKind : int {
   PK_EMBED_IM2COL = 0, PK_EMBED_GEMM, PK_LN_WINDOW, PK_QKV_GEMM, PK_ATTN, PK_PROJ_GEMM, PK_LN_ROWS, PK_FC1_GEMM,
-  PK_FC2_GEMM, PK_MERGE_LN, PK_MERGE_GEMM, PK_FINAL_LN, PK_HEAD, PK_COUNT
+  PK_FC2_GEMM, PK_MERGE_LN, PK_MERGE_GEMM, PK_FINAL_LN, PK_HEAD, PK_FUSED_MLP, PK_COUNT
 };
 struct ProfScope {
   int cat;
@@ -133,6 +133,11 @@ struct GemmParams {
 
 int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
                 cudaStream_t stream);
+
+// fused fc1 + GELU + fc2 + residual (hidden activation stays on chip); built for C = 96 / 192
+bool fused_mlp_supported(int C);
+int launch_fused_mlp(const __half* a, const __half* w1, const float* b1, const __half* w2, const float* b2, float* x,
+                     int M, int C, cudaStream_t stream);
 
 // ----------------------------------------------------------------------------------------------
 // memory-bound row kernels

@@ -29,6 +29,7 @@ PROTOTYPES = {
     "kvq_pack_bias_table": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "kvq_linear_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "kvq_linear_resid_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kvq_mlp_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "kvq_ln_window": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
                               POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "kvq_window_rows": (c_int64, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32)]),

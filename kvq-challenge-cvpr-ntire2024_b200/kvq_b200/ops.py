@@ -75,6 +75,14 @@ def linear_resid_f32(a, w, bias=None, resid=None, out=None):
     return out
 
 
+def mlp_fused(a, w1, b1, w2, b2, x):
+    """In place: x[M,C] (f32) += fc2(gelu(fc1(a) + b1)) + b2, a f16 [M,C] (the LN2 output)."""
+    _need_cuda(a, w1, b1, w2, b2, x)
+    M, C = a.shape
+    _l.check(_l.load().kvq_mlp_fused(_p(a), _p(w1), _p(b1), _p(w2), _p(b2), _p(x), M, C, _stream()), "mlp_fused")
+    return x
+
+
 def window_rows(B, D, H, W, window, shift):
     return int(_l.load().kvq_window_rows(B, D, H, W, _l.i3(window), _l.i3(shift)))
 
