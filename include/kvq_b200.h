@@ -44,6 +44,9 @@ typedef struct KvqSwinConfig {
   int32_t frag_bias[KVQ_MAX_STAGES];  /* 1,1,1,0: stage owns a fragment_position_bias_table (GRPB) */
   int32_t head_hidden;                /* 64; 0 = backbone only */
   float ln_eps;                       /* 1e-5 */
+  int32_t split_weights;              /* bit 0 patch-embed, bit 1 PatchMerging reductions, bit 2 VQAHead fc_hid: the
+                                         weight is passed as an fp16 pair [W_hi | W_lo] (kvq_pack_split_f16, row
+                                         stride 2*ceil64(K)) so its rounding error drops from 2^-11 to 2^-22 */
 } KvqSwinConfig;
 
 /*
@@ -82,6 +85,8 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
 
 /* ---- weight packing (once per load_state_dict) ---- */
 int kvq_cast_f16(const float* in, void* out_f16, size_t n, void* stream);
+/* fp32 [rows, K] -> fp16 [rows, 2*ceil64(K)] = [hi | 0 | lo | 0] with hi = fp16(w), lo = fp16(w - hi) */
+int kvq_pack_split_f16(const float* in, void* out_f16, int rows, int K, void* stream);
 /* entries per head of a packed bias table for base window (wd,wh,ww) */
 int kvq_attn_table_len(int wd, int wh, int ww);
 /* relative_position_bias_table / fragment_position_bias_table [L, heads] (frag may be NULL) -> packed table

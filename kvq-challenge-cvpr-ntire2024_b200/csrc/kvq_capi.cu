@@ -242,9 +242,10 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
     const __half* w = WH();
     gp.bias = WF(); gp.gamma = WF(); gp.beta = WF(); gp.eps = eps;
     gp.out = xa; gp.ldo = 96;
+    gp.split_b = cfg->split_weights & 1;
     {
       ProfScope ps(PK_EMBED_GEMM, 0, st);
-      rc = launch_gemm(EPI_LN_F32, a16, 96, w, 96, gp, st);
+      rc = launch_gemm(EPI_LN_F32, a16, 96, w, gp.split_b ? 256 : 96, gp, st);
     }
     if (rc != 0) return rc;
   }
@@ -322,7 +323,8 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
       GemmParams gp{};
       gp.M = B * sd.D * ((sd.H + 1) / 2) * ((sd.W + 1) / 2); gp.N = 2 * C; gp.K = 4 * C;
       gp.out = xnext; gp.ldo = 2 * C;
-      rc = launch_gemm(EPI_RESID_F32, a16, 4 * C, red_w, 4 * C, gp, st);
+      gp.split_b = (cfg->split_weights >> 1) & 1;
+      rc = launch_gemm(EPI_RESID_F32, a16, 4 * C, red_w, gp.split_b ? 2 * ((4 * C + 63) / 64 * 64) : 4 * C, gp, st);
       if (rc != 0) return rc;
       std::swap(xcur, xnext);
       // after the first merge the big buffer is free: keep ping-ponging between the two (xa always fits)
@@ -344,14 +346,20 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
       GemmParams gp{};
       gp.M = M; gp.N = cfg->head_hidden; gp.K = sd.C;
       gp.bias = b1; gp.w2 = w2; gp.b2ptr = b2; gp.rowscore = rowscore;
+      gp.split_b = (cfg->split_weights >> 2) & 1;
       ProfScope ps(PK_HEAD, cfg->num_stages - 1, st);
-      rc = launch_gemm(EPI_HEAD, a16, sd.C, w1, sd.C, gp, st);
+      rc = launch_gemm(EPI_HEAD, a16, sd.C, w1, gp.split_b ? 2 * ((sd.C + 63) / 64 * 64) : sd.C, gp, st);
       if (rc != 0) return rc;
       rc = launch_row_mean(rowscore, score_out, B, tokens, st);
       if (rc != 0) return rc;
     }
   }
   return KVQ_OK;
+}
+
+int kvq_pack_split_f16(const float* in, void* out_f16, int rows, int K, void* stream) {
+  KVQ_REQUIRE(in && out_f16 && rows > 0 && K > 0, KVQ_ERR_BAD_SHAPE, "pack_split_f16: bad arguments");
+  return launch_pack_split(in, static_cast<__half*>(out_f16), rows, K, static_cast<cudaStream_t>(stream));
 }
 
 int kvq_cast_f16(const float* in, void* out_f16, size_t n, void* stream) {

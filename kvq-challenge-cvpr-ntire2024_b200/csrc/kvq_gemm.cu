@@ -117,6 +117,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_n = p.N / BN;
   const int tiles = num_m * num_n;
   const int nkb = (p.K + BK - 1) / BK;
+  // split-weight mode: B holds [W_hi | W_lo] along K (each padded to 64); the K loop runs twice over A
+  const int nkb_tot = p.split_b ? 2 * nkb : nkb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -146,12 +148,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nkb_tot; ++kb) {
           mbar_wait(&empty[stage], ph ^ 1);
           uint8_t* sA = smem + stage * Cfg<BN>::STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
           mbar_expect_tx(&full[stage], Cfg<BN>::STAGE_BYTES);
-          tma_load_2d(sA, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sA, &tmA, &full[stage], (kb >= nkb ? kb - nkb : kb) * BK, m_blk * BM);
           tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
@@ -166,7 +168,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nkb_tot; ++kb) {
           mbar_wait(&full[stage], ph);
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * Cfg<BN>::STAGE_BYTES);
@@ -470,7 +472,10 @@ int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmPa
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, A, p.M, p.K, static_cast<uint64_t>(lda) * 2, BM, BK, 2, 128);
   if (rc != 0) return rc;
-  rc = make_tmap_2d(&tmB, B, p.N, p.K, static_cast<uint64_t>(ldb) * 2, BN, BK, 2, 128);
+  const int kcols_b = p.split_b ? 2 * ((p.K + BK - 1) / BK * BK) : p.K;
+  KVQ_REQUIRE(!p.split_b || ldb == kcols_b, KVQ_ERR_BAD_SHAPE, "gemm: split weights need ldb == 2*ceil64(K) (%d vs %d)",
+              ldb, kcols_b);
+  rc = make_tmap_2d(&tmB, B, p.N, kcols_b, static_cast<uint64_t>(ldb) * 2, BN, BK, 2, 128);
   if (rc != 0) return rc;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();

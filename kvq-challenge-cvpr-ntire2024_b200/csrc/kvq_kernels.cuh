@@ -109,6 +109,7 @@ enum GemmEpilogue : int {
 
 struct GemmParams {
   int M, N, K;
+  int split_b;          // B = [W_hi | W_lo] (fp16 pair summing to the fp32 weight), row stride 2*ceil64(K)
   const float* bias;    // [N] or nullptr
   void* out;            // fp16 / fp32 matrix, row stride ldo elements
   int ldo;
@@ -162,6 +163,7 @@ int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, flo
                               cudaStream_t stream);
 // fp32 [B, C, tokens] -> fp16 [B*tokens, C]
 int launch_cf_to_rows(const float* in, __half* out, int B, int C, int tokens, cudaStream_t stream);
+int launch_pack_split(const float* in, __half* out, int rows, int K, cudaStream_t stream);
 // fp32 -> fp16 cast (weight packing)
 int launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream);
 

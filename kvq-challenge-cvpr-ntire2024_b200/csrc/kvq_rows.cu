@@ -262,6 +262,23 @@ cf_to_rows_kernel(const float* __restrict__ in, __half* __restrict__ out, int C,
 }
 
 // (lanes per row, chunks per lane) for a row of `chunks` float4s
+// fp32 [rows, K] -> fp16 [rows, 2*Kp]: hi at [0,K), lo = fp16(w - hi) at [Kp, Kp+K), zeros elsewhere
+__global__ void __launch_bounds__(256)
+pack_split_kernel(const float* __restrict__ in, __half* __restrict__ out, int rows, int K, int Kp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * 2 * Kp) return;
+  const int c = static_cast<int>(i % (2 * Kp));
+  const long long r = i / (2 * Kp);
+  const int k = c < Kp ? c : c - Kp;
+  __half v = __float2half_rn(0.f);
+  if (k < K) {
+    const float w = in[r * K + k];
+    const __half hi = __float2half_rn(w);
+    v = c < Kp ? hi : __float2half_rn(w - __half2float(hi));
+  }
+  out[i] = v;
+}
+
 template <typename F>
 int dispatch_ln(int chunks, F&& f) {
   if (chunks <= 24) return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 3>{});
@@ -360,6 +377,15 @@ int launch_cf_to_rows(const float* in, __half* out, int B, int C, int tokens, cu
   cf_to_rows_kernel<<<grid, 256, 0, stream>>>(in, out, C, tokens);
   count_launch();
   return check_cuda(cudaGetLastError(), "cf_to_rows_kernel launch");
+}
+
+int launch_pack_split(const float* in, __half* out, int rows, int K, cudaStream_t stream) {
+  const int Kp = (K + 63) / 64 * 64;
+  const long long n = static_cast<long long>(rows) * 2 * Kp;
+  if (n == 0) return KVQ_OK;
+  pack_split_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, out, rows, K, Kp);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "pack_split_kernel launch");
 }
 
 int launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {

@@ -12,7 +12,7 @@ MAX_STAGES = 4
 class KvqSwinConfig(ctypes.Structure):
     _fields_ = [("embed_dim", c_int32), ("num_stages", c_int32), ("depths", c_int32 * MAX_STAGES),
                 ("num_heads", c_int32 * MAX_STAGES), ("window", c_int32 * 3), ("frag_bias", c_int32 * MAX_STAGES),
-                ("head_hidden", c_int32), ("ln_eps", c_float)]
+                ("head_hidden", c_int32), ("ln_eps", c_float), ("split_weights", c_int32)]
 
 
 _I3 = c_int32 * 3
@@ -24,6 +24,7 @@ PROTOTYPES = {
     "kvq_swin3d_workspace_bytes": (c_size_t, [POINTER(KvqSwinConfig), c_int, c_int, c_int, c_int]),
     "kvq_swin3d_forward": (c_int, [POINTER(KvqSwinConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
                                    c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_pack_split_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "kvq_cast_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "kvq_attn_table_len": (c_int, [c_int, c_int, c_int]),
     "kvq_pack_bias_table": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -40,6 +40,16 @@ def cast_f16(t):
     return out
 
 
+def pack_split_f16(w2d):
+    """fp32 [rows, K] -> fp16 [rows, 2*ceil64(K)] = [hi | lo]: hi + lo reproduces the fp32 weight to 2^-22."""
+    w2d = w2d.detach().float().contiguous()
+    _need_cuda(w2d)
+    rows, K = w2d.shape
+    out = torch.empty((rows, 2 * ((K + 63) // 64 * 64)), dtype=torch.float16, device=w2d.device)
+    _l.check(_l.load().kvq_pack_split_f16(_p(w2d), _p(out), rows, K, _stream()), "pack_split_f16")
+    return out
+
+
 def attn_table_len(window):
     return _l.load().kvq_attn_table_len(*[int(w) for w in window])
 
@@ -152,7 +162,8 @@ class SwinWeights:
     `head_prefix` select the sub-module (e.g. 'swin_tiny_grpb_backbone.' / 'swin_tiny_grpb_head.')."""
 
     def __init__(self, sd, device, prefix="", head_prefix=None, embed_dim=96, depths=(2, 2, 6, 2),
-                 num_heads=(3, 6, 12, 24), window=(8, 7, 7), frag_biases=(True, True, True, False), eps=1e-5):
+                 num_heads=(3, 6, 12, 24), window=(8, 7, 7), frag_biases=(True, True, True, False), eps=1e-5,
+                 split_weights=7):
         self.device = torch.device(device)
         self.cfg = _l.KvqSwinConfig()
         self.cfg.embed_dim = embed_dim
@@ -163,16 +174,20 @@ class SwinWeights:
             self.cfg.window[i] = int(window[i])
         self.cfg.ln_eps = eps
         self.cfg.head_hidden = 0
+        # fp16 hi/lo weight pairs for the few GEMMs whose weight rounding dominates the score error (patch-embed,
+        # the three PatchMerging reductions, VQAHead.fc_hid): measured 7.2e-4 -> see DESIGN.md section 2
+        self.cfg.split_weights = int(split_weights)
         self.depths, self.final_dim = tuple(depths), embed_dim * 2 ** (len(depths) - 1)
 
         def f32(k):
             return sd[k].detach().to(self.device, torch.float32).contiguous()
 
-        def f16(k, shape=None):
+        def f16(k, shape=None, split=False):
             t = f32(k)
-            return cast_f16(t.reshape(shape) if shape is not None else t)
+            t = t.reshape(shape) if shape is not None else t
+            return pack_split_f16(t.reshape(t.shape[0], -1)) if split else cast_f16(t)
 
-        ts = [f16(prefix + "patch_embed.proj.weight", (embed_dim, -1)), f32(prefix + "patch_embed.proj.bias"),
+        ts = [f16(prefix + "patch_embed.proj.weight", (embed_dim, -1), split=bool(split_weights & 1)), f32(prefix + "patch_embed.proj.bias"),
               f32(prefix + "patch_embed.norm.weight"), f32(prefix + "patch_embed.norm.bias")]
         for s, depth in enumerate(depths):
             for j in range(depth):
@@ -192,12 +207,13 @@ class SwinWeights:
             pos += 13 * depth
             if s < len(depths) - 1:
                 b = f"{prefix}layers.{s}.downsample."
-                merged += [f32(b + "norm.weight"), f32(b + "norm.bias"), f16(b + "reduction.weight")]
+                merged += [f32(b + "norm.weight"), f32(b + "norm.bias"),
+                           f16(b + "reduction.weight", split=bool(split_weights & 2))]
         merged += [f32(prefix + "norm.weight"), f32(prefix + "norm.bias")]
         if head_prefix is not None:
             hid = sd[head_prefix + "fc_hid.weight"].shape[0]
             self.cfg.head_hidden = int(hid)
-            merged += [f16(head_prefix + "fc_hid.weight", (hid, -1)), f32(head_prefix + "fc_hid.bias"),
+            merged += [f16(head_prefix + "fc_hid.weight", (hid, -1), split=bool(split_weights & 4)), f32(head_prefix + "fc_hid.bias"),
                        f32(head_prefix + "fc_last.weight").reshape(-1).contiguous(),
                        f32(head_prefix + "fc_last.bias").reshape(-1).contiguous()]
         self.tensors = merged

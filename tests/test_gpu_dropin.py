@@ -50,7 +50,7 @@ def test_vqa_network_matches_reference_golden():
         feat = m.swin_tiny_grpb_backbone({"technical": x})
         s3 = m.swin_tiny_grpb_head(feat)
     assert torch.equal(feat, f)
-    assert (s3 - s).abs().max().item() < 2e-4       # head input is rounded to fp16 from fp32 feat in both paths
+    assert (s3 - s).abs().max().item() < 5e-4       # stand-alone head: fp16 fc_hid weights; fused call: hi/lo pair
 
     # changing a parameter invalidates the packed weights
     with torch.no_grad():
