@@ -343,26 +343,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int i = row - win_g * ntok;
         const int slab = i / p.geom.SL;
         const int kv_row = slab * ATT_SLAB + (i - slab * p.geom.SL);
-#pragma unroll 1
-        for (int c = c_begin; c < NCHUNK; c += c_step) {
-          const int c0 = c * CW;
-          uint32_t r[CW];
-          tmem_ld_chunk<CW>(taddr + c0, r);
+        constexpr int MYCH = (NCHUNK + 1) / 2;
+        if (n_blk != bias_nblk) {     // bias slice of this warp's chunks -> private smem, once per n-block
+          __syncwarp();
+#pragma unroll
+          for (int ci = 0; ci < MYCH; ++ci) {
+            const int c0 = (c_begin + ci * c_step) * CW;
+            if (lane < CW && c0 < BN) stile[ci * CW + lane] = __ldg(p.bias + nbase + c0 + lane);
+          }
+          bias_nblk = n_blk;
+          __syncwarp();
+        }
+        uint32_t r[2][CW];
+        tmem_ld_chunk<CW>(taddr + c_begin * CW, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < MYCH; ++ci) {
+          const int c0 = (c_begin + ci * c_step) * CW;
+          if (c0 >= BN) break;
+          tmem_wait_ld();
+          if (ci + 1 < MYCH && c0 + c_step * CW < BN) tmem_ld_chunk<CW>(taddr + c0 + c_step * CW, r[(ci + 1) & 1]);
+          const uint32_t* rc = r[ci & 1];
           const int n0 = nbase + c0;
           const int which = n0 / p.C;
           const int cin = n0 - which * p.C;       // channel inside q / k / v
           const int head = cin >> 5;
           const int kc0 = (cin & 31) >> 3;        // first 16-byte chunk of the head's 32 channels
-          const float sc = which == 0 ? p.qscale : 1.0f;
-          float4 bv[CW / 4];
-#pragma unroll
-          for (int j = 0; j < CW / 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-          tmem_wait_ld();
+          const float2 sc2 = splat2(which == 0 ? p.qscale : 1.0f);
           uint32_t h[CW / 2];
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) {
-            h[2 * j] = pack_half2((__uint_as_float(r[4 * j]) + bv[j].x) * sc, (__uint_as_float(r[4 * j + 1]) + bv[j].y) * sc);
-            h[2 * j + 1] = pack_half2((__uint_as_float(r[4 * j + 2]) + bv[j].z) * sc, (__uint_as_float(r[4 * j + 3]) + bv[j].w) * sc);
+            const float4 bb = *reinterpret_cast<const float4*>(stile + ci * CW + 4 * j);
+            const float2 v01 = fmul2(fadd2(make_float2(__uint_as_float(rc[4 * j]), __uint_as_float(rc[4 * j + 1])), make_float2(bb.x, bb.y)), sc2);
+            const float2 v23 = fmul2(fadd2(make_float2(__uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3])), make_float2(bb.z, bb.w)), sc2);
+            h[2 * j] = pack_half2(v01.x, v01.y);
+            h[2 * j + 1] = pack_half2(v23.x, v23.y);
           }
           if (row_ok) {
             const int rimg = which == 0 ? i : kv_row;
