@@ -308,7 +308,9 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=4, help="clips timed by the CPU baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of CUDA-graph replay")
-    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the dominant kernel")
+    ap.add_argument("--traffic", type=float, default=292.9e6,
+                    help="dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (stage-0 "
+                         "window_attn_fast_kernel at batch 8) from the ncu --set full capture in profiles/r01_summary.md")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
