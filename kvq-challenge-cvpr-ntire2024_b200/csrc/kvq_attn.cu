@@ -797,17 +797,33 @@ int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, in
   return check_cuda(cudaGetLastError(), "pack_bias_kernel launch");
 }
 
+static int resolve_variant(int variant) {
+  if (variant != 0) return variant;   // tuning knob: KVQ_ATTN_VARIANT=2 generic kernel, 5 = two-CTA flash-style kernel
+  static int env_variant = -1;
+  if (env_variant < 0) {
+    const char* e = getenv("KVQ_ATTN_VARIANT");
+    env_variant = e ? atoi(e) : 0;
+  }
+  return env_variant;
+}
+
+static bool full_window(const WinGeom& g, const int base_win[3]) {
+  return g.wd == 8 && g.wh == 7 && g.ww == 7 && base_win[0] == 8 && base_win[1] == 7 && base_win[2] == 7 &&
+         (g.sd == 0 || g.sd == 4) && (g.sh == 0 || g.sh == 3) && (g.sw == 0 || g.sw == 3);
+}
+
+int window_attn_pitch(const WinGeom& g, const int base_win[3], int variant) {
+  return (resolve_variant(variant) == 5 && full_window(g, base_win)) ? ATT2_PITCH : ATT_SLAB;
+}
+
 int launch_window_attn(const AttnParams& p_in, cudaStream_t stream) {
   AttnParams p = p_in;
-  if (p.variant == 0) {  // tuning knob: KVQ_ATTN_VARIANT=2 generic kernel, 4 = 16-warp fast kernel
-    static int env_variant = -1;
-    if (env_variant < 0) {
-      const char* e = getenv("KVQ_ATTN_VARIANT");
-      env_variant = e ? atoi(e) : 0;
-    }
-    p.variant = env_variant;
-  }
+  p.variant = resolve_variant(p.variant);
   const WinGeom& g = p.geom;
+  {
+    const int bw[3] = {p.base_wd, p.base_wh, p.base_ww};
+    if (p.variant == 5 && full_window(g, bw) && 2 * p.heads <= 2 * num_sms()) return launch_window_attn2(p, stream);
+  }
   KVQ_REQUIRE(p.C == p.heads * ATT_HD, KVQ_ERR_BAD_SHAPE, "attn: C=%d must be heads(%d) x 32", p.C, p.heads);
   KVQ_REQUIRE(g.wd * ATT_SLAB <= ATT_ROWS && g.SL <= ATT_SLAB - 1 && g.wd <= p.base_wd && g.wh <= p.base_wh &&
                   g.ww <= p.base_ww,

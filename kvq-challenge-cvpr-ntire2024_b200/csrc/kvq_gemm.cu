@@ -342,7 +342,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int win_g = row / ntok;
         const int i = row - win_g * ntok;
         const int slab = i / p.geom.SL;
-        const int kv_row = slab * ATT_SLAB + (i - slab * p.geom.SL);
+        const int pitch = p.att_pitch;
+        const int kv_rows = 8 * pitch;                         // 400 or 416 key slots
+        const int kv_bytes = kv_rows * ATT_HD * 2;
+        const size_t unit_bytes = static_cast<size_t>(ATT_IMG_BYTES) + 2 * kv_bytes;
+        const int kv_row = slab * pitch + (i - slab * p.geom.SL);
         constexpr int MYCH = (NCHUNK + 1) / 2;
         if (n_blk != bias_nblk) {     // bias slice of this warp's chunks -> private smem, once per n-block
           __syncwarp();
@@ -380,16 +384,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (row_ok) {
             const int rimg = which == 0 ? i : kv_row;
-            uint8_t* dst = reinterpret_cast<uint8_t*>(p.img) +
-                           (static_cast<size_t>(win_g) * p.heads + head) * ATT_UNIT_BYTES +
-                           static_cast<size_t>(which) * ATT_IMG_BYTES;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(p.img) + (static_cast<size_t>(win_g) * p.heads + head) * unit_bytes +
+                           (which == 0 ? 0 : ATT_IMG_BYTES + (which - 1) * kv_bytes);
 #pragma unroll
             for (int j = 0; j < CW / 8; ++j)
               st_global_v4(dst + att_img_offset(rimg, kc0 + j), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
             // the last token of a slab also zeroes the padded K/V key slots behind it (P is 0 there, but 0 * NaN
             // from uninitialised workspace would poison PV); the last token of the window zeroes all the rest
             if (which != 0 && (i - slab * p.geom.SL) == p.geom.SL - 1) {
-              const int end = (i == ntok - 1) ? ATT_ROWS : (slab + 1) * ATT_SLAB;
+              const int end = (i == ntok - 1) ? kv_rows : (slab + 1) * pitch;
               for (int rz = kv_row + 1; rz < end; ++rz) {
 #pragma unroll
                 for (int j = 0; j < CW / 8; ++j) st_global_v4(dst + att_img_offset(rz, kc0 + j), 0u, 0u, 0u, 0u);

@@ -91,6 +91,14 @@ constexpr int ATT_HD = 32;
 constexpr int ATT_IMG_BYTES = ATT_ROWS * ATT_HD * 2;  // 25 600
 constexpr int ATT_UNIT_BYTES = 3 * ATT_IMG_BYTES;     // 76 800
 
+// second-generation layout (kvq_attn2.cu): 52-slot key pitch so that four temporal slabs fill one 208-key MMA block;
+// unit = Q (400 rows) | K (416 rows) | V (416 rows)
+constexpr int ATT2_PITCH = 52;
+constexpr int ATT2_KV_ROWS = 8 * ATT2_PITCH;               // 416
+constexpr int ATT2_KV_BYTES = ATT2_KV_ROWS * ATT_HD * 2;   // 26 624
+constexpr int ATT2_Q_BYTES = ATT_IMG_BYTES;                // 25 600
+constexpr int ATT2_UNIT_BYTES = ATT2_Q_BYTES + 2 * ATT2_KV_BYTES;   // 78 848
+
 __host__ __device__ __forceinline__ int att_img_offset(int r, int chunk) {  // byte offset of a 16 B chunk
   return (r >> 3) * 512 + chunk * 128 + (r & 7) * 16;
 }
@@ -119,6 +127,7 @@ struct GemmParams {
   WinGeom geom;
   // EPI_QKV_IMG
   __half* img;          // unit-major operand images
+  int att_pitch;        // key-slot pitch per temporal slab: ATT_SLAB (50) or ATT2_PITCH (52)
   int C;                // channels (N == 3C)
   int heads;
   float qscale;
@@ -190,5 +199,8 @@ int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, in
 // debug builds (-DKVQ_TIMING) only: 1 + fills out16; production build returns 0
 int debug_attn_timers(unsigned long long* out16, int reset);
 int launch_window_attn(const AttnParams& p, cudaStream_t stream);
+// which operand-image layout launch_window_attn will consume for this geometry: returns the key pitch (50 or 52)
+int window_attn_pitch(const WinGeom& g, const int base_win[3], int variant);
+int launch_window_attn2(const AttnParams& p, cudaStream_t stream);
 
 }  // namespace kvq
