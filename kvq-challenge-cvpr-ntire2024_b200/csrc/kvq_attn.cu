@@ -798,11 +798,14 @@ int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, in
 }
 
 static int resolve_variant(int variant) {
-  if (variant != 0) return variant;   // tuning knob: KVQ_ATTN_VARIANT=2 generic kernel, 5 = two-CTA flash-style kernel
+  // 5 (default) = two-CTA flash-style kernel (kvq_attn2.cu) for full (8,7,7) windows; tuning knob
+  // KVQ_ATTN_VARIANT: 1 = first-generation persistent kernel, 2 = generic kernel everywhere
+  if (variant != 0) return variant;
   static int env_variant = -1;
   if (env_variant < 0) {
     const char* e = getenv("KVQ_ATTN_VARIANT");
-    env_variant = e ? atoi(e) : 0;
+    env_variant = e ? atoi(e) : 5;
+    if (env_variant == 0) env_variant = 5;
   }
   return env_variant;
 }

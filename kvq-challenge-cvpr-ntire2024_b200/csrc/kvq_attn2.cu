@@ -32,8 +32,8 @@ constexpr int COMPACT_LEN = 2536;
 constexpr int S2_K = 0;
 constexpr int S2_V = ATT2_KV_BYTES;
 constexpr int S2_Q = 2 * ATT2_KV_BYTES;          // 2 x 8192
-constexpr int S2_SMALL = S2_Q + 2 * 8192;        // 2048 B
-constexpr int S2_TAB = S2_SMALL + 2048;
+constexpr int S2_SMALL = S2_Q + 2 * 8192;        // 6144 B
+constexpr int S2_TAB = S2_SMALL + 6144;
 constexpr int S2_SMEM = S2_TAB + TAB_LEN * 8 + 128;
 constexpr int T_S = 0;                           // TMEM columns
 constexpr int T_O = BLK;
@@ -42,8 +42,11 @@ struct Small2 {
   float fhc[8], fwc[8], rhm[8], rwm[8], rdm[8];
   uint64_t bar_tab, bar_kv, bar_q[2], bar_qe[2], bar_s, bar_p, bar_c, bar_o;
   uint32_t tmem_slot;
+  float tmax[2][4][8];          // tail tile: per-block local maxima [block][warp][row]
+  float tl[4][8];               // tail tile: per-warp partial row sums
+  alignas(16) float to[4][8][32];   // tail tile: per-warp partial outputs
 };
-static_assert(sizeof(Small2) <= 2048, "Small2 overflows its slot");
+static_assert(sizeof(Small2) <= 6144, "Small2 overflows its slot");
 
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
   float2 v;
@@ -234,7 +237,6 @@ window_attn2_kernel(const AttnParams p, const float2* __restrict__ tabs, int uni
 #pragma unroll 1
       for (int t = 0; t < 4; ++t) {
         const bool tail = (t == 3);
-        const bool active = !tail || q == 0;   // the 8 tail rows are replicated in every lane group; warp 0 owns them
         const int ri = tail ? 384 + (lane & 7) : t * 128 + q * 32 + lane;
         const int d_i = ri / 49, hw_i = ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
         float Ah[7], Aw[7];
@@ -257,13 +259,13 @@ window_attn2_kernel(const AttnParams p, const float2* __restrict__ tabs, int uni
         const uint32_t trow0 = smem_u32(stab) + 8u * static_cast<uint32_t>((d_i + 7) * TS_D + (h_i + 6) * TS_H + (w_i + 6));
 
         float m_run = -INFINITY, l_run = 0.f;
+        if (!tail) {
 #pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {
-          mbar_wait(&sm.bar_s, n_s & 1);
-          ++n_s;
-          __syncwarp();
-          tc_fence_after();
-          if (active) {
+          for (int blk = 0; blk < 2; ++blk) {
+            mbar_wait(&sm.bar_s, n_s & 1);
+            ++n_s;
+            __syncwarp();
+            tc_fence_after();
             // ---- pass 1: bias (+ mask), block max, write back ----
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
@@ -325,35 +327,136 @@ window_attn2_kernel(const AttnParams p, const float2* __restrict__ tabs, int uni
             }
             m_run = m_new;
             tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.bar_p);
           }
-          tc_fence_before();
+          // ---- epilogue: O / l -> global ----
+          mbar_wait(&sm.bar_o, n_o & 1);
+          ++n_o;
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.bar_p);
-        }
-        // ---- epilogue: O / l -> global ----
-        mbar_wait(&sm.bar_o, n_o & 1);
-        ++n_o;
-        __syncwarp();
-        tc_fence_after();
-        if (active) {
+          tc_fence_after();
           uint32_t o[32];
           tmem_ld_x32(trow + T_O, o);
           tmem_wait_ld();
-          if (!tail || lane < 8) {
-            const float inv = 1.0f / l_run;
-            __half* dst = p.out + (static_cast<size_t>(win_g) * 392 + ri) * p.C + head * ATT_HD;
+          const float inv = 1.0f / l_run;
+          __half* dst = p.out + (static_cast<size_t>(win_g) * 392 + ri) * p.C + head * ATT_HD;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+            v.y = pack_half2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+            v.z = pack_half2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+            v.w = pack_half2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + j) = v;
+          }
+          tc_fence_before();
+        } else {
+          // ================= tail tile: the 8 rows 384..391 are replicated in every lane group (SBO = 0), so the
+          // four warps split the KEYS instead: warp q owns slab q of each block, writes zeros into the P columns of
+          // the other slabs, and the four partial outputs / row sums are added through shared memory ==============
+#pragma unroll 1
+          for (int blk = 0; blk < 2; ++blk) {
+            mbar_wait(&sm.bar_s, n_s & 1);
+            ++n_s;
+            __syncwarp();
+            tc_fence_after();
+            const int d = blk * 4 + q;
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            const uint32_t ta = trow + T_S + q * ATT2_PITCH;
+            if (masked) {
+              const float dm = (sm.rdm[d] != rd_i) ? MASK_L2 : 0.f;
+              pass1_slab52<true>(ta, trow0 - 8u * (d * TS_D), Ah, Aw, fminf(fminf(hlo, wlo), dm),
+                                 fminf(fminf(hlo, whi_m), dm), fminf(fminf(hhi, wlo), dm), fminf(fminf(hhi, whi_m), dm),
+                                 mx);
+            } else {
+              pass1_slab52<false>(ta, trow0 - 8u * (d * TS_D), Ah, Aw, 0.f, 0.f, 0.f, 0.f, mx);
+            }
+            tmem_wait_st();
+            if (lane < 8) sm.tmax[blk][q][lane] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            named_bar_sync(1, 128);
+            const int rl = lane & 7;
+            const float m_blk = fmaxf(fmaxf(sm.tmax[blk][0][rl], sm.tmax[blk][1][rl]),
+                                      fmaxf(sm.tmax[blk][2][rl], sm.tmax[blk][3][rl]));
+            const float m_new = fmaxf(m_run, m_blk);
+            const float alpha = fast_exp2(m_run - m_new);
+            // own slab -> registers -> probabilities
+            uint32_t r[52], h[26];
+            tmem_ld_x32(ta, r);
+            tmem_ld_x16(ta + 32, r + 32);
+            tmem_ld_x4(ta + 48, r + 48);
+            tmem_wait_ld();
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 52; k += 2) {
+              const float e0 = fast_exp2(__uint_as_float(r[k]) - m_new), e1 = fast_exp2(__uint_as_float(r[k + 1]) - m_new);
+              sum += e0 + e1;
+              h[k >> 1] = pack_half2(e0, e1);
+            }
+            // zero the whole P block of this lane group, then drop the own slab's 26 packed columns in
+            {
+              uint32_t z[32];
+#pragma unroll
+              for (int k = 0; k < 32; ++k) z[k] = 0u;
+              tmem_st_x32(trow + T_S, z);
+              tmem_st_x32(trow + T_S + 32, z);
+              tmem_st_x32(trow + T_S + 64, z);
+              tmem_st_x8(trow + T_S + 96, z);
+              tmem_wait_st();
+              tmem_st_x16(trow + T_S + 26 * q, h);
+              tmem_st_x8(trow + T_S + 26 * q + 16, h + 16);
+              tmem_st_x2(trow + T_S + 26 * q + 24, h + 24);
+            }
+            l_run = fmaf(l_run, alpha, sum);
+            if (blk == 1) {
+              uint32_t o[32];
+              tmem_ld_x32(trow + T_O, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+              tmem_st_x32(trow + T_O, o);
+            }
+            m_run = m_new;
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.bar_p);
+          }
+          mbar_wait(&sm.bar_o, n_o & 1);
+          ++n_o;
+          __syncwarp();
+          tc_fence_after();
+          {
+            uint32_t o[32];
+            tmem_ld_x32(trow + T_O, o);
+            tmem_wait_ld();
+            if (lane < 8) {
+              sm.tl[q][lane] = l_run;
+#pragma unroll
+              for (int k = 0; k < 32; k += 4)
+                *reinterpret_cast<uint4*>(&sm.to[q][lane][k]) = make_uint4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+            }
+          }
+          tc_fence_before();
+          named_bar_sync(1, 128);
+          if (q == 0 && lane < 8) {
+            const float inv = 1.0f / (sm.tl[0][lane] + sm.tl[1][lane] + sm.tl[2][lane] + sm.tl[3][lane]);
+            __half* dst = p.out + (static_cast<size_t>(win_g) * 392 + 384 + lane) * p.C + head * ATT_HD;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              uint4 v;
-              v.x = pack_half2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
-              v.y = pack_half2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
-              v.z = pack_half2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
-              v.w = pack_half2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
-              *reinterpret_cast<uint4*>(dst + j) = v;
+              float v[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                v[k] = (sm.to[0][lane][j + k] + sm.to[1][lane][j + k] + sm.to[2][lane][j + k] + sm.to[3][lane][j + k]) * inv;
+              uint4 pk;
+              pk.x = pack_half2(v[0], v[1]);
+              pk.y = pack_half2(v[2], v[3]);
+              pk.z = pack_half2(v[4], v[5]);
+              pk.w = pack_half2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(dst + j) = pk;
             }
           }
         }
-        tc_fence_before();
       }
     }
   }
