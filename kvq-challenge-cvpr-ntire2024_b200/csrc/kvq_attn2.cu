@@ -288,31 +288,33 @@ window_attn2_kernel(const AttnParams p, const float2* __restrict__ tabs, int uni
             // ---- pass 2: P = exp2(v - m) packed fp16, written into TMEM over the columns already consumed ----
             const float2 negm2 = make_float2(-m_new, -m_new);
             float2 sum2 = make_float2(0.f, 0.f);
-#pragma unroll 1
-            for (int c = 0; c < 192; c += 32) {
-              uint32_t r[32], h[16];
-              tmem_ld_x32(trow + T_S + c, r);
-              tmem_wait_ld();
+            // TMEM loads run one chunk ahead of the exp2 / pack / store of the previous chunk
+            auto exp_pack = [&](const uint32_t* r, uint32_t* h, int n) {
 #pragma unroll
-              for (int k = 0; k < 32; k += 2) {
+              for (int k = 0; k < n; k += 2) {
                 const float2 dd = fadd2(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), negm2);
                 const float2 ee = make_float2(fast_exp2(dd.x), fast_exp2(dd.y));
                 sum2 = fadd2(sum2, ee);
                 h[k >> 1] = pack_half2(ee.x, ee.y);
               }
-              tmem_st_x16(trow + T_S + (c >> 1), h);
-            }
+            };
             {
-              uint32_t r[16], h[8];
-              tmem_ld_x16(trow + T_S + 192, r);
-              tmem_wait_ld();
-#pragma unroll
-              for (int k = 0; k < 16; k += 2) {
-                const float2 dd = fadd2(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), negm2);
-                const float2 ee = make_float2(fast_exp2(dd.x), fast_exp2(dd.y));
-                sum2 = fadd2(sum2, ee);
-                h[k >> 1] = pack_half2(ee.x, ee.y);
+              uint32_t ra[32], rb[32], h[16];
+              tmem_ld_x32(trow + T_S, ra);
+#pragma unroll 1
+              for (int c = 0; c < 192; c += 64) {
+                tmem_wait_ld();
+                tmem_ld_x32(trow + T_S + c + 32, rb);
+                exp_pack(ra, h, 32);
+                tmem_st_x16(trow + T_S + (c >> 1), h);
+                tmem_wait_ld();
+                if (c + 64 < 192) tmem_ld_x32(trow + T_S + c + 64, ra);
+                else tmem_ld_x16(trow + T_S + 192, ra);
+                exp_pack(rb, h, 32);
+                tmem_st_x16(trow + T_S + ((c + 32) >> 1), h);
               }
+              tmem_wait_ld();
+              exp_pack(ra, h, 16);
               tmem_st_x8(trow + T_S + 96, h);
             }
             l_run = fmaf(l_run, alpha, sum2.x + sum2.y);
