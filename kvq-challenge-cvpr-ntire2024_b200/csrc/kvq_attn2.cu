@@ -133,9 +133,12 @@ window_attn2_kernel(const AttnParams p, const float2* __restrict__ tabs, int uni
     mbar_init(&sm.bar_c, 1);
     mbar_init(&sm.bar_o, 1);
     mbar_fence_init();
+    // the bias table is a weight: fetch it while the previous kernel (the QKV GEMM) is still draining ...
     mbar_expect_tx(&sm.bar_tab, TAB_LEN * 8);
     bulk_load_1d(stab, tabs + static_cast<size_t>(p.heads) * COMPACT_LEN + static_cast<size_t>(head) * TAB_LEN,
                  TAB_LEN * 8, &sm.bar_tab);
+    pdl_launch_dependents();
+    pdl_wait();   // ... the operand images are its output
     if (static_cast<int>(blockIdx.x) < units) {
       load_kv(blockIdx.x);
       load_q(blockIdx.x, 0, 0);
@@ -149,6 +152,7 @@ window_attn2_kernel(const AttnParams p, const float2* __restrict__ tabs, int uni
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_slot;
+  pdl_wait();   // every thread: global stores of this kernel must not pass the previous grid's completion
 
   if (warp == 4) {
     // =============================== control warp ===============================
@@ -487,10 +491,9 @@ int launch_window_attn2(const AttnParams& p, cudaStream_t stream) {
   }
   int grid = 2 * num_sms() / p.heads * p.heads;   // two CTAs per SM; multiple of heads so a CTA keeps its table
   if (grid > units) grid = static_cast<int>(units);
-  window_attn2_kernel<<<grid, A2_THREADS, S2_SMEM, stream>>>(p, reinterpret_cast<const float2*>(p.packed_tab),
-                                                             static_cast<int>(units));
   count_launch();
-  return check_cuda(cudaGetLastError(), "window_attn2_kernel launch");
+  return launch_pdl(window_attn2_kernel, dim3(grid), dim3(A2_THREADS), S2_SMEM, stream, p,
+                    reinterpret_cast<const float2*>(p.packed_tab), static_cast<int>(units));
 }
 
 }  // namespace kvq

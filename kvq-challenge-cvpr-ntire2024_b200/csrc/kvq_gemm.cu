@@ -141,6 +141,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -496,9 +498,8 @@ int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmPa
   if (rc != 0) return rc;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, p);
   count_launch();
-  return check_cuda(cudaGetLastError(), "gemm_kernel launch");
+  return launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN>::SMEM, stream, tmA, tmB, p);
 }
 
 template <int EPI>

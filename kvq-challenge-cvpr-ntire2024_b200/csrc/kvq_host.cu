@@ -2,6 +2,7 @@
 // driver-API tensor-map encoder (resolved through the runtime so the library does not link libcuda).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -119,6 +120,15 @@ int prof_collect(float* ms, int* launches, int ncat) {
   g_prof.used = 0;
   g_prof.cat.clear();
   return static_cast<int>(pairs);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("KVQ_PDL");
+    on = (e != nullptr && atoi(e) != 0) ? 1 : 0;   // measured on B200: -3.6 % with PDL on, so it is opt-in
+  }
+  return on == 1;
 }
 
 int num_sms() {

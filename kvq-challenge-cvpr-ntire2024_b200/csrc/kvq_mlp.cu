@@ -126,6 +126,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -323,9 +325,8 @@ int launch_mlp_impl(const __half* a, const __half* w1, const float* b1, const __
   if (rc != 0) return rc;
   const int tiles = (M + TILE_M - 1) / TILE_M;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  fused_mlp_kernel<C><<<grid, MLP_THREADS, Cfg::SMEM, stream>>>(tmA, tmW1, tmW2, b1, b2, x, M);
   count_launch();
-  return check_cuda(cudaGetLastError(), "fused_mlp_kernel launch");
+  return launch_pdl(fused_mlp_kernel<C>, dim3(grid), dim3(MLP_THREADS), Cfg::SMEM, stream, tmA, tmW1, tmW2, b1, b2, x, M);
 }
 
 }  // namespace

@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_window_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, int rows, int C, WinGeom g) {
   constexpr int RPW = 32 / LPR;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   int row = (blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5)) * RPW + lane / LPR;
   const bool live = row < rows;
@@ -113,6 +115,8 @@ ln_rows_kernel(const float* __restrict__ x, __half* __restrict__ out, float* __r
                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int C,
                int tokens_per_clip) {
   constexpr int RPW = 32 / LPR;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   int row = (blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5)) * RPW + lane / LPR;
   const bool live = row < rows;
@@ -134,6 +138,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_merge_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int rows, int D, int H, int W, int C) {
   constexpr int RPW = 32 / LPR;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   int row = (blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5)) * RPW + lane / LPR;
   const bool live = row < rows;
@@ -157,6 +163,8 @@ ln_merge_kernel(const float* __restrict__ x, __half* __restrict__ out, const flo
 __global__ void __launch_bounds__(256)
 patch_im2col_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int T, int H, int W, int D, int Hs,
                     int Ws, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   // ws fastest so a warp reads 512 contiguous bytes of one input row; the 8 B stores merge in L2
@@ -190,6 +198,8 @@ patch_im2col_kernel(const float* __restrict__ x, __half* __restrict__ out, int B
 __global__ void __launch_bounds__(256)
 row_mean_kernel(const float* __restrict__ rowscore, float* __restrict__ score, int tokens) {
   __shared__ float part[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const float* src = rowscore + static_cast<size_t>(blockIdx.x) * tokens;
   float s = 0.f;
   for (int i = threadIdx.x; i < tokens; i += blockDim.x) s += src[i];
@@ -301,10 +311,9 @@ int launch_ln_window(const float* x, __half* out, const float* gamma, const floa
   return dispatch_ln(C / 4, [&](auto lpr, auto mv) {
     constexpr int RPC = (ROW_THREADS / 32) * (32 / decltype(lpr)::value);
     const int grid = static_cast<int>((rows + RPC - 1) / RPC);
-    ln_window_kernel<decltype(lpr)::value, decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(
-        x, out, gamma, beta, eps, static_cast<int>(rows), C, g);
     count_launch();
-    return check_cuda(cudaGetLastError(), "ln_window_kernel launch");
+    return launch_pdl(ln_window_kernel<decltype(lpr)::value, decltype(mv)::value>, dim3(grid), dim3(ROW_THREADS), 0,
+                      stream, x, out, gamma, beta, eps, static_cast<int>(rows), C, g);
   });
 }
 
@@ -314,10 +323,9 @@ int launch_ln_rows(const float* x, __half* out, float* feat_cf, const float* gam
   return dispatch_ln(C / 4, [&](auto lpr, auto mv) {
     constexpr int RPC = (ROW_THREADS / 32) * (32 / decltype(lpr)::value);
     const int grid = (M + RPC - 1) / RPC;
-    ln_rows_kernel<decltype(lpr)::value, decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(
-        x, out, feat_cf, gamma, beta, eps, M, C, tokens_per_clip);
     count_launch();
-    return check_cuda(cudaGetLastError(), "ln_rows_kernel launch");
+    return launch_pdl(ln_rows_kernel<decltype(lpr)::value, decltype(mv)::value>, dim3(grid), dim3(ROW_THREADS), 0,
+                      stream, x, out, feat_cf, gamma, beta, eps, M, C, tokens_per_clip);
   });
 }
 
@@ -329,10 +337,9 @@ int launch_ln_merge(const float* x, __half* out, const float* gamma, const float
   return dispatch_ln(C, [&](auto lpr, auto mv) {
     constexpr int RPC = (ROW_THREADS / 32) * (32 / decltype(lpr)::value);
     const int grid = static_cast<int>((rows + RPC - 1) / RPC);
-    ln_merge_kernel<decltype(lpr)::value, decltype(mv)::value><<<grid, ROW_THREADS, 0, stream>>>(
-        x, out, gamma, beta, eps, static_cast<int>(rows), D, H, W, C);
     count_launch();
-    return check_cuda(cudaGetLastError(), "ln_merge_kernel launch");
+    return launch_pdl(ln_merge_kernel<decltype(lpr)::value, decltype(mv)::value>, dim3(grid), dim3(ROW_THREADS), 0,
+                      stream, x, out, gamma, beta, eps, static_cast<int>(rows), D, H, W, C);
   });
 }
 
@@ -341,15 +348,14 @@ int launch_patch_im2col(const float* x, __half* out, int B, int T, int H, int W,
   const long long total = static_cast<long long>(B) * D * Hs * Ws * 24;
   const long long grid = (total + 255) / 256;
   KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "im2col: grid too large");
-  patch_im2col_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(x, out, B, T, H, W, D, Hs, Ws, total);
   count_launch();
-  return check_cuda(cudaGetLastError(), "patch_im2col_kernel launch");
+  return launch_pdl(patch_im2col_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0, stream, x, out, B, T, H, W, D,
+                    Hs, Ws, total);
 }
 
 int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cudaStream_t stream) {
-  row_mean_kernel<<<B, 256, 0, stream>>>(rowscore, score, tokens);
   count_launch();
-  return check_cuda(cudaGetLastError(), "row_mean_kernel launch");
+  return launch_pdl(row_mean_kernel, dim3(B), dim3(256), 0, stream, rowscore, score, tokens);
 }
 
 int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
