@@ -194,7 +194,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;         // TMEM lane quadrant this warp may touch
     const int half = ew >> 2;       // which interleaved set of column chunks this warp drains
     // epilogues that need the whole output row in one thread run on the half-0 warps only
-    constexpr bool kWholeRow = (EPI == EPI_LN_F32 || EPI == EPI_HEAD);
+    constexpr bool kWholeRow = (EPI == EPI_HEAD);
     const int c_begin = kWholeRow ? 0 : half;
     const int c_step = kWholeRow ? 1 : 2;
     const bool active = !kWholeRow || half == 0;
@@ -403,53 +403,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else if constexpr (EPI == EPI_LN_F32) {
-        // whole output row lives in this thread's TMEM lane: exact two-pass LayerNorm, then a third read to write
-        if (active) {
-          float mean = 0.f;
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += CW) {
-            uint32_t r[CW];
-            tmem_ld_chunk<CW>(taddr + c0, r);
-            tmem_wait_ld();
+        // PatchEmbed3D bias + LayerNorm(96): the two warps that share a lane quadrant each own half of the row's
+        // column chunks; one TMEM pass accumulates sum / sum-of-squares, the halves are combined through shared
+        // memory (named barrier over the 8 epilogue warps), a second pass normalises and stores.
+        constexpr int MYCH = (NCHUNK + 1) / 2;
+        float* sstat = stile;                         // this warp's 32 x {sum, sumsq} partials
+        float* pstat = reinterpret_cast<float*>(staging + (ew ^ 4) * (32 * 36 * 4 + 32 * 8));   // partner warp's
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < CW; ++j) mean += __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
+        for (int ci = 0; ci < MYCH; ++ci) {
+          const int c0 = (c_begin + ci * c_step) * CW;
+          if (c0 >= BN) break;
+          uint32_t r[CW];
+          tmem_ld_chunk<CW>(taddr + c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float v = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
+            s1 += v;
+            s2 = fmaf(v, v, s2);
           }
-          mean *= (1.0f / BN);
-          float var = 0.f;
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += CW) {
-            uint32_t r[CW];
-            tmem_ld_chunk<CW>(taddr + c0, r);
-            tmem_wait_ld();
+        }
+        sstat[2 * lane] = s1;
+        sstat[2 * lane + 1] = s2;
+        named_bar_sync(2, EPI_WARPS * 32);
+        s1 += pstat[2 * lane];
+        s2 += pstat[2 * lane + 1];
+        const float mean = s1 * (1.0f / BN);
+        const float rstd = rsqrtf(fmaxf(s2 * (1.0f / BN) - mean * mean, 0.f) + p.eps);
+        float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo;
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              const float d = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j) - mean;
-              var += d * d;
-            }
-          }
-          const float rstd = rsqrtf(var * (1.0f / BN) + p.eps);
-          float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo;
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += CW) {
-            uint32_t r[CW];
-            tmem_ld_chunk<CW>(taddr + c0, r);
-            tmem_wait_ld();
-            if (row_ok) {
+        for (int ci = 0; ci < MYCH; ++ci) {
+          const int c0 = (c_begin + ci * c_step) * CW;
+          if (c0 >= BN) break;
+          uint32_t r[CW];
+          tmem_ld_chunk<CW>(taddr + c0, r);
+          tmem_wait_ld();
+          if (row_ok) {
 #pragma unroll
-              for (int j = 0; j < CW; j += 4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-                const float4 gg = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + j));
-                const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + j));
-                float4 v;
-                v.x = (__uint_as_float(r[j]) + bb.x - mean) * rstd * gg.x + be.x;
-                v.y = (__uint_as_float(r[j + 1]) + bb.y - mean) * rstd * gg.y + be.y;
-                v.z = (__uint_as_float(r[j + 2]) + bb.z - mean) * rstd * gg.z + be.z;
-                v.w = (__uint_as_float(r[j + 3]) + bb.w - mean) * rstd * gg.w + be.w;
-                *reinterpret_cast<float4*>(orow + c0 + j) = v;
-              }
+            for (int j = 0; j < CW; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              const float4 gg = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + j));
+              const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + j));
+              float4 v;
+              v.x = (__uint_as_float(r[j]) + bb.x - mean) * rstd * gg.x + be.x;
+              v.y = (__uint_as_float(r[j + 1]) + bb.y - mean) * rstd * gg.y + be.y;
+              v.z = (__uint_as_float(r[j + 2]) + bb.z - mean) * rstd * gg.z + be.z;
+              v.w = (__uint_as_float(r[j + 3]) + bb.w - mean) * rstd * gg.w + be.w;
+              *reinterpret_cast<float4*>(orow + c0 + j) = v;
             }
           }
         }
+        named_bar_sync(2, EPI_WARPS * 32);            // partials are rewritten by the next tile
       } else if constexpr (EPI == EPI_HEAD) {
         if (active) {
           float acc = 0.f;
