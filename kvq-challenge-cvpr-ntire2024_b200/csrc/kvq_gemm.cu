@@ -14,6 +14,8 @@
 //   EPI_GELU_F16  Mlp.fc1 + GELU(erf) :64-89
 //   EPI_LN_F32    PatchEmbed3D proj bias + LayerNorm :715-733
 //   EPI_HEAD      VQAHead fc_hid + GELU + fc_last (models/head.py:60-68)
+#include <cstdlib>
+
 #include "kvq_common.cuh"
 #include "kvq_kernels.cuh"
 
@@ -30,16 +32,19 @@ constexpr int STAGING_BYTES = EPI_WARPS * (32 * 36 * 4 + 32 * 8);   // per warp:
 
 // One CTA per SM: a deep TMA ring (the large-K GEMMs are latency-bound with fewer than 4 stages in flight) and
 // double-buffered accumulators so 8 epilogue warps drain tile t while the tensor pipe works on tile t+1.
-template <int BN>
+// MT = 128-row sub-tiles per CTA tile: MT = 2 (256 x BLOCK_N tile, two MMAs per K step sharing the B tile) cuts
+// the operand bytes pulled from L2 per FLOP by 30 % -- the stage-2/3 GEMMs (K >= 384) are L2-bandwidth bound
+// with 128 x 192 tiles -- at the price of single-buffered accumulators.
+template <int BN, int MT = 1>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN >= 192 ? 4 : 6;
-  static constexpr int ACC_STAGES = 2;
+  static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  static constexpr int STAGES = MT == 2 ? 3 : (BN >= 192 ? 4 : 6);
+  static constexpr int ACC_STAGES = MT == 2 ? 1 : 2;
   static constexpr int CW = (BN % 64 == 0) ? 32 : 16;       // TMEM columns per epilogue chunk
   static constexpr int NCHUNK = BN / CW;
   static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
-  static constexpr int TMEM_NEED = ACC_STAGES * BN;
+  static constexpr int TMEM_NEED = ACC_STAGES * MT * BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_NEED <= 512 && SMEM <= 227 * 1024, "tile configuration exceeds the SM");
 };
@@ -93,17 +98,17 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t* r) {
   else tmem_ld_x16(taddr, r);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  constexpr int STAGES = Cfg<BN>::STAGES;
-  constexpr int ACC = Cfg<BN>::ACC_STAGES;
-  constexpr int CW = Cfg<BN>::CW;
-  constexpr int NCHUNK = Cfg<BN>::NCHUNK;
-  uint8_t* staging = smem + STAGES * Cfg<BN>::STAGE_BYTES;
+  constexpr int STAGES = Cfg<BN, MT>::STAGES;
+  constexpr int ACC = Cfg<BN, MT>::ACC_STAGES;
+  constexpr int CW = Cfg<BN, MT>::CW;
+  constexpr int NCHUNK = Cfg<BN, MT>::NCHUNK;
+  uint8_t* staging = smem + STAGES * Cfg<BN, MT>::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
@@ -113,7 +118,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (p.M + BM - 1) / BM;
+  constexpr int TM = BM * MT;                 // rows per CTA tile
+  const int num_m = (p.M + TM - 1) / TM;
   const int num_n = p.N / BN;
   const int tiles = num_m * num_n;
   const int nkb = (p.K + BK - 1) / BK;
@@ -134,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg<BN>::TMEM_COLS);
+    tmem_alloc(tmem_slot, Cfg<BN, MT>::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -152,10 +158,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
         for (int kb = 0; kb < nkb_tot; ++kb) {
           mbar_wait(&empty[stage], ph ^ 1);
-          uint8_t* sA = smem + stage * Cfg<BN>::STAGE_BYTES;
-          uint8_t* sB = sA + A_BYTES;
-          mbar_expect_tx(&full[stage], Cfg<BN>::STAGE_BYTES);
-          tma_load_2d(sA, &tmA, &full[stage], (kb >= nkb ? kb - nkb : kb) * BK, m_blk * BM);
+          uint8_t* sA = smem + stage * Cfg<BN, MT>::STAGE_BYTES;
+          uint8_t* sB = sA + MT * A_BYTES;
+          mbar_expect_tx(&full[stage], Cfg<BN, MT>::STAGE_BYTES);
+          tma_load_2d(sA, &tmA, &full[stage], (kb >= nkb ? kb - nkb : kb) * BK, m_blk * TM);
           tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
@@ -169,18 +175,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * MT * BN);
         for (int kb = 0; kb < nkb_tot; ++kb) {
           mbar_wait(&full[stage], ph);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * Cfg<BN>::STAGE_BYTES);
-          const uint64_t da = umma_smem_desc(sA, 16, 1024, UMMA_SW_128);
-          const uint64_t db = umma_smem_desc(sA + A_BYTES, 16, 1024, UMMA_SW_128);
+          const uint32_t sA = smem_u32(smem + stage * Cfg<BN, MT>::STAGE_BYTES);
+          const uint64_t db = umma_smem_desc(sA + MT * A_BYTES, 16, 1024, UMMA_SW_128);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advancing 16 halfs (32 B) inside the 128 B swizzle row = +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = umma_smem_desc(sA + mt * A_BYTES, 16, 1024, UMMA_SW_128);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing 16 halfs (32 B) inside the 128 B swizzle row = +2 in the (addr >> 4) field
+              umma_f16_ss(d_tmem + mt * BN, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
@@ -192,12 +201,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     const int ew = warp - 2;        // 0..7
     const int q = warp & 3;         // TMEM lane quadrant this warp may touch
-    const int half = ew >> 2;       // which interleaved set of column chunks this warp drains
+    const int half = ew >> 2;       // MT == 1: which interleaved set of column chunks this warp drains;
+                                    // MT == 2: which 128-row sub-tile (the warp then drains every chunk of its rows)
     // epilogues that need the whole output row in one thread run on the half-0 warps only
     constexpr bool kWholeRow = (EPI == EPI_HEAD);
-    const int c_begin = kWholeRow ? 0 : half;
-    const int c_step = kWholeRow ? 1 : 2;
+    const int c_begin = (kWholeRow || MT == 2) ? 0 : half;
+    constexpr int c_step = (kWholeRow || MT == 2) ? 1 : 2;
     const bool active = !kWholeRow || half == 0;
+    const int msub = MT == 2 ? half : 0;
     float* stile = reinterpret_cast<float*>(staging + ew * (32 * 36 * 4 + 32 * 8));
     long long* srow = reinterpret_cast<long long*>(stile + 32 * 36);
     int as = 0;
@@ -210,14 +221,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
         tc_fence_after();
       }
-      const int row = m_blk * BM + q * 32 + lane;
+      const int row = m_blk * TM + msub * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>((as * MT + msub) * BN);
       const int nbase = n_blk * BN;
 
       if constexpr (EPI == EPI_GELU_F16 || EPI == EPI_STORE_F16) {
         __half* orow = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + nbase;
-        constexpr int MYCH = (NCHUNK + 1) / 2;
+        constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
         // this warp's bias slice lives in its private smem tile; refreshed only when the CTA moves to another n-block
         if (n_blk != bias_nblk) {
           __syncwarp();
@@ -254,7 +266,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // transpose through the warp's smem tile (80 B row pitch: conflict-free both ways) so that every store
           // instruction writes whole 32 B sectors: 32/SEGS rows x (CW*2) contiguous bytes instead of 32 x 16 B
           constexpr int SEGS = CW / 8;                    // 16-byte segments per row chunk
-          uint8_t* st16 = reinterpret_cast<uint8_t*>(stile) + 512;
+          uint8_t* st16 = reinterpret_cast<uint8_t*>(stile) + 1024;   // (bias slice occupies the first <= 768 B)
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < SEGS; ++j)
@@ -266,7 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int it = 0; it < SEGS; ++it) {
             const int rr = it * RPI + rl;
             const uint4 v = *reinterpret_cast<const uint4*>(st16 + rr * 80 + seg * 16);
-            const int grow = m_blk * BM + q * 32 + rr;
+            const int grow = m_blk * TM + msub * BM + q * 32 + rr;
             if (grow < p.M)
               st_global_v4(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldo + nbase + c0 + 8 * seg,
                            v.x, v.y, v.z, v.w);
@@ -289,15 +301,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         srow[lane] = ok ? orow_idx * p.ldo : -1;
         constexpr int LPRW = CW / 4;          // lanes per row on the global side
         constexpr int RPI = 32 / LPRW;        // rows per instruction
-        constexpr int MYCH = (NCHUNK + 1) / 2;  // chunks this warp drains
+        constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;  // chunks this warp drains
         const int sub = lane % LPRW, rsel = lane / LPRW;
         __syncwarp();
         // prefetch the residual rows while the tensor pipe is still producing this tile: the HBM latency of the
         // fp32 stream is hidden behind the accumulator wait instead of being paid once per chunk
-        float4 pre[MYCH][LPRW];
+        constexpr int PF = MYCH < 3 ? MYCH : 3;   // chunks whose residual is prefetched (register budget)
+        float4 pre[PF][LPRW];
         if (p.resid != nullptr) {
 #pragma unroll
-          for (int ci = 0; ci < MYCH; ++ci) {
+          for (int ci = 0; ci < PF; ++ci) {
             const int c0 = (c_begin + ci * c_step) * CW;
 #pragma unroll
             for (int it = 0; it < LPRW; ++it) {
@@ -332,7 +345,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float4 v = *reinterpret_cast<const float4*>(stile + rr * 36 + 4 * sub);
               v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
               if (p.resid != nullptr) {
-                v.x += pre[ci][it].x; v.y += pre[ci][it].y; v.z += pre[ci][it].z; v.w += pre[ci][it].w;
+                float4 rv;
+                if (ci < PF) rv = pre[ci < PF ? ci : 0][it];
+                else rv = *reinterpret_cast<const float4*>(p.resid + off + nbase + c0 + 4 * sub);
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
               }
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + nbase + c0 + 4 * sub) = v;
             }
@@ -349,7 +365,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kv_bytes = kv_rows * ATT_HD * 2;
         const size_t unit_bytes = static_cast<size_t>(ATT_IMG_BYTES) + 2 * kv_bytes;
         const int kv_row = slab * pitch + (i - slab * p.geom.SL);
-        constexpr int MYCH = (NCHUNK + 1) / 2;
+        constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
         if (n_blk != bias_nblk) {     // bias slice of this warp's chunks -> private smem, once per n-block
           __syncwarp();
 #pragma unroll
@@ -406,7 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // PatchEmbed3D bias + LayerNorm(96): the two warps that share a lane quadrant each own half of the row's
         // column chunks; one TMEM pass accumulates sum / sum-of-squares, the halves are combined through shared
         // memory (named barrier over the 8 epilogue warps), a second pass normalises and stores.
-        constexpr int MYCH = (NCHUNK + 1) / 2;
+        constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
         float* sstat = stile;                         // this warp's 32 x {sum, sumsq} partials
         float* pstat = reinterpret_cast<float*>(staging + (ew ^ 4) * (32 * 36 * 4 + 32 * 8));   // partner warp's
         float s1 = 0.f, s2 = 0.f;
@@ -482,33 +498,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg<BN>::TMEM_COLS);
+    tmem_dealloc(tmem_base, Cfg<BN, MT>::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT = 1>
 int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    KVQ_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    KVQ_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::SMEM));
     attr_set = true;
   }
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d(&tmA, A, p.M, p.K, static_cast<uint64_t>(lda) * 2, BM, BK, 2, 128);
+  int rc = make_tmap_2d(&tmA, A, p.M, p.K, static_cast<uint64_t>(lda) * 2, BM * MT, BK, 2, 128);
   if (rc != 0) return rc;
   const int kcols_b = p.split_b ? 2 * ((p.K + BK - 1) / BK * BK) : p.K;
   KVQ_REQUIRE(!p.split_b || ldb == kcols_b, KVQ_ERR_BAD_SHAPE, "gemm: split weights need ldb == 2*ceil64(K) (%d vs %d)",
               ldb, kcols_b);
   rc = make_tmap_2d(&tmB, B, p.N, kcols_b, static_cast<uint64_t>(ldb) * 2, BN, BK, 2, 128);
   if (rc != 0) return rc;
-  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int tiles = ((p.M + BM * MT - 1) / (BM * MT)) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   count_launch();
-  return launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN>::SMEM, stream, tmA, tmB, p);
+  return launch_pdl(gemm_kernel<BN, EPI, MT>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, MT>::SMEM, stream, tmA, tmB, p);
+}
+
+// 256-row tiles (opt-in, KVQ_GEMM_BIG_TILES=1): fewer L2 bytes per FLOP, but at batch 8 the stage-2/3 GEMMs then have
+// only ~1.3 waves of tiles and lose the accumulator double buffering -- measured 1.3-2x slower, so off by default
+inline bool use_big_tiles(const GemmParams& p) {
+  static const int mode = []() { const char* e = getenv("KVQ_GEMM_BIG_TILES"); return e ? atoi(e) : 0; }();
+  return mode != 0 && p.K >= 384 && (p.M + 255) / 256 * (p.N / 192) >= num_sms();
 }
 
 template <int EPI>
 int launch_bn(const __half* A, int lda, const __half* B, int ldb, const GemmParams& p, cudaStream_t stream) {
+  if (p.N % 192 == 0 && use_big_tiles(p)) return launch_impl<192, EPI, 2>(A, lda, B, ldb, p, stream);
   if (p.N % 192 == 0) return launch_impl<192, EPI>(A, lda, B, ldb, p, stream);
   if (p.N % 96 == 0) return launch_impl<96, EPI>(A, lda, B, ldb, p, stream);
   if (p.N % 64 == 0) return launch_impl<64, EPI>(A, lda, B, ldb, p, stream);
@@ -536,6 +560,7 @@ int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, con
     case EPI_QKV_IMG:
       KVQ_REQUIRE(p.N == 3 * p.C && p.C % 32 == 0 && p.bias != nullptr, KVQ_ERR_BAD_SHAPE,
                   "gemm(qkv): N=%d C=%d (need N == 3C, C %% 32 == 0, bias)", p.N, p.C);
+      if (p.N % 192 == 0 && use_big_tiles(p)) return launch_impl<192, EPI_QKV_IMG, 2>(A, lda, B, ldb, p, stream);
       if (p.N % 192 == 0) return launch_impl<192, EPI_QKV_IMG>(A, lda, B, ldb, p, stream);
       if (p.N % 96 == 0) return launch_impl<96, EPI_QKV_IMG>(A, lda, B, ldb, p, stream);
       set_error("gemm(qkv): N=%d is not a multiple of 96", p.N);
