@@ -127,7 +127,7 @@ def layer_norm(x, w, b, eps=1e-5):
     return F.layer_norm(x, (x.shape[-1],), w, b, eps)
 
 
-def window_attention(xw, p, num_heads, tabs, frag_bias, shifted, cast=_ident):
+def window_attention(xw, p, num_heads, tabs, frag_bias, shifted, cast=_ident, base_window=BASE_WINDOW):
     """WindowAttention3D.forward (:245-322) up to, not including, proj.  xw: [B, nW*N, C] window-ordered rows."""
     B, _, C = xw.shape
     N, nW = tabs["N"], tabs["nW"]
@@ -137,7 +137,8 @@ def window_attention(xw, p, num_heads, tabs, frag_bias, shifted, cast=_ident):
     q, k, v = qkv[0] * (hd ** -0.5), qkv[1], qkv[2]                        # [B,nW,nH,N,hd]
     logits = cast(q) @ cast(k).transpose(-2, -1)
     frag_tab = p("attn.fragment_position_bias_table") if frag_bias else None
-    logits = logits + attention_bias(tabs, p("attn.relative_position_bias_table"), frag_tab, shifted)[None]
+    logits = logits + attention_bias(tabs, p("attn.relative_position_bias_table"), frag_tab, shifted,
+                                     base_window=base_window)[None]
     probs = torch.softmax(logits, dim=-1)
     return (cast(probs) @ cast(v)).permute(0, 1, 3, 2, 4).reshape(B, nW * N, C)
 
@@ -150,14 +151,14 @@ def swin_block(x, p, num_heads, window, shift, frag_bias, cast=_ident):
     Dp = math.ceil(D / win[0]) * win[0]
     Hp = math.ceil(H / win[1]) * win[1]
     Wp = math.ceil(W / win[2]) * win[2]
-    tabs = token_tables((Dp, Hp, Wp), win, sh)
+    tabs = token_tables((Dp, Hp, Wp), win, sh, base_window=tuple(window))
     N, nW = tabs["N"], tabs["nW"]
     hd = C // num_heads
 
     xn = layer_norm(x, p("norm1.weight"), p("norm1.bias"))
     xn = F.pad(xn, (0, 0, 0, Wp - W, 0, Hp - H, 0, Dp - D))              # zeros AFTER LN (:416-424)
     xw = xn.reshape(B, Dp * Hp * Wp, C)[:, tabs["src"].reshape(-1)]       # [B, nW*N, C]
-    o = window_attention(xw, p, num_heads, tabs, frag_bias, shifted, cast)
+    o = window_attention(xw, p, num_heads, tabs, frag_bias, shifted, cast, base_window=tuple(window))
     o = F.linear(cast(o), cast(p("attn.proj.weight")), p("attn.proj.bias"))
     # inverse remap: slot -> original coordinate; padded coordinates are cropped (:472-488)
     out = torch.zeros(B, Dp * Hp * Wp, C, dtype=x.dtype)

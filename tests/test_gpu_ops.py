@@ -74,8 +74,11 @@ def _block_params(C, heads, frag, seed):
     return synth.synth_state_dict(shapes, seed)
 
 
+# attention kernel generations: 0 = library default (two-CTA flash-style kernel for full (8,7,7) windows, generic
+# kernel otherwise), 1 = first-generation persistent kernel, 2 = generic kernel everywhere
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("geom", GEOMS, ids=[f"D{g[1]}H{g[2]}W{g[3]}C{g[4]}s{g[6][0]}{g[6][1]}{g[6][2]}" for g in GEOMS])
-def test_ln_window_and_attention(geom):
+def test_ln_window_and_attention(geom, variant):
     from kvq_b200 import ops
     from oracle import swin3d
     B, D, H, W, C, heads, shift, frag = geom
@@ -103,7 +106,7 @@ def test_ln_window_and_attention(geom):
     tab = ops.pack_bias_table(sd["attn.relative_position_bias_table"].to(dev),
                               sd["attn.fragment_position_bias_table"].to(dev) if frag else None, window, heads)
     o = ops.window_attention(xw, ops.cast_f16(sd["attn.qkv.weight"].to(dev)), sd["attn.qkv.bias"].to(dev), tab,
-                             B, D, H, W, heads, window, shift)
+                             B, D, H, W, heads, window, shift, debug_variant=variant)
     o = o.float().cpu().reshape(o_ref.shape)
     assert torch.isfinite(o).all()
     err = (o - o_ref).abs().max().item()

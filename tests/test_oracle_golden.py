@@ -18,19 +18,21 @@ def _load(path):
     g = np.load(path)
     shape = tuple(int(v) for v in g["shape"])
     fb = [bool(b) for b in g["frag_biases"]]
-    sd = synth.synth_state_dict(synth.swin_shapes(frag_biases=fb), int(g["wseed"]))
+    arch = dict(window=tuple(int(v) for v in g["window"]) if "window" in g else (8, 7, 7),
+                depths=tuple(int(v) for v in g["depths"]) if "depths" in g else (2, 2, 6, 2))
+    sd = synth.synth_state_dict(synth.swin_shapes(frag_biases=fb, **arch), int(g["wseed"]))
     sd.update(synth.synth_state_dict(synth.vqa_head_shapes(), int(g["wseed"])))
     x = synth.clip_input(shape, int(g["xseed"]))
-    return g, shape, fb, sd, x
+    return g, shape, fb, sd, x, arch
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_oracle_matches_reference_golden(path):
-    g, shape, fb, sd, x = _load(path)
+    g, shape, fb, sd, x, arch = _load(path)
     if shape[2] > 32 and os.environ.get("KVQ_SLOW_TESTS") != "1":
         pytest.skip("96-frame case takes ~1 min on CPU; set KVQ_SLOW_TESTS=1")
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    feat = swin3d.swin3d_forward(sd, x, frag_biases=fb)
+    feat = swin3d.swin3d_forward(sd, x, frag_biases=fb, **arch)
     score = swin3d.vqa_head(sd, feat).numpy()
     assert list(feat.shape) == [int(v) for v in g["feat_shape"]]
     st = int(g["feat_stride"])

@@ -26,6 +26,10 @@ SWIN_CASES = [
     ("swin_t32_224", (2, 3, 32, 224, 224), 14, 3, {}),           # BASELINE config 2 geometry
     ("swin_t96_224", (1, 3, 96, 224, 224), 15, 25, {}),          # 96-frame val clip
     ("swin_plain_t16_112", (1, 3, 16, 112, 112), 16, 26, {"frag_biases": [0, 0, 0, 0]}),  # swin_3d_tiny
+    # swin_tiny_grpb_m (model.py:39-43): window (4,4,4), no fragment tables
+    ("swin_m444_t16_96", (1, 3, 16, 96, 96), 17, 27, {"frag_biases": [0, 0, 0, 0], "window_size": (4, 4, 4)}),
+    # swin_small (swin_backbone.py:1093-1095): depths [2,2,18,2]
+    ("swin_small_t16_64", (1, 3, 16, 64, 64), 18, 28, {"frag_biases": [0, 0, 0, 0], "depths": [2, 2, 18, 2]}),
 ]
 
 
@@ -33,9 +37,12 @@ def gen_swin(ref):
     keys_written = False
     for name, shape, wseed, xseed, kw in SWIN_CASES:
         fb = kw.get("frag_biases", [True, True, True, False])
-        m = ref.swin.SwinTransformer3D(pretrained=None, use_checkpoint=False, frag_biases=fb)
+        window = tuple(kw.get("window_size", (8, 7, 7)))
+        depths = list(kw.get("depths", [2, 2, 6, 2]))
+        m = ref.swin.SwinTransformer3D(pretrained=None, use_checkpoint=False, frag_biases=fb, window_size=window,
+                                       depths=depths)
         head = ref.head.VQAHead(in_channels=768, hidden_channels=64)
-        sd = synth.synth_state_dict(synth.swin_shapes(frag_biases=fb), wseed)
+        sd = synth.synth_state_dict(synth.swin_shapes(frag_biases=fb, window=window, depths=depths), wseed)
         hd = synth.synth_state_dict(synth.vqa_head_shapes(), wseed)
         missing = m.load_state_dict(sd, strict=False)
         assert not missing.unexpected_keys, missing
@@ -51,7 +58,8 @@ def gen_swin(ref):
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), score=score.numpy(),
                             feat=fs.numpy().astype(np.float32), feat_stride=np.int64(16 if fs is not feat else 1),
                             feat_shape=np.array(feat.shape), shape=np.array(shape), wseed=wseed, xseed=xseed,
-                            frag_biases=np.array([int(bool(b)) for b in fb]),
+                            frag_biases=np.array([int(bool(b)) for b in fb]), window=np.array(window),
+                            depths=np.array(depths),
                             feat_absmean=feat.abs().mean().numpy())
         print(name, tuple(feat.shape), "score", score.flatten().tolist(), "absmean", feat.abs().mean().item())
         if not keys_written:
