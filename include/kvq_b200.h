@@ -131,6 +131,61 @@ int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float*
                            int fragments_h, int fragments_w, int fsize, int aligned, const float mean[3],
                            const float std[3], void* stream);
 
+/* ---- SimpleVQA spatial branch (config/kwai_simpleVQA_test.yml): ResNet-50 per frame + mean/std pools + head ---- */
+typedef struct KvqResNetConfig {
+  int32_t layers[4];   /* 3,4,6,3 Bottleneck blocks (models/backbones/simpleVQA_model.py:276 resnet50) */
+  int32_t feat3d_dim;  /* 2304: width of batch['feat'], the pre-extracted SlowFast features (:226); 0 = none */
+  int32_t head;        /* 1: simpleVQAHead (models/head.py:10-31) follows, score_out is written */
+} KvqResNetConfig;
+
+/*
+ * Weight pointer table for kvq_simplevqa_forward.  Every convolution is passed with its BatchNorm folded in
+ * (eval mode): w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps); weights are fp16
+ * [Cout, Kp] with the K index tap-major / channel-minor ((dh*kw + dw)*Cin + c, zero padded to Kp % 8 == 0), biases
+ * fp32 [Cout]:
+ *   [0],[1]  conv1+bn1 (7x7/2, Kp = 152)
+ *   then per layer, per block: conv1+bn1, conv2+bn2, conv3+bn3 and, for the first block of a layer,
+ *   downsample.0+downsample.1  (w, b each)
+ *   then (head) w_eff f32 [feature_dim] = quality.1.weight @ quality.0.weight,
+ *               b_eff f32 [1] = quality.1.weight @ quality.0.bias + quality.1.bias
+ */
+int kvq_resnet_num_weights(const KvqResNetConfig* cfg);
+/* 2*(512+1024+2048) + feat3d_dim = 9472 */
+int kvq_resnet_feature_dim(const KvqResNetConfig* cfg);
+size_t kvq_simplevqa_workspace_bytes(const KvqResNetConfig* cfg, int B, int T, int H, int W);
+/*
+ * Replaces VQA_Network.forward for the 'simpleVQA' key (models/model.py:93-121): ResNet.forward
+ * (simpleVQA_model.py:220-264) + simpleVQAHead.forward (head.py:28-31).
+ *   x         f32 [B,3,T,H,W]   (batch['simpleVQA'])
+ *   feat3d    f32 [B,T,feat3d_dim] (batch['feat'])
+ *   feat_out  f32 [B,T,feature_dim]  (the backbone's return value)
+ *   score_out f32 [B]                (head output: mean over frames)
+ */
+int kvq_simplevqa_forward(const KvqResNetConfig* cfg, const void* const* weights, int num_weights, const float* x,
+                          const float* feat3d, int B, int T, int H, int W, float* feat_out, float* score_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- convolution building blocks (channels-last fp16 activations [B,T,H,W,C]) ---- */
+/* out[M,ldo] = act(A[M,K] * W[N,K]^T + bias + resid): conv-as-GEMM with folded BN (Bottleneck.forward :106-126).
+ * N (rows of W) is a multiple of 64; columns >= nvalid (0 = N) are padding and never stored */
+int kvq_conv_gemm_f16(const void* a_f16, int lda, const void* w_f16, const float* bias, const void* resid_f16, int ldr,
+                      void* out_f16, int ldo, int M, int N, int K, int nvalid, int relu, void* stream);
+/* gather [B,T,H,W,C] -> [B*To*Ho*Wo, Kp] patches, K index ((dt*kh + dh)*kw + dw)*C + c, zero padding (nn.Conv3d) */
+int kvq_im2col_cl_f16(const void* in_f16, void* out_f16, int B, int T, int H, int W, int C, const int32_t kernel[3],
+                      const int32_t stride[3], const int32_t pad[3], int Kp, void* stream);
+/* same for the 3-channel fp32 NCDHW network input */
+int kvq_im2col_stem_f32(const float* in, void* out_f16, int N, int T, int H, int W, const int32_t kernel[3],
+                        const int32_t stride[3], const int32_t pad[3], int Kp, void* stream);
+/* nn.MaxPool2d(3, 2, 1) (:153) on [N,H,W,C] */
+int kvq_maxpool_hw_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream);
+/* per (n, c) weighted mean over L (weights NULL = 1/L) and, if out_std != NULL, the unbiased std
+ * (global_std_pool2d :18-20, nn.AdaptiveAvgPool2d :165); in f16 [N,L,C]; outputs f32 with row stride ldo */
+int kvq_pool_stats_f16(const void* in_f16, const float* weights, float* out_mean, float* out_std, int N, int L, int C,
+                       int ldo, void* stream);
+/* score[g] = mean over the `group` rows of g of dot(x[row,:K], w) + *b */
+int kvq_rowdot_mean_f32(const float* x, const float* w, const float* b, float* score, int rows, int K, int group,
+                        void* stream);
+
 /* ---- measurement hooks (bench.py): kernels launched so far by this process, and optional CUDA-event timing of
  * every kernel of kvq_swin3d_forward grouped by (kind, stage).  Timing is OFF unless enabled. ---- */
 long long kvq_launch_count(void);

@@ -167,7 +167,7 @@ int kvq_profile_num_categories(void) { return PK_COUNT * 4; }
 const char* kvq_profile_category_name(int cat) {
   static const char* kinds[PK_COUNT] = {"embed_im2col", "embed_gemm", "ln_window", "qkv_gemm", "window_attn",
                                         "proj_gemm", "ln_rows", "fc1_gemm", "fc2_gemm", "merge_ln", "merge_gemm",
-                                        "final_ln", "head", "fused_mlp"};
+                                        "final_ln", "head", "fused_mlp", "conv_im2col", "conv_gemm", "conv_pool"};
   static thread_local char buf[48];
   if (cat < 0 || cat >= PK_COUNT * 4) return "?";
   snprintf(buf, sizeof(buf), "%s.s%d", kinds[cat / 4], cat % 4);
@@ -391,6 +391,245 @@ int kvq_linear_resid_f32(const void* a_f16, const void* w_f16, const float* bias
   gp.bias = bias; gp.out = out; gp.ldo = N; gp.resid = resid;
   return launch_gemm(EPI_RESID_F32, static_cast<const __half*>(a_f16), K, static_cast<const __half*>(w_f16), K, gp,
                      static_cast<cudaStream_t>(stream));
+}
+
+int kvq_conv_gemm_f16(const void* a_f16, int lda, const void* w_f16, const float* bias, const void* resid_f16, int ldr,
+                      void* out_f16, int ldo, int M, int N, int K, int nvalid, int relu, void* stream) {
+  GemmParams gp{};
+  gp.M = M; gp.N = N; gp.K = K;
+  gp.bias = bias; gp.out = out_f16; gp.ldo = ldo;
+  gp.resid_h = static_cast<const __half*>(resid_f16); gp.ldr = ldr;
+  gp.relu = relu; gp.nvalid = nvalid;
+  return launch_gemm(EPI_CONV_F16, static_cast<const __half*>(a_f16), lda, static_cast<const __half*>(w_f16), K, gp,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int kvq_im2col_cl_f16(const void* in_f16, void* out_f16, int B, int T, int H, int W, int C, const int32_t kernel[3],
+                      const int32_t stride[3], const int32_t pad[3], int Kp, void* stream) {
+  KVQ_REQUIRE(in_f16 && out_f16 && kernel && stride && pad, KVQ_ERR_BAD_SHAPE, "im2col: NULL argument");
+  return launch_im2col_cl(static_cast<const __half*>(in_f16), static_cast<__half*>(out_f16), B, T, H, W, C, kernel[0],
+                          kernel[1], kernel[2], stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Kp,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int kvq_im2col_stem_f32(const float* in, void* out_f16, int N, int T, int H, int W, const int32_t kernel[3],
+                        const int32_t stride[3], const int32_t pad[3], int Kp, void* stream) {
+  KVQ_REQUIRE(in && out_f16 && kernel && stride && pad, KVQ_ERR_BAD_SHAPE, "im2col_stem: NULL argument");
+  return launch_im2col_stem(in, static_cast<__half*>(out_f16), N, T, H, W, kernel[0], kernel[1], kernel[2], stride[0],
+                            stride[1], stride[2], pad[0], pad[1], pad[2], Kp, static_cast<cudaStream_t>(stream));
+}
+
+int kvq_maxpool_hw_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream) {
+  return launch_maxpool_hw(static_cast<const __half*>(in_f16), static_cast<__half*>(out_f16), N, H, W, C,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int kvq_pool_stats_f16(const void* in_f16, const float* weights, float* out_mean, float* out_std, int N, int L, int C,
+                       int ldo, void* stream) {
+  KVQ_REQUIRE(in_f16 && out_mean, KVQ_ERR_BAD_SHAPE, "pool_stats: NULL argument");
+  return launch_pool_stats(static_cast<const __half*>(in_f16), weights, out_mean, out_std, N, L, C, ldo,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int kvq_rowdot_mean_f32(const float* x, const float* w, const float* b, float* score, int rows, int K, int group,
+                        void* stream) {
+  KVQ_REQUIRE(x && w && score, KVQ_ERR_BAD_SHAPE, "rowdot_mean: NULL argument");
+  return launch_rowdot_mean(x, w, b, score, rows, K, group, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SimpleVQA spatial branch: torchvision-style ResNet-50 run per frame + multi-scale mean/std pooling
+// (models/backbones/simpleVQA_model.py:220-264) + simpleVQAHead (models/head.py:10-31)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct ResPlan {
+  int Hs, Ws, Hp, Wp;         // after the stem conv / after the max pool
+  size_t col_bytes, act_bytes;  // im2col scratch; one activation buffer (5 of them)
+  size_t total;
+};
+
+constexpr int RES_STEM_KP = 152;  // 7*7*3 = 147 padded to 16-byte rows
+
+inline int conv_out(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
+
+int make_res_plan(const KvqResNetConfig* cfg, int B, int T, int H, int W, ResPlan* pl) {
+  KVQ_REQUIRE(cfg != nullptr, KVQ_ERR_BAD_SHAPE, "config is NULL");
+  KVQ_REQUIRE(B >= 1 && T >= 1 && H >= 32 && W >= 32, KVQ_ERR_BAD_SHAPE, "resnet: input %dx3x%dx%dx%d too small", B, T,
+              H, W);
+  for (int s = 0; s < 4; ++s) KVQ_REQUIRE(cfg->layers[s] >= 1, KVQ_ERR_BAD_SHAPE, "layers[%d]=%d", s, cfg->layers[s]);
+  KVQ_REQUIRE(cfg->feat3d_dim >= 0 && cfg->feat3d_dim % 4 == 0, KVQ_ERR_BAD_SHAPE, "feat3d_dim=%d (multiple of 4)",
+              cfg->feat3d_dim);
+  const size_t N = static_cast<size_t>(B) * T;
+  pl->Hs = conv_out(H, 7, 2, 3); pl->Ws = conv_out(W, 7, 2, 3);
+  pl->Hp = conv_out(pl->Hs, 3, 2, 1); pl->Wp = conv_out(pl->Ws, 3, 2, 1);
+  size_t col = N * pl->Hs * pl->Ws * RES_STEM_KP * 2;
+  size_t act = N * pl->Hs * pl->Ws * 64 * 2;
+  int h = pl->Hp, w = pl->Wp;
+  for (int s = 0; s < 4; ++s) {
+    const int planes = 64 << s;
+    const int stride = s == 0 ? 1 : 2;
+    const int ho = conv_out(h, 3, stride, 1), wo = conv_out(w, 3, stride, 1);
+    act = std::max(act, N * h * w * static_cast<size_t>(planes) * 2);        // conv1 output at the input resolution
+    act = std::max(act, N * ho * wo * static_cast<size_t>(planes) * 4 * 2);  // block output
+    col = std::max(col, N * ho * wo * static_cast<size_t>(planes) * 9 * 2);  // 3x3 im2col
+    if (stride == 2) col = std::max(col, N * ho * wo * static_cast<size_t>(planes) * 2 * 2);  // strided 1x1 gather
+    h = ho; w = wo;
+  }
+  KVQ_REQUIRE(N * pl->Hs * pl->Ws < (1ull << 31), KVQ_ERR_BAD_SHAPE, "resnet: %zu stem rows (int32 overflow)",
+              N * pl->Hs * pl->Ws);
+  const size_t slack = 256 * 4608 * 2;  // TMA tile overhang past the last row
+  pl->col_bytes = align_up(col + slack, 256);
+  pl->act_bytes = align_up(act + slack, 256);
+  pl->total = pl->col_bytes + 5 * pl->act_bytes;
+  return KVQ_OK;
+}
+
+int conv_gemm(const __half* A, int lda, const void* w, const void* b, const __half* resid, int ldr, __half* out, int M,
+              int N, int K, bool relu, int stage, cudaStream_t st) {
+  GemmParams gp{};
+  gp.M = M; gp.N = N; gp.K = K;
+  gp.bias = static_cast<const float*>(b);
+  gp.out = out; gp.ldo = N;
+  gp.resid_h = resid; gp.ldr = ldr;
+  gp.relu = relu ? 1 : 0;
+  ProfScope ps(PK_CONV_GEMM, stage, st);
+  return launch_gemm(EPI_CONV_F16, A, lda, static_cast<const __half*>(w), K, gp, st);
+}
+
+}  // namespace
+
+int kvq_resnet_num_weights(const KvqResNetConfig* cfg) {
+  if (cfg == nullptr) return KVQ_ERR_BAD_SHAPE;
+  int n = 2;
+  for (int s = 0; s < 4; ++s) n += 2 * (3 * cfg->layers[s] + 1);
+  if (cfg->head) n += 2;
+  return n;
+}
+
+int kvq_resnet_feature_dim(const KvqResNetConfig* cfg) {
+  if (cfg == nullptr) return KVQ_ERR_BAD_SHAPE;
+  return 2 * (512 + 1024 + 2048) + cfg->feat3d_dim;
+}
+
+size_t kvq_simplevqa_workspace_bytes(const KvqResNetConfig* cfg, int B, int T, int H, int W) {
+  ResPlan pl;
+  if (make_res_plan(cfg, B, T, H, W, &pl) != 0) return 0;
+  return pl.total;
+}
+
+int kvq_simplevqa_forward(const KvqResNetConfig* cfg, const void* const* weights, int num_weights, const float* x,
+                          const float* feat3d, int B, int T, int H, int W, float* feat_out, float* score_out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  ResPlan pl;
+  int rc = make_res_plan(cfg, B, T, H, W, &pl);
+  if (rc != 0) return rc;
+  KVQ_REQUIRE(num_weights == kvq_resnet_num_weights(cfg), KVQ_ERR_BAD_SHAPE, "resnet: %d weight pointers, expected %d",
+              num_weights, kvq_resnet_num_weights(cfg));
+  KVQ_REQUIRE(x && feat_out && workspace && weights, KVQ_ERR_BAD_SHAPE, "resnet: NULL argument");
+  KVQ_REQUIRE(cfg->feat3d_dim == 0 || feat3d != nullptr, KVQ_ERR_BAD_SHAPE, "resnet: feat3d is NULL");
+  KVQ_REQUIRE(!cfg->head || score_out != nullptr, KVQ_ERR_BAD_SHAPE, "resnet: score_out is NULL");
+  KVQ_REQUIRE(workspace_bytes >= pl.total, KVQ_ERR_WORKSPACE, "resnet: workspace %zu < %zu bytes", workspace_bytes,
+              pl.total);
+  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, KVQ_ERR_MISALIGNED, "workspace not 256 B aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* wp = static_cast<uint8_t*>(workspace);
+  __half* col = reinterpret_cast<__half*>(wp);
+  __half* act[5];
+  for (int i = 0; i < 5; ++i) act[i] = reinterpret_cast<__half*>(wp + pl.col_bytes + i * pl.act_bytes);
+  const int N = B * T;
+  const int fdim = kvq_resnet_feature_dim(cfg);
+  int wi = 0;
+  auto W_ = [&]() { return weights[wi++]; };
+
+  // stem: conv 7x7/2 + BN + ReLU (:235-237), max pool 3x3/2 (:238); frames are the T axis of x (:225-231)
+  {
+    ProfScope ps(PK_CONV_IM2COL, 0, st);
+    rc = launch_im2col_stem(x, col, B, T, H, W, 1, 7, 7, 1, 2, 2, 0, 3, 3, RES_STEM_KP, st);
+  }
+  if (rc != 0) return rc;
+  {
+    const void* w = W_(); const void* b = W_();
+    rc = conv_gemm(col, RES_STEM_KP, w, b, nullptr, 0, act[0], N * pl.Hs * pl.Ws, 64, RES_STEM_KP, true, 0, st);
+  }
+  if (rc != 0) return rc;
+  {
+    ProfScope ps(PK_CONV_POOL, 0, st);
+    rc = launch_maxpool_hw(act[0], act[1], N, pl.Hs, pl.Ws, 64, st);
+  }
+  if (rc != 0) return rc;
+
+  __half* cur = act[1];
+  int ci = 1;  // index of `cur`
+  int h = pl.Hp, w = pl.Wp, cin = 64, col_off = 0;
+  for (int s = 0; s < 4; ++s) {
+    const int planes = 64 << s, cout = planes * 4;
+    for (int j = 0; j < cfg->layers[s]; ++j) {
+      const int stride = (j == 0 && s > 0) ? 2 : 1;
+      const int ho = conv_out(h, 3, stride, 1), wo = conv_out(w, 3, stride, 1);
+      const int M = N * h * w, Mo = N * ho * wo;
+      __half* t1 = act[(ci + 1) % 5];
+      __half* t2 = act[(ci + 2) % 5];
+      __half* idn = act[(ci + 3) % 5];
+      __half* out = act[(ci + 4) % 5];
+      const void* w1 = W_(); const void* b1 = W_();
+      const void* w2 = W_(); const void* b2 = W_();
+      const void* w3 = W_(); const void* b3 = W_();
+      // Bottleneck.forward (:106-126): 1x1 -> 3x3 (stride here) -> 1x1, + identity / downsample, ReLU
+      rc = conv_gemm(cur, cin, w1, b1, nullptr, 0, t1, M, planes, cin, true, s, st);
+      if (rc != 0) return rc;
+      {
+        ProfScope ps(PK_CONV_IM2COL, s, st);
+        rc = launch_im2col_cl(t1, col, N, 1, h, w, planes, 1, 3, 3, 1, stride, stride, 0, 1, 1, 9 * planes, st);
+      }
+      if (rc != 0) return rc;
+      rc = conv_gemm(col, 9 * planes, w2, b2, nullptr, 0, t2, Mo, planes, 9 * planes, true, s, st);
+      if (rc != 0) return rc;
+      const __half* resid = cur;
+      if (j == 0) {
+        const void* wd = W_(); const void* bd = W_();
+        const __half* a = cur;
+        if (stride == 2) {
+          ProfScope ps(PK_CONV_IM2COL, s, st);
+          rc = launch_im2col_cl(cur, col, N, 1, h, w, cin, 1, 1, 1, 1, 2, 2, 0, 0, 0, cin, st);
+          if (rc != 0) return rc;
+          a = col;
+        }
+        rc = conv_gemm(a, cin, wd, bd, nullptr, 0, idn, Mo, cout, cin, false, s, st);
+        if (rc != 0) return rc;
+        resid = idn;
+      }
+      rc = conv_gemm(t2, planes, w3, b3, resid, cout, out, Mo, cout, planes, true, s, st);
+      if (rc != 0) return rc;
+      cur = out;
+      ci = (ci + 4) % 5;
+      cin = cout;
+      h = ho; w = wo;
+    }
+    if (s >= 1) {
+      // AdaptiveAvgPool2d(1) + global_std_pool2d of layer2/3/4 (:242-251), concatenated in that order (:252)
+      ProfScope ps(PK_CONV_POOL, s, st);
+      rc = launch_pool_stats(cur, nullptr, feat_out + col_off, feat_out + col_off + cout, N, h * w, cout, fdim, st);
+      if (rc != 0) return rc;
+      col_off += 2 * cout;
+    }
+  }
+  if (cfg->feat3d_dim > 0) {
+    // torch.cat((x, x_3D_features), dim=1) (:256)
+    KVQ_CUDA(cudaMemcpy2DAsync(feat_out + col_off, static_cast<size_t>(fdim) * 4, feat3d,
+                               static_cast<size_t>(cfg->feat3d_dim) * 4, static_cast<size_t>(cfg->feat3d_dim) * 4, N,
+                               cudaMemcpyDeviceToDevice, st));
+  }
+  if (cfg->head) {
+    // simpleVQAHead (head.py:22-31): Linear(9472,128) -> Linear(128,1) has no activation in between, so it is the
+    // single affine map w_eff = W2 W1, b_eff = W2 b1 + b2 (folded in fp32 at pack time); then the mean over frames
+    const float* weff = static_cast<const float*>(W_());
+    const float* beff = static_cast<const float*>(W_());
+    ProfScope ps(PK_HEAD, 0, st);
+    rc = launch_rowdot_mean(feat_out, weff, beff, score_out, N, fdim, T, st);
+    if (rc != 0) return rc;
+  }
+  return KVQ_OK;
 }
 
 int kvq_mlp_fused(const void* a_f16, const void* w1_f16, const float* b1, const void* w2_f16, const float* b2, float* x,

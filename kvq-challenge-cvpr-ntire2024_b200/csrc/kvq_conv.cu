@@ -1,0 +1,310 @@
+// Convolution-side row kernels for the SimpleVQA ResNet-50 spatial branch (models/backbones/simpleVQA_model.py:129-264)
+// and the SlowFast motion trunk (SlowFast_features.py:26-77).  Activations are channels-last fp16 ([B,T,H,W,C]), so a
+// 1x1 convolution IS the row GEMM of kvq_gemm.cu and a kxkxk convolution is an im2col gather (16-byte chunks, K index
+// tap-major so a chunk never straddles two taps) followed by the same GEMM with the folded-BatchNorm / residual / ReLU
+// epilogue (EPI_CONV_F16).  All kernels here are HBM-bound gathers / reductions: 16-byte accesses, grid-stride loops
+// sized to the SM count.
+#include "kvq_common.cuh"
+#include "kvq_kernels.cuh"
+
+namespace kvq {
+
+namespace {
+
+constexpr int CONV_THREADS = 256;
+
+inline int grid_for(long long items, int threads, int per_sm = 8) {
+  long long blocks = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+struct ConvGeom {
+  int B, T, H, W, C;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  int To, Ho, Wo;
+  int K, Kp;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS)
+im2col_cl_kernel(const __half* __restrict__ in, __half* __restrict__ out, const ConvGeom g, long long chunks) {
+  pdl_wait();
+  const int kchunks = g.Kp >> 3;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < chunks;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = idx / kchunks;
+    const int k = static_cast<int>(idx - m * kchunks) << 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (k < g.K) {
+      const int tap = k / g.C, c = k - tap * g.C;
+      const int dw = tap % g.kw, dh = (tap / g.kw) % g.kh, dt = tap / (g.kw * g.kh);
+      long long r = m;
+      const int wo = static_cast<int>(r % g.Wo); r /= g.Wo;
+      const int ho = static_cast<int>(r % g.Ho); r /= g.Ho;
+      const int to = static_cast<int>(r % g.To); r /= g.To;
+      const int b = static_cast<int>(r);
+      const int t = to * g.st - g.pt + dt, h = ho * g.sh - g.ph + dh, w = wo * g.sw - g.pw + dw;
+      if (t >= 0 && t < g.T && h >= 0 && h < g.H && w >= 0 && w < g.W)
+        v = __ldg(reinterpret_cast<const uint4*>(in + ((((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W + w) * g.C + c)));
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = v;
+  }
+  pdl_launch_dependents();
+}
+
+// stem: fp32 NCDHW input with 3 channels; one half2 (two consecutive k) per thread
+__global__ void __launch_bounds__(CONV_THREADS)
+im2col_stem_kernel(const float* __restrict__ in, __half* __restrict__ out, const ConvGeom g, long long pairs) {
+  pdl_wait();
+  const int kpairs = g.Kp >> 1;
+  const long long plane = static_cast<long long>(g.T) * g.H * g.W;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < pairs;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = idx / kpairs;
+    const int k0 = static_cast<int>(idx - m * kpairs) << 1;
+    long long r = m;
+    const int wo = static_cast<int>(r % g.Wo); r /= g.Wo;
+    const int ho = static_cast<int>(r % g.Ho); r /= g.Ho;
+    const int to = static_cast<int>(r % g.To); r /= g.To;
+    const int b = static_cast<int>(r);
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = k0 + e;
+      if (k < g.K) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int dw = tap % g.kw, dh = (tap / g.kw) % g.kh, dt = tap / (g.kw * g.kh);
+        const int t = to * g.st - g.pt + dt, h = ho * g.sh - g.ph + dh, w = wo * g.sw - g.pw + dw;
+        if (t >= 0 && t < g.T && h >= 0 && h < g.H && w >= 0 && w < g.W)
+          v[e] = __ldg(in + (static_cast<long long>(b) * 3 + c) * plane + (static_cast<long long>(t) * g.H + h) * g.W + w);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(out + idx * 2) = pack_half2(v[0], v[1]);
+  }
+  pdl_launch_dependents();
+}
+
+__global__ void __launch_bounds__(CONV_THREADS)
+maxpool_hw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int Ho, int Wo,
+                  long long chunks) {
+  pdl_wait();
+  const int cch = C >> 3;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < chunks;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = idx;
+    const int c = static_cast<int>(r % cch) << 3; r /= cch;
+    const int wo = static_cast<int>(r % Wo); r /= Wo;
+    const int ho = static_cast<int>(r % Ho); r /= Ho;
+    const int n = static_cast<int>(r);
+    __half2 best[4];
+    bool any = false;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int h = ho * 2 - 1 + dh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int w = wo * 2 - 1 + dw;
+        if (w < 0 || w >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + h) * W + w) * C + c));
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+        if (!any) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) best[j] = hv[j];
+          any = true;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) best[j] = __hmax2(best[j], hv[j]);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(best);
+  }
+  pdl_launch_dependents();
+}
+
+// block = (n, 256-channel slab): 32 channel groups of 8 x 8 partitions of the L axis; two passes (mean, then centred
+// sum of squares) so the unbiased std does not cancel in fp32
+__global__ void __launch_bounds__(CONV_THREADS)
+pool_stats_kernel(const __half* __restrict__ in, const float* __restrict__ weights, float* __restrict__ out_mean,
+                  float* __restrict__ out_std, int L, int C, int ldo) {
+  pdl_wait();
+  __shared__ float red[8][32][8];
+  __shared__ float mean_s[32][8];
+  const int n = blockIdx.x;
+  const int cg = threadIdx.x & 31, lp = threadIdx.x >> 5;
+  const int c = (blockIdx.y * 32 + cg) << 3;
+  const bool ok = c < C;
+  const __half* base = in + static_cast<long long>(n) * L * C + c;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (ok) {
+    for (int l = lp; l < L; l += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(l) * C));
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+      const float wgt = weights != nullptr ? __ldg(weights + l) : 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hv[j]);
+        acc[2 * j] = fmaf(f.x, wgt, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(f.y, wgt, acc[2 * j + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[lp][cg][j] = acc[j];
+  __syncthreads();
+  if (lp == 0) {
+    const float scale = weights != nullptr ? 1.f : 1.f / static_cast<float>(L);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][cg][j];
+      s *= scale;
+      mean_s[cg][j] = s;
+      if (ok) out_mean[static_cast<long long>(n) * ldo + c + j] = s;
+    }
+  }
+  if (out_std == nullptr) { pdl_launch_dependents(); return; }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (ok) {
+    float mu[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mu[j] = mean_s[cg][j];
+    for (int l = lp; l < L; l += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(l) * C));
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hv[j]);
+        const float a = f.x - mu[2 * j], b = f.y - mu[2 * j + 1];
+        acc[2 * j] = fmaf(a, a, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(b, b, acc[2 * j + 1]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[lp][cg][j] = acc[j];
+  __syncthreads();
+  if (lp == 0 && ok) {
+    // torch.std default: unbiased (L - 1); L == 1 gives NaN there too
+    const float inv = 1.f / static_cast<float>(L - 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][cg][j];
+      out_std[static_cast<long long>(n) * ldo + c + j] = sqrtf(s * inv);
+    }
+  }
+  pdl_launch_dependents();
+}
+
+// block per group of `group` consecutive rows: score = mean_rows(dot(x_row, w)) + b
+__global__ void __launch_bounds__(CONV_THREADS)
+rowdot_mean_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                   float* __restrict__ score, int K,
+                   int group) {
+  pdl_wait();
+  __shared__ float red[CONV_THREADS / 32];
+  const float* base = x + static_cast<long long>(blockIdx.x) * group * K;
+  float acc = 0.f;
+  const int k4 = K >> 2;
+  for (int r = 0; r < group; ++r) {
+    const float4* row = reinterpret_cast<const float4*>(base + static_cast<long long>(r) * K);
+    for (int i = threadIdx.x; i < k4; i += blockDim.x) {
+      const float4 a = __ldg(row + i);
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + i);
+      acc += (a.x * ww.x + a.y * ww.y) + (a.z * ww.z + a.w * ww.w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CONV_THREADS / 32; ++i) s += red[i];
+    score[blockIdx.x] = s / static_cast<float>(group) + (b != nullptr ? __ldg(b) : 0.f);
+  }
+  pdl_launch_dependents();
+}
+
+int fill_geom(ConvGeom& g, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh, int sw, int pt,
+              int ph, int pw, int Kp) {
+  KVQ_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && kt > 0 && kh > 0 && kw > 0 && st > 0 && sh > 0 && sw > 0 &&
+                  pt >= 0 && ph >= 0 && pw >= 0,
+              KVQ_ERR_BAD_SHAPE, "im2col: bad geometry B=%d T=%d H=%d W=%d C=%d k=(%d,%d,%d) s=(%d,%d,%d)", B, T, H, W,
+              C, kt, kh, kw, st, sh, sw);
+  g = ConvGeom{B, T, H, W, C, kt, kh, kw, st, sh, sw, pt, ph, pw, 0, 0, 0, 0, 0};
+  g.To = (T + 2 * pt - kt) / st + 1;
+  g.Ho = (H + 2 * ph - kh) / sh + 1;
+  g.Wo = (W + 2 * pw - kw) / sw + 1;
+  g.K = kt * kh * kw * C;
+  g.Kp = Kp;
+  KVQ_REQUIRE(g.To > 0 && g.Ho > 0 && g.Wo > 0, KVQ_ERR_BAD_SHAPE, "im2col: empty output %dx%dx%d", g.To, g.Ho, g.Wo);
+  KVQ_REQUIRE(Kp >= g.K && Kp % 8 == 0, KVQ_ERR_BAD_SHAPE, "im2col: Kp=%d must be a multiple of 8 and >= K=%d", Kp, g.K);
+  return KVQ_OK;
+}
+
+}  // namespace
+
+int launch_im2col_cl(const __half* in, __half* out, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st,
+                     int sh, int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream) {
+  ConvGeom g;
+  const int rc = fill_geom(g, B, T, H, W, C, kt, kh, kw, st, sh, sw, pt, ph, pw, Kp);
+  if (rc != 0) return rc;
+  KVQ_REQUIRE(C % 8 == 0, KVQ_ERR_MISALIGNED, "im2col: channels-last input needs C %% 8 == 0 (got %d)", C);
+  const long long chunks = static_cast<long long>(B) * g.To * g.Ho * g.Wo * (Kp / 8);
+  count_launch();
+  return launch_pdl(im2col_cl_kernel, dim3(grid_for(chunks, CONV_THREADS)), dim3(CONV_THREADS), 0, stream, in, out, g,
+                    chunks);
+}
+
+int launch_im2col_stem(const float* in, __half* out, int N, int T, int H, int W, int kt, int kh, int kw, int st, int sh,
+                       int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream) {
+  ConvGeom g;
+  const int rc = fill_geom(g, N, T, H, W, 3, kt, kh, kw, st, sh, sw, pt, ph, pw, Kp);
+  if (rc != 0) return rc;
+  const long long pairs = static_cast<long long>(N) * g.To * g.Ho * g.Wo * (Kp / 2);
+  count_launch();
+  return launch_pdl(im2col_stem_kernel, dim3(grid_for(pairs, CONV_THREADS)), dim3(CONV_THREADS), 0, stream, in, out, g,
+                    pairs);
+}
+
+int launch_maxpool_hw(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t stream) {
+  KVQ_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, KVQ_ERR_BAD_SHAPE,
+              "maxpool: bad shape N=%d H=%d W=%d C=%d (C %% 8 == 0)", N, H, W, C);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long chunks = static_cast<long long>(N) * Ho * Wo * (C / 8);
+  count_launch();
+  return launch_pdl(maxpool_hw_kernel, dim3(grid_for(chunks, CONV_THREADS)), dim3(CONV_THREADS), 0, stream, in, out, N,
+                    H, W, C, Ho, Wo, chunks);
+}
+
+int launch_pool_stats(const __half* in, const float* weights, float* out_mean, float* out_std, int N, int L, int C,
+                      int ldo, cudaStream_t stream) {
+  KVQ_REQUIRE(N > 0 && L > 0 && C > 0 && C % 8 == 0 && ldo >= C, KVQ_ERR_BAD_SHAPE,
+              "pool_stats: bad shape N=%d L=%d C=%d ldo=%d", N, L, C, ldo);
+  count_launch();
+  return launch_pdl(pool_stats_kernel, dim3(N, (C + 255) / 256), dim3(CONV_THREADS), 0, stream, in, weights, out_mean,
+                    out_std, L, C, ldo);
+}
+
+int launch_rowdot_mean(const float* x, const float* w, const float* b, float* score, int rows, int K, int group,
+                       cudaStream_t stream) {
+  KVQ_REQUIRE(rows > 0 && K > 0 && K % 4 == 0 && group > 0 && rows % group == 0, KVQ_ERR_BAD_SHAPE,
+              "rowdot_mean: rows=%d K=%d group=%d (K %% 4 == 0, rows %% group == 0)", rows, K, group);
+  count_launch();
+  return launch_pdl(rowdot_mean_kernel, dim3(rows / group), dim3(CONV_THREADS), 0, stream, x, w, b, score, K, group);
+}
+
+}  // namespace kvq

@@ -286,6 +286,69 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         (void)orow;
         (void)row_ok;
+      } else if constexpr (EPI == EPI_CONV_F16) {
+        // conv-as-GEMM epilogue: folded-BN shift, optional fp16 residual, optional ReLU, fp16 channels-last output
+        constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
+        const int nvalid = p.nvalid > 0 ? p.nvalid : p.N;
+        if (n_blk != bias_nblk) {
+          __syncwarp();
+#pragma unroll
+          for (int ci = 0; ci < MYCH; ++ci) {
+            const int c0 = (c_begin + ci * c_step) * CW;
+            if (lane < CW && c0 < BN)
+              stile[ci * CW + lane] = (p.bias != nullptr && nbase + c0 + lane < nvalid) ? __ldg(p.bias + nbase + c0 + lane) : 0.f;
+          }
+          bias_nblk = n_blk;
+          __syncwarp();
+        }
+        uint32_t r[2][CW];
+        tmem_ld_chunk<CW>(taddr + c_begin * CW, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < MYCH; ++ci) {
+          const int c0 = (c_begin + ci * c_step) * CW;
+          if (c0 >= BN) break;
+          // this thread's residual chunk (CW halfs) is fetched while the accumulator chunk is in flight
+          uint4 rs[CW / 8];
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) rs[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (p.resid_h != nullptr && row_ok) {
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j)
+              if (nbase + c0 + 8 * j < nvalid)
+                rs[j] = *reinterpret_cast<const uint4*>(p.resid_h + static_cast<size_t>(row) * p.ldr + nbase + c0 + 8 * j);
+          }
+          tmem_wait_ld();
+          if (ci + 1 < MYCH && c0 + c_step * CW < BN) tmem_ld_chunk<CW>(taddr + c0 + c_step * CW, r[(ci + 1) & 1]);
+          const uint32_t* rc = r[ci & 1];
+          uint32_t h[CW / 2];
+#pragma unroll
+          for (int j = 0; j < CW / 2; ++j) {
+            const uint32_t rw = reinterpret_cast<const uint32_t*>(rs)[j];
+            const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rw));
+            float v0 = __uint_as_float(rc[2 * j]) + stile[ci * CW + 2 * j] + rf.x;
+            float v1 = __uint_as_float(rc[2 * j + 1]) + stile[ci * CW + 2 * j + 1] + rf.y;
+            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            h[j] = pack_half2(v0, v1);
+          }
+          constexpr int SEGS = CW / 8;
+          uint8_t* st16 = reinterpret_cast<uint8_t*>(stile) + 1024;
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < SEGS; ++j)
+            *reinterpret_cast<uint4*>(st16 + lane * 80 + j * 16) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          __syncwarp();
+          constexpr int RPI = 32 / SEGS;
+          const int seg = lane / RPI, rl = lane % RPI;
+#pragma unroll
+          for (int it = 0; it < SEGS; ++it) {
+            const int rr = it * RPI + rl;
+            const uint4 v = *reinterpret_cast<const uint4*>(st16 + rr * 80 + seg * 16);
+            const int grow = m_blk * TM + msub * BM + q * 32 + rr;
+            if (grow < p.M && nbase + c0 + 8 * seg < nvalid)
+              st_global_v4(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldo + nbase + c0 + 8 * seg,
+                           v.x, v.y, v.z, v.w);
+          }
+        }
       } else if constexpr (EPI == EPI_RESID_F32) {
         // Row-per-thread TMEM reads are transposed through a per-warp smem tile so that global traffic is
         // row-contiguous: CW/4 lanes cover one output row (full 32 B sectors for the fp32 read-modify-write).
@@ -554,6 +617,15 @@ int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, con
     case EPI_STORE_F16:
       KVQ_REQUIRE(p.ldo % 8 == 0, KVQ_ERR_MISALIGNED, "gemm: fp16 output stride %d not 16 B aligned", p.ldo);
       return launch_bn<EPI_STORE_F16>(A, lda, B, ldb, p, stream);
+    case EPI_CONV_F16:
+      KVQ_REQUIRE(p.ldo % 8 == 0 && (p.resid_h == nullptr || p.ldr % 8 == 0), KVQ_ERR_MISALIGNED,
+                  "gemm(conv): fp16 output / residual strides %d / %d not 16 B aligned", p.ldo, p.ldr);
+      KVQ_REQUIRE(p.nvalid == 0 || (p.nvalid % 8 == 0 && p.nvalid <= p.N), KVQ_ERR_BAD_SHAPE,
+                  "gemm(conv): nvalid=%d must be a multiple of 8 and <= N=%d", p.nvalid, p.N);
+      if (p.N % 192 == 0) return launch_impl<192, EPI_CONV_F16>(A, lda, B, ldb, p, stream);
+      if (p.N % 64 == 0) return launch_impl<64, EPI_CONV_F16>(A, lda, B, ldb, p, stream);
+      set_error("gemm(conv): N=%d (padded output channels) must be a multiple of 64", p.N);
+      return KVQ_ERR_BAD_SHAPE;
     case EPI_RESID_F32:
       KVQ_REQUIRE(p.ldo % 4 == 0, KVQ_ERR_MISALIGNED, "gemm: fp32 output stride %d not 16 B aligned", p.ldo);
       return launch_bn<EPI_RESID_F32>(A, lda, B, ldb, p, stream);

@@ -19,7 +19,8 @@ int prof_collect(float* ms, int* launches, int ncat);
 // timing categories: kind * 4 + stage
 enum ProfKind : int {
   PK_EMBED_IM2COL = 0, PK_EMBED_GEMM, PK_LN_WINDOW, PK_QKV_GEMM, PK_ATTN, PK_PROJ_GEMM, PK_LN_ROWS, PK_FC1_GEMM,
-  PK_FC2_GEMM, PK_MERGE_LN, PK_MERGE_GEMM, PK_FINAL_LN, PK_HEAD, PK_FUSED_MLP, PK_COUNT
+  PK_FC2_GEMM, PK_MERGE_LN, PK_MERGE_GEMM, PK_FINAL_LN, PK_HEAD, PK_FUSED_MLP, PK_CONV_IM2COL, PK_CONV_GEMM, PK_CONV_POOL,
+  PK_COUNT
 };
 struct ProfScope {
   int cat;
@@ -113,6 +114,7 @@ enum GemmEpilogue : int {
   EPI_LN_F32 = 3,    // out_f[m, :] = LayerNorm(acc + bias) * gamma + beta, N == BLOCK_N  (PatchEmbed3D :715-733)
   EPI_HEAD = 4,      // rowscore[m] = sum_n gelu(acc + bias[n]) * w2[n] + b2      (VQAHead, head.py:60-68)
   EPI_STORE_F16 = 5, // out_h[m, n] = acc + bias[n]
+  EPI_CONV_F16 = 6,  // out_h[m, n] = act(acc + bias[n] + resid_h[m, n]), n < nvalid   (conv + folded BN + ReLU)
 };
 
 struct GemmParams {
@@ -122,6 +124,10 @@ struct GemmParams {
   void* out;            // fp16 / fp32 matrix, row stride ldo elements
   int ldo;
   const float* resid;   // EPI_RESID_F32: nullptr = no residual; may alias out
+  const __half* resid_h; // EPI_CONV_F16: fp16 residual [M, ldr] or nullptr
+  int ldr;
+  int relu;             // EPI_CONV_F16: apply ReLU
+  int nvalid;           // EPI_CONV_F16: columns >= nvalid are padding (not stored); 0 = N
   // EPI_RESID_F32 row remap (proj): rows are window-ordered; rows_in = nW*N per clip, rows_out = tokens per clip
   int remap;            // 0 = identity
   WinGeom geom;
@@ -173,6 +179,22 @@ int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, flo
 // fp32 [B, C, tokens] -> fp16 [B*tokens, C]
 int launch_cf_to_rows(const float* in, __half* out, int B, int C, int tokens, cudaStream_t stream);
 int launch_pack_split(const float* in, __half* out, int rows, int K, cudaStream_t stream);
+// ---- convolution support (SimpleVQA ResNet-50 / SlowFast): channels-last fp16 activations ----
+// in [B,T,H,W,C] -> A [B*To*Ho*Wo, Kp], K index = ((dt*kh + dh)*kw + dw)*C + c, zero padding, Kp >= kt*kh*kw*C
+int launch_im2col_cl(const __half* in, __half* out, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st,
+                     int sh, int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream);
+// stem: in fp32 [N,3,T,H,W] (NCDHW) -> A [N*To*Ho*Wo, Kp], K index = ((dt*kh + dh)*kw + dw)*3 + c
+int launch_im2col_stem(const float* in, __half* out, int N, int T, int H, int W, int kt, int kh, int kw, int st, int sh,
+                       int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream);
+// max pool (1,3,3) / stride (1,2,2) / pad (0,1,1) on [N,H,W,C] fp16
+int launch_maxpool_hw(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t stream);
+// per (n, c): weighted mean over the HW (or THW) axis and optional unbiased std; in [N, L, C] fp16; weights fp32 [L]
+// or nullptr (uniform); outputs fp32 with row stride ldo: mean at out_mean[n*ldo + c], std at out_std[n*ldo + c]
+int launch_pool_stats(const __half* in, const float* weights, float* out_mean, float* out_std, int N, int L, int C,
+                      int ldo, cudaStream_t stream);
+// out[n] = dot(x[n, :K], w) + *b (b: device scalar or nullptr); then mean over groups of `group` consecutive rows -> score[n / group]
+int launch_rowdot_mean(const float* x, const float* w, const float* b, float* score, int rows, int K, int group,
+                       cudaStream_t stream);
 // fp32 -> fp16 cast (weight packing)
 int launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream);
 

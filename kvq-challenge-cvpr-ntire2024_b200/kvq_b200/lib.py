@@ -15,6 +15,10 @@ class KvqSwinConfig(ctypes.Structure):
                 ("head_hidden", c_int32), ("ln_eps", c_float), ("split_weights", c_int32)]
 
 
+class KvqResNetConfig(ctypes.Structure):
+    _fields_ = [("layers", c_int32 * 4), ("feat3d_dim", c_int32), ("head", c_int32)]
+
+
 _I3 = c_int32 * 3
 _F3 = c_float * 3
 
@@ -44,6 +48,20 @@ PROTOTYPES = {
                              c_void_p, c_size_t, c_void_p]),
     "kvq_fragment_gather_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_int, POINTER(c_float), POINTER(c_float), c_void_p]),
+    "kvq_resnet_num_weights": (c_int, [POINTER(KvqResNetConfig)]),
+    "kvq_resnet_feature_dim": (c_int, [POINTER(KvqResNetConfig)]),
+    "kvq_simplevqa_workspace_bytes": (c_size_t, [POINTER(KvqResNetConfig), c_int, c_int, c_int, c_int]),
+    "kvq_simplevqa_forward": (c_int, [POINTER(KvqResNetConfig), POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int,
+                                      c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_conv_gemm_f16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_void_p]),
+    "kvq_im2col_cl_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32),
+                                  POINTER(c_int32), POINTER(c_int32), c_int, c_void_p]),
+    "kvq_im2col_stem_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int32),
+                                    POINTER(c_int32), POINTER(c_int32), c_int, c_void_p]),
+    "kvq_maxpool_hw_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "kvq_pool_stats_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "kvq_rowdot_mean_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kvq_launch_count": (ctypes.c_longlong, []),
     "kvq_profile_enable": (None, [c_int]),
     "kvq_profile_num_categories": (c_int, []),

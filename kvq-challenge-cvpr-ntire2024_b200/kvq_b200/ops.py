@@ -288,3 +288,220 @@ class SwinWeights:
             score = score_out if score_out is not None else torch.empty(B, dtype=torch.float32, device=x.device)
         self._launch(x, feat, score, ws)
         return feat, score
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# convolution building blocks + the SimpleVQA spatial branch
+# ---------------------------------------------------------------------------------------------------------------
+def _i3(v):
+    return (ctypes.c_int32 * 3)(*[int(a) for a in v])
+
+
+def pack_conv_weight(w, bn=None, eps=1e-5, pad_out=64):
+    """Conv weight [Cout,Cin,*k] (+ eval-mode BatchNorm (gamma, beta, mean, var)) -> (fp16 [Np, Kp] tap-major /
+    channel-minor with the BN scale folded in, fp32 [Np] shift).  Np = Cout rounded up to `pad_out`, Kp to 8."""
+    w = w.detach().float()
+    cout = w.shape[0]
+    if bn is not None:
+        g, b, m, v = [t.detach().float() for t in bn]
+        scale = g / torch.sqrt(v + eps)
+        shift = b - m * scale
+        w = w * scale.reshape(-1, *([1] * (w.dim() - 1)))
+    else:
+        shift = torch.zeros(cout, device=w.device)
+    perm = (0,) + tuple(range(2, w.dim())) + (1,)
+    w2 = w.permute(*perm).reshape(cout, -1)
+    K = w2.shape[1]
+    Kp, Np = (K + 7) // 8 * 8, (cout + pad_out - 1) // pad_out * pad_out
+    wp = torch.zeros((Np, Kp), dtype=torch.float32, device=w.device)
+    wp[:cout, :K] = w2
+    sp = torch.zeros(Np, dtype=torch.float32, device=w.device)
+    sp[:cout] = shift
+    return cast_f16(wp.contiguous()), sp.contiguous()
+
+
+def conv_gemm_f16(a, w, bias=None, resid=None, relu=False, nvalid=0, out=None):
+    """out[M, :nvalid] = act(a[M,K] @ w[N,K]^T + bias + resid); a / resid / out fp16 row-major (may be column slices)."""
+    M, K = a.shape
+    N = w.shape[0]
+    nv = nvalid if nvalid else N
+    if out is None:
+        out = torch.empty((M, nv), dtype=torch.float16, device=a.device)
+    for t in (a, out, resid):
+        if t is not None and (not t.is_cuda or t.stride(1) != 1):
+            raise RuntimeError("kvq_b200: conv_gemm_f16 takes row-major CUDA tensors (no CPU fallback exists)")
+    _need_cuda(w, bias)
+    rc = _l.load().kvq_conv_gemm_f16(_p(a), a.stride(0), _p(w), _p(bias), _p(resid),
+                                     resid.stride(0) if resid is not None else 0, _p(out), out.stride(0), M, N, K,
+                                     int(nvalid), int(bool(relu)), _stream())
+    _l.check(rc, "conv_gemm_f16")
+    return out
+
+
+def conv_out_size(n, k, s, p):
+    return (n + 2 * p - k) // s + 1
+
+
+def im2col_cl_f16(x, kernel, stride, pad, Kp=None):
+    """x f16 [B,T,H,W,C] -> (patch matrix f16 [B*To*Ho*Wo, Kp], (To,Ho,Wo))."""
+    _need_cuda(x)
+    B, T, H, W, C = x.shape
+    od = [conv_out_size(n, k, s, p) for n, k, s, p in zip((T, H, W), kernel, stride, pad)]
+    K = kernel[0] * kernel[1] * kernel[2] * C
+    Kp = Kp or (K + 7) // 8 * 8
+    out = torch.empty((B * od[0] * od[1] * od[2], Kp), dtype=torch.float16, device=x.device)
+    _l.check(_l.load().kvq_im2col_cl_f16(_p(x), _p(out), B, T, H, W, C, _i3(kernel), _i3(stride), _i3(pad), Kp,
+                                         _stream()), "im2col_cl_f16")
+    return out, tuple(od)
+
+
+def im2col_stem_f32(x, kernel, stride, pad, Kp=None):
+    """x f32 [N,3,T,H,W] -> (patch matrix f16 [N*To*Ho*Wo, Kp], (To,Ho,Wo))."""
+    _need_cuda(x)
+    N, C, T, H, W = x.shape
+    if C != 3:
+        raise RuntimeError("kvq_b200: im2col_stem_f32 is the 3-channel network-input gather")
+    od = [conv_out_size(n, k, s, p) for n, k, s, p in zip((T, H, W), kernel, stride, pad)]
+    K = kernel[0] * kernel[1] * kernel[2] * 3
+    Kp = Kp or (K + 7) // 8 * 8
+    out = torch.empty((N * od[0] * od[1] * od[2], Kp), dtype=torch.float16, device=x.device)
+    _l.check(_l.load().kvq_im2col_stem_f32(_p(x), _p(out), N, T, H, W, _i3(kernel), _i3(stride), _i3(pad), Kp,
+                                           _stream()), "im2col_stem_f32")
+    return out, tuple(od)
+
+
+def maxpool_hw_f16(x):
+    """nn.MaxPool2d(3, 2, 1) on channels-last f16 [N,H,W,C]."""
+    _need_cuda(x)
+    N, H, W, C = x.shape
+    out = torch.empty((N, conv_out_size(H, 3, 2, 1), conv_out_size(W, 3, 2, 1), C), dtype=torch.float16,
+                      device=x.device)
+    _l.check(_l.load().kvq_maxpool_hw_f16(_p(x), _p(out), N, H, W, C, _stream()), "maxpool_hw_f16")
+    return out
+
+
+def pool_stats_f16(x, weights=None, want_std=True):
+    """x f16 [N,L,C] -> (mean f32 [N,C], unbiased std f32 [N,C] or None); weights f32 [L] = weighted sum instead."""
+    _need_cuda(x, weights)
+    N, L, C = x.shape
+    mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
+    std = torch.empty((N, C), dtype=torch.float32, device=x.device) if want_std else None
+    _l.check(_l.load().kvq_pool_stats_f16(_p(x), _p(weights), _p(mean), _p(std), N, L, C, C, _stream()),
+             "pool_stats_f16")
+    return mean, std
+
+
+def rowdot_mean_f32(x, w, b, group):
+    """score[g] = mean over `group` consecutive rows of (x[row] . w) + b; x f32 [rows,K], w f32 [K], b f32 [1]."""
+    _need_cuda(x, w, b)
+    rows, K = x.shape
+    score = torch.empty(rows // group, dtype=torch.float32, device=x.device)
+    _l.check(_l.load().kvq_rowdot_mean_f32(_p(x), _p(w), _p(b), _p(score), rows, K, group, _stream()),
+             "rowdot_mean_f32")
+    return score
+
+
+def fold_simplevqa_head(sd, prefix):
+    """simpleVQAHead.quality = Linear(F,128) -> Linear(128,1) with nothing in between (head.py:22-26): one affine map."""
+    w0, b0 = sd[prefix + "quality.0.weight"].detach().double(), sd[prefix + "quality.0.bias"].detach().double()
+    w1, b1 = sd[prefix + "quality.1.weight"].detach().double(), sd[prefix + "quality.1.bias"].detach().double()
+    return (w1 @ w0).reshape(-1).float().contiguous(), (w1 @ b0 + b1).reshape(1).float().contiguous()
+
+
+class SimpleVQAWeights:
+    """Device-resident packed weights of the SimpleVQA ResNet-50 (+ simpleVQAHead) in the order include/kvq_b200.h
+    documents.  `sd` maps the REFERENCE state_dict names (simpleVQA_model.py:129-218; head.py:10-31) to tensors."""
+
+    def __init__(self, sd, device, prefix="", head_prefix=None, layers=(3, 4, 6, 3), feat3d_dim=2304, eps=1e-5):
+        self.device = torch.device(device)
+        self.cfg = _l.KvqResNetConfig()
+        for i, n in enumerate(layers):
+            self.cfg.layers[i] = int(n)
+        self.cfg.feat3d_dim = int(feat3d_dim)
+        self.cfg.head = int(head_prefix is not None)
+
+        def t(k):
+            return sd[k].detach().to(self.device, torch.float32)
+
+        def conv_bn(conv, bn):
+            return list(pack_conv_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
+                                                              ("weight", "bias", "running_mean", "running_var")], eps))
+
+        ts = conv_bn(prefix + "conv1", prefix + "bn1")
+        for s, depth in enumerate(layers):
+            for j in range(depth):
+                b = f"{prefix}layer{s + 1}.{j}."
+                ts += conv_bn(b + "conv1", b + "bn1") + conv_bn(b + "conv2", b + "bn2") + conv_bn(b + "conv3", b + "bn3")
+                if j == 0:
+                    ts += conv_bn(b + "downsample.0", b + "downsample.1")
+        if head_prefix is not None:
+            dsd = {k: v.to(self.device) for k, v in sd.items() if k.startswith(head_prefix)}
+            ts += list(fold_simplevqa_head(dsd, head_prefix))
+        self.tensors = ts
+        n = _l.load().kvq_resnet_num_weights(ctypes.byref(self.cfg))
+        if n != len(ts):
+            raise RuntimeError(f"kvq_b200: ResNet weight table has {len(ts)} entries, library expects {n}")
+        self.ptrs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in ts])
+        self.feature_dim = _l.load().kvq_resnet_feature_dim(ctypes.byref(self.cfg))
+        self._ws = None
+        self._graphs = {}
+
+    def workspace(self, B, T, H, W):
+        need = _l.load().kvq_simplevqa_workspace_bytes(ctypes.byref(self.cfg), B, T, H, W)
+        if need == 0:
+            raise RuntimeError(f"kvq_b200: cannot plan a [{B},3,{T},{H},{W}] SimpleVQA forward: {_l.last_error()}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._graphs = {}
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _launch(self, x, feat3d, feats, score, ws):
+        B, _, T, H, W = x.shape
+        rc = _l.load().kvq_simplevqa_forward(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(x), _p(feat3d),
+                                             B, T, H, W, _p(feats), _p(score), _p(ws), ws.numel(), _stream())
+        _l.check(rc, "simplevqa_forward")
+
+    def forward(self, x, feat3d, graph=None):
+        """x f32 [B,3,T,H,W], feat3d f32 [B,T,feat3d_dim] -> (feats f32 [B,T,feature_dim], score f32 [B] or None)."""
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("kvq_b200: input frames must be float32 CUDA tensors (no CPU fallback exists)")
+        x = x.contiguous()
+        B, _, T, H, W = x.shape
+        if self.cfg.feat3d_dim > 0:
+            feat3d = feat3d.to(x.device, torch.float32).contiguous()
+            if tuple(feat3d.shape) != (B, T, self.cfg.feat3d_dim):
+                raise RuntimeError(f"kvq_b200: batch['feat'] is {tuple(feat3d.shape)}, expected "
+                                   f"{(B, T, self.cfg.feat3d_dim)}")
+        else:
+            feat3d = None
+        ws = self.workspace(B, T, H, W)
+        if graph is None:
+            graph = os.environ.get("KVQ_CUDA_GRAPH", "0") == "1"
+
+        def alloc():
+            return (torch.empty((B, T, self.feature_dim), dtype=torch.float32, device=x.device),
+                    torch.empty(B, dtype=torch.float32, device=x.device) if self.cfg.head else None)
+
+        if graph:
+            key = (x.data_ptr(), feat3d.data_ptr() if feat3d is not None else 0, tuple(x.shape), ws.data_ptr())
+            entry = self._graphs.get(key)
+            if entry is None:
+                feats, score = alloc()
+                self._launch(x, feat3d, feats, score, ws)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = _l.load().kvq_launch_count()
+                with torch.cuda.graph(g):
+                    self._launch(x, feat3d, feats, score, ws)
+                nodes = int(_l.load().kvq_launch_count() - n0)
+                if len(self._graphs) >= 8:
+                    self._graphs.pop(next(iter(self._graphs)))
+                entry = self._graphs[key] = (g, feats, score, nodes, feat3d)
+            entry[0].replay()
+            global GRAPH_KERNEL_LAUNCHES
+            GRAPH_KERNEL_LAUNCHES += entry[3]
+            return entry[1], entry[2]
+        feats, score = alloc()
+        self._launch(x, feat3d, feats, score, ws)
+        return feats, score

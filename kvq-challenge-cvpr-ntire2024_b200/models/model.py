@@ -10,9 +10,11 @@ import torch.nn as nn
 
 from .backbones.swin_backbone import SwinTransformer3D as VideoBackbone
 from .backbones.swin_backbone import swin_3d_small, swin_3d_tiny
-from .head import VQAHead
+from .backbones.simpleVQA_model import resnet50 as simpleVQA_Backbone
+from .head import VQAHead, simpleVQAHead
 
-__all__ = ["VQA_Network", "VideoBackbone", "VQAHead", "swin_3d_tiny", "swin_3d_small"]
+__all__ = ["VQA_Network", "VideoBackbone", "VQAHead", "simpleVQAHead", "simpleVQA_Backbone", "swin_3d_tiny",
+           "swin_3d_small"]
 
 SWIN_KEYS = ("swin_tiny", "swin_tiny_grpb", "swin_tiny_grpb_m", "swin_small")
 
@@ -35,10 +37,12 @@ class VQA_Network(nn.Module):
                 backbone = VideoBackbone(window_size=(4, 4, 4), frag_biases=[0, 0, 0, 0])    # model.py:39-43
             elif key == "swin_small":
                 backbone = swin_3d_small(**hypers.get("backbone", {}))
+            elif key == "simpleVQA":
+                backbone = simpleVQA_Backbone(pretrained=True)                              # model.py:52-55
             else:
                 raise NotImplementedError(
                     f"kvq_b200: model key '{key}' is not on the B200 hot path yet (DESIGN.md, out-of-scope table)")
-            head = VQAHead(**hypers["head"])
+            head = simpleVQAHead(**hypers["head"]) if key == "simpleVQA" else VQAHead(**hypers["head"])
             self.key_names.append(key)
             setattr(self, key + "_backbone", backbone)
             setattr(self, key + "_head", head)
@@ -50,7 +54,7 @@ class VQA_Network(nn.Module):
         scores, feats = [], {}
         for key in self.key_names:
             backbone, head = getattr(self, key + "_backbone"), getattr(self, key + "_head")
-            x = inputs["technical"]
+            x = inputs if key == "simpleVQA" else inputs["technical"]   # the ResNet reads batch['simpleVQA'] + ['feat']
             feat, score = backbone.forward_with_head(x, head, want_feat=return_pooled_feats, graph=self.use_cuda_graph)
             scores.append(score)
             if return_pooled_feats:

@@ -99,3 +99,52 @@ def swin_network_state_dict(seed, key="swin_tiny_grpb", **kw):
 def clip_input(shape, seed):
     """Synthetic normalised frames, [B,3,T,H,W] fp32 ~ N(0,1) (ImageNet-normalised scale)."""
     return torch.randn(tuple(shape), generator=torch.Generator().manual_seed(seed))
+
+
+def resnet50_shapes(prefix="", layers=(3, 4, 6, 3), feat_dim=9472, hidden=128):
+    """Float parameter / buffer shapes of the reference's per-frame ResNet-50 (simpleVQA_model.py:129-218), including
+    its own unused `quality` regressor (:168) so that a strict load_state_dict works."""
+    s = {prefix + "conv1.weight": (64, 3, 7, 7)}
+
+    def bn(p, c):
+        for leaf in ("weight", "bias", "running_mean", "running_var"):
+            s[p + leaf] = (c,)
+
+    bn(prefix + "bn1.", 64)
+    cin = 64
+    for i, depth in enumerate(layers):
+        planes = 64 << i
+        for j in range(depth):
+            b = f"{prefix}layer{i + 1}.{j}."
+            s[b + "conv1.weight"] = (planes, cin, 1, 1)
+            bn(b + "bn1.", planes)
+            s[b + "conv2.weight"] = (planes, planes, 3, 3)
+            bn(b + "bn2.", planes)
+            s[b + "conv3.weight"] = (planes * 4, planes, 1, 1)
+            bn(b + "bn3.", planes * 4)
+            if j == 0:
+                s[b + "downsample.0.weight"] = (planes * 4, cin, 1, 1)
+                bn(b + "downsample.1.", planes * 4)
+            cin = planes * 4
+    s.update(simplevqa_head_shapes(prefix, feat_dim, hidden))
+    return s
+
+
+def simplevqa_head_shapes(prefix="", feat_dim=9472, hidden=128):
+    return {prefix + "quality.0.weight": (hidden, feat_dim), prefix + "quality.0.bias": (hidden,),
+            prefix + "quality.1.weight": (1, hidden), prefix + "quality.1.bias": (1,)}
+
+
+def simplevqa_network_state_dict(seed, key="simpleVQA"):
+    """Seeded weights of VQA_Network({'simpleVQA': ...}).  The generic 1/fan_in draw keeps the pooled features O(1)
+    through the 16 residual blocks (measured |feat| mean ~1.5, max ~15, like ImageNet-trained features); a ReLU gain
+    of sqrt(2) makes them grow past the fp16 range, which no trained checkpoint does."""
+    shapes = dict(resnet50_shapes(prefix=f"{key}_backbone."))
+    shapes.update(simplevqa_head_shapes(prefix=f"{key}_head."))
+    return synth_state_dict(shapes, seed)
+
+
+def motion_features(shape, seed):
+    """Stand-in for the pre-extracted SlowFast features batch['feat'] [B,T,2304] (non-negative: they are pooled
+    post-ReLU activations in the reference pipeline)."""
+    return torch.randn(tuple(shape), generator=torch.Generator().manual_seed(seed)).abs()

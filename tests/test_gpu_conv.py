@@ -1,0 +1,114 @@
+"""GPU parity tests of the convolution building blocks (channels-last fp16) against fp32 torch on the same
+fp16-rounded operands.  All calls go through libkvq_b200.so."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+@pytest.mark.parametrize("M,N,K,resid,relu,nvalid", [
+    (1000, 64, 152, False, True, 0),      # stem: K tail zero-filled by TMA
+    (3000, 256, 64, True, True, 0),       # bottleneck conv3 + identity
+    (777, 192, 576, False, False, 0),     # BLOCK_N = 192, no activation (downsample branch)
+    (128 * 150 + 3, 64, 64, True, True, 0),   # more tiles than SMs
+    (500, 64, 72, False, True, 8),        # padded output channels: only 8 valid columns are stored
+    (640, 2048, 512, True, True, 0),      # many N blocks
+])
+def test_conv_gemm(M, N, K, resid, relu, nvalid):
+    from kvq_b200 import ops
+    a = _rand((M, K), 1).half()
+    w = (_rand((N, K), 2) / math.sqrt(K)).half()
+    b = _rand((N,), 3, 0.1)
+    nv = nvalid or N
+    r = _rand((M, nv), 4).half() if resid else None
+    ref = a.float() @ w.float().t() + b
+    ref = ref[:, :nv]
+    if resid:
+        ref = ref + r.float()
+    if relu:
+        ref = F.relu(ref)
+    out = torch.full((M, nv + 8), 7.0, dtype=torch.float16, device=DEV)       # column slice: guard columns stay 7
+    ops.conv_gemm_f16(a.to(DEV), w.to(DEV), b.to(DEV), r.to(DEV) if resid else None, relu=relu, nvalid=nvalid,
+                      out=out[:, :nv])
+    got = out.float().cpu()
+    assert (got[:, nv:] == 7.0).all()
+    assert (got[:, :nv] - ref).abs().max().item() < 8e-3, (got[:, :nv] - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("B,T,H,W,C,kernel,stride,pad", [
+    (2, 1, 14, 14, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),     # ResNet 3x3
+    (3, 1, 15, 11, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),    # stride-2 3x3 on odd sizes
+    (2, 1, 9, 13, 256, (1, 1, 1), (1, 2, 2), (0, 0, 0)),     # strided 1x1 gather (downsample)
+    (1, 8, 6, 7, 16, (3, 1, 1), (1, 1, 1), (1, 0, 0)),       # SlowFast temporal conv
+    (1, 16, 6, 6, 8, (5, 1, 1), (4, 1, 1), (2, 0, 0)),       # SlowFast fast->slow lateral (alpha = 4)
+    (1, 4, 5, 5, 8, (3, 3, 3), (1, 1, 1), (1, 1, 1)),        # full 3-D
+])
+def test_im2col_cl_matches_conv3d(B, T, H, W, C, kernel, stride, pad):
+    """(im2col @ W^T) must equal F.conv3d with W permuted tap-major / channel-minor -- exercises gather + layout."""
+    from kvq_b200 import ops
+    x = _rand((B, C, T, H, W), 5).half()
+    wt = _rand((24, C) + kernel, 6).half()
+    ref = F.conv3d(x.float(), wt.float(), stride=stride, padding=pad)           # [B,24,To,Ho,Wo]
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    col, od = ops.im2col_cl_f16(xcl, kernel, stride, pad)
+    assert od == tuple(ref.shape[2:])
+    w2 = wt.permute(0, 2, 3, 4, 1).reshape(24, -1)
+    got = (col.float().cpu()[:, :w2.shape[1]] @ w2.float().t()).view(B, *od, 24).permute(0, 4, 1, 2, 3)
+    assert (got - ref).abs().max().item() < 1e-3 * math.sqrt(w2.shape[1])
+    assert (col[:, w2.shape[1]:] == 0).all()
+
+
+@pytest.mark.parametrize("N,T,H,W,kernel,stride,pad", [
+    (3, 1, 33, 47, (1, 7, 7), (1, 2, 2), (0, 3, 3)),         # ResNet stem, per-frame (T folded into N by the caller)
+    (1, 4, 32, 32, (1, 7, 7), (1, 2, 2), (0, 3, 3)),         # T axis of [B,3,T,H,W]
+    (1, 8, 20, 20, (5, 7, 7), (1, 2, 2), (2, 3, 3)),         # SlowFast fast stem
+])
+def test_im2col_stem(N, T, H, W, kernel, stride, pad):
+    from kvq_b200 import ops
+    x = _rand((N, 3, T, H, W), 7)
+    wt = _rand((16, 3) + kernel, 8).half()
+    ref = F.conv3d(x.half().float(), wt.float(), stride=stride, padding=pad)
+    col, od = ops.im2col_stem_f32(x.to(DEV), kernel, stride, pad)
+    assert od == tuple(ref.shape[2:]) and col.shape[1] % 8 == 0
+    w2 = wt.permute(0, 2, 3, 4, 1).reshape(16, -1)
+    got = (col.float().cpu()[:, :w2.shape[1]] @ w2.float().t()).view(N, *od, 16).permute(0, 4, 1, 2, 3)
+    assert (got - ref).abs().max().item() < 1e-3 * math.sqrt(w2.shape[1])
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 32, 32, 64), (3, 17, 23, 64), (1, 5, 4, 8)])
+def test_maxpool(N, H, W, C):
+    from kvq_b200 import ops
+    x = _rand((N, C, H, W), 9).half()
+    ref = F.max_pool2d(x.float(), 3, 2, 1)
+    got = ops.maxpool_hw_f16(x.permute(0, 2, 3, 1).contiguous().to(DEV)).float().cpu().permute(0, 3, 1, 2)
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("N,L,C", [(4, 49, 512), (3, 196, 2048), (2, 4, 1024), (1, 784, 264)])
+def test_pool_stats(N, L, C):
+    from kvq_b200 import ops
+    x = (_rand((N, L, C), 10) + 0.5).relu().half()
+    mean, std = ops.pool_stats_f16(x.to(DEV))
+    assert (mean.cpu() - x.float().mean(dim=1)).abs().max().item() < 1e-5
+    assert (std.cpu() - x.float().std(dim=1)).abs().max().item() < 1e-5
+    wts = torch.rand(L, generator=torch.Generator().manual_seed(11))
+    wmean, none = ops.pool_stats_f16(x.to(DEV), weights=wts.to(DEV), want_std=False)
+    assert none is None
+    assert (wmean.cpu() - (x.float() * wts.view(1, L, 1)).sum(dim=1)).abs().max().item() < 1e-4 * L ** 0.5
+
+
+def test_rowdot_mean():
+    from kvq_b200 import ops
+    x, w, b = _rand((24, 9472), 12), _rand((9472,), 13, 0.01), _rand((1,), 14)
+    ref = (x @ w + b).view(3, 8).mean(dim=1)
+    got = ops.rowdot_mean_f32(x.to(DEV), w.to(DEV), b.to(DEV), group=8).cpu()
+    assert (got - ref).abs().max().item() < 1e-5
