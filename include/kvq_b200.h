@@ -165,6 +165,39 @@ int kvq_simplevqa_forward(const KvqResNetConfig* cfg, const void* const* weights
                           const float* feat3d, int B, int T, int H, int W, float* feat_out, float* score_out,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- SlowFast-R50 motion features (SlowFast_features.py; trunk = pytorchvideo.models.hub.slowfast_r50 blocks 0..4,
+ * absent offline -> restated in oracle/slowfast.py, PARITY UNPINNED) ---- */
+typedef struct KvqSlowFastConfig {
+  int32_t depths[4];    /* 3,4,6,3 bottleneck blocks per stage, both pathways */
+  int32_t alpha;        /* 4: fast frames per slow frame = temporal stride of conv_fast_to_slow (7,1,1) */
+  int32_t slow_pool[3]; /* 8,7,7   blocks[5].pool[0] = AvgPool3d kernel, stride 1 (SlowFast_features.py:148) */
+  int32_t fast_pool[3]; /* 32,7,7  blocks[5].pool[1] (:149) */
+} KvqSlowFastConfig;
+
+/*
+ * Weight pointer table for kvq_slowfast_forward: every convolution with its eval-mode BatchNorm folded in, as an
+ * (fp16 [round64(Cout), round8(K)] tap-major / channel-minor weight, fp32 [round64(Cout)] shift) pair, in this order:
+ *   slow stem, fast stem, block-0 fusion (conv_fast_to_slow + norm);
+ *   then per stage s = 0..3: every slow res block (branch1 first for block 0; conv_a, conv_b, conv_c), every fast
+ *   res block (same), then for s < 3 the stage's fusion.
+ */
+int kvq_slowfast_num_weights(const KvqSlowFastConfig* cfg);
+size_t kvq_slowfast_workspace_bytes(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int W);
+/*
+ * Replaces slowfast.forward (SlowFast_features.py:155-165):
+ *   slow f32 [B,3,Ts,H,W], fast f32 [B,3,Tf,H,W]  (the two pathways pack_pathway_output returns)
+ *   slow_out f32 [B,2048], fast_out f32 [B,256]   (= slow_feature / fast_feature [B,C,1,1,1])
+ */
+int kvq_slowfast_forward(const KvqSlowFastConfig* cfg, const void* const* weights, int num_weights, const float* slow,
+                         const float* fast, int B, int Ts, int Tf, int H, int W, float* slow_out, float* fast_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* torch.linspace(0, T-1, T // alpha).long() (SlowFast_features.py:127-131), fp32 arithmetic as torch evaluates it;
+ * HOST function: writes the indices to out[0..cap) and returns their number */
+int kvq_slow_frame_indices(int T, int alpha, int32_t* out, int cap);
+/* device side of pack_pathway_output (:112-135): slow_out[B,3,T//alpha,H,W] = index_select(frames[B,3,T,H,W], 2, idx) */
+int kvq_pack_pathway_slow_f32(const float* frames, float* slow_out, int B, int T, int H, int W, int alpha,
+                              void* stream);
+
 /* ---- convolution building blocks (channels-last fp16 activations [B,T,H,W,C]) ---- */
 /* out[M,ldo] = act(A[M,K] * W[N,K]^T + bias + resid): conv-as-GEMM with folded BN (Bottleneck.forward :106-126).
  * N (rows of W) is a multiple of 64; columns >= nvalid (0 = N) are padding and never stored */

@@ -29,13 +29,15 @@ struct ConvGeom {
 };
 
 __global__ void __launch_bounds__(CONV_THREADS)
-im2col_cl_kernel(const __half* __restrict__ in, __half* __restrict__ out, const ConvGeom g, long long chunks) {
+im2col_cl_kernel(const __half* __restrict__ in, __half* __restrict__ out, const ConvGeom g, long long row0,
+                 long long chunks) {
   pdl_wait();
   const int kchunks = g.Kp >> 3;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < chunks;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = idx / kchunks;
-    const int k = static_cast<int>(idx - m * kchunks) << 3;
+    const long long ml = idx / kchunks;
+    const long long m = row0 + ml;
+    const int k = static_cast<int>(idx - ml * kchunks) << 3;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (k < g.K) {
       const int tap = k / g.C, c = k - tap * g.C;
@@ -56,14 +58,16 @@ im2col_cl_kernel(const __half* __restrict__ in, __half* __restrict__ out, const 
 
 // stem: fp32 NCDHW input with 3 channels; one half2 (two consecutive k) per thread
 __global__ void __launch_bounds__(CONV_THREADS)
-im2col_stem_kernel(const float* __restrict__ in, __half* __restrict__ out, const ConvGeom g, long long pairs) {
+im2col_stem_kernel(const float* __restrict__ in, __half* __restrict__ out, const ConvGeom g, long long row0,
+                   long long pairs) {
   pdl_wait();
   const int kpairs = g.Kp >> 1;
   const long long plane = static_cast<long long>(g.T) * g.H * g.W;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < pairs;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = idx / kpairs;
-    const int k0 = static_cast<int>(idx - m * kpairs) << 1;
+    const long long ml = idx / kpairs;
+    const long long m = row0 + ml;
+    const int k0 = static_cast<int>(idx - ml * kpairs) << 1;
     long long r = m;
     const int wo = static_cast<int>(r % g.Wo); r /= g.Wo;
     const int ho = static_cast<int>(r % g.Ho); r /= g.Ho;
@@ -88,7 +92,7 @@ im2col_stem_kernel(const float* __restrict__ in, __half* __restrict__ out, const
 
 __global__ void __launch_bounds__(CONV_THREADS)
 maxpool_hw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int Ho, int Wo,
-                  long long chunks) {
+                  int ldo, long long chunks) {
   pdl_wait();
   const int cch = C >> 3;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < chunks;
@@ -120,7 +124,8 @@ maxpool_hw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N
         }
       }
     }
-    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(best);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * ldo + c) =
+        *reinterpret_cast<const uint4*>(best);
   }
   pdl_launch_dependents();
 }
@@ -238,6 +243,41 @@ rowdot_mean_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   pdl_launch_dependents();
 }
 
+// windows of an AvgPool(k, stride 1, no padding) over n positions that cover position p
+__device__ __forceinline__ int pool_cover(int p, int n, int k) {
+  const int lo = p - k + 1 > 0 ? p - k + 1 : 0, hi = p < n - k ? p : n - k;
+  return hi - lo + 1;
+}
+
+__global__ void __launch_bounds__(CONV_THREADS)
+pool_window_weights_kernel(float* __restrict__ out, int T, int H, int W, int kt, int kh, int kw) {
+  pdl_wait();
+  const int L = T * H * W;
+  const float norm = 1.f / (static_cast<float>(T - kt + 1) * (H - kh + 1) * (W - kw + 1) * kt * kh * kw);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const int w = i % W, h = (i / W) % H, t = i / (W * H);
+    out[i] = static_cast<float>(pool_cover(t, T, kt) * pool_cover(h, H, kh) * pool_cover(w, W, kw)) * norm;
+  }
+  pdl_launch_dependents();
+}
+
+struct FrameIdx { int v[64]; };
+
+// out[bc, i, :] = in[bc, idx[i], :]; one float4 per thread (plane % 4 == 0)
+__global__ void __launch_bounds__(CONV_THREADS)
+select_frames_kernel(const float4* __restrict__ in, float4* __restrict__ out, int T, int n, long long plane4,
+                     const FrameIdx idx, long long total4) {
+  pdl_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long frame = i / plane4, off = i - frame * plane4;
+    const long long bc = frame / n;
+    const int fi = static_cast<int>(frame - bc * n);
+    out[i] = __ldg(in + (bc * T + idx.v[fi]) * plane4 + off);
+  }
+  pdl_launch_dependents();
+}
+
 int fill_geom(ConvGeom& g, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh, int sw, int pt,
               int ph, int pw, int Kp) {
   KVQ_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && kt > 0 && kh > 0 && kw > 0 && st > 0 && sh > 0 && sw > 0 &&
@@ -258,36 +298,46 @@ int fill_geom(ConvGeom& g, int B, int T, int H, int W, int C, int kt, int kh, in
 }  // namespace
 
 int launch_im2col_cl(const __half* in, __half* out, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st,
-                     int sh, int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream) {
+                     int sh, int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream, long long row0,
+                     long long rows) {
   ConvGeom g;
   const int rc = fill_geom(g, B, T, H, W, C, kt, kh, kw, st, sh, sw, pt, ph, pw, Kp);
   if (rc != 0) return rc;
   KVQ_REQUIRE(C % 8 == 0, KVQ_ERR_MISALIGNED, "im2col: channels-last input needs C %% 8 == 0 (got %d)", C);
-  const long long chunks = static_cast<long long>(B) * g.To * g.Ho * g.Wo * (Kp / 8);
+  const long long total = static_cast<long long>(B) * g.To * g.Ho * g.Wo;
+  if (rows < 0) rows = total - row0;
+  KVQ_REQUIRE(row0 >= 0 && rows > 0 && row0 + rows <= total, KVQ_ERR_BAD_SHAPE,
+              "im2col: row range [%lld, +%lld) outside %lld output rows", row0, rows, total);
+  const long long chunks = rows * (Kp / 8);
   count_launch();
   return launch_pdl(im2col_cl_kernel, dim3(grid_for(chunks, CONV_THREADS)), dim3(CONV_THREADS), 0, stream, in, out, g,
-                    chunks);
+                    row0, chunks);
 }
 
 int launch_im2col_stem(const float* in, __half* out, int N, int T, int H, int W, int kt, int kh, int kw, int st, int sh,
-                       int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream) {
+                       int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream, long long row0, long long rows) {
   ConvGeom g;
   const int rc = fill_geom(g, N, T, H, W, 3, kt, kh, kw, st, sh, sw, pt, ph, pw, Kp);
   if (rc != 0) return rc;
-  const long long pairs = static_cast<long long>(N) * g.To * g.Ho * g.Wo * (Kp / 2);
+  const long long total = static_cast<long long>(N) * g.To * g.Ho * g.Wo;
+  if (rows < 0) rows = total - row0;
+  KVQ_REQUIRE(row0 >= 0 && rows > 0 && row0 + rows <= total, KVQ_ERR_BAD_SHAPE,
+              "im2col: row range [%lld, +%lld) outside %lld output rows", row0, rows, total);
+  const long long pairs = rows * (Kp / 2);
   count_launch();
   return launch_pdl(im2col_stem_kernel, dim3(grid_for(pairs, CONV_THREADS)), dim3(CONV_THREADS), 0, stream, in, out, g,
-                    pairs);
+                    row0, pairs);
 }
 
-int launch_maxpool_hw(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t stream) {
-  KVQ_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, KVQ_ERR_BAD_SHAPE,
-              "maxpool: bad shape N=%d H=%d W=%d C=%d (C %% 8 == 0)", N, H, W, C);
+int launch_maxpool_hw(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t stream, int ldo) {
+  if (ldo <= 0) ldo = C;
+  KVQ_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ldo >= C && ldo % 8 == 0, KVQ_ERR_BAD_SHAPE,
+              "maxpool: bad shape N=%d H=%d W=%d C=%d ldo=%d (C, ldo %% 8 == 0)", N, H, W, C, ldo);
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long chunks = static_cast<long long>(N) * Ho * Wo * (C / 8);
   count_launch();
   return launch_pdl(maxpool_hw_kernel, dim3(grid_for(chunks, CONV_THREADS)), dim3(CONV_THREADS), 0, stream, in, out, N,
-                    H, W, C, Ho, Wo, chunks);
+                    H, W, C, Ho, Wo, ldo, chunks);
 }
 
 int launch_pool_stats(const __half* in, const float* weights, float* out_mean, float* out_std, int N, int L, int C,
@@ -305,6 +355,29 @@ int launch_rowdot_mean(const float* x, const float* w, const float* b, float* sc
               "rowdot_mean: rows=%d K=%d group=%d (K %% 4 == 0, rows %% group == 0)", rows, K, group);
   count_launch();
   return launch_pdl(rowdot_mean_kernel, dim3(rows / group), dim3(CONV_THREADS), 0, stream, x, w, b, score, K, group);
+}
+
+int launch_pool_window_weights(float* out, int T, int H, int W, int kt, int kh, int kw, cudaStream_t stream) {
+  KVQ_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && T >= kt && H >= kh && W >= kw, KVQ_ERR_BAD_SHAPE,
+              "avg pool kernel (%d,%d,%d) larger than the %dx%dx%d map (AvgPool3d would raise)", kt, kh, kw, T, H, W);
+  count_launch();
+  return launch_pdl(pool_window_weights_kernel, dim3(grid_for(static_cast<long long>(T) * H * W, CONV_THREADS)),
+                    dim3(CONV_THREADS), 0, stream, out, T, H, W, kt, kh, kw);
+}
+
+int launch_select_frames(const float* in, float* out, int BC, int T, long long plane, const int* idx, int n,
+                         cudaStream_t stream) {
+  KVQ_REQUIRE(BC > 0 && T > 0 && n > 0 && n <= 64 && plane > 0 && plane % 4 == 0, KVQ_ERR_BAD_SHAPE,
+              "select_frames: BC=%d T=%d n=%d plane=%lld (n <= 64, H*W %% 4 == 0)", BC, T, n, plane);
+  FrameIdx fi;
+  for (int i = 0; i < n; ++i) {
+    KVQ_REQUIRE(idx[i] >= 0 && idx[i] < T, KVQ_ERR_BAD_SHAPE, "select_frames: index %d outside [0,%d)", idx[i], T);
+    fi.v[i] = idx[i];
+  }
+  const long long total4 = static_cast<long long>(BC) * n * (plane / 4);
+  count_launch();
+  return launch_pdl(select_frames_kernel, dim3(grid_for(total4, CONV_THREADS)), dim3(CONV_THREADS), 0, stream,
+                    reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), T, n, plane / 4, fi, total4);
 }
 
 }  // namespace kvq

@@ -182,12 +182,20 @@ int launch_pack_split(const float* in, __half* out, int rows, int K, cudaStream_
 // ---- convolution support (SimpleVQA ResNet-50 / SlowFast): channels-last fp16 activations ----
 // in [B,T,H,W,C] -> A [B*To*Ho*Wo, Kp], K index = ((dt*kh + dh)*kw + dw)*C + c, zero padding, Kp >= kt*kh*kw*C
 int launch_im2col_cl(const __half* in, __half* out, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st,
-                     int sh, int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream);
+                     int sh, int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream, long long row0 = 0,
+                     long long rows = -1);   // [row0, row0 + rows) of the output rows only (out = first row of the range)
 // stem: in fp32 [N,3,T,H,W] (NCDHW) -> A [N*To*Ho*Wo, Kp], K index = ((dt*kh + dh)*kw + dw)*3 + c
 int launch_im2col_stem(const float* in, __half* out, int N, int T, int H, int W, int kt, int kh, int kw, int st, int sh,
-                       int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream);
+                       int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream, long long row0 = 0,
+                       long long rows = -1);
 // max pool (1,3,3) / stride (1,2,2) / pad (0,1,1) on [N,H,W,C] fp16
-int launch_maxpool_hw(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t stream);
+int launch_maxpool_hw(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t stream, int ldo = 0);
+// weights of "AvgPool3d(kernel, stride 1) then global mean" over a [T,H,W] map: w[t,h,w] = (windows covering the
+// position) / (number of windows * kernel volume); out fp32 [T*H*W]
+int launch_pool_window_weights(float* out, int T, int H, int W, int kt, int kh, int kw, cudaStream_t stream);
+// pack_pathway_output (SlowFast_features.py:112-135): slow[b,c,i] = frames[b,c,idx[i]], idx = linspace(0,T-1,T/4).long()
+int launch_select_frames(const float* in, float* out, int BC, int T, long long plane, const int* idx, int n,
+                         cudaStream_t stream);
 // per (n, c): weighted mean over the HW (or THW) axis and optional unbiased std; in [N, L, C] fp16; weights fp32 [L]
 // or nullptr (uniform); outputs fp32 with row stride ldo: mean at out_mean[n*ldo + c], std at out_std[n*ldo + c]
 int launch_pool_stats(const __half* in, const float* weights, float* out_mean, float* out_std, int N, int L, int C,

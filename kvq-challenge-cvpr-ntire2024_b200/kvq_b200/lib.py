@@ -19,6 +19,10 @@ class KvqResNetConfig(ctypes.Structure):
     _fields_ = [("layers", c_int32 * 4), ("feat3d_dim", c_int32), ("head", c_int32)]
 
 
+class KvqSlowFastConfig(ctypes.Structure):
+    _fields_ = [("depths", c_int32 * 4), ("alpha", c_int32), ("slow_pool", c_int32 * 3), ("fast_pool", c_int32 * 3)]
+
+
 _I3 = c_int32 * 3
 _F3 = c_float * 3
 
@@ -53,6 +57,12 @@ PROTOTYPES = {
     "kvq_simplevqa_workspace_bytes": (c_size_t, [POINTER(KvqResNetConfig), c_int, c_int, c_int, c_int]),
     "kvq_simplevqa_forward": (c_int, [POINTER(KvqResNetConfig), POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int,
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_slowfast_num_weights": (c_int, [POINTER(KvqSlowFastConfig)]),
+    "kvq_slowfast_workspace_bytes": (c_size_t, [POINTER(KvqSlowFastConfig), c_int, c_int, c_int, c_int, c_int]),
+    "kvq_slowfast_forward": (c_int, [POINTER(KvqSlowFastConfig), POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int,
+                                     c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_slow_frame_indices": (c_int, [c_int, c_int, POINTER(c_int32), c_int]),
+    "kvq_pack_pathway_slow_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "kvq_conv_gemm_f16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_void_p]),
     "kvq_im2col_cl_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32),

@@ -505,3 +505,135 @@ class SimpleVQAWeights:
         feats, score = alloc()
         self._launch(x, feat3d, feats, score, ws)
         return feats, score
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SlowFast-R50 motion features (SlowFast_features.py:112-165)
+# ---------------------------------------------------------------------------------------------------------------
+def slow_frame_indices(T, alpha=4):
+    """torch.linspace(0, T-1, T // alpha).long() (SlowFast_features.py:127-131), evaluated by the library."""
+    buf = (ctypes.c_int32 * 64)()
+    n = _l.load().kvq_slow_frame_indices(int(T), int(alpha), buf, 64)
+    if n < 0:
+        _l.check(n, "slow_frame_indices")
+    return [int(buf[i]) for i in range(n)]
+
+
+def pack_pathway_slow(frames, alpha=4):
+    """frames f32 [B,3,T,H,W] (CUDA) -> slow pathway [B,3,T//alpha,H,W]."""
+    _need_cuda(frames)
+    frames = frames.contiguous()
+    B, C, T, H, W = frames.shape
+    if C != 3 or frames.dtype != torch.float32:
+        raise RuntimeError("kvq_b200: pack_pathway_slow takes float32 [B,3,T,H,W] frames")
+    out = torch.empty((B, 3, T // alpha, H, W), dtype=torch.float32, device=frames.device)
+    _l.check(_l.load().kvq_pack_pathway_slow_f32(_p(frames), _p(out), B, T, H, W, int(alpha), _stream()),
+             "pack_pathway_slow_f32")
+    return out
+
+
+class SlowFastWeights:
+    """Device-resident packed weights of the SlowFast-R50 trunk in the order include/kvq_b200.h documents.  `sd` maps
+    the state_dict names of the reference's `slowfast` module (`feature_extraction.<block>.` + pytorchvideo's names,
+    oracle/slowfast.py) to tensors."""
+
+    DEPTHS = (3, 4, 6, 3)
+
+    def __init__(self, sd, device, prefix="feature_extraction.", depths=DEPTHS, alpha=4, slow_pool=(8, 7, 7),
+                 fast_pool=(32, 7, 7), eps=1e-5):
+        self.device = torch.device(device)
+        self.cfg = _l.KvqSlowFastConfig()
+        for i, n in enumerate(depths):
+            self.cfg.depths[i] = int(n)
+        self.cfg.alpha = int(alpha)
+        for i in range(3):
+            self.cfg.slow_pool[i] = int(slow_pool[i])
+            self.cfg.fast_pool[i] = int(fast_pool[i])
+
+        def t(k):
+            return sd[k].detach().to(self.device, torch.float32)
+
+        def conv_bn(conv, bn):
+            return list(pack_conv_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
+                                                              ("weight", "bias", "running_mean", "running_var")], eps))
+
+        p = prefix + "0."
+        ts = conv_bn(p + "multipathway_blocks.0.conv", p + "multipathway_blocks.0.norm")
+        ts += conv_bn(p + "multipathway_blocks.1.conv", p + "multipathway_blocks.1.norm")
+        ts += conv_bn(p + "multipathway_fusion.conv_fast_to_slow", p + "multipathway_fusion.norm")
+        for s, depth in enumerate(depths):
+            p = f"{prefix}{s + 1}."
+            for path in (0, 1):
+                for j in range(depth):
+                    b = f"{p}multipathway_blocks.{path}.res_blocks.{j}."
+                    if j == 0:
+                        ts += conv_bn(b + "branch1_conv", b + "branch1_norm")
+                    for c in "abc":
+                        ts += conv_bn(b + "branch2.conv_" + c, b + "branch2.norm_" + c)
+            if s < 3:
+                ts += conv_bn(p + "multipathway_fusion.conv_fast_to_slow", p + "multipathway_fusion.norm")
+        self.tensors = ts
+        n = _l.load().kvq_slowfast_num_weights(ctypes.byref(self.cfg))
+        if n != len(ts):
+            raise RuntimeError(f"kvq_b200: SlowFast weight table has {len(ts)} entries, library expects {n}")
+        self.ptrs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in ts])
+        self.slow_dim, self.fast_dim = 2048, 256
+        self._ws = None
+        self._graphs = {}
+
+    def workspace(self, B, Ts, Tf, H, W):
+        need = _l.load().kvq_slowfast_workspace_bytes(ctypes.byref(self.cfg), B, Ts, Tf, H, W)
+        if need == 0:
+            raise RuntimeError(f"kvq_b200: cannot plan a SlowFast forward on slow [{B},3,{Ts},{H},{W}] / fast "
+                               f"[{B},3,{Tf},{H},{W}]: {_l.last_error()}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._graphs = {}
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _launch(self, slow, fast, so, fo, ws):
+        B, _, Ts, H, W = slow.shape
+        rc = _l.load().kvq_slowfast_forward(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(slow), _p(fast),
+                                            B, Ts, fast.shape[2], H, W, _p(so), _p(fo), _p(ws), ws.numel(), _stream())
+        _l.check(rc, "slowfast_forward")
+
+    def forward(self, slow, fast, graph=None):
+        """slow f32 [B,3,Ts,H,W], fast f32 [B,3,Tf,H,W] -> (slow_feature f32 [B,2048], fast_feature f32 [B,256])."""
+        for x in (slow, fast):
+            if not x.is_cuda or x.dtype != torch.float32:
+                raise RuntimeError("kvq_b200: SlowFast pathways must be float32 CUDA tensors (no CPU fallback exists)")
+        slow, fast = slow.contiguous(), fast.contiguous()
+        B, _, Ts, H, W = slow.shape
+        if fast.shape[0] != B or tuple(fast.shape[3:]) != (H, W) or slow.shape[1] != 3 or fast.shape[1] != 3:
+            raise RuntimeError(f"kvq_b200: pathway shapes {tuple(slow.shape)} / {tuple(fast.shape)} do not match")
+        ws = self.workspace(B, Ts, fast.shape[2], H, W)
+        if graph is None:
+            graph = os.environ.get("KVQ_CUDA_GRAPH", "0") == "1"
+
+        def alloc():
+            return (torch.empty((B, self.slow_dim), dtype=torch.float32, device=slow.device),
+                    torch.empty((B, self.fast_dim), dtype=torch.float32, device=slow.device))
+
+        if graph:
+            key = (slow.data_ptr(), fast.data_ptr(), tuple(slow.shape), tuple(fast.shape), ws.data_ptr())
+            entry = self._graphs.get(key)
+            if entry is None:
+                so, fo = alloc()
+                self._launch(slow, fast, so, fo, ws)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = _l.load().kvq_launch_count()
+                with torch.cuda.graph(g):
+                    self._launch(slow, fast, so, fo, ws)
+                nodes = int(_l.load().kvq_launch_count() - n0)
+                if len(self._graphs) >= 8:
+                    self._graphs.pop(next(iter(self._graphs)))
+                entry = self._graphs[key] = (g, so, fo, nodes)
+            entry[0].replay()
+            global GRAPH_KERNEL_LAUNCHES
+            GRAPH_KERNEL_LAUNCHES += entry[3]
+            return entry[1], entry[2]
+        so, fo = alloc()
+        self._launch(slow, fast, so, fo, ws)
+        return so, fo

@@ -148,3 +148,55 @@ def motion_features(shape, seed):
     """Stand-in for the pre-extracted SlowFast features batch['feat'] [B,T,2304] (non-negative: they are pooled
     post-ReLU activations in the reference pipeline)."""
     return torch.randn(tuple(shape), generator=torch.Generator().manual_seed(seed)).abs()
+
+
+def slowfast_shapes(prefix="feature_extraction."):
+    """Float parameter / buffer shapes of slowfast().feature_extraction (SlowFast_features.py:137-152) = blocks[0..4]
+    of pytorchvideo's slowfast_r50, under pytorchvideo's module names (oracle/slowfast.py header)."""
+    s = {}
+
+    def bn(p, c):
+        for leaf in ("weight", "bias", "running_mean", "running_var"):
+            s[p + leaf] = (c,)
+
+    p = prefix + "0."
+    s[p + "multipathway_blocks.0.conv.weight"] = (64, 3, 1, 7, 7)
+    bn(p + "multipathway_blocks.0.norm.", 64)
+    s[p + "multipathway_blocks.1.conv.weight"] = (8, 3, 5, 7, 7)
+    bn(p + "multipathway_blocks.1.norm.", 8)
+    s[p + "multipathway_fusion.conv_fast_to_slow.weight"] = (16, 8, 7, 1, 1)
+    bn(p + "multipathway_fusion.norm.", 16)
+    cs, cf = 80, 8
+    for i, depth in enumerate((3, 4, 6, 3)):
+        p = f"{prefix}{i + 1}."
+        for path, (cin, inner, ka) in enumerate(((cs, 64 << i, (1, 1, 3, 3)[i]), (cf, 8 << i, 3))):
+            for j in range(depth):
+                b = f"{p}multipathway_blocks.{path}.res_blocks.{j}."
+                c_in = cin if j == 0 else inner * 4
+                if j == 0:
+                    s[b + "branch1_conv.weight"] = (inner * 4, c_in, 1, 1, 1)
+                    bn(b + "branch1_norm.", inner * 4)
+                s[b + "branch2.conv_a.weight"] = (inner, c_in, ka, 1, 1)
+                bn(b + "branch2.norm_a.", inner)
+                s[b + "branch2.conv_b.weight"] = (inner, inner, 1, 3, 3)
+                bn(b + "branch2.norm_b.", inner)
+                s[b + "branch2.conv_c.weight"] = (inner * 4, inner, 1, 1, 1)
+                bn(b + "branch2.norm_c.", inner * 4)
+        cs, cf = (64 << i) * 4, (8 << i) * 4
+        if i < 3:
+            s[p + "multipathway_fusion.conv_fast_to_slow.weight"] = (2 * cf, cf, 7, 1, 1)
+            bn(p + "multipathway_fusion.norm.", 2 * cf)
+            cs += 2 * cf
+    return s
+
+
+def slowfast_state_dict(seed, prefix="feature_extraction."):
+    """Seeded weights of the SlowFast trunk (pretrained Kinetics weights are unavailable offline)."""
+    return synth_state_dict(slowfast_shapes(prefix), seed)
+
+
+def slowfast_frames(shape, seed):
+    """Synthetic Kinetics-normalised frames [B,3,T,H,W] ((v - 0.45) / 0.225 of uniform [0,1] pixels,
+    SlowFast_features.py:173-174)."""
+    u = torch.rand(tuple(shape), generator=torch.Generator().manual_seed(seed))
+    return (u - 0.45) / 0.225
