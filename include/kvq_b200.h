@@ -143,7 +143,7 @@ typedef struct KvqResNetConfig {
  * (eval mode): w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps); weights are fp16
  * [Cout, Kp] with the K index tap-major / channel-minor ((dh*kw + dw)*Cin + c, zero padded to Kp % 8 == 0), biases
  * fp32 [Cout]:
- *   [0],[1]  conv1+bn1 (7x7/2, Kp = 152)
+ *   [0],[1]  conv1+bn1 (7x7/2) in the stem layout of kvq_stem_conv_f16
  *   then per layer, per block: conv1+bn1, conv2+bn2, conv3+bn3 and, for the first block of a layer,
  *   downsample.0+downsample.1  (w, b each)
  *   then (head) w_eff f32 [feature_dim] = quality.1.weight @ quality.0.weight,
@@ -177,7 +177,7 @@ typedef struct KvqSlowFastConfig {
 /*
  * Weight pointer table for kvq_slowfast_forward: every convolution with its eval-mode BatchNorm folded in, as an
  * (fp16 [round64(Cout), round8(K)] tap-major / channel-minor weight, fp32 [round64(Cout)] shift) pair, in this order:
- *   slow stem, fast stem, block-0 fusion (conv_fast_to_slow + norm);
+ *   slow stem, fast stem (both in the stem layout of kvq_stem_conv_f16), block-0 fusion (conv_fast_to_slow + norm);
  *   then per stage s = 0..3: every slow res block (branch1 first for block 0; conv_a, conv_b, conv_c), every fast
  *   res block (same), then for s < 3 the stage's fusion.
  */
@@ -209,6 +209,14 @@ int kvq_im2col_cl_f16(const void* in_f16, void* out_f16, int B, int T, int H, in
 /* same for the 3-channel fp32 NCDHW network input */
 int kvq_im2col_stem_f32(const float* in, void* out_f16, int N, int T, int H, int W, const int32_t kernel[3],
                         const int32_t stride[3], const int32_t pad[3], int Kp, void* stream);
+/* Implicit-GEMM stem: Conv3d(3 -> cout, (kt,7,7), stride (1,2,2), padding (kt/2,3,3)) + folded BN shift + ReLU
+ * (simpleVQA_model.py:235-237 with kt = 1, cout = 64; SlowFast stems kt = 1 / cout = 64 and kt = 5 / cout = 8).
+ *   x f32 [N,3,T,H,W]; out f16 [N*T*Hs*Ws, cout] channels-last
+ *   w_packed f16 [kt*3][rows][64], rows = kvq_stem_weight_rows(cout): block (dt*3 + c), row n, column dy*8 + dx holds
+ *   w[n][c][dt][dy][dx] * bn_scale[n] (zero for dy = 7, dx = 7, n >= cout); shift f32 [rows] */
+int kvq_stem_weight_rows(int cout);
+int kvq_stem_conv_f16(const float* x, const void* w_packed_f16, const float* shift, void* out_f16, int N, int T, int H,
+                      int W, int kt, int cout, void* stream);
 /* nn.MaxPool2d(3, 2, 1) (:153) on [N,H,W,C] */
 int kvq_maxpool_hw_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream);
 /* per (n, c) weighted mean over L (weights NULL = 1/L) and, if out_std != NULL, the unbiased std

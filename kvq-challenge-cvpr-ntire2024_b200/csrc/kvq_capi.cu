@@ -167,7 +167,7 @@ int kvq_profile_num_categories(void) { return PK_COUNT * 4; }
 const char* kvq_profile_category_name(int cat) {
   static const char* kinds[PK_COUNT] = {"embed_im2col", "embed_gemm", "ln_window", "qkv_gemm", "window_attn",
                                         "proj_gemm", "ln_rows", "fc1_gemm", "fc2_gemm", "merge_ln", "merge_gemm",
-                                        "final_ln", "head", "fused_mlp", "conv_im2col", "conv_gemm", "conv_pool"};
+                                        "final_ln", "head", "fused_mlp", "conv_im2col", "conv_gemm", "conv_pool", "conv_stem"};
   static thread_local char buf[48];
   if (cat < 0 || cat >= PK_COUNT * 4) return "?";
   snprintf(buf, sizeof(buf), "%s.s%d", kinds[cat / 4], cat % 4);
@@ -419,6 +419,14 @@ int kvq_im2col_stem_f32(const float* in, void* out_f16, int N, int T, int H, int
                             stride[1], stride[2], pad[0], pad[1], pad[2], Kp, static_cast<cudaStream_t>(stream));
 }
 
+int kvq_stem_conv_f16(const float* x, const void* w_packed_f16, const float* shift, void* out_f16, int N, int T, int H,
+                      int W, int kt, int cout, void* stream) {
+  return launch_stem_conv(x, static_cast<const __half*>(w_packed_f16), shift, static_cast<__half*>(out_f16), N, T, H, W,
+                          kt, cout, static_cast<cudaStream_t>(stream));
+}
+
+int kvq_stem_weight_rows(int cout) { return stem_weight_rows(cout); }
+
 int kvq_maxpool_hw_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream) {
   return launch_maxpool_hw(static_cast<const __half*>(in_f16), static_cast<__half*>(out_f16), N, H, W, C,
                            static_cast<cudaStream_t>(stream));
@@ -449,8 +457,6 @@ struct ResPlan {
   size_t total;
 };
 
-constexpr int RES_STEM_KP = 152;  // 7*7*3 = 147 padded to 16-byte rows
-
 inline int conv_out(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
 
 int make_res_plan(const KvqResNetConfig* cfg, int B, int T, int H, int W, ResPlan* pl) {
@@ -463,7 +469,7 @@ int make_res_plan(const KvqResNetConfig* cfg, int B, int T, int H, int W, ResPla
   const size_t N = static_cast<size_t>(B) * T;
   pl->Hs = conv_out(H, 7, 2, 3); pl->Ws = conv_out(W, 7, 2, 3);
   pl->Hp = conv_out(pl->Hs, 3, 2, 1); pl->Wp = conv_out(pl->Ws, 3, 2, 1);
-  size_t col = N * pl->Hs * pl->Ws * RES_STEM_KP * 2;
+  size_t col = 0;
   size_t act = N * pl->Hs * pl->Ws * 64 * 2;
   int h = pl->Hp, w = pl->Wp;
   for (int s = 0; s < 4; ++s) {
@@ -542,15 +548,12 @@ int kvq_simplevqa_forward(const KvqResNetConfig* cfg, const void* const* weights
   int wi = 0;
   auto W_ = [&]() { return weights[wi++]; };
 
-  // stem: conv 7x7/2 + BN + ReLU (:235-237), max pool 3x3/2 (:238); frames are the T axis of x (:225-231)
-  {
-    ProfScope ps(PK_CONV_IM2COL, 0, st);
-    rc = launch_im2col_stem(x, col, B, T, H, W, 1, 7, 7, 1, 2, 2, 0, 3, 3, RES_STEM_KP, st);
-  }
-  if (rc != 0) return rc;
+  // stem: conv 7x7/2 + BN + ReLU (:235-237), max pool 3x3/2 (:238); frames are the T axis of x (:225-231).
+  // Implicit GEMM straight from the fp32 NCDHW input (kvq_stem.cu): no patch matrix
   {
     const void* w = W_(); const void* b = W_();
-    rc = conv_gemm(col, RES_STEM_KP, w, b, nullptr, 0, act[0], N * pl.Hs * pl.Ws, 64, RES_STEM_KP, true, 0, st);
+    ProfScope ps(PK_CONV_STEM, 0, st);
+    rc = launch_stem_conv(x, static_cast<const __half*>(w), static_cast<const float*>(b), act[0], B, T, H, W, 1, 64, st);
   }
   if (rc != 0) return rc;
   {

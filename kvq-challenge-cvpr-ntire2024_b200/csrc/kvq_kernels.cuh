@@ -19,7 +19,7 @@ int prof_collect(float* ms, int* launches, int ncat);
 // timing categories: kind * 4 + stage
 enum ProfKind : int {
   PK_EMBED_IM2COL = 0, PK_EMBED_GEMM, PK_LN_WINDOW, PK_QKV_GEMM, PK_ATTN, PK_PROJ_GEMM, PK_LN_ROWS, PK_FC1_GEMM,
-  PK_FC2_GEMM, PK_MERGE_LN, PK_MERGE_GEMM, PK_FINAL_LN, PK_HEAD, PK_FUSED_MLP, PK_CONV_IM2COL, PK_CONV_GEMM, PK_CONV_POOL,
+  PK_FC2_GEMM, PK_MERGE_LN, PK_MERGE_GEMM, PK_FINAL_LN, PK_HEAD, PK_FUSED_MLP, PK_CONV_IM2COL, PK_CONV_GEMM, PK_CONV_POOL, PK_CONV_STEM,
   PK_COUNT
 };
 struct ProfScope {
@@ -188,6 +188,11 @@ int launch_im2col_cl(const __half* in, __half* out, int B, int T, int H, int W, 
 int launch_im2col_stem(const float* in, __half* out, int N, int T, int H, int W, int kt, int kh, int kw, int st, int sh,
                        int sw, int pt, int ph, int pw, int Kp, cudaStream_t stream, long long row0 = 0,
                        long long rows = -1);
+// implicit-GEMM stem: Conv3d(3 -> cout, (kt,7,7), stride (1,2,2), pad (kt/2,3,3)) + shift + ReLU on fp32 NCDHW input;
+// w_packed fp16 [kt*3][stem_weight_rows(cout)][64] with k = dy*8 + dx per (frame tap, channel) block; out [N*T*Hs*Ws, cout]
+int stem_weight_rows(int cout);
+int launch_stem_conv(const float* x, const __half* w_packed, const float* shift, __half* out, int N, int T, int H, int W,
+                     int kt, int cout, cudaStream_t stream);
 // max pool (1,3,3) / stride (1,2,2) / pad (0,1,1) on [N,H,W,C] fp16
 int launch_maxpool_hw(const __half* in, __half* out, int N, int H, int W, int C, cudaStream_t stream, int ldo = 0);
 // weights of "AvgPool3d(kernel, stride 1) then global mean" over a [T,H,W] map: w[t,h,w] = (windows covering the

@@ -21,8 +21,6 @@ inline int round8(int v) { return (v + 7) / 8 * 8; }
 inline int round64(int v) { return (v + 63) / 64 * 64; }
 
 constexpr int SF_FUSE_KT = 7;          // conv_fast_to_slow kernel (7,1,1), stride (alpha,1,1), padding (3,0,0)
-constexpr int SF_SLOW_STEM_KP = 152;   // 1*7*7*3 = 147
-constexpr int SF_FAST_STEM_KP = 736;   // 5*7*7*3 = 735
 constexpr int SF_SLOW_KA[4] = {1, 1, 3, 3};
 constexpr int SF_FAST_KA[4] = {3, 3, 3, 3};
 constexpr size_t SF_SLACK = 256 * 4608 * 2;  // TMA tile overhang past the last row of a buffer
@@ -58,8 +56,7 @@ int make_sf_plan(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int
   KVQ_REQUIRE(nf * pl->Hs * pl->Ws < (1ull << 31), KVQ_ERR_BAD_SHAPE, "slowfast: %zu stem rows (int32 overflow)",
               nf * pl->Hs * pl->Ws);
   size_t sa = ns * pl->Hs * pl->Ws * 64 * 2, fa = nf * pl->Hs * pl->Ws * 8 * 2;
-  size_t col = std::max(ns * pl->Hs * pl->Ws * SF_SLOW_STEM_KP * 2, nf * pl->Hs * pl->Ws * SF_FAST_STEM_KP * 2);
-  size_t max_row = SF_FAST_STEM_KP * 2;
+  size_t col = 0, max_row = 0;
   sa = std::max(sa, ns * pl->Hp * pl->Wp * 80 * 2);
   col = std::max(col, ns * pl->Hp * pl->Wp * static_cast<size_t>(SF_FUSE_KT * 8) * 2);
   int h = pl->Hp, w = pl->Wp, cs = 80, cf = 8;
@@ -147,24 +144,10 @@ int conv_op(const SfCtx& cx, const __half* in, int B, int T, int H, int W, int C
   return KVQ_OK;
 }
 
-// stem: fp32 NCDHW input -> conv (kt,7,7)/s(1,2,2) + BN + ReLU -> [B,T,Hs,Ws,cout] fp16
-int stem_op(const SfCtx& cx, const float* x, int B, int T, int H, int W, int kt, int Kp, const ConvW& cw, int cout,
-            __half* out, int Hs, int Ws) {
-  const long long M = static_cast<long long>(B) * T * Hs * Ws;
-  long long chunk = static_cast<long long>((cx.col_bytes - SF_SLACK) / (static_cast<size_t>(Kp) * 2)) / 128 * 128;
-  KVQ_REQUIRE(chunk >= 128, KVQ_ERR_WORKSPACE, "slowfast: im2col scratch too small for the stem");
-  for (long long m0 = 0; m0 < M; m0 += chunk) {
-    const long long rows = std::min(chunk, M - m0);
-    int rc;
-    {
-      ProfScope ps(PK_CONV_IM2COL, 0, cx.st);
-      rc = launch_im2col_stem(x, cx.col, B, T, H, W, kt, 7, 7, 1, 2, 2, kt / 2, 3, 3, Kp, cx.st, m0, rows);
-    }
-    if (rc != 0) return rc;
-    rc = gemm_conv(cx.col, Kp, cw, round64(cout), cout, Kp, nullptr, 0, out + m0 * cout, cout, rows, true, 0, cx.st);
-    if (rc != 0) return rc;
-  }
-  return KVQ_OK;
+// stem: fp32 NCDHW input -> conv (kt,7,7)/s(1,2,2) + BN + ReLU -> [B,T,Hs,Ws,cout] fp16 (implicit GEMM, kvq_stem.cu)
+int stem_op(const SfCtx& cx, const float* x, int B, int T, int H, int W, int kt, const ConvW& cw, int cout, __half* out) {
+  ProfScope ps(PK_CONV_STEM, 0, cx.st);
+  return launch_stem_conv(x, cw.w, cw.b, out, B, T, H, W, kt, cout, cx.st);
 }
 
 struct Pathway {
@@ -296,14 +279,14 @@ int kvq_slowfast_forward(const KvqSlowFastConfig* cfg, const void* const* weight
   // block 0: stems (conv + BN + ReLU, max pool (1,3,3)/s(1,2,2)/p(0,1,1)); the slow pool output leaves room for the
   // 16 fused channels
   const ConvW ws = next(), wf = next(), wfuse0 = next();
-  rc = stem_op(cx, slow, B, Ts, H, W, 1, SF_SLOW_STEM_KP, ws, 64, S.act[0], pl.Hs, pl.Ws);
+  rc = stem_op(cx, slow, B, Ts, H, W, 1, ws, 64, S.act[0]);
   if (rc != 0) return rc;
   {
     ProfScope ps(PK_CONV_POOL, 0, st);
     rc = launch_maxpool_hw(S.act[0], S.act[1], B * Ts, pl.Hs, pl.Ws, 64, st, 80);
   }
   if (rc != 0) return rc;
-  rc = stem_op(cx, fast, B, Tf, H, W, 5, SF_FAST_STEM_KP, wf, 8, F.act[0], pl.Hs, pl.Ws);
+  rc = stem_op(cx, fast, B, Tf, H, W, 5, wf, 8, F.act[0]);
   if (rc != 0) return rc;
   {
     ProfScope ps(PK_CONV_POOL, 0, st);

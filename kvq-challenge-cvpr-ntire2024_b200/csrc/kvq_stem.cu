@@ -1,0 +1,240 @@
+// Implicit-GEMM stem convolution for 3-channel fp32 network inputs: Conv3d(3 -> cout, (KT,7,7), stride (1,2,2),
+// padding (KT/2,3,3)) + folded BatchNorm + ReLU, fp16 channels-last output.  Serves
+//   SlowFast slow stem  (KT = 1, cout 64), fast stem (KT = 5, cout 8)      -- oracle/slowfast.py:_stem
+//   SimpleVQA ResNet-50 conv1 + bn1 + relu (KT = 1, cout 64; frames = the T axis) -- simpleVQA_model.py:235-237
+//
+// No patch matrix ever reaches HBM (the explicit im2col of the fast stem is 772 MB per 32x256x256 clip).  A CTA owns an
+// 8 x 16 tile of output pixels and walks the output frames of its work item:
+//   * the input halo (22 x 38 pixels x 3 channels) of each needed frame is converted to fp16 into a KT-slot ring in
+//     shared memory (one new frame per output frame),
+//   * per (frame tap dt, channel c) the 128 threads build the [128 pixels x 64] K-block (k = dy*8 + dx; the dy = 7 /
+//     dx = 7 slots carry zero weights) straight into the 128B-swizzled UMMA layout: 4 aligned 32-bit shared loads and
+//     one conflict-free 16-byte shared store per kernel row,
+//   * one thread issues 4 tcgen05.mma (M128 x N{16,64} x K16) per K-block into a TMEM accumulator; the A tile is
+//     double-buffered so the build of block k+1 overlaps the MMAs of block k,
+//   * epilogue: tcgen05.ld (thread = pixel) -> + shift, ReLU -> fp16 -> 16-byte stores.
+// Two CTAs per SM overlap each other's load / build / epilogue phases.
+#include <algorithm>
+
+#include "kvq_common.cuh"
+#include "kvq_kernels.cuh"
+
+namespace kvq {
+
+namespace {
+
+constexpr int ST_THREADS = 128;
+constexpr int ST_TY = 8, ST_TX = 16;          // output pixels per tile
+constexpr int ST_PR = 22, ST_PC = 48;         // halo rows / row pitch (halfs); pitch % 64 == 48 keeps the loads conflict-free
+constexpr int ST_PCV = 38;                    // halo columns actually read
+constexpr int ST_SLOT = 3 * ST_PR * ST_PC;    // halfs per frame slot
+constexpr int ST_A_BYTES = 128 * 128;         // one K-block of A: 128 rows x 64 halfs
+
+struct StemParams {
+  const float* x;        // [N,3,T,H,W]
+  const __half* w;       // [KT*3][NP][64]
+  const float* shift;    // [NP]
+  __half* out;           // [N*T*Hs*Ws, COUT]
+  int N, T, H, W, Hs, Ws;
+  int tseg, nseg, ty, tx;
+  int items;
+};
+
+template <int KT, int NP>
+struct StemCfg {
+  static constexpr int KB = KT * 3;
+  static constexpr int B_BYTES = KB * NP * 128;
+  static constexpr int PATCH_BYTES = KT * ST_SLOT * 2;
+  static constexpr int SMEM = 2 * ST_A_BYTES + B_BYTES + PATCH_BYTES + 64 + 1024;
+  static constexpr int TMEM_COLS = NP <= 32 ? 32 : 64;
+};
+
+template <int KT, int NP, int COUT>
+__global__ void __launch_bounds__(ST_THREADS, 2)
+stem_conv_kernel(const StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  using C = StemCfg<KT, NP>;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * ST_A_BYTES;
+  __half* patch = reinterpret_cast<__half*>(sB + C::B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + C::PATCH_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  pdl_wait();
+  // weights -> 128B-swizzled K-major B tiles, one [NP x 64] tile per K-block
+  for (int i = tid; i < C::KB * NP * 8; i += ST_THREADS) {
+    const int chunk = i & 7, n = (i >> 3) % NP, kb = i / (8 * NP);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w) + i);
+    *reinterpret_cast<uint4*>(sB + kb * (NP * 128) + (n >> 3) * 1024 + (n & 7) * 128 + ((chunk ^ (n & 7)) << 4)) = v;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+  pdl_launch_dependents();
+
+  const int py = tid >> 4, px = tid & 15;
+  const long long plane = static_cast<long long>(p.H) * p.W;
+  constexpr uint32_t idesc = umma_idesc_f16(128, NP, 0, 0);
+  uint32_t uses[2] = {0u, 0u};      // commits issued so far on each A buffer (uniform across the CTA)
+  float shift[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) shift[j] = __ldg(p.shift + j);
+
+  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    int r = item;
+    const int xt = r % p.tx; r /= p.tx;
+    const int yt = r % p.ty; r /= p.ty;
+    const int seg = r % p.nseg;
+    const int n = r / p.nseg;
+    const int y0 = yt * ST_TY, x0 = xt * ST_TX;
+    const int t_begin = seg * p.tseg, t_end = min(t_begin + p.tseg, p.T);
+    const float* xn = p.x + static_cast<long long>(n) * 3 * p.T * plane;
+
+    // halo of input frame f -> ring slot (f mod KT); zeros outside the clip / frame
+    auto load_frame = [&](int f) {
+      const int slot = ((f % KT) + KT) % KT;
+      __half* dst = patch + slot * ST_SLOT;
+      const bool f_ok = f >= 0 && f < p.T;
+      for (int i = tid; i < 3 * ST_PR * 40; i += ST_THREADS) {
+        const int col = i % 40, rr = (i / 40) % ST_PR, c = i / (40 * ST_PR);
+        if (col >= ST_PCV) continue;
+        const int iy = 2 * y0 - 3 + rr, ix = 2 * x0 - 3 + col;
+        float v = 0.f;
+        if (f_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+          v = __ldg(xn + (static_cast<long long>(c) * p.T + f) * plane + static_cast<long long>(iy) * p.W + ix);
+        dst[(c * ST_PR + rr) * ST_PC + col] = __float2half_rn(v);
+      }
+    };
+    __syncthreads();   // every build of the previous item has been issued before its ring is overwritten
+    for (int f = t_begin - KT / 2; f < t_begin + KT / 2; ++f) load_frame(f);
+
+    for (int t = t_begin; t < t_end; ++t) {
+      load_frame(t + KT / 2);
+      __syncthreads();
+      for (int kb = 0; kb < C::KB; ++kb) {
+        const int dt = kb / 3, c = kb - dt * 3;
+        const int buf = kb & 1;
+        if (uses[buf] > 0) mbar_wait(&bars[buf], (uses[buf] - 1) & 1);   // the MMAs that read this buffer are done
+        const int f = t + dt - KT / 2;
+        const int slot = ((f % KT) + KT) % KT;
+        const __half* src = patch + slot * ST_SLOT + c * (ST_PR * ST_PC) + (2 * py) * ST_PC + 2 * px;
+        uint8_t* arow = sA + buf * ST_A_BYTES + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll
+        for (int dy = 0; dy < 8; ++dy) {
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + dy * ST_PC);
+          *reinterpret_cast<uint4*>(arow + ((dy ^ (tid & 7)) << 4)) = make_uint4(s32[0], s32[1], s32[2], s32[3]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const uint64_t da = umma_smem_desc(smem_u32(sA + buf * ST_A_BYTES), 16, 1024, UMMA_SW_128);
+          const uint64_t db = umma_smem_desc(smem_u32(sB + kb * (NP * 128)), 16, 1024, UMMA_SW_128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&bars[buf]);
+        }
+        ++uses[buf];
+      }
+      // accumulator complete once the last commit lands (a commit covers every earlier MMA of the issuing thread)
+      constexpr int last = (C::KB - 1) & 1;
+      mbar_wait(&bars[last], (uses[last] - 1) & 1);
+      tc_fence_after();
+      const int y = y0 + py, x = x0 + px;
+      const bool ok = y < p.Hs && x < p.Ws;
+      const long long row = ((static_cast<long long>(n) * p.T + t) * p.Hs + y) * p.Ws + x;
+      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(warp * 32) << 16);
+      if constexpr (COUT == 8) {
+        uint32_t a[8];
+        tmem_ld_x8(taddr, a);
+        tmem_wait_ld();
+        uint32_t h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          h[j] = pack_half2(fmaxf(__uint_as_float(a[2 * j]) + shift[2 * j], 0.f),
+                            fmaxf(__uint_as_float(a[2 * j + 1]) + shift[2 * j + 1], 0.f));
+        if (ok) *reinterpret_cast<uint4*>(p.out + row * COUT) = make_uint4(h[0], h[1], h[2], h[3]);
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          uint32_t a[32];
+          tmem_ld_x32(taddr + c0, a);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              h[e] = pack_half2(fmaxf(__uint_as_float(a[8 * j + 2 * e]) + shift[c0 + 8 * j + 2 * e], 0.f),
+                                fmaxf(__uint_as_float(a[8 * j + 2 * e + 1]) + shift[c0 + 8 * j + 2 * e + 1], 0.f));
+            if (ok) *reinterpret_cast<uint4*>(p.out + row * COUT + c0 + 8 * j) = make_uint4(h[0], h[1], h[2], h[3]);
+          }
+        }
+      }
+      tc_fence_before();   // the next frame's first MMA overwrites the accumulator: order it after these loads
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_acc, C::TMEM_COLS);
+}
+
+template <int KT, int NP, int COUT>
+int launch_stem_t(const StemParams& p, cudaStream_t stream) {
+  using C = StemCfg<KT, NP>;
+  static bool configured = false;
+  if (!configured) {
+    KVQ_CUDA(cudaFuncSetAttribute(stem_conv_kernel<KT, NP, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  const int grid = std::min(p.items, 2 * num_sms());
+  count_launch();
+  return launch_pdl(stem_conv_kernel<KT, NP, COUT>, dim3(grid), dim3(ST_THREADS), C::SMEM, stream, p);
+}
+
+}  // namespace
+
+int stem_weight_rows(int cout) { return cout <= 16 ? 16 : 64; }
+
+int launch_stem_conv(const float* x, const __half* w_packed, const float* shift, __half* out, int N, int T, int H, int W,
+                     int kt, int cout, cudaStream_t stream) {
+  KVQ_REQUIRE(x && w_packed && shift && out, KVQ_ERR_BAD_SHAPE, "stem_conv: NULL argument");
+  KVQ_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0, KVQ_ERR_BAD_SHAPE, "stem_conv: empty input %dx3x%dx%dx%d", N, T, H, W);
+  KVQ_REQUIRE((kt == 1 && cout == 64) || (kt == 5 && cout == 8), KVQ_ERR_BAD_SHAPE,
+              "stem_conv: built for (kt=1, cout=64) and (kt=5, cout=8); got kt=%d cout=%d", kt, cout);
+  StemParams p{};
+  p.x = x; p.w = w_packed; p.shift = shift; p.out = out;
+  p.N = N; p.T = T; p.H = H; p.W = W;
+  p.Hs = (H + 6 - 7) / 2 + 1; p.Ws = (W + 6 - 7) / 2 + 1;
+  p.ty = (p.Hs + ST_TY - 1) / ST_TY; p.tx = (p.Ws + ST_TX - 1) / ST_TX;
+  // frames of a work item share the (kt-1)-frame halo ring; split T only as far as needed to fill the machine
+  int tseg = kt == 1 ? 1 : T;
+  const long long per = static_cast<long long>(N) * p.ty * p.tx;
+  while (kt > 1 && tseg > 4 && per * ((T + tseg - 1) / tseg) < 4LL * num_sms()) tseg = (tseg + 1) / 2;
+  p.tseg = tseg;
+  p.nseg = (T + tseg - 1) / tseg;
+  const long long items = per * p.nseg;
+  KVQ_REQUIRE(items < (1LL << 31), KVQ_ERR_BAD_SHAPE, "stem_conv: %lld work items", items);
+  p.items = static_cast<int>(items);
+  if (kt == 1) return launch_stem_t<1, 64, 64>(p, stream);
+  return launch_stem_t<5, 16, 8>(p, stream);
+}
+
+}  // namespace kvq

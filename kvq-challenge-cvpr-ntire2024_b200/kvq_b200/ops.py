@@ -320,6 +320,42 @@ def pack_conv_weight(w, bn=None, eps=1e-5, pad_out=64):
     return cast_f16(wp.contiguous()), sp.contiguous()
 
 
+def pack_stem_weight(w, bn=None, eps=1e-5):
+    """Stem conv weight [Cout,3,kt,7,7] (+ eval-mode BatchNorm) -> (fp16 [kt*3, rows, 64] in the layout
+    kvq_stem_conv_f16 documents, fp32 [rows] shift)."""
+    w = w.detach().float()
+    if w.dim() == 4:
+        w = w.unsqueeze(2)
+    cout, cin, kt, kh, kw = w.shape
+    if cin != 3 or kh != 7 or kw != 7:
+        raise RuntimeError(f"kvq_b200: stem weight {tuple(w.shape)} is not [Cout,3,kt,7,7]")
+    if bn is not None:
+        g, b, m, v = [t.detach().float() for t in bn]
+        scale = g / torch.sqrt(v + eps)
+        shift = b - m * scale
+        w = w * scale.reshape(-1, 1, 1, 1, 1)
+    else:
+        shift = torch.zeros(cout, device=w.device)
+    rows = _l.load().kvq_stem_weight_rows(cout)
+    wp = torch.zeros((kt, 3, rows, 8, 8), dtype=torch.float32, device=w.device)
+    wp[:, :, :cout, :7, :7] = w.permute(2, 1, 0, 3, 4)
+    sp = torch.zeros(rows, dtype=torch.float32, device=w.device)
+    sp[:cout] = shift
+    return cast_f16(wp.reshape(kt * 3, rows, 64).contiguous()), sp.contiguous()
+
+
+def stem_conv_f16(x, w_packed, shift, kt, cout):
+    """x f32 [N,3,T,H,W] -> f16 [N,T,Hs,Ws,cout] = relu(conv(kt,7,7)/s(1,2,2)/p(kt//2,3,3) + shift)."""
+    _need_cuda(x, w_packed, shift)
+    x = x.contiguous()
+    N, _, T, H, W = x.shape
+    Hs, Ws = conv_out_size(H, 7, 2, 3), conv_out_size(W, 7, 2, 3)
+    out = torch.empty((N, T, Hs, Ws, cout), dtype=torch.float16, device=x.device)
+    _l.check(_l.load().kvq_stem_conv_f16(_p(x), _p(w_packed), _p(shift), _p(out), N, T, H, W, int(kt), int(cout),
+                                         _stream()), "stem_conv_f16")
+    return out
+
+
 def conv_gemm_f16(a, w, bias=None, resid=None, relu=False, nvalid=0, out=None):
     """out[M, :nvalid] = act(a[M,K] @ w[N,K]^T + bias + resid); a / resid / out fp16 row-major (may be column slices)."""
     M, K = a.shape
@@ -427,7 +463,11 @@ class SimpleVQAWeights:
             return list(pack_conv_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
                                                               ("weight", "bias", "running_mean", "running_var")], eps))
 
-        ts = conv_bn(prefix + "conv1", prefix + "bn1")
+        def stem_bn(conv, bn):
+            return list(pack_stem_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
+                                                              ("weight", "bias", "running_mean", "running_var")], eps))
+
+        ts = stem_bn(prefix + "conv1", prefix + "bn1")
         for s, depth in enumerate(layers):
             for j in range(depth):
                 b = f"{prefix}layer{s + 1}.{j}."
@@ -557,9 +597,13 @@ class SlowFastWeights:
             return list(pack_conv_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
                                                               ("weight", "bias", "running_mean", "running_var")], eps))
 
+        def stem_bn(conv, bn):
+            return list(pack_stem_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
+                                                              ("weight", "bias", "running_mean", "running_var")], eps))
+
         p = prefix + "0."
-        ts = conv_bn(p + "multipathway_blocks.0.conv", p + "multipathway_blocks.0.norm")
-        ts += conv_bn(p + "multipathway_blocks.1.conv", p + "multipathway_blocks.1.norm")
+        ts = stem_bn(p + "multipathway_blocks.0.conv", p + "multipathway_blocks.0.norm")
+        ts += stem_bn(p + "multipathway_blocks.1.conv", p + "multipathway_blocks.1.norm")
         ts += conv_bn(p + "multipathway_fusion.conv_fast_to_slow", p + "multipathway_fusion.norm")
         for s, depth in enumerate(depths):
             p = f"{prefix}{s + 1}."

@@ -112,3 +112,26 @@ def test_rowdot_mean():
     ref = (x @ w + b).view(3, 8).mean(dim=1)
     got = ops.rowdot_mean_f32(x.to(DEV), w.to(DEV), b.to(DEV), group=8).cpu()
     assert (got - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("N,T,H,W,kt,cout", [
+    (2, 3, 64, 64, 1, 64),        # ResNet / slow stem, whole tiles
+    (1, 2, 37, 53, 1, 64),        # ragged frame: partial tiles in both directions
+    (1, 8, 48, 80, 5, 8),         # fast stem: 5-frame halo ring, clip-boundary zero padding
+    (2, 32, 40, 40, 5, 8),        # T split into segments across work items
+    (1, 5, 224, 224, 5, 8),
+])
+def test_stem_conv_matches_conv3d(N, T, H, W, kt, cout):
+    from kvq_b200 import ops
+    x = _rand((N, 3, T, H, W), 21)
+    w = _rand((cout, 3, kt, 7, 7), 22) / math.sqrt(3 * kt * 49)
+    bn = [1.0 + 0.2 * _rand((cout,), 23), 0.1 * _rand((cout,), 24), 0.1 * _rand((cout,), 25),
+          0.5 + torch.rand(cout, generator=torch.Generator().manual_seed(26))]
+    wp, sp = ops.pack_stem_weight(w.to(DEV), [t.to(DEV) for t in bn])
+    got = ops.stem_conv_f16(x.to(DEV), wp, sp, kt, cout).float().cpu()
+    scale = bn[0] / torch.sqrt(bn[3] + 1e-5)
+    wf = (w * scale.view(-1, 1, 1, 1, 1)).half().float()
+    ref = F.relu(F.conv3d(x.half().float(), wf, bn[1] - bn[2] * scale, stride=(1, 2, 2), padding=(kt // 2, 3, 3)))
+    ref = ref.permute(0, 2, 3, 4, 1)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 5e-3, (got - ref).abs().max().item()
