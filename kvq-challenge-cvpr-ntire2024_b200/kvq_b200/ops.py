@@ -143,13 +143,17 @@ IMAGENET_STD = (58.395, 57.12, 57.375)
 
 
 def fragment_gather_u8(frames, offsets, fragments_h=7, fragments_w=7, fsize=32, aligned=8, mean=IMAGENET_MEAN,
-                       std=IMAGENET_STD):
+                       std=IMAGENET_STD, out=None):
     """frames u8 [B,T,3,Hs,Ws], offsets i32 [B,2,fh,fw,T//aligned] -> f32 [B,3,T,fh*fsize,fw*fsize] normalised."""
     _need_cuda(frames, offsets)
     if frames.dtype != torch.uint8 or offsets.dtype != torch.int32:
         raise RuntimeError("fragment_gather_u8: frames must be uint8 and offsets int32")
     B, T, _, Hs, Ws = frames.shape
-    out = torch.empty((B, 3, T, fragments_h * fsize, fragments_w * fsize), dtype=torch.float32, device=frames.device)
+    shape = (B, 3, T, fragments_h * fsize, fragments_w * fsize)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=frames.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise RuntimeError(f"fragment_gather_u8: out must be a contiguous float32 {shape} tensor")
     _l.check(_l.load().kvq_fragment_gather_u8(_p(frames), _p(offsets), _p(out), B, T, Hs, Ws, fragments_h, fragments_w,
                                               fsize, aligned, _l.f3(mean), _l.f3(std), _stream()), "fragment_gather_u8")
     return out
@@ -559,14 +563,17 @@ def slow_frame_indices(T, alpha=4):
     return [int(buf[i]) for i in range(n)]
 
 
-def pack_pathway_slow(frames, alpha=4):
+def pack_pathway_slow(frames, alpha=4, out=None):
     """frames f32 [B,3,T,H,W] (CUDA) -> slow pathway [B,3,T//alpha,H,W]."""
     _need_cuda(frames)
     frames = frames.contiguous()
     B, C, T, H, W = frames.shape
     if C != 3 or frames.dtype != torch.float32:
         raise RuntimeError("kvq_b200: pack_pathway_slow takes float32 [B,3,T,H,W] frames")
-    out = torch.empty((B, 3, T // alpha, H, W), dtype=torch.float32, device=frames.device)
+    if out is None:
+        out = torch.empty((B, 3, T // alpha, H, W), dtype=torch.float32, device=frames.device)
+    elif tuple(out.shape) != (B, 3, T // alpha, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise RuntimeError("pack_pathway_slow: out must be a contiguous float32 [B,3,T//alpha,H,W] tensor")
     _l.check(_l.load().kvq_pack_pathway_slow_f32(_p(frames), _p(out), B, T, H, W, int(alpha), _stream()),
              "pack_pathway_slow_f32")
     return out

@@ -50,4 +50,31 @@ def gen_simplevqa(ref):
               feats[..., :7168].abs().mean().item(), "max", feats[..., :7168].abs().max().item())
 
 
-GENERATORS = {"simplevqa": gen_simplevqa}
+# (name, [C,T,H,W], kwargs, seed)
+FRAGMENT_CASES = [
+    ("fragments_7x7_t16_300x270", (3, 16, 300, 270), dict(fragments_h=7, fragments_w=7, fsize_h=32, fsize_w=32, aligned=8), 51),
+    ("fragments_2x3_t8_100x150", (3, 8, 100, 150), dict(fragments_h=2, fragments_w=3, fsize_h=32, fsize_w=32, aligned=4), 52),
+    ("fragments_upsample_t4_60x90", (3, 4, 60, 90), dict(fragments_h=3, fragments_w=3, fsize_h=32, fsize_w=32, aligned=2), 53),
+    ("fragments_tight_t8_64x96", (3, 8, 64, 96), dict(fragments_h=2, fragments_w=3, fsize_h=32, fsize_w=32, aligned=8), 54),
+]
+
+
+def gen_fragments(ref):
+    """datasets/fusion_datasets.get_spatial_fragments on uint8-valued frames, offsets drawn from the seeded GLOBAL RNG
+    (the reference has no generator argument)."""
+    for name, shape, kw, seed in FRAGMENT_CASES:
+        video = torch.randint(0, 256, shape, generator=torch.Generator().manual_seed(seed)).float()
+        torch.manual_seed(seed)
+        out = ref.fusion.get_spatial_fragments(video, **kw)
+        import hashlib
+        o = out.numpy()
+        digest = hashlib.sha256(np.ascontiguousarray(o).tobytes()).hexdigest()
+        if o.size > 200000:        # large case: keep every 4th frame / pixel as uint8 plus the digest of the whole array
+            assert (o == np.round(o)).all()
+            o = o[:, ::4, ::4, ::4].astype(np.uint8)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), out=o, sha256=np.array(digest), shape=np.array(shape),
+                            seed=seed, **{k: np.array(v) for k, v in kw.items()})
+        print(name, tuple(out.shape), float(out.mean()))
+
+
+GENERATORS = {"simplevqa": gen_simplevqa, "fragments": gen_fragments}
