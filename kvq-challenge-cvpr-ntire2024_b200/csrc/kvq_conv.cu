@@ -28,30 +28,45 @@ struct ConvGeom {
   int K, Kp;
 };
 
+// G lanes share one output row and stride over its 16-byte chunks (tap-major, channel-minor), so the row decode
+// (three 32-bit divisions) is paid once per row and the (tap, channel) position advances by carries, not divisions.
+// G is chosen by the host so that every lane moves several chunks per row: G*16 contiguous bytes per row per store.
+template <int G>
 __global__ void __launch_bounds__(CONV_THREADS)
-im2col_cl_kernel(const __half* __restrict__ in, __half* __restrict__ out, const ConvGeom g, long long row0,
-                 long long chunks) {
+im2col_cl_kernel(const __half* __restrict__ in, __half* __restrict__ out, const ConvGeom g, long long row0, int rows) {
   pdl_wait();
-  const int kchunks = g.Kp >> 3;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < chunks;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long ml = idx / kchunks;
-    const long long m = row0 + ml;
-    const int k = static_cast<int>(idx - ml * kchunks) << 3;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (k < g.K) {
-      const int tap = k / g.C, c = k - tap * g.C;
-      const int dw = tap % g.kw, dh = (tap / g.kw) % g.kh, dt = tap / (g.kw * g.kh);
-      long long r = m;
-      const int wo = static_cast<int>(r % g.Wo); r /= g.Wo;
-      const int ho = static_cast<int>(r % g.Ho); r /= g.Ho;
-      const int to = static_cast<int>(r % g.To); r /= g.To;
-      const int b = static_cast<int>(r);
-      const int t = to * g.st - g.pt + dt, h = ho * g.sh - g.ph + dh, w = wo * g.sw - g.pw + dw;
-      if (t >= 0 && t < g.T && h >= 0 && h < g.H && w >= 0 && w < g.W)
-        v = __ldg(reinterpret_cast<const uint4*>(in + ((((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W + w) * g.C + c)));
+  const int kchunks = g.Kp >> 3, cpt = g.C >> 3, kvalid = g.K >> 3;
+  const int lane_g = threadIdx.x % G;
+  constexpr int RPB = CONV_THREADS / G;
+  // (dt, dh, dw, c8) of this lane's first chunk: thread constants
+  int tap0 = lane_g / cpt;
+  const int c80 = lane_g - tap0 * cpt;
+  const int dw0 = tap0 % g.kw; tap0 /= g.kw;
+  const int dh0 = tap0 % g.kh;
+  const int dt0 = tap0 / g.kh;
+  for (int r = blockIdx.x * RPB + threadIdx.x / G; r < rows; r += gridDim.x * RPB) {
+    const long long m = row0 + r;
+    unsigned q = static_cast<unsigned>(m % (static_cast<long long>(g.To) * g.Ho * g.Wo));
+    const int b = static_cast<int>(m / (static_cast<long long>(g.To) * g.Ho * g.Wo));
+    const int wo = q % g.Wo; q /= g.Wo;
+    const int ho = q % g.Ho;
+    const int to = q / g.Ho;
+    const int t0 = to * g.st - g.pt, h0 = ho * g.sh - g.ph, w0 = wo * g.sw - g.pw;
+    const __half* src_b = in + static_cast<long long>(b) * g.T * g.H * g.W * g.C;
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<long long>(r) * g.Kp);
+    int dt = dt0, dh = dh0, dw = dw0, c8 = c80;
+    for (int j = lane_g; j < kchunks; j += G) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      const int t = t0 + dt, h = h0 + dh, w = w0 + dw;
+      if (j < kvalid && t >= 0 && t < g.T && h >= 0 && h < g.H && w >= 0 && w < g.W)
+        v = __ldg(reinterpret_cast<const uint4*>(src_b + ((static_cast<long long>(t) * g.H + h) * g.W + w) * g.C) + c8);
+      dst[j] = v;
+      c8 += G;
+      while (c8 >= cpt) {
+        c8 -= cpt;
+        if (++dw == g.kw) { dw = 0; if (++dh == g.kh) { dh = 0; ++dt; } }
+      }
     }
-    *reinterpret_cast<uint4*>(out + idx * 8) = v;
   }
   pdl_launch_dependents();
 }
@@ -308,10 +323,19 @@ int launch_im2col_cl(const __half* in, __half* out, int B, int T, int H, int W, 
   if (rows < 0) rows = total - row0;
   KVQ_REQUIRE(row0 >= 0 && rows > 0 && row0 + rows <= total, KVQ_ERR_BAD_SHAPE,
               "im2col: row range [%lld, +%lld) outside %lld output rows", row0, rows, total);
-  const long long chunks = rows * (Kp / 8);
+  KVQ_REQUIRE(rows < (1LL << 31), KVQ_ERR_BAD_SHAPE, "im2col: %lld rows in one launch", rows);
+  const int kchunks = Kp / 8;
+  const int G = kchunks >= 32 ? 8 : kchunks >= 16 ? 4 : kchunks >= 8 ? 2 : 1;
+  const long long threads = rows * G;
+  const int grid = grid_for(threads, CONV_THREADS);
+  const int nrows = static_cast<int>(rows);
   count_launch();
-  return launch_pdl(im2col_cl_kernel, dim3(grid_for(chunks, CONV_THREADS)), dim3(CONV_THREADS), 0, stream, in, out, g,
-                    row0, chunks);
+  switch (G) {
+    case 8: return launch_pdl(im2col_cl_kernel<8>, dim3(grid), dim3(CONV_THREADS), 0, stream, in, out, g, row0, nrows);
+    case 4: return launch_pdl(im2col_cl_kernel<4>, dim3(grid), dim3(CONV_THREADS), 0, stream, in, out, g, row0, nrows);
+    case 2: return launch_pdl(im2col_cl_kernel<2>, dim3(grid), dim3(CONV_THREADS), 0, stream, in, out, g, row0, nrows);
+    default: return launch_pdl(im2col_cl_kernel<1>, dim3(grid), dim3(CONV_THREADS), 0, stream, in, out, g, row0, nrows);
+  }
 }
 
 int launch_im2col_stem(const float* in, __half* out, int N, int T, int H, int W, int kt, int kh, int kw, int st, int sh,

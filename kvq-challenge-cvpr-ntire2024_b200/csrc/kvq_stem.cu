@@ -105,19 +105,32 @@ stem_conv_kernel(const StemParams p) {
     const int t_begin = seg * p.tseg, t_end = min(t_begin + p.tseg, p.T);
     const float* xn = p.x + static_cast<long long>(n) * 3 * p.T * plane;
 
-    // halo of input frame f -> ring slot (f mod KT); zeros outside the clip / frame
+    // halo of input frame f -> ring slot (f mod KT); zeros outside the clip / frame.  A thread owns one column pair
+    // (19 pairs x 6 row groups = 114 active threads) and walks the 3 x 22 halo rows: two scalar loads (the pair starts
+    // at an odd column, so no aligned float2), one packed 32-bit shared store, no divisions in the loop.
+    const int lf_pair = tid % 19, lf_grp = tid / 19;
+    const int lf_ix = 2 * x0 - 3 + 2 * lf_pair;
+    const bool lf_ok0 = lf_ix >= 0 && lf_ix < p.W, lf_ok1 = lf_ix + 1 >= 0 && lf_ix + 1 < p.W;
     auto load_frame = [&](int f) {
       const int slot = ((f % KT) + KT) % KT;
-      __half* dst = patch + slot * ST_SLOT;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(patch + slot * ST_SLOT) + lf_pair;
       const bool f_ok = f >= 0 && f < p.T;
-      for (int i = tid; i < 3 * ST_PR * 40; i += ST_THREADS) {
-        const int col = i % 40, rr = (i / 40) % ST_PR, c = i / (40 * ST_PR);
-        if (col >= ST_PCV) continue;
-        const int iy = 2 * y0 - 3 + rr, ix = 2 * x0 - 3 + col;
-        float v = 0.f;
-        if (f_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-          v = __ldg(xn + (static_cast<long long>(c) * p.T + f) * plane + static_cast<long long>(iy) * p.W + ix);
-        dst[(c * ST_PR + rr) * ST_PC + col] = __float2half_rn(v);
+      if (lf_grp < 6) {
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          const float* src = xn + (static_cast<long long>(c) * p.T + f) * plane + lf_ix;
+#pragma unroll 2
+          for (int rr = lf_grp; rr < ST_PR; rr += 6) {
+            const int iy = 2 * y0 - 3 + rr;
+            float v0 = 0.f, v1 = 0.f;
+            if (f_ok && iy >= 0 && iy < p.H) {
+              const float* row = src + static_cast<long long>(iy) * p.W;
+              if (lf_ok0) v0 = __ldg(row);
+              if (lf_ok1) v1 = __ldg(row + 1);
+            }
+            dst[(c * ST_PR + rr) * (ST_PC / 2)] = pack_half2(v0, v1);
+          }
+        }
       }
     };
     __syncthreads();   // every build of the previous item has been issued before its ring is overwritten
