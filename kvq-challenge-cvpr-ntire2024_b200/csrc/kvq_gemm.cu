@@ -39,7 +39,7 @@ template <int BN, int MT = 1>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
-  static constexpr int STAGES = MT == 2 ? 3 : (BN >= 192 ? 4 : 6);
+  static constexpr int STAGES = MT == 2 ? 3 : (BN >= 256 ? 3 : BN >= 192 ? 4 : BN >= 128 ? 5 : 6);
   static constexpr int ACC_STAGES = MT == 2 ? 1 : 2;
   static constexpr int CW = (BN % 64 == 0) ? 32 : 16;       // TMEM columns per epilogue chunk
   static constexpr int NCHUNK = BN / CW;
@@ -622,7 +622,14 @@ int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, con
                   "gemm(conv): fp16 output / residual strides %d / %d not 16 B aligned", p.ldo, p.ldr);
       KVQ_REQUIRE(p.nvalid == 0 || (p.nvalid % 8 == 0 && p.nvalid <= p.N), KVQ_ERR_BAD_SHAPE,
                   "gemm(conv): nvalid=%d must be a multiple of 8 and <= N=%d", p.nvalid, p.N);
-      if (p.N % 192 == 0) return launch_impl<192, EPI_CONV_F16>(A, lda, B, ldb, p, stream);
+      {
+        // widest tile that still leaves at least one tile per SM: a 128 x 64 tile pulls 3 operand bytes per 128 FLOP
+        // out of L2 (L2-bound at ~1/3 of the tensor peak), a 128 x 256 tile 1.5
+        const long long mt = (p.M + BM - 1) / BM;
+        if (p.N % 256 == 0 && mt * (p.N / 256) >= num_sms()) return launch_impl<256, EPI_CONV_F16>(A, lda, B, ldb, p, stream);
+        if (p.N % 192 == 0 && mt * (p.N / 192) >= num_sms()) return launch_impl<192, EPI_CONV_F16>(A, lda, B, ldb, p, stream);
+        if (p.N % 128 == 0 && mt * (p.N / 128) >= num_sms()) return launch_impl<128, EPI_CONV_F16>(A, lda, B, ldb, p, stream);
+      }
       if (p.N % 64 == 0) return launch_impl<64, EPI_CONV_F16>(A, lda, B, ldb, p, stream);
       set_error("gemm(conv): N=%d (padded output channels) must be a multiple of 64", p.N);
       return KVQ_ERR_BAD_SHAPE;

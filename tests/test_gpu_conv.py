@@ -22,6 +22,10 @@ def _rand(shape, seed, scale=1.0):
     (128 * 150 + 3, 64, 64, True, True, 0),   # more tiles than SMs
     (500, 64, 72, False, True, 8),        # padded output channels: only 8 valid columns are stored
     (640, 2048, 512, True, True, 0),      # many N blocks
+    (128 * 160 + 5, 256, 64, True, True, 0),      # >= 1 tile per SM at BLOCK_N = 256
+    (128 * 80, 512, 576, False, True, 0),         # BLOCK_N = 256, two N blocks, K tail
+    (128 * 100 + 77, 256, 128, True, False, 0),   # BLOCK_N = 128
+    (128 * 150, 384, 192, False, True, 0),        # BLOCK_N = 192
 ])
 def test_conv_gemm(M, N, K, resid, relu, nvalid):
     from kvq_b200 import ops
