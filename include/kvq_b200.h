@@ -203,6 +203,14 @@ int kvq_pack_pathway_slow_f32(const float* frames, float* slow_out, int B, int T
  * N (rows of W) is a multiple of 64; columns >= nvalid (0 = N) are padding and never stored */
 int kvq_conv_gemm_f16(const void* a_f16, int lda, const void* w_f16, const float* bias, const void* resid_f16, int ldr,
                       void* out_f16, int ldo, int M, int N, int K, int nvalid, int relu, void* stream);
+/* Implicit-GEMM convolution (nn.Conv2d / nn.Conv3d + folded BN + residual + ReLU; Bottleneck.forward :106-126, the
+ * SlowFast res blocks) on a channels-last fp16 activation in [B,T,H,W,C], C % 64 == 0: no patch matrix -- the GEMM's
+ * TMA producer walks (tap, 64-channel block) over a 5-D tensor map, stride = TMA traversal stride, padding = TMA
+ * out-of-bounds zero fill.  w f16 [N, kt*kh*kw*C] tap-major / channel-minor, N % 64 == 0;
+ * out[m, 0:nvalid] (row stride ldo), m = ((b*To + t)*Ho + h)*Wo + w */
+int kvq_conv_implicit_f16(const void* in_f16, const void* w_f16, const float* bias, const void* resid_f16, int ldr,
+                          void* out_f16, int ldo, int B, int T, int H, int W, int C, const int32_t kernel[3],
+                          const int32_t stride[3], const int32_t pad[3], int N, int nvalid, int relu, void* stream);
 /* gather [B,T,H,W,C] -> [B*To*Ho*Wo, Kp] patches, K index ((dt*kh + dh)*kw + dw)*C + c, zero padding (nn.Conv3d) */
 int kvq_im2col_cl_f16(const void* in_f16, void* out_f16, int B, int T, int H, int W, int C, const int32_t kernel[3],
                       const int32_t stride[3], const int32_t pad[3], int Kp, void* stream);

@@ -419,6 +419,22 @@ int kvq_im2col_stem_f32(const float* in, void* out_f16, int N, int T, int H, int
                             stride[1], stride[2], pad[0], pad[1], pad[2], Kp, static_cast<cudaStream_t>(stream));
 }
 
+int kvq_conv_implicit_f16(const void* in_f16, const void* w_f16, const float* bias, const void* resid_f16, int ldr,
+                          void* out_f16, int ldo, int B, int T, int H, int W, int C, const int32_t kernel[3],
+                          const int32_t stride[3], const int32_t pad[3], int N, int nvalid, int relu, void* stream) {
+  KVQ_REQUIRE(in_f16 && w_f16 && out_f16 && kernel && stride && pad, KVQ_ERR_BAD_SHAPE, "conv_implicit: NULL argument");
+  GemmParams gp{};
+  gp.N = N;
+  gp.bias = bias;
+  gp.out = out_f16; gp.ldo = ldo;
+  gp.resid_h = static_cast<const __half*>(resid_f16); gp.ldr = ldr;
+  gp.relu = relu;
+  gp.nvalid = nvalid;
+  return launch_conv_implicit(static_cast<const __half*>(in_f16), B, T, H, W, C, kernel[0], kernel[1], kernel[2],
+                              stride[0], stride[1], stride[2], pad[0], pad[1], pad[2],
+                              static_cast<const __half*>(w_f16), gp, static_cast<cudaStream_t>(stream));
+}
+
 int kvq_stem_conv_f16(const float* x, const void* w_packed_f16, const float* shift, void* out_f16, int N, int T, int H,
                       int W, int kt, int cout, void* stream) {
   return launch_stem_conv(x, static_cast<const __half*>(w_packed_f16), shift, static_cast<__half*>(out_f16), N, T, H, W,
@@ -503,6 +519,29 @@ int conv_gemm(const __half* A, int lda, const void* w, const void* b, const __ha
   return launch_gemm(EPI_CONV_F16, A, lda, static_cast<const __half*>(w), K, gp, st);
 }
 
+// k x k spatial convolution (stride, pad) on [N,H,W,C] fp16: implicit GEMM when C % 64 == 0, else im2col + GEMM
+int conv_spatial(const __half* in, int N, int H, int W, int C, int k, int stride, int pad, const void* w, const void* b,
+                 __half* out, int cout, bool relu, __half* col, int stage, cudaStream_t st) {
+  if (conv_implicit_supported(C, 1, k, k, 1, stride, stride)) {
+    GemmParams gp{};
+    gp.N = cout;
+    gp.bias = static_cast<const float*>(b);
+    gp.out = out; gp.ldo = cout;
+    gp.relu = relu ? 1 : 0;
+    ProfScope ps(PK_CONV_GEMM, stage, st);
+    return launch_conv_implicit(in, N, 1, H, W, C, 1, k, k, 1, stride, stride, 0, pad, pad,
+                                static_cast<const __half*>(w), gp, st);
+  }
+  const int Ho = conv_out(H, k, stride, pad), Wo = conv_out(W, k, stride, pad);
+  int rc;
+  {
+    ProfScope ps(PK_CONV_IM2COL, stage, st);
+    rc = launch_im2col_cl(in, col, N, 1, H, W, C, 1, k, k, 1, stride, stride, 0, pad, pad, k * k * C, st);
+  }
+  if (rc != 0) return rc;
+  return conv_gemm(col, k * k * C, w, b, nullptr, 0, out, N * Ho * Wo, cout, k * k * C, relu, stage, st);
+}
+
 }  // namespace
 
 int kvq_resnet_num_weights(const KvqResNetConfig* cfg) {
@@ -581,24 +620,13 @@ int kvq_simplevqa_forward(const KvqResNetConfig* cfg, const void* const* weights
       // Bottleneck.forward (:106-126): 1x1 -> 3x3 (stride here) -> 1x1, + identity / downsample, ReLU
       rc = conv_gemm(cur, cin, w1, b1, nullptr, 0, t1, M, planes, cin, true, s, st);
       if (rc != 0) return rc;
-      {
-        ProfScope ps(PK_CONV_IM2COL, s, st);
-        rc = launch_im2col_cl(t1, col, N, 1, h, w, planes, 1, 3, 3, 1, stride, stride, 0, 1, 1, 9 * planes, st);
-      }
-      if (rc != 0) return rc;
-      rc = conv_gemm(col, 9 * planes, w2, b2, nullptr, 0, t2, Mo, planes, 9 * planes, true, s, st);
+      rc = conv_spatial(t1, N, h, w, planes, 3, stride, 1, w2, b2, t2, planes, true, col, s, st);
       if (rc != 0) return rc;
       const __half* resid = cur;
       if (j == 0) {
         const void* wd = W_(); const void* bd = W_();
-        const __half* a = cur;
-        if (stride == 2) {
-          ProfScope ps(PK_CONV_IM2COL, s, st);
-          rc = launch_im2col_cl(cur, col, N, 1, h, w, cin, 1, 1, 1, 1, 2, 2, 0, 0, 0, cin, st);
-          if (rc != 0) return rc;
-          a = col;
-        }
-        rc = conv_gemm(a, cin, wd, bd, nullptr, 0, idn, Mo, cout, cin, false, s, st);
+        if (stride == 2) rc = conv_spatial(cur, N, h, w, cin, 1, 2, 0, wd, bd, idn, cout, false, col, s, st);
+        else rc = conv_gemm(cur, cin, wd, bd, nullptr, 0, idn, Mo, cout, cin, false, s, st);
         if (rc != 0) return rc;
         resid = idn;
       }

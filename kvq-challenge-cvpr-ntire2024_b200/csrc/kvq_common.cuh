@@ -52,6 +52,8 @@ int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cud
 
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                  uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes);
+int make_tmap_conv5d(CUtensorMap* out, const void* base, int B, int T, int H, int W, int C, int bt, int bh, int bw,
+                     int st, int sh, int sw);
 
 // ----------------------------------------------------------------------------------------------
 // device helpers
@@ -142,6 +144,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
       : "memory");
 }
 // 1-D bulk copy global -> shared (TMA engine, no tensor map); bytes % 16 == 0, both addresses 16 B aligned.

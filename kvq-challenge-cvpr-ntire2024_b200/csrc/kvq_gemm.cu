@@ -119,7 +119,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int TM = BM * MT;                 // rows per CTA tile
-  const int num_m = (p.M + TM - 1) / TM;
+  const bool conv_mode = (EPI == EPI_CONV_F16) && p.conv.on != 0;
+  const int num_m = conv_mode ? p.M / BM : (p.M + TM - 1) / TM;     // conv: p.M = tiles * 128 (padded tile grid)
   const int num_n = p.N / BN;
   const int tiles = num_m * num_n;
   const int nkb = (p.K + BK - 1) / BK;
@@ -156,12 +157,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        int cw0 = 0, ch0 = 0, ct0 = 0, cb = 0, cblocks = 1;
+        if constexpr (EPI == EPI_CONV_F16) {
+          if (conv_mode) {   // tile -> (clip, t/h/w block); coordinates of its first input pixel for tap (0,0,0)
+            int r = m_blk;
+            const int tw = r % p.conv.nw; r /= p.conv.nw;
+            const int th = r % p.conv.nh; r /= p.conv.nh;
+            const int tt = r % p.conv.nt;
+            cb = r / p.conv.nt;
+            cw0 = tw * p.conv.bw * p.conv.sw - p.conv.pw;
+            ch0 = th * p.conv.bh * p.conv.sh - p.conv.ph;
+            ct0 = tt * p.conv.bt * p.conv.st - p.conv.pt;
+            cblocks = p.conv.C / BK;
+          }
+        }
+        int tap_w = 0, tap_h = 0, tap_t = 0, cblk = 0;
         for (int kb = 0; kb < nkb_tot; ++kb) {
           mbar_wait(&empty[stage], ph ^ 1);
           uint8_t* sA = smem + stage * Cfg<BN, MT>::STAGE_BYTES;
           uint8_t* sB = sA + MT * A_BYTES;
           mbar_expect_tx(&full[stage], Cfg<BN, MT>::STAGE_BYTES);
-          tma_load_2d(sA, &tmA, &full[stage], (kb >= nkb ? kb - nkb : kb) * BK, m_blk * TM);
+          if (EPI == EPI_CONV_F16 && conv_mode) {
+            tma_load_5d(sA, &tmA, &full[stage], cblk * BK, cw0 + tap_w, ch0 + tap_h, ct0 + tap_t, cb);
+            if (++cblk == cblocks) {
+              cblk = 0;
+              if (++tap_w == p.conv.kw) { tap_w = 0; if (++tap_h == p.conv.kh) { tap_h = 0; ++tap_t; } }
+            }
+          } else {
+            tma_load_2d(sA, &tmA, &full[stage], (kb >= nkb ? kb - nkb : kb) * BK, m_blk * TM);
+          }
           tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
@@ -290,6 +314,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // conv-as-GEMM epilogue: folded-BN shift, optional fp16 residual, optional ReLU, fp16 channels-last output
         constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
         const int nvalid = p.nvalid > 0 ? p.nvalid : p.N;
+        // output row of this thread's accumulator row: identity, or (implicit conv) the pixel of the tile's
+        // bt x bh x bw block; -1 = outside the map.  Shared with the other lanes for the transposed stores.
+        long long orow = row_ok ? row : -1;
+        if (conv_mode) {
+          int r = m_blk;
+          const int tw = r % p.conv.nw; r /= p.conv.nw;
+          const int th = r % p.conv.nh; r /= p.conv.nh;
+          const int tt = r % p.conv.nt;
+          const int b = r / p.conv.nt;
+          int l = q * 32 + lane;
+          const int lw = l % p.conv.bw; l /= p.conv.bw;
+          const int lh = l % p.conv.bh;
+          const int lt = l / p.conv.bh;
+          const int ow = tw * p.conv.bw + lw, oh = th * p.conv.bh + lh, ot = tt * p.conv.bt + lt;
+          orow = (ow < p.conv.Wo && oh < p.conv.Ho && ot < p.conv.To)
+                     ? ((static_cast<long long>(b) * p.conv.To + ot) * p.conv.Ho + oh) * p.conv.Wo + ow
+                     : -1;
+        }
+        __syncwarp();
+        srow[lane] = orow;
+        __syncwarp();
         if (n_blk != bias_nblk) {
           __syncwarp();
 #pragma unroll
@@ -311,11 +356,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint4 rs[CW / 8];
 #pragma unroll
           for (int j = 0; j < CW / 8; ++j) rs[j] = make_uint4(0u, 0u, 0u, 0u);
-          if (p.resid_h != nullptr && row_ok) {
+          if (p.resid_h != nullptr && orow >= 0) {
 #pragma unroll
             for (int j = 0; j < CW / 8; ++j)
               if (nbase + c0 + 8 * j < nvalid)
-                rs[j] = *reinterpret_cast<const uint4*>(p.resid_h + static_cast<size_t>(row) * p.ldr + nbase + c0 + 8 * j);
+                rs[j] = *reinterpret_cast<const uint4*>(p.resid_h + orow * p.ldr + nbase + c0 + 8 * j);
           }
           tmem_wait_ld();
           if (ci + 1 < MYCH && c0 + c_step * CW < BN) tmem_ld_chunk<CW>(taddr + c0 + c_step * CW, r[(ci + 1) & 1]);
@@ -343,10 +388,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int it = 0; it < SEGS; ++it) {
             const int rr = it * RPI + rl;
             const uint4 v = *reinterpret_cast<const uint4*>(st16 + rr * 80 + seg * 16);
-            const int grow = m_blk * TM + msub * BM + q * 32 + rr;
-            if (grow < p.M && nbase + c0 + 8 * seg < nvalid)
-              st_global_v4(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(grow) * p.ldo + nbase + c0 + 8 * seg,
-                           v.x, v.y, v.z, v.w);
+            const long long grow = srow[rr];
+            if (grow >= 0 && nbase + c0 + 8 * seg < nvalid)
+              st_global_v4(reinterpret_cast<__half*>(p.out) + grow * p.ldo + nbase + c0 + 8 * seg, v.x, v.y, v.z, v.w);
           }
         }
       } else if constexpr (EPI == EPI_RESID_F32) {
@@ -603,7 +647,73 @@ int launch_bn(const __half* A, int lda, const __half* B, int ldb, const GemmPara
   return KVQ_ERR_BAD_SHAPE;
 }
 
+template <int BN>
+int launch_conv_impl(const CUtensorMap& tmA, const __half* Wt, int K, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    KVQ_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI_CONV_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<BN, 1>::SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tmB;
+  int rc = make_tmap_2d(&tmB, Wt, p.N, K, static_cast<uint64_t>(K) * 2, BN, BK, 2, 128);
+  if (rc != 0) return rc;
+  const int tiles = (p.M / BM) * (p.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  count_launch();
+  return launch_pdl(gemm_kernel<BN, EPI_CONV_F16, 1>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, 1>::SMEM, stream, tmA,
+                    tmB, p);
+}
+
 }  // namespace
+
+bool conv_implicit_supported(int C, int kt, int kh, int kw, int st, int sh, int sw) {
+  static const int off = []() { const char* e = getenv("KVQ_CONV_EXPLICIT"); return e ? atoi(e) : 0; }();
+  return off == 0 && C % 64 == 0 && kt * kh * kw >= 1 && st >= 1 && sh >= 1 && sw >= 1;
+}
+
+int launch_conv_implicit(const __half* in, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh,
+                         int sw, int pt, int ph, int pw, const __half* Wt, GemmParams p, cudaStream_t stream) {
+  KVQ_REQUIRE(conv_implicit_supported(C, kt, kh, kw, st, sh, sw), KVQ_ERR_BAD_SHAPE,
+              "implicit conv needs C %% 64 == 0 (C=%d)", C);
+  KVQ_REQUIRE(p.N % 64 == 0 && p.ldo % 8 == 0 && (p.resid_h == nullptr || p.ldr % 8 == 0), KVQ_ERR_MISALIGNED,
+              "implicit conv: N=%d ldo=%d ldr=%d", p.N, p.ldo, p.ldr);
+  KVQ_REQUIRE(p.nvalid == 0 || (p.nvalid % 8 == 0 && p.nvalid <= p.N), KVQ_ERR_BAD_SHAPE, "implicit conv: nvalid=%d",
+              p.nvalid);
+  const int To = (T + 2 * pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+  KVQ_REQUIRE(To > 0 && Ho > 0 && Wo > 0, KVQ_ERR_BAD_SHAPE, "implicit conv: empty output %dx%dx%d", To, Ho, Wo);
+  // 128-pixel tile bt x bh x bw (powers of two) with the least padding; ties go to the widest rows
+  int best_bw = 0, best_bh = 0, best_bt = 0;
+  long long best = -1;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    if (bw * sw > 256) continue;
+    for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+      const int bt = 128 / (bw * bh);
+      if (bh * sh > 256 || bt * st > 256) continue;
+      const long long cover = static_cast<long long>((To + bt - 1) / bt) * bt * ((Ho + bh - 1) / bh) * bh *
+                              ((Wo + bw - 1) / bw) * bw;
+      if (best < 0 || cover < best) { best = cover; best_bw = bw; best_bh = bh; best_bt = bt; }
+    }
+  }
+  p.conv.on = 1;
+  p.conv.C = C; p.conv.kt = kt; p.conv.kh = kh; p.conv.kw = kw;
+  p.conv.st = st; p.conv.sh = sh; p.conv.sw = sw; p.conv.pt = pt; p.conv.ph = ph; p.conv.pw = pw;
+  p.conv.To = To; p.conv.Ho = Ho; p.conv.Wo = Wo;
+  p.conv.bt = best_bt; p.conv.bh = best_bh; p.conv.bw = best_bw;
+  p.conv.nt = (To + best_bt - 1) / best_bt; p.conv.nh = (Ho + best_bh - 1) / best_bh;
+  p.conv.nw = (Wo + best_bw - 1) / best_bw;
+  const long long tiles_m = static_cast<long long>(B) * p.conv.nt * p.conv.nh * p.conv.nw;
+  KVQ_REQUIRE(tiles_m * BM < (1LL << 31), KVQ_ERR_BAD_SHAPE, "implicit conv: %lld tiles", tiles_m);
+  p.M = static_cast<int>(tiles_m * BM);
+  p.K = kt * kh * kw * C;
+  CUtensorMap tmA;
+  int rc = make_tmap_conv5d(&tmA, in, B, T, H, W, C, best_bt, best_bh, best_bw, st, sh, sw);
+  if (rc != 0) return rc;
+  if (p.N % 256 == 0 && tiles_m * (p.N / 256) >= num_sms()) return launch_conv_impl<256>(tmA, Wt, p.K, p, stream);
+  if (p.N % 192 == 0 && tiles_m * (p.N / 192) >= num_sms()) return launch_conv_impl<192>(tmA, Wt, p.K, p, stream);
+  if (p.N % 128 == 0 && tiles_m * (p.N / 128) >= num_sms()) return launch_conv_impl<128>(tmA, Wt, p.K, p, stream);
+  return launch_conv_impl<64>(tmA, Wt, p.K, p, stream);
+}
 
 int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
                 cudaStream_t stream) {

@@ -72,6 +72,32 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return KVQ_OK;
 }
 
+// channels-last activation [B,T,H,W,C] fp16 as a 5-D tensor (C innermost); box = 64 channels x (bw x bh x bt) pixels of
+// one clip, traversed with the convolution stride (TMA loads ceil(box/stride) elements per dim), 128 B swizzle.
+// Out-of-range coordinates (negative or past the extent) are zero-filled = the convolution's zero padding.
+int make_tmap_conv5d(CUtensorMap* out, const void* base, int B, int T, int H, int W, int C, int bt, int bh, int bw,
+                     int st, int sh, int sw) {
+  EncodeTiledFn enc = get_encode();
+  KVQ_REQUIRE(enc != nullptr, KVQ_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && C % 64 == 0, KVQ_ERR_MISALIGNED,
+              "conv TMA: base %p must be 16 B aligned and C=%d a multiple of 64", base, C);
+  KVQ_REQUIRE(bt * st <= 256 && bh * sh <= 256 && bw * sw <= 256, KVQ_ERR_BAD_SHAPE, "conv TMA: box too large");
+  cuuint64_t gdim[5] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[4] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                        static_cast<cuuint64_t>(H) * W * C * 2, static_cast<cuuint64_t>(T) * H * W * C * 2};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(bw * sw), static_cast<cuuint32_t>(bh * sh),
+                       static_cast<cuuint32_t>(bt * st), 1};
+  cuuint32_t estr[5] = {1, static_cast<cuuint32_t>(sw), static_cast<cuuint32_t>(sh), static_cast<cuuint32_t>(st), 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KVQ_REQUIRE(r == CUDA_SUCCESS, KVQ_ERR_DRIVER,
+              "cuTensorMapEncodeTiled(conv) failed (%d) dims=%dx%dx%dx%dx%d box=%dx%dx%d stride=%dx%dx%d",
+              static_cast<int>(r), B, T, H, W, C, bt, bh, bw, st, sh, sw);
+  return KVQ_OK;
+}
+
 // ---- optional per-kernel-category device timing (bench.py's roofline leg) and a launch counter ----
 namespace {
 struct ProfState {

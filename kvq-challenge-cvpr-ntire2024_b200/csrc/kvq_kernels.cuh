@@ -128,6 +128,15 @@ struct GemmParams {
   int ldr;
   int relu;             // EPI_CONV_F16: apply ReLU
   int nvalid;           // EPI_CONV_F16: columns >= nvalid are padding (not stored); 0 = N
+  // EPI_CONV_F16 implicit-GEMM mode (conv.on): A is the channels-last activation [B,T,H,W,C] behind a 5-D tensor map;
+  // an M tile is a bt x bh x bw block of output pixels of one clip, K runs over (tap, 64-channel block)
+  struct ConvImplicit {
+    int on;
+    int C, kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int To, Ho, Wo;        // output map
+    int bt, bh, bw;        // tile (bt*bh*bw == 128)
+    int nt, nh, nw;        // tiles per dim
+  } conv;
   // EPI_RESID_F32 row remap (proj): rows are window-ordered; rows_in = nW*N per clip, rows_out = tokens per clip
   int remap;            // 0 = identity
   WinGeom geom;
@@ -149,6 +158,12 @@ struct GemmParams {
 
 int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
                 cudaStream_t stream);
+// implicit-GEMM convolution on a channels-last fp16 activation in [B,T,H,W,C] (C % 64 == 0): out[m, 0:nvalid] =
+// act(conv(in) + bias (+ resid)); W fp16 [N, kt*kh*kw*C] tap-major / channel-minor.  p carries bias / out / ldo /
+// resid_h / ldr / relu / nvalid / N; M, K and the tiling are filled in here.
+bool conv_implicit_supported(int C, int kt, int kh, int kw, int st, int sh, int sw);
+int launch_conv_implicit(const __half* in, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh,
+                         int sw, int pt, int ph, int pw, const __half* Wt, GemmParams p, cudaStream_t stream);
 
 // fused fc1 + GELU + fc2 + residual (hidden activation stays on chip); built for C = 96 / 192
 bool fused_mlp_supported(int C);

@@ -123,6 +123,19 @@ int conv_op(const SfCtx& cx, const __half* in, int B, int T, int H, int W, int C
   const long long M = static_cast<long long>(B) * To * Ho * Wo;
   const bool pointwise = k[0] * k[1] * k[2] == 1 && s[0] * s[1] * s[2] == 1;
   if (pointwise) return gemm_conv(in, C, cw, Np, cout, C, resid, ldr, out, ldo, M, relu, stage, cx.st);
+  if (conv_implicit_supported(C, k[0], k[1], k[2], s[0], s[1], s[2])) {
+    // C >= 64: the patch matrix never exists -- the GEMM's TMA producer walks (tap, channel block) over the activation
+    GemmParams gp{};
+    gp.N = Np;
+    gp.bias = cw.b;
+    gp.out = out; gp.ldo = ldo;
+    gp.resid_h = resid; gp.ldr = ldr;
+    gp.relu = relu ? 1 : 0;
+    gp.nvalid = cout == Np ? 0 : cout;
+    ProfScope ps(PK_CONV_GEMM, stage, cx.st);
+    return launch_conv_implicit(in, B, T, H, W, C, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], cw.w, gp,
+                                cx.st);
+  }
   const int Kp = round8(k[0] * k[1] * k[2] * C);
   long long chunk = static_cast<long long>((cx.col_bytes - SF_SLACK) / (static_cast<size_t>(Kp) * 2));
   chunk = chunk / 128 * 128;

@@ -378,6 +378,21 @@ def conv_gemm_f16(a, w, bias=None, resid=None, relu=False, nvalid=0, out=None):
     return out
 
 
+def conv_implicit_f16(x, w, bias, kernel, stride, pad, resid=None, relu=False, nvalid=0):
+    """x f16 [B,T,H,W,C] (C % 64 == 0), w f16 [N, kt*kh*kw*C] -> f16 [B*To*Ho*Wo, nvalid or N] (implicit GEMM)."""
+    _need_cuda(x, w, bias, resid)
+    B, T, H, W, C = x.shape
+    od = [conv_out_size(n, k, s, p) for n, k, s, p in zip((T, H, W), kernel, stride, pad)]
+    N = w.shape[0]
+    nv = nvalid if nvalid else N
+    out = torch.empty((B * od[0] * od[1] * od[2], nv), dtype=torch.float16, device=x.device)
+    rc = _l.load().kvq_conv_implicit_f16(_p(x), _p(w), _p(bias), _p(resid), resid.stride(0) if resid is not None else 0,
+                                         _p(out), out.stride(0), B, T, H, W, C, _i3(kernel), _i3(stride), _i3(pad), N,
+                                         int(nvalid), int(bool(relu)), _stream())
+    _l.check(rc, "conv_implicit_f16")
+    return out, tuple(od)
+
+
 def conv_out_size(n, k, s, p):
     return (n + 2 * p - k) // s + 1
 

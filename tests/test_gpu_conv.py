@@ -139,3 +139,34 @@ def test_stem_conv_matches_conv3d(N, T, H, W, kt, cout):
     ref = ref.permute(0, 2, 3, 4, 1)
     assert got.shape == ref.shape
     assert (got - ref).abs().max().item() < 5e-3, (got - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("B,T,H,W,C,N,kernel,stride,pad,resid", [
+    (2, 1, 16, 16, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), False),      # ResNet 3x3, whole tiles
+    (3, 1, 14, 14, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), True),     # 14x14 map: padded tile grid, + residual
+    (2, 1, 15, 11, 64, 64, (1, 3, 3), (1, 2, 2), (0, 1, 1), False),      # stride 2 on odd sizes (TMA traversal stride)
+    (2, 1, 9, 13, 256, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), False),     # strided 1x1 (downsample branch)
+    (1, 8, 7, 7, 128, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), False),       # SlowFast temporal conv_a, 7x7 map
+    (2, 8, 8, 8, 64, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), True),
+    (1, 32, 6, 6, 64, 128, (7, 1, 1), (4, 1, 1), (3, 0, 0), False),      # fast->slow lateral: temporal stride 4
+    (1, 4, 9, 10, 64, 64, (3, 3, 3), (1, 2, 1), (1, 1, 1), False),       # full 3-D, mixed strides
+    (16, 1, 56, 56, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), False),     # more tiles than SMs
+])
+def test_conv_implicit_matches_conv3d(B, T, H, W, C, N, kernel, stride, pad, resid):
+    from kvq_b200 import ops
+    x = _rand((B, C, T, H, W), 31).half()
+    wt = (_rand((N, C) + kernel, 32) / math.sqrt(C * kernel[0] * kernel[1] * kernel[2])).half()
+    bias = _rand((N,), 33, 0.1)
+    ref = F.conv3d(x.float(), wt.float(), bias, stride=stride, padding=pad)          # [B,N,To,Ho,Wo]
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(-1, N)
+    r = _rand(tuple(ref.shape), 34).half() if resid else None
+    if resid:
+        ref = ref + r.float()
+    ref = F.relu(ref)
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    w2 = wt.permute(0, 2, 3, 4, 1).reshape(N, -1).contiguous().to(DEV)
+    got, od = ops.conv_implicit_f16(xcl, w2, bias.to(DEV), kernel, stride, pad, resid=r.to(DEV) if resid else None,
+                                    relu=True)
+    assert got.shape == ref.shape
+    err = (got.float().cpu() - ref).abs().max().item()
+    assert err < 8e-3, err
