@@ -23,10 +23,11 @@ namespace kvq {
 
 namespace {
 
-constexpr int ST_THREADS = 128;
+constexpr int ST_BUILDERS = 128;              // 4 builder / epilogue warps: thread = output pixel of the tile
+constexpr int ST_THREADS = 160;               // + warp 4: single-thread tcgen05.mma issuer
+constexpr int ST_STAGES = 3;                  // A-tile ring
 constexpr int ST_TY = 8, ST_TX = 16;          // output pixels per tile
 constexpr int ST_PR = 22, ST_PC = 48;         // halo rows / row pitch (halfs); pitch % 64 == 48 keeps the loads conflict-free
-constexpr int ST_PCV = 38;                    // halo columns actually read
 constexpr int ST_SLOT = 3 * ST_PR * ST_PC;    // halfs per frame slot
 constexpr int ST_A_BYTES = 128 * 128;         // one K-block of A: 128 rows x 64 halfs
 
@@ -45,10 +46,14 @@ struct StemCfg {
   static constexpr int KB = KT * 3;
   static constexpr int B_BYTES = KB * NP * 128;
   static constexpr int PATCH_BYTES = KT * ST_SLOT * 2;
-  static constexpr int SMEM = 2 * ST_A_BYTES + B_BYTES + PATCH_BYTES + 64 + 1024;
-  static constexpr int TMEM_COLS = NP <= 32 ? 32 : 64;
+  static constexpr int SMEM = ST_STAGES * ST_A_BYTES + B_BYTES + PATCH_BYTES + 128 + 1024;
+  static constexpr int TMEM_COLS = 2 * NP <= 32 ? 32 : 2 * NP <= 64 ? 64 : 128;   // two accumulators
 };
 
+// Roles: the 128 builder threads own the halo ring and the A-tile ring and run ahead of the tensor pipe (they block
+// only on the `empty` barrier of a stage used three K-blocks earlier); one thread of warp 4 issues the MMAs and commits
+// them to `empty` / `accfull`.  The epilogue of frame-tile n runs on the builder warps after they have built the K-blocks
+// of frame-tile n+1 (two TMEM accumulators), so nobody waits for the tensor pipe in steady state.
 template <int KT, int NP, int COUT>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_conv_kernel(const StemParams p) {
@@ -57,15 +62,19 @@ stem_conv_kernel(const StemParams p) {
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   using C = StemCfg<KT, NP>;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + 2 * ST_A_BYTES;
+  uint8_t* sB = smem + ST_STAGES * ST_A_BYTES;
   __half* patch = reinterpret_cast<__half*>(sB + C::B_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + C::PATCH_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* full = bars;                       // [ST_STAGES]  builders -> MMA   (one arrive per builder warp)
+  uint64_t* empty = bars + ST_STAGES;          // [ST_STAGES]  MMA commit -> builders
+  uint64_t* accfull = bars + 2 * ST_STAGES;    // [2]          MMA commit -> epilogue
+  uint64_t* accempty = accfull + 2;            // [2]          epilogue -> MMA     (one arrive per builder warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 4); }
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -87,126 +96,164 @@ stem_conv_kernel(const StemParams p) {
   const uint32_t tmem_acc = *tmem_slot;
   pdl_launch_dependents();
 
-  const int py = tid >> 4, px = tid & 15;
-  const long long plane = static_cast<long long>(p.H) * p.W;
-  constexpr uint32_t idesc = umma_idesc_f16(128, NP, 0, 0);
-  uint32_t uses[2] = {0u, 0u};      // commits issued so far on each A buffer (uniform across the CTA)
-  float shift[COUT];
-#pragma unroll
-  for (int j = 0; j < COUT; ++j) shift[j] = __ldg(p.shift + j);
-
-  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-    int r = item;
-    const int xt = r % p.tx; r /= p.tx;
-    const int yt = r % p.ty; r /= p.ty;
-    const int seg = r % p.nseg;
-    const int n = r / p.nseg;
-    const int y0 = yt * ST_TY, x0 = xt * ST_TX;
-    const int t_begin = seg * p.tseg, t_end = min(t_begin + p.tseg, p.T);
-    const float* xn = p.x + static_cast<long long>(n) * 3 * p.T * plane;
-
-    // halo of input frame f -> ring slot (f mod KT); zeros outside the clip / frame.  A thread owns one column pair
-    // (19 pairs x 6 row groups = 114 active threads) and walks the 3 x 22 halo rows: two scalar loads (the pair starts
-    // at an odd column, so no aligned float2), one packed 32-bit shared store, no divisions in the loop.
-    const int lf_pair = tid % 19, lf_grp = tid / 19;
-    const int lf_ix = 2 * x0 - 3 + 2 * lf_pair;
-    const bool lf_ok0 = lf_ix >= 0 && lf_ix < p.W, lf_ok1 = lf_ix + 1 >= 0 && lf_ix + 1 < p.W;
-    auto load_frame = [&](int f) {
-      const int slot = ((f % KT) + KT) % KT;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(patch + slot * ST_SLOT) + lf_pair;
-      const bool f_ok = f >= 0 && f < p.T;
-      if (lf_grp < 6) {
-#pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
-          const float* src = xn + (static_cast<long long>(c) * p.T + f) * plane + lf_ix;
-#pragma unroll 2
-          for (int rr = lf_grp; rr < ST_PR; rr += 6) {
-            const int iy = 2 * y0 - 3 + rr;
-            float v0 = 0.f, v1 = 0.f;
-            if (f_ok && iy >= 0 && iy < p.H) {
-              const float* row = src + static_cast<long long>(iy) * p.W;
-              if (lf_ok0) v0 = __ldg(row);
-              if (lf_ok1) v1 = __ldg(row + 1);
-            }
-            dst[(c * ST_PR + rr) * (ST_PC / 2)] = pack_half2(v0, v1);
-          }
-        }
-      }
-    };
-    __syncthreads();   // every build of the previous item has been issued before its ring is overwritten
-    for (int f = t_begin - KT / 2; f < t_begin + KT / 2; ++f) load_frame(f);
-
-    for (int t = t_begin; t < t_end; ++t) {
-      load_frame(t + KT / 2);
-      __syncthreads();
-      for (int kb = 0; kb < C::KB; ++kb) {
-        const int dt = kb / 3, c = kb - dt * 3;
-        const int buf = kb & 1;
-        if (uses[buf] > 0) mbar_wait(&bars[buf], (uses[buf] - 1) & 1);   // the MMAs that read this buffer are done
-        const int f = t + dt - KT / 2;
-        const int slot = ((f % KT) + KT) % KT;
-        const __half* src = patch + slot * ST_SLOT + c * (ST_PR * ST_PC) + (2 * py) * ST_PC + 2 * px;
-        uint8_t* arow = sA + buf * ST_A_BYTES + (tid >> 3) * 1024 + (tid & 7) * 128;
-#pragma unroll
-        for (int dy = 0; dy < 8; ++dy) {
-          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + dy * ST_PC);
-          *reinterpret_cast<uint4*>(arow + ((dy ^ (tid & 7)) << 4)) = make_uint4(s32[0], s32[1], s32[2], s32[3]);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+  if (warp == 4) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, NP, 0, 0);
+      uint32_t it = 0, n = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int seg = (item / (p.tx * p.ty)) % p.nseg;
+        const int t_begin = seg * p.tseg, t_end = min(t_begin + p.tseg, p.T);
+        for (int t = t_begin; t < t_end; ++t, ++n) {
+          const uint32_t acc = n & 1;
+          if (n >= 2) mbar_wait(&accempty[acc], ((n >> 1) - 1) & 1);
           tc_fence_after();
-          const uint64_t da = umma_smem_desc(smem_u32(sA + buf * ST_A_BYTES), 16, 1024, UMMA_SW_128);
-          const uint64_t db = umma_smem_desc(smem_u32(sB + kb * (NP * 128)), 16, 1024, UMMA_SW_128);
+          for (int kb = 0; kb < C::KB; ++kb, ++it) {
+            const uint32_t s = it % ST_STAGES;
+            mbar_wait(&full[s], (it / ST_STAGES) & 1);
+            tc_fence_after();
+            const uint64_t da = umma_smem_desc(smem_u32(sA + s * ST_A_BYTES), 16, 1024, UMMA_SW_128);
+            const uint64_t db = umma_smem_desc(smem_u32(sB + kb * (NP * 128)), 16, 1024, UMMA_SW_128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem_acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&bars[buf]);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_acc + acc * NP, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);
+          }
+          umma_commit(&accfull[acc]);
         }
-        ++uses[buf];
       }
-      // accumulator complete once the last commit lands (a commit covers every earlier MMA of the issuing thread)
-      constexpr int last = (C::KB - 1) & 1;
-      mbar_wait(&bars[last], (uses[last] - 1) & 1);
+    }
+  } else {
+    // ---------------- builders / epilogue ----------------
+    const int py = tid >> 4, px = tid & 15;
+    const long long plane = static_cast<long long>(p.H) * p.W;
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(warp * 32) << 16);
+    uint32_t it = 0, n = 0;
+    long long prev_row = -1;
+    bool have_prev = false;
+
+    auto epilogue = [&](uint32_t m, long long row) {
+      const uint32_t acc = m & 1;
+      mbar_wait(&accfull[acc], (m >> 1) & 1);
       tc_fence_after();
-      const int y = y0 + py, x = x0 + px;
-      const bool ok = y < p.Hs && x < p.Ws;
-      const long long row = ((static_cast<long long>(n) * p.T + t) * p.Hs + y) * p.Ws + x;
-      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(warp * 32) << 16);
       if constexpr (COUT == 8) {
         uint32_t a[8];
-        tmem_ld_x8(taddr, a);
+        tmem_ld_x8(taddr + acc * NP, a);
         tmem_wait_ld();
         uint32_t h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          h[j] = pack_half2(fmaxf(__uint_as_float(a[2 * j]) + shift[2 * j], 0.f),
-                            fmaxf(__uint_as_float(a[2 * j + 1]) + shift[2 * j + 1], 0.f));
-        if (ok) *reinterpret_cast<uint4*>(p.out + row * COUT) = make_uint4(h[0], h[1], h[2], h[3]);
+          h[j] = pack_half2(fmaxf(__uint_as_float(a[2 * j]) + __ldg(p.shift + 2 * j), 0.f),
+                            fmaxf(__uint_as_float(a[2 * j + 1]) + __ldg(p.shift + 2 * j + 1), 0.f));
+        if (row >= 0) *reinterpret_cast<uint4*>(p.out + row * COUT) = make_uint4(h[0], h[1], h[2], h[3]);
       } else {
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 32) {
           uint32_t a[32];
-          tmem_ld_x32(taddr + c0, a);
+          tmem_ld_x32(taddr + acc * NP + c0, a);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint32_t h[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              h[e] = pack_half2(fmaxf(__uint_as_float(a[8 * j + 2 * e]) + shift[c0 + 8 * j + 2 * e], 0.f),
-                                fmaxf(__uint_as_float(a[8 * j + 2 * e + 1]) + shift[c0 + 8 * j + 2 * e + 1], 0.f));
-            if (ok) *reinterpret_cast<uint4*>(p.out + row * COUT + c0 + 8 * j) = make_uint4(h[0], h[1], h[2], h[3]);
+              h[e] = pack_half2(fmaxf(__uint_as_float(a[8 * j + 2 * e]) + __ldg(p.shift + c0 + 8 * j + 2 * e), 0.f),
+                                fmaxf(__uint_as_float(a[8 * j + 2 * e + 1]) + __ldg(p.shift + c0 + 8 * j + 2 * e + 1), 0.f));
+            if (row >= 0) *reinterpret_cast<uint4*>(p.out + row * COUT + c0 + 8 * j) = make_uint4(h[0], h[1], h[2], h[3]);
           }
         }
       }
-      tc_fence_before();   // the next frame's first MMA overwrites the accumulator: order it after these loads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&accempty[acc]);
+    };
+
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int r = item;
+      const int xt = r % p.tx; r /= p.tx;
+      const int yt = r % p.ty; r /= p.ty;
+      const int seg = r % p.nseg;
+      const int nclip = r / p.nseg;
+      const int y0 = yt * ST_TY, x0 = xt * ST_TX;
+      const int t_begin = seg * p.tseg, t_end = min(t_begin + p.tseg, p.T);
+      const float* xn = p.x + static_cast<long long>(nclip) * 3 * p.T * plane;
+
+      // halo of input frame f -> ring slot (f mod KT); zeros outside the clip / frame.  A thread owns one column pair
+      // (19 pairs x 6 row groups = 114 active threads) and 3 x 4 halo rows.  The global loads of frame t+1's halo are
+      // issued BEFORE the K-blocks of frame t are built and land in registers meanwhile; they are converted and
+      // stored after the build (the ring slot they replace is still being read until then).
+      const int lf_pair = tid % 19, lf_grp = tid / 19;
+      const int lf_ix = 2 * x0 - 3 + 2 * lf_pair;
+      const bool lf_ok0 = lf_grp < 6 && lf_ix >= 0 && lf_ix < p.W, lf_ok1 = lf_grp < 6 && lf_ix + 1 >= 0 && lf_ix + 1 < p.W;
+      constexpr int LF_ROWS = (ST_PR + 5) / 6;     // 4
+      float hv[3][LF_ROWS][2];
+      auto fetch_frame = [&](int f) {
+        const bool f_ok = f >= 0 && f < p.T;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* src = xn + (static_cast<long long>(c) * p.T + f) * plane + lf_ix;
+#pragma unroll
+          for (int k = 0; k < LF_ROWS; ++k) {
+            const int iy = 2 * y0 - 3 + lf_grp + 6 * k;
+            const bool ok = f_ok && iy >= 0 && iy < p.H && lf_grp + 6 * k < ST_PR;
+            const float* row = src + static_cast<long long>(iy) * p.W;
+            hv[c][k][0] = (ok && lf_ok0) ? __ldg(row) : 0.f;
+            hv[c][k][1] = (ok && lf_ok1) ? __ldg(row + 1) : 0.f;
+          }
+        }
+      };
+      auto store_frame = [&](int f) {
+        const int slot = ((f % KT) + KT) % KT;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(patch + slot * ST_SLOT) + lf_pair;
+        if (lf_grp < 6) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < LF_ROWS; ++k)
+              if (lf_grp + 6 * k < ST_PR) dst[(c * ST_PR + lf_grp + 6 * k) * (ST_PC / 2)] = pack_half2(hv[c][k][0], hv[c][k][1]);
+        }
+      };
+      named_bar_sync(1, ST_BUILDERS);   // every builder is done reading the previous item's ring
+      for (int f = t_begin - KT / 2; f < t_begin + KT / 2; ++f) { fetch_frame(f); store_frame(f); }
+      fetch_frame(t_begin + KT / 2);
+
+      for (int t = t_begin; t < t_end; ++t, ++n) {
+        if (t > t_begin) named_bar_sync(1, ST_BUILDERS);   // the slot about to be overwritten was read by frame t-1
+        store_frame(t + KT / 2);
+        named_bar_sync(1, ST_BUILDERS);
+        if (t + 1 < t_end) fetch_frame(t + 1 + KT / 2);    // in flight while this frame's K-blocks are built
+        for (int kb = 0; kb < C::KB; ++kb, ++it) {
+          const int dt = kb / 3, c = kb - dt * 3;
+          const uint32_t s = it % ST_STAGES;
+          if (it >= ST_STAGES) mbar_wait(&empty[s], ((it / ST_STAGES) - 1) & 1);   // MMAs that read this stage are done
+          const int f = t + dt - KT / 2;
+          const int slot = ((f % KT) + KT) % KT;
+          const __half* src = patch + slot * ST_SLOT + c * (ST_PR * ST_PC) + (2 * py) * ST_PC + 2 * px;
+          uint8_t* arow = sA + s * ST_A_BYTES + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll
+          for (int dy = 0; dy < 8; ++dy) {
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + dy * ST_PC);
+            *reinterpret_cast<uint4*>(arow + ((dy ^ (tid & 7)) << 4)) = make_uint4(s32[0], s32[1], s32[2], s32[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+        }
+        if (have_prev) epilogue(n - 1, prev_row);
+        const int y = y0 + py, x = x0 + px;
+        prev_row = (y < p.Hs && x < p.Ws) ? ((static_cast<long long>(nclip) * p.T + t) * p.Hs + y) * p.Ws + x : -1;
+        have_prev = true;
+      }
     }
+    if (have_prev) epilogue(n - 1, prev_row);
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_acc, C::TMEM_COLS);
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, C::TMEM_COLS);
+  }
 }
 
 template <int KT, int NP, int COUT>
