@@ -7,11 +7,12 @@
 // 8 x 16 tile of output pixels and walks the output frames of its work item:
 //   * the input halo (22 x 38 pixels x 3 channels) of each needed frame is converted to fp16 into a KT-slot ring in
 //     shared memory (one new frame per output frame),
-//   * per (frame tap dt, channel c) the 128 threads build the [128 pixels x 64] K-block (k = dy*8 + dx; the dy = 7 /
-//     dx = 7 slots carry zero weights) straight into the 128B-swizzled UMMA layout: 4 aligned 32-bit shared loads and
-//     one conflict-free 16-byte shared store per kernel row,
-//   * one thread issues 4 tcgen05.mma (M128 x N{16,64} x K16) per K-block into a TMEM accumulator; the A tile is
-//     double-buffered so the build of block k+1 overlaps the MMAs of block k,
+//   * per (frame tap dt, channel c) the 128 builder threads assemble the [128 pixels x 64] K-block (k = dy*8 + dx; the
+//     dy = 7 / dx = 7 slots carry zero weights) in registers -- 4 aligned 32-bit shared loads per kernel row -- and
+//     write it with one tcgen05.st into a 3-stage ring of A tiles IN TENSOR MEMORY (thread = pixel = TMEM lane): the
+//     A operand never goes back through shared memory (the shared-memory store path was the measured limiter),
+//   * one thread issues 4 tcgen05.mma (A from TMEM, B from smem; M128 x N{16,64} x K16) per K-block into one of two
+//     TMEM accumulators,
 //   * epilogue: tcgen05.ld (thread = pixel) -> + shift, ReLU -> fp16 -> 16-byte stores.
 // Two CTAs per SM overlap each other's load / build / epilogue phases.
 #include <algorithm>
@@ -29,7 +30,7 @@ constexpr int ST_STAGES = 3;                  // A-tile ring
 constexpr int ST_TY = 8, ST_TX = 16;          // output pixels per tile
 constexpr int ST_PR = 22, ST_PC = 48;         // halo rows / row pitch (halfs); pitch % 64 == 48 keeps the loads conflict-free
 constexpr int ST_SLOT = 3 * ST_PR * ST_PC;    // halfs per frame slot
-constexpr int ST_A_BYTES = 128 * 128;         // one K-block of A: 128 rows x 64 halfs
+constexpr int ST_A_COLS = 32;                 // one K-block of A in TMEM: 64 halfs per row = 32 columns
 
 struct StemParams {
   const float* x;        // [N,3,T,H,W]
@@ -46,8 +47,10 @@ struct StemCfg {
   static constexpr int KB = KT * 3;
   static constexpr int B_BYTES = KB * NP * 128;
   static constexpr int PATCH_BYTES = KT * ST_SLOT * 2;
-  static constexpr int SMEM = ST_STAGES * ST_A_BYTES + B_BYTES + PATCH_BYTES + 128 + 1024;
-  static constexpr int TMEM_COLS = 2 * NP <= 32 ? 32 : 2 * NP <= 64 ? 64 : 128;   // two accumulators
+  static constexpr int SMEM = B_BYTES + PATCH_BYTES + 128 + 1024;
+  static constexpr int T_A = 2 * NP;                                               // A ring after the two accumulators
+  static constexpr int TMEM_COLS = T_A + ST_STAGES * ST_A_COLS <= 128 ? 128 : 256;
+  static constexpr int CTAS = TMEM_COLS <= 128 ? 3 : 2;
 };
 
 // Roles: the 128 builder threads own the halo ring and the A-tile ring and run ahead of the tensor pipe (they block
@@ -55,14 +58,13 @@ struct StemCfg {
 // them to `empty` / `accfull`.  The epilogue of frame-tile n runs on the builder warps after they have built the K-blocks
 // of frame-tile n+1 (two TMEM accumulators), so nobody waits for the tensor pipe in steady state.
 template <int KT, int NP, int COUT>
-__global__ void __launch_bounds__(ST_THREADS, 2)
+__global__ void __launch_bounds__(ST_THREADS, (StemCfg<KT, NP>::CTAS))
 stem_conv_kernel(const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   using C = StemCfg<KT, NP>;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + ST_STAGES * ST_A_BYTES;
+  uint8_t* sB = smem;
   __half* patch = reinterpret_cast<__half*>(sB + C::B_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + C::PATCH_BYTES);
   uint64_t* full = bars;                       // [ST_STAGES]  builders -> MMA   (one arrive per builder warp)
@@ -112,11 +114,11 @@ stem_conv_kernel(const StemParams p) {
             const uint32_t s = it % ST_STAGES;
             mbar_wait(&full[s], (it / ST_STAGES) & 1);
             tc_fence_after();
-            const uint64_t da = umma_smem_desc(smem_u32(sA + s * ST_A_BYTES), 16, 1024, UMMA_SW_128);
+            const uint32_t ta = tmem_acc + C::T_A + s * ST_A_COLS;
             const uint64_t db = umma_smem_desc(smem_u32(sB + kb * (NP * 128)), 16, 1024, UMMA_SW_128);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16_ss(tmem_acc + acc * NP, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+              umma_f16_ts(tmem_acc + acc * NP, ta + 8 * k, db + static_cast<uint64_t>(2 * k), idesc,
                           (kb > 0 || k > 0) ? 1u : 0u);
             umma_commit(&empty[s]);
           }
@@ -230,13 +232,16 @@ stem_conv_kernel(const StemParams p) {
           const int f = t + dt - KT / 2;
           const int slot = ((f % KT) + KT) % KT;
           const __half* src = patch + slot * ST_SLOT + c * (ST_PR * ST_PC) + (2 * py) * ST_PC + 2 * px;
-          uint8_t* arow = sA + s * ST_A_BYTES + (tid >> 3) * 1024 + (tid & 7) * 128;
+          uint32_t a[32];                       // this pixel's 64-half K-block row: column j = halfs (2j, 2j+1)
 #pragma unroll
           for (int dy = 0; dy < 8; ++dy) {
             const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + dy * ST_PC);
-            *reinterpret_cast<uint4*>(arow + ((dy ^ (tid & 7)) << 4)) = make_uint4(s32[0], s32[1], s32[2], s32[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[4 * dy + j] = s32[j];
           }
-          fence_proxy_async_smem();
+          tmem_st_x32(taddr + C::T_A + s * ST_A_COLS, a);
+          tmem_wait_st();
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[s]);
         }
@@ -264,7 +269,7 @@ int launch_stem_t(const StemParams& p, cudaStream_t stream) {
     KVQ_CUDA(cudaFuncSetAttribute(stem_conv_kernel<KT, NP, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
-  const int grid = std::min(p.items, 2 * num_sms());
+  const int grid = std::min(p.items, C::CTAS * num_sms());
   count_launch();
   return launch_pdl(stem_conv_kernel<KT, NP, COUT>, dim3(grid), dim3(ST_THREADS), C::SMEM, stream, p);
 }
