@@ -29,6 +29,9 @@ constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilog
 constexpr int EPI_WARPS = 8;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int STAGING_BYTES = EPI_WARPS * (32 * 36 * 4 + 32 * 8);   // per warp: 32x36 fp32 tile + 32 row offsets
+constexpr int MAX_BIAS_N = 4096;
+constexpr int BIAS_BYTES = MAX_BIAS_N * 4;   // the whole bias vector, staged once per CTA (a per-tile __ldg refresh
+                                             // of the n-block's slice cost ~13 % of the epilogue's issue samples)
 
 // One CTA per SM: a deep TMA ring (the large-K GEMMs are latency-bound with fewer than 4 stages in flight) and
 // double-buffered accumulators so 8 epilogue warps drain tile t while the tensor pipe works on tile t+1.
@@ -43,7 +46,7 @@ struct Cfg {
   static constexpr int ACC_STAGES = MT == 2 ? 1 : 2;
   static constexpr int CW = (BN % 64 == 0) ? 32 : 16;       // TMEM columns per epilogue chunk
   static constexpr int NCHUNK = BN / CW;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_BYTES;
   static constexpr int TMEM_NEED = ACC_STAGES * MT * BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_NEED <= 512 && SMEM <= 227 * 1024, "tile configuration exceeds the SM");
@@ -115,6 +118,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* sbias = reinterpret_cast<float*>(bars + 32);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,13 +140,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], EPI_WARPS);
+      mbar_init(&tempty[i], (EPI == EPI_CONV_F16 && MT == 1) ? EPI_WARPS / 2 : EPI_WARPS);
     }
     mbar_fence_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg<BN, MT>::TMEM_COLS);
     tmem_relinquish();
+  }
+  if constexpr (EPI != EPI_LN_F32 && EPI != EPI_HEAD) {
+    // bias is a weight (never produced by the previous kernel): stage it before the dependency wait
+    const int nb = p.N < MAX_BIAS_N ? p.N : MAX_BIAS_N;
+    const int nval = (EPI == EPI_CONV_F16 && p.nvalid > 0) ? p.nvalid : p.N;
+    for (int i = threadIdx.x; i < nb; i += GEMM_THREADS)
+      sbias[i] = (p.bias != nullptr && i < nval) ? __ldg(p.bias + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -229,8 +240,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     // MT == 2: which 128-row sub-tile (the warp then drains every chunk of its rows)
     // epilogues that need the whole output row in one thread run on the half-0 warps only
     constexpr bool kWholeRow = (EPI == EPI_HEAD);
-    const int c_begin = (kWholeRow || MT == 2) ? 0 : half;
-    constexpr int c_step = (kWholeRow || MT == 2) ? 1 : 2;
+    // conv epilogue: the two warp sets take alternate TILES (= alternate accumulator stages) instead of alternate
+    // column chunks, so two tiles' load -> TMEM -> store latency chains overlap.  The thin-K convolutions
+    // (K = 8..96, one k-block per tile) are bound by exactly that chain.
+    constexpr bool kTileSplit = (EPI == EPI_CONV_F16 && MT == 1);
+    const int c_begin = (kWholeRow || MT == 2 || kTileSplit) ? 0 : half;
+    constexpr int c_step = (kWholeRow || MT == 2 || kTileSplit) ? 1 : 2;
     const bool active = !kWholeRow || half == 0;
     const int msub = MT == 2 ? half : 0;
     float* stile = reinterpret_cast<float*>(staging + ew * (32 * 36 * 4 + 32 * 8));
@@ -240,7 +255,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int bias_nblk = -1;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-      if constexpr (EPI != EPI_RESID_F32) {   // (the residual epilogue prefetches x before it waits)
+      if constexpr (kTileSplit) {
+        if (as != half) {                     // the other warp set owns this tile / accumulator stage
+          if (++as == ACC) { as = 0; aph ^= 1; }
+          continue;
+        }
+      }
+      if constexpr (EPI != EPI_RESID_F32 && EPI != EPI_CONV_F16) {   // (those two prefetch their residual first)
         mbar_wait(&tfull[as], aph);
         __syncwarp();
         tc_fence_after();
@@ -260,7 +281,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int ci = 0; ci < MYCH; ++ci) {
             const int c0 = (c_begin + ci * c_step) * CW;
-            if (lane < CW && c0 < BN) stile[ci * CW + lane] = p.bias != nullptr ? __ldg(p.bias + nbase + c0 + lane) : 0.f;
+            if (lane < CW && c0 < BN) stile[ci * CW + lane] = sbias[nbase + c0 + lane];
           }
           bias_nblk = n_blk;
           __syncwarp();
@@ -312,7 +333,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         (void)row_ok;
       } else if constexpr (EPI == EPI_CONV_F16) {
         // conv-as-GEMM epilogue: folded-BN shift, optional fp16 residual, optional ReLU, fp16 channels-last output
-        constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
+        constexpr int MYCH = (MT == 2 || kTileSplit) ? NCHUNK : (NCHUNK + 1) / 2;
         const int nvalid = p.nvalid > 0 ? p.nvalid : p.N;
         // output row of this thread's accumulator row: identity, or (implicit conv) the pixel of the tile's
         // bt x bh x bw block; -1 = outside the map.  Shared with the other lanes for the transposed stores.
@@ -341,27 +362,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int ci = 0; ci < MYCH; ++ci) {
             const int c0 = (c_begin + ci * c_step) * CW;
             if (lane < CW && c0 < BN)
-              stile[ci * CW + lane] = (p.bias != nullptr && nbase + c0 + lane < nvalid) ? __ldg(p.bias + nbase + c0 + lane) : 0.f;
+              stile[ci * CW + lane] = sbias[nbase + c0 + lane];
           }
           bias_nblk = n_blk;
           __syncwarp();
         }
+        // this thread's residual row is fetched one chunk ahead, and the first chunk BEFORE the accumulator wait: the
+        // thin-K convolutions are bound by this load's latency, not by the tensor pipe
+        uint4 rsb[2][CW / 8];
+        auto load_resid = [&](int ci, uint4* dst) {
+          const int c0 = (c_begin + ci * c_step) * CW;
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (p.resid_h != nullptr && orow >= 0 && c0 < BN) {
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j)
+              if (nbase + c0 + 8 * j < nvalid)
+                dst[j] = *reinterpret_cast<const uint4*>(p.resid_h + orow * p.ldr + nbase + c0 + 8 * j);
+          }
+        };
+        load_resid(0, rsb[0]);
+        mbar_wait(&tfull[as], aph);
+        __syncwarp();
+        tc_fence_after();
         uint32_t r[2][CW];
         tmem_ld_chunk<CW>(taddr + c_begin * CW, r[0]);
 #pragma unroll
         for (int ci = 0; ci < MYCH; ++ci) {
           const int c0 = (c_begin + ci * c_step) * CW;
           if (c0 >= BN) break;
-          // this thread's residual chunk (CW halfs) is fetched while the accumulator chunk is in flight
-          uint4 rs[CW / 8];
-#pragma unroll
-          for (int j = 0; j < CW / 8; ++j) rs[j] = make_uint4(0u, 0u, 0u, 0u);
-          if (p.resid_h != nullptr && orow >= 0) {
-#pragma unroll
-            for (int j = 0; j < CW / 8; ++j)
-              if (nbase + c0 + 8 * j < nvalid)
-                rs[j] = *reinterpret_cast<const uint4*>(p.resid_h + orow * p.ldr + nbase + c0 + 8 * j);
-          }
+          if (ci + 1 < MYCH) load_resid(ci + 1, rsb[(ci + 1) & 1]);
+          const uint4* rs = rsb[ci & 1];
           tmem_wait_ld();
           if (ci + 1 < MYCH && c0 + c_step * CW < BN) tmem_ld_chunk<CW>(taddr + c0 + c_step * CW, r[(ci + 1) & 1]);
           const uint32_t* rc = r[ci & 1];
@@ -437,7 +468,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t r[CW];
           tmem_ld_chunk<CW>(taddr + c0, r);
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c0) + sub);
+          bb = *(reinterpret_cast<const float4*>(sbias + nbase + c0) + sub);
           tmem_wait_ld();
           __syncwarp();                       // previous chunk's readers are done with the tile
 #pragma unroll
@@ -478,7 +509,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int ci = 0; ci < MYCH; ++ci) {
             const int c0 = (c_begin + ci * c_step) * CW;
-            if (lane < CW && c0 < BN) stile[ci * CW + lane] = __ldg(p.bias + nbase + c0 + lane);
+            if (lane < CW && c0 < BN) stile[ci * CW + lane] = sbias[nbase + c0 + lane];
           }
           bias_nblk = n_blk;
           __syncwarp();
@@ -676,8 +707,8 @@ int launch_conv_implicit(const __half* in, int B, int T, int H, int W, int C, in
                          int sw, int pt, int ph, int pw, const __half* Wt, GemmParams p, cudaStream_t stream) {
   KVQ_REQUIRE(conv_implicit_supported(C, kt, kh, kw, st, sh, sw), KVQ_ERR_BAD_SHAPE,
               "implicit conv needs C %% 64 == 0 (C=%d)", C);
-  KVQ_REQUIRE(p.N % 64 == 0 && p.ldo % 8 == 0 && (p.resid_h == nullptr || p.ldr % 8 == 0), KVQ_ERR_MISALIGNED,
-              "implicit conv: N=%d ldo=%d ldr=%d", p.N, p.ldo, p.ldr);
+  KVQ_REQUIRE(p.N % 64 == 0 && p.N <= MAX_BIAS_N && p.ldo % 8 == 0 && (p.resid_h == nullptr || p.ldr % 8 == 0),
+              KVQ_ERR_MISALIGNED, "implicit conv: N=%d ldo=%d ldr=%d", p.N, p.ldo, p.ldr);
   KVQ_REQUIRE(p.nvalid == 0 || (p.nvalid % 8 == 0 && p.nvalid <= p.N), KVQ_ERR_BAD_SHAPE, "implicit conv: nvalid=%d",
               p.nvalid);
   const int To = (T + 2 * pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
@@ -718,6 +749,7 @@ int launch_conv_implicit(const __half* in, int B, int T, int H, int W, int C, in
 int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,
                 cudaStream_t stream) {
   KVQ_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, KVQ_ERR_BAD_SHAPE, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
+  KVQ_REQUIRE(p.N <= MAX_BIAS_N, KVQ_ERR_BAD_SHAPE, "gemm: N=%d exceeds the %d-entry bias stage", p.N, MAX_BIAS_N);
   KVQ_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, KVQ_ERR_MISALIGNED,
               "gemm: K=%d lda=%d ldb=%d must be multiples of 8 halfs (16 B TMA rows)", p.K, lda, ldb);
   switch (epi) {
