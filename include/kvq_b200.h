@@ -141,8 +141,8 @@ typedef struct KvqResNetConfig {
 /*
  * Weight pointer table for kvq_simplevqa_forward.  Every convolution is passed with its BatchNorm folded in
  * (eval mode): w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps); weights are fp16
- * [Cout, Kp] with the K index tap-major / channel-minor ((dh*kw + dw)*Cin + c, zero padded to Kp % 8 == 0), biases
- * fp32 [Cout]:
+ * [Cout, Kp] with the K index tap-major / channel-minor ((dh*kw + dw)*Cin + c, zero padded to Kp % 64 == 0 so that
+ * every 64-wide TMA box of the contraction is full), biases fp32 [Cout]:
  *   [0],[1]  conv1+bn1 (7x7/2) in the stem layout of kvq_stem_conv_f16
  *   then per layer, per block: conv1+bn1, conv2+bn2, conv3+bn3 and, for the first block of a layer,
  *   downsample.0+downsample.1  (w, b each)
@@ -176,10 +176,15 @@ typedef struct KvqSlowFastConfig {
 
 /*
  * Weight pointer table for kvq_slowfast_forward: every convolution with its eval-mode BatchNorm folded in, as an
- * (fp16 [round64(Cout), round8(K)] tap-major / channel-minor weight, fp32 [round64(Cout)] shift) pair, in this order:
+ * (fp16 [round64(Cout), round64(K)] tap-major / channel-minor weight, fp32 [round64(Cout)] shift) pair, in this order:
  *   slow stem, fast stem (both in the stem layout of kvq_stem_conv_f16), block-0 fusion (conv_fast_to_slow + norm);
  *   then per stage s = 0..3: every slow res block (branch1 first for block 0; conv_a, conv_b, conv_c), every fast
  *   res block (same), then for s < 3 the stage's fusion.
+ * Row-folded twins: a fast-pathway 1x1x1 convolution with C = 8, 16 or 32 input channels (conv_c of stages 0..2 and
+ * the stride-1 branch1 of stage 0) is followed in the table by a second pair (fp16 [g*Cout, 64], fp32 [g*Cout]),
+ * g = 64 / C: the block-diagonal weight W'[j*Cout + n, j*C + k] = w'[n, k] and the shift repeated g times.  The
+ * library contracts g consecutive activation rows as one 64-wide row with it (same output bytes, full TMA boxes,
+ * g times fewer tiles) whenever the row count is a multiple of g.
  */
 int kvq_slowfast_num_weights(const KvqSlowFastConfig* cfg);
 size_t kvq_slowfast_workspace_bytes(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int W);

@@ -533,13 +533,14 @@ int conv_spatial(const __half* in, int N, int H, int W, int C, int k, int stride
                                 static_cast<const __half*>(w), gp, st);
   }
   const int Ho = conv_out(H, k, stride, pad), Wo = conv_out(W, k, stride, pad);
+  const int Kp = (k * k * C + 63) / 64 * 64;   // packed weights carry the same zero columns
   int rc;
   {
     ProfScope ps(PK_CONV_IM2COL, stage, st);
-    rc = launch_im2col_cl(in, col, N, 1, H, W, C, 1, k, k, 1, stride, stride, 0, pad, pad, k * k * C, st);
+    rc = launch_im2col_cl(in, col, N, 1, H, W, C, 1, k, k, 1, stride, stride, 0, pad, pad, Kp, st);
   }
   if (rc != 0) return rc;
-  return conv_gemm(col, k * k * C, w, b, nullptr, 0, out, N * Ho * Wo, cout, k * k * C, relu, stage, st);
+  return conv_gemm(col, Kp, w, b, nullptr, 0, out, N * Ho * Wo, cout, Kp, relu, stage, st);
 }
 
 }  // namespace

@@ -17,7 +17,6 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int conv_out(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
-inline int round8(int v) { return (v + 7) / 8 * 8; }
 inline int round64(int v) { return (v + 63) / 64 * 64; }
 
 constexpr int SF_FUSE_KT = 7;          // conv_fast_to_slow kernel (7,1,1), stride (alpha,1,1), padding (3,0,0)
@@ -58,7 +57,7 @@ int make_sf_plan(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int
   size_t sa = ns * pl->Hs * pl->Ws * 64 * 2, fa = nf * pl->Hs * pl->Ws * 8 * 2;
   size_t col = 0, max_row = 0;
   sa = std::max(sa, ns * pl->Hp * pl->Wp * 80 * 2);
-  col = std::max(col, ns * pl->Hp * pl->Wp * static_cast<size_t>(SF_FUSE_KT * 8) * 2);
+  col = std::max(col, ns * pl->Hp * pl->Wp * static_cast<size_t>(round64(SF_FUSE_KT * 8)) * 2);
   int h = pl->Hp, w = pl->Wp, cs = 80, cf = 8;
   for (int s = 0; s < 4; ++s) {
     const int is = 64 << s, jf = 8 << s, stride = s == 0 ? 1 : 2;
@@ -68,13 +67,15 @@ int make_sf_plan(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int
     sa = std::max({sa, rs * is * 2, rso * static_cast<size_t>(cs_out) * 2});
     fa = std::max({fa, rf * jf * 2, rfo * static_cast<size_t>(4 * jf) * 2});
     // conv_a (ka,1,1) at the input resolution, conv_b (1,3,3) and the strided 1x1 gather at the output resolution
-    const size_t ka_s = static_cast<size_t>(SF_SLOW_KA[s]) * std::max(cs, 4 * is);
-    const size_t ka_f = static_cast<size_t>(SF_FAST_KA[s]) * std::max(cf, 4 * jf);
+    const size_t ka_s = round64(SF_SLOW_KA[s] * std::max(cs, 4 * is));
+    const size_t ka_f = round64(SF_FAST_KA[s] * std::max(cf, 4 * jf));
     if (SF_SLOW_KA[s] > 1) { col = std::max(col, rs * ka_s * 2); max_row = std::max(max_row, ka_s * 2); }
-    col = std::max({col, rf * ka_f * 2, rso * static_cast<size_t>(9 * is) * 2, rfo * static_cast<size_t>(9 * jf) * 2});
+    col = std::max({col, rf * ka_f * 2, rso * static_cast<size_t>(9 * is) * 2,
+                    rfo * static_cast<size_t>(round64(9 * jf)) * 2});
     max_row = std::max({max_row, ka_f * 2, static_cast<size_t>(9 * is) * 2});
-    if (stride == 2) col = std::max({col, rso * static_cast<size_t>(cs) * 2, rfo * static_cast<size_t>(cf) * 2});
-    if (s < 3) col = std::max(col, rso * static_cast<size_t>(SF_FUSE_KT * 4 * jf) * 2);
+    if (stride == 2) col = std::max({col, rso * static_cast<size_t>(round64(cs)) * 2,
+                                     rfo * static_cast<size_t>(round64(cf)) * 2});
+    if (s < 3) col = std::max(col, rso * static_cast<size_t>(round64(SF_FUSE_KT * 4 * jf)) * 2);
     cs = cs_out; cf = 4 * jf;
     h = ho; w = wo;
   }
@@ -91,7 +92,16 @@ int make_sf_plan(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int
 struct ConvW {
   const __half* w;
   const float* b;
+  const __half* wf = nullptr;   // row-folded twin (pointwise layers with fewer than 64 input channels), see fold_rows()
+  const float* bf = nullptr;
 };
+
+// A pointwise convolution with C < 64 input channels makes every 64-wide TMA box mostly out of bounds and every
+// 128-row tile nearly empty (measured: a 2 M-row K = 8 GEMM takes 3x longer than K = 64).  g = 64 / C consecutive
+// rows of the contiguous [M, C] activation ARE one row of a [M/g, 64] matrix; multiplying it by the block-diagonal
+// weight [g*N, 64] (W on the diagonal blocks, packed once at load time) yields [M/g, g*N] = the same bytes as the
+// [M, N] output.  The extra MMA work is on zeros and the tensor pipe is idle here anyway.
+inline int fold_rows(int C) { return (C == 8 || C == 16 || C == 32) ? 64 / C : 1; }
 
 struct SfCtx {
   __half* col;
@@ -109,12 +119,12 @@ int gemm_conv(const __half* A, int lda, const ConvW& cw, int Np, int nvalid, int
   gp.relu = relu ? 1 : 0;
   gp.nvalid = nvalid == Np ? 0 : nvalid;
   ProfScope ps(PK_CONV_GEMM, stage, st);
-  return launch_gemm(EPI_CONV_F16, A, lda, cw.w, K, gp, st);
+  return launch_gemm(EPI_CONV_F16, A, lda, cw.w, round64(K), gp, st);   // packed weights: row stride round64(K)
 }
 
 // One convolution on a channels-last activation [B,T,H,W,C] (row stride C): 1x1x1 / stride 1 is the row GEMM itself;
 // anything else gathers the patch matrix in L2-sized row chunks and runs the GEMM per chunk.
-//   out[m, 0:cout] (row stride ldo) = act(conv + bias (+ resid[m, 0:cout])); weights [round64(cout), round8(K)]
+//   out[m, 0:cout] (row stride ldo) = act(conv + bias (+ resid[m, 0:cout])); weights [round64(cout), round64(K)]
 int conv_op(const SfCtx& cx, const __half* in, int B, int T, int H, int W, int C, const int k[3], const int s[3],
             const int p[3], const ConvW& cw, int cout, const __half* resid, int ldr, __half* out, int ldo, bool relu,
             int stage) {
@@ -122,7 +132,15 @@ int conv_op(const SfCtx& cx, const __half* in, int B, int T, int H, int W, int C
   const int To = conv_out(T, k[0], s[0], p[0]), Ho = conv_out(H, k[1], s[1], p[1]), Wo = conv_out(W, k[2], s[2], p[2]);
   const long long M = static_cast<long long>(B) * To * Ho * Wo;
   const bool pointwise = k[0] * k[1] * k[2] == 1 && s[0] * s[1] * s[2] == 1;
-  if (pointwise) return gemm_conv(in, C, cw, Np, cout, C, resid, ldr, out, ldo, M, relu, stage, cx.st);
+  if (pointwise) {
+    const int g = fold_rows(C);
+    if (g > 1 && cw.wf != nullptr && M % g == 0 && ldo == cout && (resid == nullptr || ldr == cout) &&
+        (g * cout) % 64 == 0) {
+      ConvW f{cw.wf, cw.bf};
+      return gemm_conv(in, 64, f, g * cout, g * cout, 64, resid, g * cout, out, g * cout, M / g, relu, stage, cx.st);
+    }
+    return gemm_conv(in, C, cw, Np, cout, C, resid, ldr, out, ldo, M, relu, stage, cx.st);
+  }
   if (conv_implicit_supported(C, k[0], k[1], k[2], s[0], s[1], s[2])) {
     // C >= 64: the patch matrix never exists -- the GEMM's TMA producer walks (tap, channel block) over the activation
     GemmParams gp{};
@@ -136,7 +154,8 @@ int conv_op(const SfCtx& cx, const __half* in, int B, int T, int H, int W, int C
     return launch_conv_implicit(in, B, T, H, W, C, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], cw.w, gp,
                                 cx.st);
   }
-  const int Kp = round8(k[0] * k[1] * k[2] * C);
+  // gathered K is padded to whole 64-wide TMA boxes (weights are packed with the same zero columns)
+  const int Kp = round64(k[0] * k[1] * k[2] * C);
   long long chunk = static_cast<long long>((cx.col_bytes - SF_SLACK) / (static_cast<size_t>(Kp) * 2));
   chunk = chunk / 128 * 128;
   KVQ_REQUIRE(chunk >= 128, KVQ_ERR_WORKSPACE, "slowfast: im2col scratch of %zu bytes cannot hold 128 rows of K=%d",
@@ -177,9 +196,14 @@ int res_stage(const SfCtx& cx, Pathway& P, const void* const* weights, int& wi, 
   const int one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
   const int ho = conv_out(h, 3, stride, 1), wo = conv_out(w, 3, stride, 1);
   const int cout = 4 * inner;
-  auto next = [&]() {
+  auto next = [&](bool folded = false) {
     ConvW c{static_cast<const __half*>(weights[wi]), static_cast<const float*>(weights[wi + 1])};
     wi += 2;
+    if (folded) {
+      c.wf = static_cast<const __half*>(weights[wi]);
+      c.bf = static_cast<const float*>(weights[wi + 1]);
+      wi += 2;
+    }
     return c;
   };
   for (int j = 0; j < depth; ++j) {
@@ -195,13 +219,13 @@ int res_stage(const SfCtx& cx, Pathway& P, const void* const* weights, int& wi, 
     int ldr = P.C;
     int rc;
     if (j == 0) {
-      const ConvW c1 = next();
+      const ConvW c1 = next(sj == 1 && fold_rows(P.C) > 1);
       const int s1[3] = {1, sj, sj};
       rc = conv_op(cx, cur, B, P.T, hi, wj, P.C, one, s1, zero, c1, cout, nullptr, 0, idn, cout, false, stage);
       if (rc != 0) return rc;
       resid = idn; ldr = cout;
     }
-    const ConvW ca = next(), cb = next(), cc = next();
+    const ConvW ca = next(), cb = next(), cc = next(fold_rows(inner) > 1);
     const int kA[3] = {ka, 1, 1}, pA[3] = {ka / 2, 0, 0};
     rc = conv_op(cx, cur, B, P.T, hi, wj, P.C, kA, one, pA, ca, inner, nullptr, 0, t1, inner, true, stage);
     if (rc != 0) return rc;
@@ -223,7 +247,11 @@ extern "C" {
 int kvq_slowfast_num_weights(const KvqSlowFastConfig* cfg) {
   if (cfg == nullptr) return KVQ_ERR_BAD_SHAPE;
   int n = 6;
-  for (int s = 0; s < 4; ++s) n += 2 * 2 * (3 * cfg->depths[s] + 1) + (s < 3 ? 2 : 0);
+  for (int s = 0; s < 4; ++s) {
+    n += 2 * 2 * (3 * cfg->depths[s] + 1) + (s < 3 ? 2 : 0);
+    if (fold_rows(8 << s) > 1) n += 2 * cfg->depths[s];   // folded twins of the fast pathway's conv_c
+    if (s == 0) n += 2;                                    // ... and of its stride-1 branch1 (8 -> 32 channels)
+  }
   return n;
 }
 

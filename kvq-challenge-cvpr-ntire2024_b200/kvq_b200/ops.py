@@ -301,9 +301,11 @@ def _i3(v):
     return (ctypes.c_int32 * 3)(*[int(a) for a in v])
 
 
-def pack_conv_weight(w, bn=None, eps=1e-5, pad_out=64):
+def pack_conv_weight(w, bn=None, eps=1e-5, pad_out=64, fold=False):
     """Conv weight [Cout,Cin,*k] (+ eval-mode BatchNorm (gamma, beta, mean, var)) -> (fp16 [Np, Kp] tap-major /
-    channel-minor with the BN scale folded in, fp32 [Np] shift).  Np = Cout rounded up to `pad_out`, Kp to 8."""
+    channel-minor with the BN scale folded in, fp32 [Np] shift).  Np = Cout rounded up to `pad_out`, Kp to 64 (whole
+    TMA boxes).  fold=True (pointwise conv with 8/16/32 input channels) also returns the row-folded twin
+    (fp16 [g*Cout, 64] block-diagonal, fp32 [g*Cout]) documented in include/kvq_b200.h."""
     w = w.detach().float()
     cout = w.shape[0]
     if bn is not None:
@@ -316,12 +318,21 @@ def pack_conv_weight(w, bn=None, eps=1e-5, pad_out=64):
     perm = (0,) + tuple(range(2, w.dim())) + (1,)
     w2 = w.permute(*perm).reshape(cout, -1)
     K = w2.shape[1]
-    Kp, Np = (K + 7) // 8 * 8, (cout + pad_out - 1) // pad_out * pad_out
+    Kp, Np = (K + 63) // 64 * 64, (cout + pad_out - 1) // pad_out * pad_out
     wp = torch.zeros((Np, Kp), dtype=torch.float32, device=w.device)
     wp[:cout, :K] = w2
     sp = torch.zeros(Np, dtype=torch.float32, device=w.device)
     sp[:cout] = shift
-    return cast_f16(wp.contiguous()), sp.contiguous()
+    packed = (cast_f16(wp.contiguous()), sp.contiguous())
+    if not fold:
+        return packed
+    if K not in (8, 16, 32) or (64 // K * cout) % 64 != 0:
+        raise RuntimeError(f"kvq_b200: cannot row-fold a [{cout},{K}] pointwise weight")
+    g = 64 // K
+    wf = torch.zeros((g * cout, 64), dtype=torch.float32, device=w.device)
+    for j in range(g):
+        wf[j * cout:(j + 1) * cout, j * K:(j + 1) * K] = w2
+    return packed + (cast_f16(wf.contiguous()), shift.repeat(g).contiguous())
 
 
 def pack_stem_weight(w, bn=None, eps=1e-5):
@@ -615,9 +626,10 @@ class SlowFastWeights:
         def t(k):
             return sd[k].detach().to(self.device, torch.float32)
 
-        def conv_bn(conv, bn):
+        def conv_bn(conv, bn, fold=False):
             return list(pack_conv_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
-                                                              ("weight", "bias", "running_mean", "running_var")], eps))
+                                                              ("weight", "bias", "running_mean", "running_var")], eps,
+                                         fold=fold))
 
         def stem_bn(conv, bn):
             return list(pack_stem_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
@@ -632,10 +644,12 @@ class SlowFastWeights:
             for path in (0, 1):
                 for j in range(depth):
                     b = f"{p}multipathway_blocks.{path}.res_blocks.{j}."
+                    inner = (8 << s) if path == 1 else (64 << s)
                     if j == 0:
-                        ts += conv_bn(b + "branch1_conv", b + "branch1_norm")
-                    for c in "abc":
+                        ts += conv_bn(b + "branch1_conv", b + "branch1_norm", fold=(path == 1 and s == 0))
+                    for c in "ab":
                         ts += conv_bn(b + "branch2.conv_" + c, b + "branch2.norm_" + c)
+                    ts += conv_bn(b + "branch2.conv_c", b + "branch2.norm_c", fold=inner in (8, 16, 32))
             if s < 3:
                 ts += conv_bn(p + "multipathway_fusion.conv_fast_to_slow", p + "multipathway_fusion.norm")
         self.tensors = ts
