@@ -54,6 +54,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
                  uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes);
 int make_tmap_conv5d(CUtensorMap* out, const void* base, int B, int T, int H, int W, int C, int bt, int bh, int bw,
                      int st, int sh, int sw);
+// output side of the conv epilogue: [B,To,Ho,Wo,(row stride ldo)] fp16 with `cols` valid channels; box = 32 channels x
+// (bw x bh x bt) pixels, 64 B swizzle (TMA store clips everything outside the extents)
+int make_tmap_out5d(CUtensorMap* out, const void* base, int B, int To, int Ho, int Wo, int cols, int ldo, int bt, int bh,
+                    int bw);
 
 // ----------------------------------------------------------------------------------------------
 // device helpers
@@ -165,6 +169,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

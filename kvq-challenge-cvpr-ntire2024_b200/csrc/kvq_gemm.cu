@@ -28,7 +28,8 @@ constexpr int BK = 64;  // 64 halfs = one 128 B swizzle row
 constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int EPI_WARPS = 8;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int STAGING_BYTES = EPI_WARPS * (32 * 36 * 4 + 32 * 8);   // per warp: 32x36 fp32 tile + 32 row offsets
+constexpr int WARP_STAGING = 5120;   // per warp: 32x36 fp32 tile (or two 2 KB TMA-store boxes) + 32 row offsets; 512 B aligned
+constexpr int STAGING_BYTES = EPI_WARPS * WARP_STAGING;
 constexpr int MAX_BIAS_N = 4096;
 constexpr int BIAS_BYTES = MAX_BIAS_N * 4;   // the whole bias vector, staged once per CTA (a per-tile __ldg refresh
                                              // of the n-block's slice cost ~13 % of the epilogue's issue samples)
@@ -103,7 +104,8 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t* r) {
 
 template <int BN, int EPI, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -248,11 +250,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int c_step = (kWholeRow || MT == 2 || kTileSplit) ? 1 : 2;
     const bool active = !kWholeRow || half == 0;
     const int msub = MT == 2 ? half : 0;
-    float* stile = reinterpret_cast<float*>(staging + ew * (32 * 36 * 4 + 32 * 8));
+    float* stile = reinterpret_cast<float*>(staging + ew * WARP_STAGING);
     long long* srow = reinterpret_cast<long long*>(stile + 32 * 36);
     int as = 0;
     uint32_t aph = 0;
     int bias_nblk = -1;
+    uint32_t nstore = 0;          // conv epilogue: TMA stores issued by this warp (selects the smem box)
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       if constexpr (kTileSplit) {
@@ -336,9 +339,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         constexpr int MYCH = (MT == 2 || kTileSplit) ? NCHUNK : (NCHUNK + 1) / 2;
         const int nvalid = p.nvalid > 0 ? p.nvalid : p.N;
         // output row of this thread's accumulator row: identity, or (implicit conv) the pixel of the tile's
-        // bt x bh x bw block; -1 = outside the map.  Shared with the other lanes for the transposed stores.
+        // bt x bh x bw block; -1 = outside the map
         long long orow = row_ok ? row : -1;
-        if (conv_mode) {
+        if (conv_mode && p.resid_h != nullptr) {   // (only the residual load needs the per-thread row)
           int r = m_blk;
           const int tw = r % p.conv.nw; r /= p.conv.nw;
           const int th = r % p.conv.nh; r /= p.conv.nh;
@@ -352,20 +355,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           orow = (ow < p.conv.Wo && oh < p.conv.Ho && ot < p.conv.To)
                      ? ((static_cast<long long>(b) * p.conv.To + ot) * p.conv.Ho + oh) * p.conv.Wo + ow
                      : -1;
-        }
-        __syncwarp();
-        srow[lane] = orow;
-        __syncwarp();
-        if (n_blk != bias_nblk) {
-          __syncwarp();
-#pragma unroll
-          for (int ci = 0; ci < MYCH; ++ci) {
-            const int c0 = (c_begin + ci * c_step) * CW;
-            if (lane < CW && c0 < BN)
-              stile[ci * CW + lane] = sbias[nbase + c0 + lane];
-          }
-          bias_nblk = n_blk;
-          __syncwarp();
         }
         // this thread's residual row is fetched one chunk ahead, and the first chunk BEFORE the accumulator wait: the
         // thin-K convolutions are bound by this load's latency, not by the tensor pipe
@@ -385,44 +374,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tfull[as], aph);
         __syncwarp();
         tc_fence_after();
+        // Each 32-row x 32-channel chunk goes registers -> 64B-swizzled smem box -> ONE TMA store (2-D rows, or the
+        // 5-D pixel block of the implicit convolution; the tensor map clips rows / pixels / channels outside the
+        // output).  The transpose + st.global path it replaces kept l1tex at 71-82 % of peak (ncu).
+        static_assert(CW == 32, "conv epilogue stores 32-channel boxes");
+        uint8_t* sbuf = reinterpret_cast<uint8_t*>(stile);            // two 2 KB boxes
+        int oc1 = m_blk * TM + q * 32, oc2 = 0, oc3 = 0, oc4 = 0;      // store coordinates above the channel dim
+        if (conv_mode) {
+          int rr = m_blk;
+          const int tw = rr % p.conv.nw; rr /= p.conv.nw;
+          const int th = rr % p.conv.nh; rr /= p.conv.nh;
+          const int tt = rr % p.conv.nt;
+          oc4 = rr / p.conv.nt;
+          int l = q * 32;
+          const int lw = l % p.conv.bw; l /= p.conv.bw;
+          oc1 = tw * p.conv.bw + lw;
+          oc2 = th * p.conv.bh + l % p.conv.bh;
+          oc3 = tt * p.conv.bt + l / p.conv.bh;
+        }
         uint32_t r[2][CW];
-        tmem_ld_chunk<CW>(taddr + c_begin * CW, r[0]);
+        tmem_ld_chunk<CW>(taddr, r[0]);
 #pragma unroll
         for (int ci = 0; ci < MYCH; ++ci) {
-          const int c0 = (c_begin + ci * c_step) * CW;
-          if (c0 >= BN) break;
+          const int c0 = ci * CW;
           if (ci + 1 < MYCH) load_resid(ci + 1, rsb[(ci + 1) & 1]);
           const uint4* rs = rsb[ci & 1];
           tmem_wait_ld();
-          if (ci + 1 < MYCH && c0 + c_step * CW < BN) tmem_ld_chunk<CW>(taddr + c0 + c_step * CW, r[(ci + 1) & 1]);
+          if (ci + 1 < MYCH) tmem_ld_chunk<CW>(taddr + c0 + CW, r[(ci + 1) & 1]);
+          if (nbase + c0 >= nvalid) continue;                          // padded output channels: nothing to store
           const uint32_t* rc = r[ci & 1];
+          const float* bs = sbias + nbase + c0;
           uint32_t h[CW / 2];
 #pragma unroll
           for (int j = 0; j < CW / 2; ++j) {
             const uint32_t rw = reinterpret_cast<const uint32_t*>(rs)[j];
             const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rw));
-            float v0 = __uint_as_float(rc[2 * j]) + stile[ci * CW + 2 * j] + rf.x;
-            float v1 = __uint_as_float(rc[2 * j + 1]) + stile[ci * CW + 2 * j + 1] + rf.y;
+            const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * j);
+            float v0 = __uint_as_float(rc[2 * j]) + bb.x + rf.x;
+            float v1 = __uint_as_float(rc[2 * j + 1]) + bb.y + rf.y;
             if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             h[j] = pack_half2(v0, v1);
           }
-          constexpr int SEGS = CW / 8;
-          uint8_t* st16 = reinterpret_cast<uint8_t*>(stile) + 1024;
+          uint8_t* buf = sbuf + (nstore & 1) * 2048;
+          if (lane == 0) tma_store_wait_read<1>();                     // the store that last used this box has read it
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < SEGS; ++j)
-            *reinterpret_cast<uint4*>(st16 + lane * 80 + j * 16) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          fence_proxy_async_smem();
           __syncwarp();
-          constexpr int RPI = 32 / SEGS;
-          const int seg = lane / RPI, rl = lane % RPI;
-#pragma unroll
-          for (int it = 0; it < SEGS; ++it) {
-            const int rr = it * RPI + rl;
-            const uint4 v = *reinterpret_cast<const uint4*>(st16 + rr * 80 + seg * 16);
-            const long long grow = srow[rr];
-            if (grow >= 0 && nbase + c0 + 8 * seg < nvalid)
-              st_global_v4(reinterpret_cast<__half*>(p.out) + grow * p.ldo + nbase + c0 + 8 * seg, v.x, v.y, v.z, v.w);
+          if (lane == 0) {
+            if (conv_mode) tma_store_5d(&tmC, buf, nbase + c0, oc1, oc2, oc3, oc4);
+            else tma_store_2d(&tmC, buf, nbase + c0, oc1);
+            tma_store_commit();
           }
+          ++nstore;
         }
       } else if constexpr (EPI == EPI_RESID_F32) {
         // Row-per-thread TMEM reads are transposed through a per-warp smem tile so that global traffic is
@@ -630,6 +637,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (++as == ACC) { as = 0; aph ^= 1; }
     }
+    if constexpr (EPI == EPI_CONV_F16) {
+      if (lane == 0) tma_store_wait_all<0>();   // bulk stores complete (and their smem boxes are free) before exit
+    }
+    (void)nstore;
   }
 
   tc_fence_before();
@@ -655,10 +666,17 @@ int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmPa
               ldb, kcols_b);
   rc = make_tmap_2d(&tmB, B, p.N, kcols_b, static_cast<uint64_t>(ldb) * 2, BN, BK, 2, 128);
   if (rc != 0) return rc;
+  CUtensorMap tmC = tmB;   // only the conv epilogue stores through a tensor map
+  if constexpr (EPI == EPI_CONV_F16) {
+    const int cols = p.nvalid > 0 ? p.nvalid : p.N;
+    rc = make_tmap_2d(&tmC, p.out, p.M, cols, static_cast<uint64_t>(p.ldo) * 2, 32, 32, 2, 64);
+    if (rc != 0) return rc;
+  }
   const int tiles = ((p.M + BM * MT - 1) / (BM * MT)) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   count_launch();
-  return launch_pdl(gemm_kernel<BN, EPI, MT>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, MT>::SMEM, stream, tmA, tmB, p);
+  return launch_pdl(gemm_kernel<BN, EPI, MT>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, MT>::SMEM, stream, tmA, tmB, tmC,
+                    p);
 }
 
 // 256-row tiles (opt-in, KVQ_GEMM_BIG_TILES=1): fewer L2 bytes per FLOP, but at batch 8 the stage-2/3 GEMMs then have
@@ -679,7 +697,8 @@ int launch_bn(const __half* A, int lda, const __half* B, int ldb, const GemmPara
 }
 
 template <int BN>
-int launch_conv_impl(const CUtensorMap& tmA, const __half* Wt, int K, const GemmParams& p, cudaStream_t stream) {
+int launch_conv_impl(const CUtensorMap& tmA, const CUtensorMap& tmC, const __half* Wt, int K, const GemmParams& p,
+                     cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     KVQ_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI_CONV_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -693,7 +712,7 @@ int launch_conv_impl(const CUtensorMap& tmA, const __half* Wt, int K, const Gemm
   const int grid = tiles < num_sms() ? tiles : num_sms();
   count_launch();
   return launch_pdl(gemm_kernel<BN, EPI_CONV_F16, 1>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, 1>::SMEM, stream, tmA,
-                    tmB, p);
+                    tmB, tmC, p);
 }
 
 }  // namespace
@@ -740,10 +759,17 @@ int launch_conv_implicit(const __half* in, int B, int T, int H, int W, int C, in
   CUtensorMap tmA;
   int rc = make_tmap_conv5d(&tmA, in, B, T, H, W, C, best_bt, best_bh, best_bw, st, sh, sw);
   if (rc != 0) return rc;
-  if (p.N % 256 == 0 && tiles_m * (p.N / 256) >= num_sms()) return launch_conv_impl<256>(tmA, Wt, p.K, p, stream);
-  if (p.N % 192 == 0 && tiles_m * (p.N / 192) >= num_sms()) return launch_conv_impl<192>(tmA, Wt, p.K, p, stream);
-  if (p.N % 128 == 0 && tiles_m * (p.N / 128) >= num_sms()) return launch_conv_impl<128>(tmA, Wt, p.K, p, stream);
-  return launch_conv_impl<64>(tmA, Wt, p.K, p, stream);
+  // a warp's 32 accumulator rows are an aligned bw_w x bh_w x bt_w sub-block of the tile's pixel block
+  const int bw_w = best_bw < 32 ? best_bw : 32;
+  const int bh_w = best_bh < 32 / bw_w ? best_bh : 32 / bw_w;
+  const int bt_w = 32 / (bw_w * bh_w);
+  CUtensorMap tmC;
+  rc = make_tmap_out5d(&tmC, p.out, B, To, Ho, Wo, p.nvalid > 0 ? p.nvalid : p.N, p.ldo, bt_w, bh_w, bw_w);
+  if (rc != 0) return rc;
+  if (p.N % 256 == 0 && tiles_m * (p.N / 256) >= num_sms()) return launch_conv_impl<256>(tmA, tmC, Wt, p.K, p, stream);
+  if (p.N % 192 == 0 && tiles_m * (p.N / 192) >= num_sms()) return launch_conv_impl<192>(tmA, tmC, Wt, p.K, p, stream);
+  if (p.N % 128 == 0 && tiles_m * (p.N / 128) >= num_sms()) return launch_conv_impl<128>(tmA, tmC, Wt, p.K, p, stream);
+  return launch_conv_impl<64>(tmA, tmC, Wt, p.K, p, stream);
 }
 
 int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,

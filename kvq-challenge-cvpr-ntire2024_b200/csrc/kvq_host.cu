@@ -98,6 +98,27 @@ int make_tmap_conv5d(CUtensorMap* out, const void* base, int B, int T, int H, in
   return KVQ_OK;
 }
 
+int make_tmap_out5d(CUtensorMap* out, const void* base, int B, int To, int Ho, int Wo, int cols, int ldo, int bt, int bh,
+                    int bw) {
+  EncodeTiledFn enc = get_encode();
+  KVQ_REQUIRE(enc != nullptr, KVQ_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ldo % 8 == 0 && cols >= 1, KVQ_ERR_MISALIGNED,
+              "out TMA: base %p / row stride %d halfs must be 16 B aligned", base, ldo);
+  cuuint64_t gdim[5] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho),
+                        static_cast<cuuint64_t>(To), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[4] = {static_cast<cuuint64_t>(ldo) * 2, static_cast<cuuint64_t>(Wo) * ldo * 2,
+                        static_cast<cuuint64_t>(Ho) * Wo * ldo * 2, static_cast<cuuint64_t>(To) * Ho * Wo * ldo * 2};
+  cuuint32_t box[5] = {32, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bt), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KVQ_REQUIRE(r == CUDA_SUCCESS, KVQ_ERR_DRIVER,
+              "cuTensorMapEncodeTiled(out) failed (%d) dims=%dx%dx%dx%dx%d ldo=%d box=%dx%dx%d", static_cast<int>(r), B,
+              To, Ho, Wo, cols, ldo, bt, bh, bw);
+  return KVQ_OK;
+}
+
 // ---- optional per-kernel-category device timing (bench.py's roofline leg) and a launch counter ----
 namespace {
 struct ProfState {
