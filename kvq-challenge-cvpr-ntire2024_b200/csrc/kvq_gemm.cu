@@ -569,7 +569,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // memory (named barrier over the 8 epilogue warps), a second pass normalises and stores.
         constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
         float* sstat = stile;                         // this warp's 32 x {sum, sumsq} partials
-        float* pstat = reinterpret_cast<float*>(staging + (ew ^ 4) * (32 * 36 * 4 + 32 * 8));   // partner warp's
+        float* pstat = reinterpret_cast<float*>(staging + (ew ^ 4) * WARP_STAGING);   // partner warp's
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int ci = 0; ci < MYCH; ++ci) {
