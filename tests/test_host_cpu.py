@@ -109,3 +109,64 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_conv_branch_host_entry_points():
+    """Planning / validation entry points of the SlowFast and SimpleVQA paths run without a GPU and report errors
+    through return codes + kvq_last_error_string (never exit / throw across the C boundary)."""
+    from kvq_b200 import lib
+    L = lib.load()
+    sf = lib.KvqSlowFastConfig()
+    for i, d in enumerate((3, 4, 6, 3)):
+        sf.depths[i] = d
+    sf.alpha = 4
+    for i, (a, b) in enumerate(zip((8, 7, 7), (32, 7, 7))):
+        sf.slow_pool[i], sf.fast_pool[i] = a, b
+    # 3 stems/fusion pairs + per stage 2 pathways x (3 convs per block + branch1) pairs + fusions + row-folded twins
+    n = L.kvq_slowfast_num_weights(ctypes.byref(sf))
+    assert n == 6 + sum(2 * 2 * (3 * d + 1) for d in (3, 4, 6, 3)) + 3 * 2 + 2 * (3 + 4 + 6) + 2
+    ws = L.kvq_slowfast_workspace_bytes(ctypes.byref(sf), 16, 8, 32, 256, 256)
+    assert 1.5e9 < ws < 4e9                                         # a few GB of 180: activations of 16 clips + scratch
+    assert L.kvq_slowfast_workspace_bytes(ctypes.byref(sf), 1, 8, 24, 224, 224) == 0
+    assert "slow frames" in lib.last_error()                       # 24 fast frames fuse to 6 slow frames, not 8
+    assert L.kvq_slowfast_workspace_bytes(ctypes.byref(sf), 1, 8, 32, 16, 16) == 0
+    assert L.kvq_slowfast_forward(ctypes.byref(sf), None, n, None, None, 1, 8, 32, 224, 224, None, None, None, 0, None) < 0
+    assert "NULL" in lib.last_error()
+    rn = lib.KvqResNetConfig()
+    for i, d in enumerate((3, 4, 6, 3)):
+        rn.layers[i] = d
+    rn.feat3d_dim, rn.head = 2304, 1
+    assert L.kvq_resnet_feature_dim(ctypes.byref(rn)) == 9472      # simpleVQAHead in_channels (kwai_simpleVQA_test.yml)
+    assert L.kvq_resnet_num_weights(ctypes.byref(rn)) == 2 + 2 * (3 * 16 + 4) + 2
+    assert L.kvq_simplevqa_workspace_bytes(ctypes.byref(rn), 1, 8, 448, 448) > 0
+    assert L.kvq_simplevqa_workspace_bytes(ctypes.byref(rn), 1, 8, 16, 16) == 0
+    assert L.kvq_stem_weight_rows(8) == 16 and L.kvq_stem_weight_rows(64) == 64
+    # implicit convolution: channel count must be a multiple of 64 (smaller widths go through the gather path)
+    rc = L.kvq_conv_implicit_f16(1, 1, None, None, 0, 1, 64, 1, 1, 8, 8, 32, lib.i3((1, 3, 3)), lib.i3((1, 1, 1)),
+                                 lib.i3((0, 1, 1)), 64, 0, 1, None)
+    assert rc < 0 and "64" in lib.last_error()
+
+
+def test_pack_conv_weight_layouts():
+    """Host-side weight packing contracts of include/kvq_b200.h (tap-major / channel-minor, K padded to 64, row-folded
+    twin, stem layout) -- checked on CPU tensors up to the fp16 cast, which needs the device."""
+    import torch.nn.functional as F
+    w = torch.randn(32, 8, 1, 1, 1)
+    g = 8
+    wf = torch.zeros(g * 32, 64)
+    for j in range(g):
+        wf[j * 32:(j + 1) * 32, j * 8:(j + 1) * 8] = w.reshape(32, 8)
+    x = torch.randn(40, 8)                                  # 40 rows = 5 folded rows
+    ref = x @ w.reshape(32, 8).t()
+    got = (x.reshape(5, 64) @ wf.t()).reshape(40, 32)       # same bytes, read as [M/g, g*N]
+    assert torch.allclose(ref, got, atol=1e-5)
+    # tap-major / channel-minor K index of a (3,1,1) convolution
+    wt = torch.randn(4, 16, 3, 1, 1)
+    xx = torch.randn(1, 16, 5, 2, 2)
+    ref = F.conv3d(xx, wt, padding=(1, 0, 0))
+    w2 = wt.permute(0, 2, 3, 4, 1).reshape(4, -1)           # what ops.pack_conv_weight builds
+    xp = F.pad(xx, (0, 0, 0, 0, 1, 1))
+    cols = torch.stack([xp[:, :, t:t + 3] for t in range(5)], dim=2)          # [1,16,5,3,2,2]
+    cols = cols.permute(0, 2, 4, 5, 3, 1).reshape(-1, 48)                       # rows (t,h,w), K = (dt, c)
+    got = (cols @ w2.t()).reshape(1, 5, 2, 2, 4).permute(0, 4, 1, 2, 3)
+    assert torch.allclose(ref, got, atol=1e-5)
