@@ -108,7 +108,7 @@ def build_workload(name, B, dev, rank):
     extra modules to keep alive).  Every step goes through the repo's public drop-in API."""
     import torch
     import models
-    from oracle import synth
+    from tools import synth          # seeded data generation only; nothing under oracle/ runs on the product path
 
     def swin_net():
         m = models.VQA_Network(MODEL_CFG)
@@ -203,7 +203,7 @@ def build_workload(name, B, dev, rank):
 
 
 def synth_model_state(seed=0):
-    from oracle import synth
+    from tools import synth
     return synth.swin_network_state_dict(seed, key="swin_tiny_grpb")
 
 
@@ -298,7 +298,7 @@ def run_reference(args):
 def reference_inputs(name):
     """One-clip host inputs of a workload, without touching CUDA."""
     import torch
-    from oracle import synth
+    from tools import synth
 
     def host(seed):
         if name in ("swin", "ksvqe_full"):
@@ -318,8 +318,6 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from kvq_b200 import lib
-    import models
-    from oracle import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

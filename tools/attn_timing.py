@@ -12,7 +12,7 @@ from kvq_b200 import lib  # noqa: E402
 lib.LIB_PATH = os.path.join(ROOT, "tools", "libkvq_b200_timing.so")
 import torch  # noqa: E402
 from kvq_b200 import ops  # noqa: E402
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 NAMES = ["table wait", "wait S(t>0)", "pass 1", "max barrier", "wait PV + O epilogue", "pass 2", "wait S(0) incl. load", "prologue/arrive"]
 

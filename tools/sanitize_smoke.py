@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "kvq-challenge-cvpr-ntire2024_b200"))
 import torch  # noqa: E402
 from kvq_b200 import ops  # noqa: E402
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 dev = torch.device("cuda:0")
 sd = synth.swin_network_state_dict(3)

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "kvq-challenge-cvpr-ntire2024_b200"))
 from kvq_b200 import lib, ops  # noqa: E402
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 
 def main():
