@@ -145,24 +145,27 @@ maxpool_hw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N
   pdl_launch_dependents();
 }
 
-// block = (n, 256-channel slab): 32 channel groups of 8 x 8 partitions of the L axis; two passes (mean, then centred
-// sum of squares) so the unbiased std does not cancel in fp32
+// block = (n, 64-channel slab): 8 channel groups of 8 channels x 32 partitions of the L axis (a warp reads four
+// 128-byte row segments per load); two passes (mean, then centred sum of squares, the second one out of L2) so the
+// unbiased std does not cancel in fp32.  64-channel slabs give N * C/64 blocks: 256+ for every pooled layer here
+// (the 256-channel slabs of the first version left 64 blocks on 148 SMs).
+constexpr int PS_CG = 8, PS_LP = CONV_THREADS / PS_CG;   // 8 channel groups x 32 L partitions
 __global__ void __launch_bounds__(CONV_THREADS)
 pool_stats_kernel(const __half* __restrict__ in, const float* __restrict__ weights, float* __restrict__ out_mean,
                   float* __restrict__ out_std, int L, int C, int ldo) {
   pdl_wait();
-  __shared__ float red[8][32][8];
-  __shared__ float mean_s[32][8];
+  __shared__ float red[PS_LP][PS_CG][8];
+  __shared__ float mean_s[PS_CG][8];
   const int n = blockIdx.x;
-  const int cg = threadIdx.x & 31, lp = threadIdx.x >> 5;
-  const int c = (blockIdx.y * 32 + cg) << 3;
+  const int cg = threadIdx.x % PS_CG, lp = threadIdx.x / PS_CG;
+  const int c = (blockIdx.y * PS_CG + cg) << 3;
   const bool ok = c < C;
   const __half* base = in + static_cast<long long>(n) * L * C + c;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (ok) {
-    for (int l = lp; l < L; l += 8) {
+    for (int l = lp; l < L; l += PS_LP) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(l) * C));
       const __half2* hv = reinterpret_cast<const __half2*>(&v);
       const float wgt = weights != nullptr ? __ldg(weights + l) : 1.f;
@@ -177,17 +180,15 @@ pool_stats_kernel(const __half* __restrict__ in, const float* __restrict__ weigh
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[lp][cg][j] = acc[j];
   __syncthreads();
-  if (lp == 0) {
-    const float scale = weights != nullptr ? 1.f : 1.f / static_cast<float>(L);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) s += red[q][cg][j];
-      s *= scale;
-      mean_s[cg][j] = s;
-      if (ok) out_mean[static_cast<long long>(n) * ldo + c + j] = s;
-    }
+  if (threadIdx.x < PS_CG * 8) {       // one thread per (channel group, channel)
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float s = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < PS_LP; ++q) s += red[q][g][j];
+    s *= weights != nullptr ? 1.f : 1.f / static_cast<float>(L);
+    mean_s[g][j] = s;
+    const int cc = ((blockIdx.y * PS_CG + g) << 3) + j;
+    if (cc < C) out_mean[static_cast<long long>(n) * ldo + cc] = s;
   }
   if (out_std == nullptr) { pdl_launch_dependents(); return; }
   __syncthreads();
@@ -197,7 +198,7 @@ pool_stats_kernel(const __half* __restrict__ in, const float* __restrict__ weigh
     float mu[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) mu[j] = mean_s[cg][j];
-    for (int l = lp; l < L; l += 8) {
+    for (int l = lp; l < L; l += PS_LP) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(l) * C));
       const __half2* hv = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
@@ -213,16 +214,14 @@ pool_stats_kernel(const __half* __restrict__ in, const float* __restrict__ weigh
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[lp][cg][j] = acc[j];
   __syncthreads();
-  if (lp == 0 && ok) {
+  if (threadIdx.x < PS_CG * 8) {
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float s = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < PS_LP; ++q) s += red[q][g][j];
+    const int cc = ((blockIdx.y * PS_CG + g) << 3) + j;
     // torch.std default: unbiased (L - 1); L == 1 gives NaN there too
-    const float inv = 1.f / static_cast<float>(L - 1);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) s += red[q][cg][j];
-      out_std[static_cast<long long>(n) * ldo + c + j] = sqrtf(s * inv);
-    }
+    if (cc < C) out_std[static_cast<long long>(n) * ldo + cc] = sqrtf(s / static_cast<float>(L - 1));
   }
   pdl_launch_dependents();
 }
@@ -369,7 +368,7 @@ int launch_pool_stats(const __half* in, const float* weights, float* out_mean, f
   KVQ_REQUIRE(N > 0 && L > 0 && C > 0 && C % 8 == 0 && ldo >= C, KVQ_ERR_BAD_SHAPE,
               "pool_stats: bad shape N=%d L=%d C=%d ldo=%d", N, L, C, ldo);
   count_launch();
-  return launch_pdl(pool_stats_kernel, dim3(N, (C + 255) / 256), dim3(CONV_THREADS), 0, stream, in, weights, out_mean,
+  return launch_pdl(pool_stats_kernel, dim3(N, (C + 63) / 64), dim3(CONV_THREADS), 0, stream, in, weights, out_mean,
                     out_std, L, C, ldo);
 }
 
