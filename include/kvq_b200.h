@@ -180,11 +180,13 @@ typedef struct KvqSlowFastConfig {
  *   slow stem, fast stem (both in the stem layout of kvq_stem_conv_f16), block-0 fusion (conv_fast_to_slow + norm);
  *   then per stage s = 0..3: every slow res block (branch1 first for block 0; conv_a, conv_b, conv_c), every fast
  *   res block (same), then for s < 3 the stage's fusion.
- * Row-folded twins: a fast-pathway 1x1x1 convolution with C = 8, 16 or 32 input channels (conv_c of stages 0..2 and
- * the stride-1 branch1 of stage 0) is followed in the table by a second pair (fp16 [g*Cout, 64], fp32 [g*Cout]),
- * g = 64 / C: the block-diagonal weight W'[j*Cout + n, j*C + k] = w'[n, k] and the shift repeated g times.  The
- * library contracts g consecutive activation rows as one 64-wide row with it (same output bytes, full TMA boxes,
- * g times fewer tiles) whenever the row count is a multiple of g.
+ * Twins: every fast-pathway convolution that READS 8, 16 or 32 channels is followed in the table by a second pair:
+ *   - 1x1x1, stride 1 (conv_c of stages 0..2, branch1 of stage 0): the row-folded pair (fp16 [g*Cout, 64],
+ *     fp32 [g*Cout]), g = 64 / C: block-diagonal W'[j*Cout + n, j*C + k] = w'[n, k], shift repeated g times.  The
+ *     library contracts g consecutive activation rows as one 64-wide row (same output bytes, full TMA boxes, g times
+ *     fewer tiles) whenever the row count is a multiple of g;
+ *   - anything else (conv_a (3,1,1), conv_b (1,3,3), the strided branch1 of stage 1, the fusions after the stem and
+ *     after stage 0): (the smem image of kvq_conv_narrow_f16, fp32 [64] shift).
  */
 int kvq_slowfast_num_weights(const KvqSlowFastConfig* cfg);
 size_t kvq_slowfast_workspace_bytes(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int W);
@@ -216,6 +218,16 @@ int kvq_conv_gemm_f16(const void* a_f16, int lda, const void* w_f16, const float
 int kvq_conv_implicit_f16(const void* in_f16, const void* w_f16, const float* bias, const void* resid_f16, int ldr,
                           void* out_f16, int ldo, int B, int T, int H, int W, int C, const int32_t kernel[3],
                           const int32_t stride[3], const int32_t pad[3], int N, int nvalid, int relu, void* stream);
+/* Narrow-channel implicit GEMM (C = 8, 16 or 32 input channels, at most 64 output channels): a K block of the
+ * contraction is 64 / C TAPS, each fetched by TMA as a [128 pixels x C] sub-tile (no swizzle / 32 B / 64 B swizzle).
+ * w_image: kvq_conv_image_kblocks(C, taps) images of 8192 bytes, image kb = the [64 x 64] fp16 weight block of taps
+ * [kb*64/C, (kb+1)*64/C) laid out exactly as the kernel's shared-memory B tile:
+ *   byte(t, n, k) = t*128*C + n*2*C + ((k/8 ^ s(n)) * 16) + (k%8)*2,  s(n) = 0 (C=8), (n>>2)&1 (C=16), (n>>1)&3 (C=32)
+ * with zero rows for n >= Cout and zero taps past the last one; bias fp32 [64] */
+int kvq_conv_image_kblocks(int C, int taps);
+int kvq_conv_narrow_f16(const void* in_f16, const void* w_image, const float* bias, const void* resid_f16, int ldr,
+                        void* out_f16, int ldo, int B, int T, int H, int W, int C, const int32_t kernel[3],
+                        const int32_t stride[3], const int32_t pad[3], int nvalid, int relu, void* stream);
 /* gather [B,T,H,W,C] -> [B*To*Ho*Wo, Kp] patches, K index ((dt*kh + dh)*kw + dw)*C + c, zero padding (nn.Conv3d) */
 int kvq_im2col_cl_f16(const void* in_f16, void* out_f16, int B, int T, int H, int W, int C, const int32_t kernel[3],
                       const int32_t stride[3], const int32_t pad[3], int Kp, void* stream);

@@ -435,6 +435,26 @@ int kvq_conv_implicit_f16(const void* in_f16, const void* w_f16, const float* bi
                               static_cast<const __half*>(w_f16), gp, static_cast<cudaStream_t>(stream));
 }
 
+int kvq_conv_narrow_f16(const void* in_f16, const void* w_image, const float* bias, const void* resid_f16, int ldr,
+                        void* out_f16, int ldo, int B, int T, int H, int W, int C, const int32_t kernel[3],
+                        const int32_t stride[3], const int32_t pad[3], int nvalid, int relu, void* stream) {
+  KVQ_REQUIRE(in_f16 && w_image && out_f16 && kernel && stride && pad, KVQ_ERR_BAD_SHAPE, "conv_narrow: NULL argument");
+  GemmParams gp{};
+  gp.N = 64;
+  gp.bias = bias;
+  gp.out = out_f16; gp.ldo = ldo;
+  gp.resid_h = static_cast<const __half*>(resid_f16); gp.ldr = ldr;
+  gp.relu = relu;
+  gp.nvalid = nvalid == 64 ? 0 : nvalid;
+  return launch_conv_narrow(static_cast<const __half*>(in_f16), B, T, H, W, C, kernel[0], kernel[1], kernel[2], stride[0],
+                            stride[1], stride[2], pad[0], pad[1], pad[2], w_image, gp, static_cast<cudaStream_t>(stream));
+}
+
+int kvq_conv_image_kblocks(int C, int taps) {
+  if (!(C == 8 || C == 16 || C == 32) || taps < 1) return KVQ_ERR_BAD_SHAPE;
+  return conv_image_kblocks(C, taps);
+}
+
 int kvq_stem_conv_f16(const float* x, const void* w_packed_f16, const float* shift, void* out_f16, int N, int T, int H,
                       int W, int kt, int cout, void* stream) {
   return launch_stem_conv(x, static_cast<const __half*>(w_packed_f16), shift, static_cast<__half*>(out_f16), N, T, H, W,

@@ -129,7 +129,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_m = conv_mode ? p.M / BM : (p.M + TM - 1) / TM;     // conv: p.M = tiles * 128 (padded tile grid)
   const int num_n = p.N / BN;
   const int tiles = num_m * num_n;
-  const int nkb = (p.K + BK - 1) / BK;
+  const bool narrow = conv_mode && p.conv.csub != 0;
+  const int nkb = (p.K + BK - 1) / BK;   // narrow mode: p.K = 64 * (number of K blocks of 64 / csub taps)
   // split-weight mode: B holds [W_hi | W_lo] along K (each padded to 64); the K loop runs twice over A
   const int nkb_tot = p.split_b ? 2 * nkb : nkb;
 
@@ -149,6 +150,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg<BN, MT>::TMEM_COLS);
     tmem_relinquish();
+  }
+  if constexpr (EPI == EPI_CONV_F16) {
+    if (narrow) {
+      // a K block whose tap count is not a multiple of 64 / csub leaves sub-tiles unloaded; their weights are zero, so
+      // the smem behind them only has to be finite: clear the ring once (0 x NaN would poison the accumulator)
+      for (int i = threadIdx.x; i < STAGES * Cfg<BN, MT>::STAGE_BYTES / 16; i += GEMM_THREADS)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();
+    }
   }
   if constexpr (EPI != EPI_LN_F32 && EPI != EPI_HEAD) {
     // bias is a weight (never produced by the previous kernel): stage it before the dependency wait
@@ -189,6 +199,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty[stage], ph ^ 1);
           uint8_t* sA = smem + stage * Cfg<BN, MT>::STAGE_BYTES;
           uint8_t* sB = sA + MT * A_BYTES;
+          if (EPI == EPI_CONV_F16 && narrow) {
+            // 64 / csub taps per K block, one [128 pixels x csub] sub-tile each; the weight image is one bulk copy
+            const int tpb = BK / p.conv.csub, sub_bytes = BM * p.conv.csub * 2;
+            const int first = kb * tpb;
+            const int ntap = p.conv.taps - first < tpb ? p.conv.taps - first : tpb;
+            mbar_expect_tx(&full[stage], static_cast<uint32_t>(ntap * sub_bytes + BN * BK * 2));
+            for (int t = 0; t < ntap; ++t) {
+              tma_load_5d(sA + t * sub_bytes, &tmA, &full[stage], 0, cw0 + tap_w, ch0 + tap_h, ct0 + tap_t, cb);
+              if (++tap_w == p.conv.kw) { tap_w = 0; if (++tap_h == p.conv.kh) { tap_h = 0; ++tap_t; } }
+            }
+            bulk_load_1d(sB, static_cast<const uint8_t*>(p.conv.wimg) + static_cast<size_t>(kb) * (BN * BK * 2),
+                         BN * BK * 2, &full[stage]);
+            if (++stage == STAGES) { stage = 0; ph ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full[stage], Cfg<BN, MT>::STAGE_BYTES);
           if (EPI == EPI_CONV_F16 && conv_mode) {
             tma_load_5d(sA, &tmA, &full[stage], cblk * BK, cw0 + tap_w, ch0 + tap_h, ct0 + tap_t, cb);
@@ -217,6 +242,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&full[stage], ph);
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * Cfg<BN, MT>::STAGE_BYTES);
+          if (EPI == EPI_CONV_F16 && narrow) {
+            // four K = 16 steps per block; where they live depends on the sub-tile width (see GemmParams::conv)
+            const uint32_t sBa = sA + A_BYTES;
+            const int cs = p.conv.csub;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              uint64_t da, db2;
+              if (cs == 8) {          // two taps per step: core matrices 8 rows x 16 B, K-adjacent one sub-tile apart
+                da = umma_smem_desc(sA + 2 * m * (BM * 16), BM * 16, 128, UMMA_SW_NONE);
+                db2 = umma_smem_desc(sBa + 2 * m * (BN * 16), BN * 16, 128, UMMA_SW_NONE);
+              } else if (cs == 16) {  // one tap per step, 32 B swizzle
+                da = umma_smem_desc(sA + m * (BM * 32), 16, 256, UMMA_SW_32);
+                db2 = umma_smem_desc(sBa + m * (BN * 32), 16, 256, UMMA_SW_32);
+              } else {                // half a tap per step, 64 B swizzle
+                da = umma_smem_desc(sA + (m >> 1) * (BM * 64) + (m & 1) * 32, 16, 512, UMMA_SW_64);
+                db2 = umma_smem_desc(sBa + (m >> 1) * (BN * 64) + (m & 1) * 32, 16, 512, UMMA_SW_64);
+              }
+              umma_f16_ss(d_tmem, da, db2, idesc, (kb > 0 || m > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; ph ^= 1; }
+            continue;
+          }
           const uint64_t db = umma_smem_desc(sA + MT * A_BYTES, 16, 1024, UMMA_SW_128);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -770,6 +818,68 @@ int launch_conv_implicit(const __half* in, int B, int T, int H, int W, int C, in
   if (p.N % 192 == 0 && tiles_m * (p.N / 192) >= num_sms()) return launch_conv_impl<192>(tmA, tmC, Wt, p.K, p, stream);
   if (p.N % 128 == 0 && tiles_m * (p.N / 128) >= num_sms()) return launch_conv_impl<128>(tmA, tmC, Wt, p.K, p, stream);
   return launch_conv_impl<64>(tmA, tmC, Wt, p.K, p, stream);
+}
+
+bool conv_narrow_supported(int C, int cout) {
+  static const int off = []() { const char* e = getenv("KVQ_CONV_EXPLICIT"); return e ? atoi(e) : 0; }();
+  return off == 0 && (C == 8 || C == 16 || C == 32) && cout >= 8 && cout <= 64 && cout % 8 == 0;
+}
+
+int conv_image_kblocks(int C, int taps) { const int tpb = 64 / C; return (taps + tpb - 1) / tpb; }
+
+int launch_conv_narrow(const __half* in, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh,
+                       int sw, int pt, int ph, int pw, const void* Wimg, GemmParams p, cudaStream_t stream) {
+  KVQ_REQUIRE(Wimg != nullptr && (C == 8 || C == 16 || C == 32), KVQ_ERR_BAD_SHAPE,
+              "narrow conv: C=%d (8, 16 or 32) and a packed weight image are required", C);
+  KVQ_REQUIRE(p.N == 64 && p.ldo % 8 == 0 && (p.resid_h == nullptr || p.ldr % 8 == 0), KVQ_ERR_MISALIGNED,
+              "narrow conv: N=%d (must be 64) ldo=%d ldr=%d", p.N, p.ldo, p.ldr);
+  KVQ_REQUIRE(p.nvalid == 0 || (p.nvalid % 8 == 0 && p.nvalid <= p.N), KVQ_ERR_BAD_SHAPE, "narrow conv: nvalid=%d",
+              p.nvalid);
+  const int To = (T + 2 * pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+  KVQ_REQUIRE(To > 0 && Ho > 0 && Wo > 0, KVQ_ERR_BAD_SHAPE, "narrow conv: empty output %dx%dx%d", To, Ho, Wo);
+  int best_bw = 0, best_bh = 0, best_bt = 0;
+  long long best = -1;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    if (bw * sw > 256) continue;
+    for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+      const int bt = 128 / (bw * bh);
+      if (bh * sh > 256 || bt * st > 256) continue;
+      const long long cover = static_cast<long long>((To + bt - 1) / bt) * bt * ((Ho + bh - 1) / bh) * bh *
+                              ((Wo + bw - 1) / bw) * bw;
+      if (best < 0 || cover < best) { best = cover; best_bw = bw; best_bh = bh; best_bt = bt; }
+    }
+  }
+  p.conv.on = 1;
+  p.conv.C = C; p.conv.kt = kt; p.conv.kh = kh; p.conv.kw = kw;
+  p.conv.st = st; p.conv.sh = sh; p.conv.sw = sw; p.conv.pt = pt; p.conv.ph = ph; p.conv.pw = pw;
+  p.conv.To = To; p.conv.Ho = Ho; p.conv.Wo = Wo;
+  p.conv.bt = best_bt; p.conv.bh = best_bh; p.conv.bw = best_bw;
+  p.conv.nt = (To + best_bt - 1) / best_bt; p.conv.nh = (Ho + best_bh - 1) / best_bh;
+  p.conv.nw = (Wo + best_bw - 1) / best_bw;
+  p.conv.csub = C; p.conv.taps = kt * kh * kw; p.conv.wimg = Wimg;
+  const long long tiles_m = static_cast<long long>(B) * p.conv.nt * p.conv.nh * p.conv.nw;
+  KVQ_REQUIRE(tiles_m * BM < (1LL << 31), KVQ_ERR_BAD_SHAPE, "narrow conv: %lld tiles", tiles_m);
+  p.M = static_cast<int>(tiles_m * BM);
+  p.K = 64 * conv_image_kblocks(C, p.conv.taps);
+  CUtensorMap tmA;
+  int rc = make_tmap_conv5d(&tmA, in, B, T, H, W, C, best_bt, best_bh, best_bw, st, sh, sw);
+  if (rc != 0) return rc;
+  const int bw_w = best_bw < 32 ? best_bw : 32;
+  const int bh_w = best_bh < 32 / bw_w ? best_bh : 32 / bw_w;
+  const int bt_w = 32 / (bw_w * bh_w);
+  CUtensorMap tmC;
+  rc = make_tmap_out5d(&tmC, p.out, B, To, Ho, Wo, p.nvalid > 0 ? p.nvalid : p.N, p.ldo, bt_w, bh_w, bw_w);
+  if (rc != 0) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    KVQ_CUDA(cudaFuncSetAttribute(gemm_kernel<64, EPI_CONV_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<64, 1>::SMEM));
+    attr_set = true;
+  }
+  const int grid = tiles_m < num_sms() ? static_cast<int>(tiles_m) : num_sms();
+  count_launch();
+  return launch_pdl(gemm_kernel<64, EPI_CONV_F16, 1>, dim3(grid), dim3(GEMM_THREADS), Cfg<64, 1>::SMEM, stream, tmA, tmA,
+                    tmC, p);
 }
 
 int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, const GemmParams& p,

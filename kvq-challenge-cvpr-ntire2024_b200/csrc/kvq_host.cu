@@ -79,18 +79,24 @@ int make_tmap_conv5d(CUtensorMap* out, const void* base, int B, int T, int H, in
                      int st, int sh, int sw) {
   EncodeTiledFn enc = get_encode();
   KVQ_REQUIRE(enc != nullptr, KVQ_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
-  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && C % 64 == 0, KVQ_ERR_MISALIGNED,
-              "conv TMA: base %p must be 16 B aligned and C=%d a multiple of 64", base, C);
+  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (C % 64 == 0 || C == 8 || C == 16 || C == 32),
+              KVQ_ERR_MISALIGNED, "conv TMA: base %p must be 16 B aligned and C=%d a multiple of 64 (or 8/16/32)", base, C);
   KVQ_REQUIRE(bt * st <= 256 && bh * sh <= 256 && bw * sw <= 256, KVQ_ERR_BAD_SHAPE, "conv TMA: box too large");
   cuuint64_t gdim[5] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                         static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
   cuuint64_t gstr[4] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
                         static_cast<cuuint64_t>(H) * W * C * 2, static_cast<cuuint64_t>(T) * H * W * C * 2};
-  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(bw * sw), static_cast<cuuint32_t>(bh * sh),
+  // narrow activations: the box is the whole channel extent, swizzle span = row bytes (16 B rows: no swizzle)
+  const int cbox = C < 64 ? C : 64;
+  const CUtensorMapSwizzle swz = cbox == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : cbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : cbox == 16 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(cbox), static_cast<cuuint32_t>(bw * sw), static_cast<cuuint32_t>(bh * sh),
                        static_cast<cuuint32_t>(bt * st), 1};
   cuuint32_t estr[5] = {1, static_cast<cuuint32_t>(sw), static_cast<cuuint32_t>(sh), static_cast<cuuint32_t>(st), 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KVQ_REQUIRE(r == CUDA_SUCCESS, KVQ_ERR_DRIVER,
               "cuTensorMapEncodeTiled(conv) failed (%d) dims=%dx%dx%dx%dx%d box=%dx%dx%d stride=%dx%dx%d",

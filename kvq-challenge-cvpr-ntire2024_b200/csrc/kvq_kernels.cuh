@@ -136,6 +136,11 @@ struct GemmParams {
     int To, Ho, Wo;        // output map
     int bt, bh, bw;        // tile (bt*bh*bw == 128)
     int nt, nh, nw;        // tiles per dim
+    // narrow-channel mode (csub = C in {8, 16, 32}; 0 = 64-channel blocks): a K block is 64 / csub TAPS, each tap one
+    // TMA sub-tile [128 pixels x csub] (no swizzle / 32 B / 64 B swizzle); the weights arrive as pre-packed smem
+    // images, one 8 KB bulk copy per K block (N = 64 only)
+    int csub, taps;
+    const void* wimg;
   } conv;
   // EPI_RESID_F32 row remap (proj): rows are window-ordered; rows_in = nW*N per clip, rows_out = tokens per clip
   int remap;            // 0 = identity
@@ -162,6 +167,11 @@ int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, con
 // act(conv(in) + bias (+ resid)); W fp16 [N, kt*kh*kw*C] tap-major / channel-minor.  p carries bias / out / ldo /
 // resid_h / ldr / relu / nvalid / N; M, K and the tiling are filled in here.
 bool conv_implicit_supported(int C, int kt, int kh, int kw, int st, int sh, int sw);
+// narrow-channel implicit convolution (C = 8 / 16 / 32, at most 64 output channels): Wimg = kvq_pack_conv_image layout
+bool conv_narrow_supported(int C, int cout);
+int conv_image_kblocks(int C, int taps);   // 8 KB images per weight
+int launch_conv_narrow(const __half* in, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh,
+                       int sw, int pt, int ph, int pw, const void* Wimg, GemmParams p, cudaStream_t stream);
 int launch_conv_implicit(const __half* in, int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh,
                          int sw, int pt, int ph, int pw, const __half* Wt, GemmParams p, cudaStream_t stream);
 

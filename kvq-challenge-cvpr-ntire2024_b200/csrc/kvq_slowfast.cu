@@ -92,8 +92,8 @@ int make_sf_plan(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int
 struct ConvW {
   const __half* w;
   const float* b;
-  const __half* wf = nullptr;   // row-folded twin (pointwise layers with fewer than 64 input channels), see fold_rows()
-  const float* bf = nullptr;
+  const __half* wf = nullptr;   // twin for layers with 8 / 16 / 32 input channels: the row-folded block-diagonal weight
+  const float* bf = nullptr;    // (pointwise, see fold_rows()) or the packed smem image of the narrow implicit GEMM
 };
 
 // A pointwise convolution with C < 64 input channels makes every 64-wide TMA box mostly out of bounds and every
@@ -153,6 +153,18 @@ int conv_op(const SfCtx& cx, const __half* in, int B, int T, int H, int W, int C
     ProfScope ps(PK_CONV_GEMM, stage, cx.st);
     return launch_conv_implicit(in, B, T, H, W, C, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], cw.w, gp,
                                 cx.st);
+  }
+  if (cw.wf != nullptr && conv_narrow_supported(C, cout)) {
+    // 8 / 16 / 32 input channels: implicit GEMM whose K blocks are 64 / C taps (kvq_gemm.cu, narrow mode)
+    GemmParams gp{};
+    gp.N = 64;
+    gp.bias = cw.bf;
+    gp.out = out; gp.ldo = ldo;
+    gp.resid_h = resid; gp.ldr = ldr;
+    gp.relu = relu ? 1 : 0;
+    gp.nvalid = cout == 64 ? 0 : cout;
+    ProfScope ps(PK_CONV_GEMM, stage, cx.st);
+    return launch_conv_narrow(in, B, T, H, W, C, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], cw.wf, gp, cx.st);
   }
   // gathered K is padded to whole 64-wide TMA boxes (weights are packed with the same zero columns)
   const int Kp = round64(k[0] * k[1] * k[2] * C);
@@ -219,13 +231,13 @@ int res_stage(const SfCtx& cx, Pathway& P, const void* const* weights, int& wi, 
     int ldr = P.C;
     int rc;
     if (j == 0) {
-      const ConvW c1 = next(sj == 1 && fold_rows(P.C) > 1);
+      const ConvW c1 = next(fold_rows(P.C) > 1);   // stride 1: row-folded twin; stride 2: narrow-conv image
       const int s1[3] = {1, sj, sj};
       rc = conv_op(cx, cur, B, P.T, hi, wj, P.C, one, s1, zero, c1, cout, nullptr, 0, idn, cout, false, stage);
       if (rc != 0) return rc;
       resid = idn; ldr = cout;
     }
-    const ConvW ca = next(), cb = next(), cc = next(fold_rows(inner) > 1);
+    const ConvW ca = next(ka > 1 && fold_rows(P.C) > 1), cb = next(fold_rows(inner) > 1), cc = next(fold_rows(inner) > 1);
     const int kA[3] = {ka, 1, 1}, pA[3] = {ka / 2, 0, 0};
     rc = conv_op(cx, cur, B, P.T, hi, wj, P.C, kA, one, pA, ca, inner, nullptr, 0, t1, inner, true, stage);
     if (rc != 0) return rc;
@@ -249,10 +261,15 @@ int kvq_slowfast_num_weights(const KvqSlowFastConfig* cfg) {
   int n = 6;
   for (int s = 0; s < 4; ++s) {
     n += 2 * 2 * (3 * cfg->depths[s] + 1) + (s < 3 ? 2 : 0);
-    if (fold_rows(8 << s) > 1) n += 2 * cfg->depths[s];   // folded twins of the fast pathway's conv_c
-    if (s == 0) n += 2;                                    // ... and of its stride-1 branch1 (8 -> 32 channels)
+    // twins of the fast pathway's narrow layers (see the header): per block conv_b + conv_c while inner < 64, conv_a
+    // while its input has < 64 channels, branch1 likewise, and the fusions that read < 64 channels
+    const int inner = 8 << s, cin0 = s == 0 ? 8 : 4 * (8 << (s - 1));
+    if (inner < 64) n += 2 * 2 * cfg->depths[s];
+    if (cin0 < 64) n += 2 + 2;                                       // branch1 + conv_a of block 0
+    if (4 * inner < 64) n += 2 * (cfg->depths[s] - 1);               // conv_a of the other blocks
+    if (s < 3 && 4 * inner < 64) n += 2;                             // the stage's fusion
   }
-  return n;
+  return n + 2;                                                      // block-0 fusion (8 channels)
 }
 
 size_t kvq_slowfast_workspace_bytes(const KvqSlowFastConfig* cfg, int B, int Ts, int Tf, int H, int W) {
@@ -310,16 +327,21 @@ int kvq_slowfast_forward(const KvqSlowFastConfig* cfg, const void* const* weight
   float* pw_fast = pw_slow + static_cast<size_t>(Ts) * pl.h5 * pl.w5;
   S.T = Ts; F.T = Tf;
   int wi = 0;
-  auto next = [&]() {
+  auto next = [&](bool twin = false) {
     ConvW c{static_cast<const __half*>(weights[wi]), static_cast<const float*>(weights[wi + 1])};
     wi += 2;
+    if (twin) {
+      c.wf = static_cast<const __half*>(weights[wi]);
+      c.bf = static_cast<const float*>(weights[wi + 1]);
+      wi += 2;
+    }
     return c;
   };
   const int one[3] = {1, 1, 1};
 
   // block 0: stems (conv + BN + ReLU, max pool (1,3,3)/s(1,2,2)/p(0,1,1)); the slow pool output leaves room for the
   // 16 fused channels
-  const ConvW ws = next(), wf = next(), wfuse0 = next();
+  const ConvW ws = next(), wf = next(), wfuse0 = next(true);   // (8-channel fusion input: narrow-conv image twin)
   rc = stem_op(cx, slow, B, Ts, H, W, 1, ws, 64, S.act[0]);
   if (rc != 0) return rc;
   {
@@ -351,7 +373,7 @@ int kvq_slowfast_forward(const KvqSlowFastConfig* cfg, const void* const* weight
     if (rc != 0) return rc;
     h = conv_out(h, 3, stride, 1); w = conv_out(w, 3, stride, 1);
     if (s < 3) {
-      const ConvW wfu = next();
+      const ConvW wfu = next(fold_rows(4 * jf) > 1);
       rc = conv_op(cx, F.act[F.ci], B, Tf, h, w, 4 * jf, kF, sF, pF, wfu, 8 * jf, nullptr, 0, S.act[S.ci] + 4 * is,
                    slow_ld, true, s);
       if (rc != 0) return rc;

@@ -72,6 +72,10 @@ PROTOTYPES = {
     "kvq_conv_implicit_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                       c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_int, c_int,
                                       c_int, c_void_p]),
+    "kvq_conv_image_kblocks": (c_int, [c_int, c_int]),
+    "kvq_conv_narrow_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_int, c_int,
+                                    c_void_p]),
     "kvq_stem_weight_rows": (c_int, [c_int]),
     "kvq_stem_conv_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p]),

@@ -335,6 +335,52 @@ def pack_conv_weight(w, bn=None, eps=1e-5, pad_out=64, fold=False):
     return packed + (cast_f16(wf.contiguous()), shift.repeat(g).contiguous())
 
 
+def pack_conv_image(w, bn=None, eps=1e-5):
+    """Conv weight [Cout<=64, C in {8,16,32}, kt, kh, kw] (+ eval-mode BatchNorm) -> (fp16 images
+    [kblocks, 4096] = the shared-memory B tiles of kvq_conv_narrow_f16, fp32 [64] shift)."""
+    w = w.detach().float()
+    if w.dim() == 4:
+        w = w.unsqueeze(2)
+    cout, C = w.shape[0], w.shape[1]
+    if C not in (8, 16, 32) or cout > 64:
+        raise RuntimeError(f"kvq_b200: pack_conv_image needs C in (8,16,32) and Cout <= 64, got {tuple(w.shape)}")
+    if bn is not None:
+        g, b, m, v = [t.detach().float() for t in bn]
+        scale = g / torch.sqrt(v + eps)
+        shift = b - m * scale
+        w = w * scale.reshape(-1, 1, 1, 1, 1)
+    else:
+        shift = torch.zeros(cout, device=w.device)
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    tpb = 64 // C
+    nkb = (taps + tpb - 1) // tpb
+    w2 = torch.zeros((64, nkb * tpb, C), dtype=torch.float32, device=w.device)
+    w2[:cout, :taps] = w.permute(0, 2, 3, 4, 1).reshape(cout, taps, C)           # tap-major (dt, dh, dw), channel-minor
+    n = torch.arange(64, device=w.device).view(64, 1, 1)
+    t = torch.arange(nkb * tpb, device=w.device).view(1, -1, 1)
+    k = torch.arange(C, device=w.device).view(1, 1, C)
+    sw = {8: torch.zeros_like(n), 16: (n >> 2) & 1, 32: (n >> 1) & 3}[C]
+    off = (t % tpb) * (64 * C) + n * C + (((k // 8) ^ sw) * 8) + (k % 8)          # in halfs, inside the K block
+    img = torch.zeros((nkb, 4096), dtype=torch.float32, device=w.device)
+    img.view(-1)[((t // tpb) * 4096 + off).reshape(-1)] = w2.reshape(-1)
+    sp = torch.zeros(64, dtype=torch.float32, device=w.device)
+    sp[:cout] = shift
+    return cast_f16(img.contiguous()), sp.contiguous()
+
+
+def conv_narrow_f16(x, w_image, bias, kernel, stride, pad, cout, resid=None, relu=False):
+    """x f16 [B,T,H,W,C] with C in (8,16,32) -> f16 [B*To*Ho*Wo, cout] through the narrow implicit GEMM."""
+    _need_cuda(x, w_image, bias, resid)
+    B, T, H, W, C = x.shape
+    od = [conv_out_size(n, k, s, p) for n, k, s, p in zip((T, H, W), kernel, stride, pad)]
+    out = torch.empty((B * od[0] * od[1] * od[2], cout), dtype=torch.float16, device=x.device)
+    rc = _l.load().kvq_conv_narrow_f16(_p(x), _p(w_image), _p(bias), _p(resid),
+                                       resid.stride(0) if resid is not None else 0, _p(out), out.stride(0), B, T, H, W, C,
+                                       _i3(kernel), _i3(stride), _i3(pad), int(cout), int(bool(relu)), _stream())
+    _l.check(rc, "conv_narrow_f16")
+    return out, tuple(od)
+
+
 def pack_stem_weight(w, bn=None, eps=1e-5):
     """Stem conv weight [Cout,3,kt,7,7] (+ eval-mode BatchNorm) -> (fp16 [kt*3, rows, 64] in the layout
     kvq_stem_conv_f16 documents, fp32 [rows] shift)."""
@@ -626,10 +672,12 @@ class SlowFastWeights:
         def t(k):
             return sd[k].detach().to(self.device, torch.float32)
 
-        def conv_bn(conv, bn, fold=False):
-            return list(pack_conv_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
-                                                              ("weight", "bias", "running_mean", "running_var")], eps,
-                                         fold=fold))
+        def conv_bn(conv, bn, fold=False, image=False):
+            stats = [t(bn + "." + leaf) for leaf in ("weight", "bias", "running_mean", "running_var")]
+            out = list(pack_conv_weight(t(conv + ".weight"), stats, eps, fold=fold))
+            if image:       # narrow-channel implicit GEMM twin (include/kvq_b200.h)
+                out += list(pack_conv_image(t(conv + ".weight"), stats, eps))
+            return out
 
         def stem_bn(conv, bn):
             return list(pack_stem_weight(t(conv + ".weight"), [t(bn + "." + leaf) for leaf in
@@ -638,20 +686,25 @@ class SlowFastWeights:
         p = prefix + "0."
         ts = stem_bn(p + "multipathway_blocks.0.conv", p + "multipathway_blocks.0.norm")
         ts += stem_bn(p + "multipathway_blocks.1.conv", p + "multipathway_blocks.1.norm")
-        ts += conv_bn(p + "multipathway_fusion.conv_fast_to_slow", p + "multipathway_fusion.norm")
+        ts += conv_bn(p + "multipathway_fusion.conv_fast_to_slow", p + "multipathway_fusion.norm", image=True)
         for s, depth in enumerate(depths):
             p = f"{prefix}{s + 1}."
             for path in (0, 1):
                 for j in range(depth):
                     b = f"{p}multipathway_blocks.{path}.res_blocks.{j}."
                     inner = (8 << s) if path == 1 else (64 << s)
-                    if j == 0:
-                        ts += conv_bn(b + "branch1_conv", b + "branch1_norm", fold=(path == 1 and s == 0))
-                    for c in "ab":
-                        ts += conv_bn(b + "branch2.conv_" + c, b + "branch2.norm_" + c)
+                    cin = inner * 4 if j > 0 else ((80 if s == 0 else (64 << (s - 1)) * 4 + (8 << (s - 1)) * 8)
+                                                   if path == 0 else (8 if s == 0 else (8 << (s - 1)) * 4))
+                    narrow_in = path == 1 and cin in (8, 16, 32)
+                    if j == 0:      # stride 1 (stage 0): row-folded twin; stride 2: narrow-conv image
+                        ts += conv_bn(b + "branch1_conv", b + "branch1_norm", fold=narrow_in and s == 0,
+                                      image=narrow_in and s > 0)
+                    ts += conv_bn(b + "branch2.conv_a", b + "branch2.norm_a", image=narrow_in)
+                    ts += conv_bn(b + "branch2.conv_b", b + "branch2.norm_b", image=path == 1 and inner in (8, 16, 32))
                     ts += conv_bn(b + "branch2.conv_c", b + "branch2.norm_c", fold=inner in (8, 16, 32))
             if s < 3:
-                ts += conv_bn(p + "multipathway_fusion.conv_fast_to_slow", p + "multipathway_fusion.norm")
+                ts += conv_bn(p + "multipathway_fusion.conv_fast_to_slow", p + "multipathway_fusion.norm",
+                              image=(8 << s) * 4 in (8, 16, 32))
         self.tensors = ts
         n = _l.load().kvq_slowfast_num_weights(ctypes.byref(self.cfg))
         if n != len(ts):

@@ -170,3 +170,34 @@ def test_conv_implicit_matches_conv3d(B, T, H, W, C, N, kernel, stride, pad, res
     assert got.shape == ref.shape
     err = (got.float().cpu() - ref).abs().max().item()
     assert err < 8e-3, err
+
+
+@pytest.mark.parametrize("B,T,H,W,C,cout,kernel,stride,pad,resid", [
+    (2, 4, 16, 16, 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1), False),       # fast res2 conv_b: 9 taps = 8 + 1 (partial K block)
+    (1, 8, 8, 8, 8, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0), False),         # fast res2 conv_a block 0: 3 taps of 8
+    (1, 8, 14, 14, 32, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0), False),      # conv_a on 32 channels: 64 B swizzle, padded tiles
+    (2, 2, 15, 11, 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1), False),     # res3 conv_b: 32 B swizzle, stride 2, odd sizes
+    (2, 4, 12, 12, 32, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), True),      # res4 conv_b + residual
+    (1, 32, 6, 6, 8, 16, (7, 1, 1), (4, 1, 1), (3, 0, 0), False),       # lateral fusion after the stem
+    (1, 16, 6, 7, 32, 64, (7, 1, 1), (4, 1, 1), (3, 0, 0), False),      # lateral fusion after res2 (64 outputs)
+    (2, 2, 9, 13, 32, 64, (1, 1, 1), (1, 2, 2), (0, 0, 0), False),      # strided branch1 of fast res3
+    (8, 32, 56, 56, 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1), False),      # many more tiles than SMs
+])
+def test_conv_narrow_matches_conv3d(B, T, H, W, C, cout, kernel, stride, pad, resid):
+    from kvq_b200 import ops
+    x = _rand((B, C, T, H, W), 41).half()
+    wt = (_rand((cout, C) + kernel, 42) / math.sqrt(C * kernel[0] * kernel[1] * kernel[2])).half()
+    bias = _rand((cout,), 43, 0.1)
+    ref = F.conv3d(x.float(), wt.float(), bias, stride=stride, padding=pad)
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(-1, cout)
+    r = _rand(tuple(ref.shape), 44).half() if resid else None
+    if resid:
+        ref = ref + r.float()
+    ref = F.relu(ref)
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    img, sp = ops.pack_conv_image(wt.float().to(DEV))
+    sp[:cout] = bias.to(DEV)
+    got, od = ops.conv_narrow_f16(xcl, img, sp, kernel, stride, pad, cout, resid=r.to(DEV) if resid else None, relu=True)
+    assert got.shape == ref.shape
+    err = (got.float().cpu() - ref).abs().max().item()
+    assert err < 8e-3, err

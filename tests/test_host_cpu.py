@@ -122,9 +122,17 @@ def test_conv_branch_host_entry_points():
     sf.alpha = 4
     for i, (a, b) in enumerate(zip((8, 7, 7), (32, 7, 7))):
         sf.slow_pool[i], sf.fast_pool[i] = a, b
-    # 3 stems/fusion pairs + per stage 2 pathways x (3 convs per block + branch1) pairs + fusions + row-folded twins
+    # 3 stems/fusion pairs + per stage 2 pathways x (3 convs per block + branch1) pairs + fusions, plus one twin pair
+    # for every fast-pathway convolution that reads 8 / 16 / 32 channels (include/kvq_b200.h)
     n = L.kvq_slowfast_num_weights(ctypes.byref(sf))
-    assert n == 6 + sum(2 * 2 * (3 * d + 1) for d in (3, 4, 6, 3)) + 3 * 2 + 2 * (3 + 4 + 6) + 2
+    base = 6 + sum(2 * 2 * (3 * d + 1) for d in (3, 4, 6, 3)) + 3 * 2
+    twins = (2 * (3 + 4 + 6)          # conv_b and conv_c while inner < 64 (stages 0..2)
+             + 2                      # branch1 + conv_a of stage 0 block 0 (8 channels in)
+             + 2                      # conv_a of stage 0 blocks 1, 2 (32 channels in)
+             + 2                      # branch1 + conv_a of stage 1 block 0 (32 channels in)
+             + 2)                     # fusions after the stem (8) and after stage 0 (32)
+    assert n == base + 2 * twins
+    assert L.kvq_conv_image_kblocks(8, 9) == 2 and L.kvq_conv_image_kblocks(32, 9) == 5 and L.kvq_conv_image_kblocks(16, 3) == 1
     ws = L.kvq_slowfast_workspace_bytes(ctypes.byref(sf), 16, 8, 32, 256, 256)
     assert 1.5e9 < ws < 4e9                                         # a few GB of 180: activations of 16 clips + scratch
     assert L.kvq_slowfast_workspace_bytes(ctypes.byref(sf), 1, 8, 24, 224, 224) == 0
