@@ -126,7 +126,9 @@ int kvq_vqa_head(const float* feat, const void* w1_f16, const float* b1, const f
                  float* score_out, int B, int C, int tokens, int hidden, void* workspace, size_t workspace_bytes,
                  void* stream);
 /* Grid mini-patch sampling (datasets/fusion_datasets.py:22-121) fused with (v - mean)/std (:1017-1020):
- * frames u8 [B,T,3,Hs,Ws] -> out f32 [B,3,T,fh*fs,fw*fs]; offsets i32 [B,2,fh,fw,T/aligned] (h then w) */
+ * frames u8 [B,T,3,Hs,Ws] -> out f32 [B,3,T,fh*fs,fw*fs]; offsets i32 [B,2,fh,fw,T/aligned] (h then w).
+ * A source smaller than the fh*fs x fw*fs canvas takes the reference's "upsample" fallback (:43-50): bilinear
+ * enlargement by 1 / min(Hs/(fh*fs), Ws/(fw*fs)) evaluated on the fly, cell grid and offsets on the ORIGINAL size */
 int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
                            int fragments_h, int fragments_w, int fsize, int aligned, const float mean[3],
                            const float std[3], void* stream);

@@ -1,6 +1,8 @@
 // HBM-bound row kernels around the GEMMs: LayerNorm prologues (with the cyclic-shift / window-partition /
 // patch-merge gathers folded into the load), patch-embed im2col, head mean, fp32->fp16 weight packing and the
 // Grid-Mini-patch fragment gather.  One warp per output row, float4 loads / 8-byte fp16 stores, fp32 statistics.
+#include <algorithm>
+
 #include "kvq_common.cuh"
 #include "kvq_kernels.cuh"
 
@@ -253,6 +255,50 @@ fragment_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __rest
   *reinterpret_cast<float4*>(out + (((static_cast<size_t>(b) * 3 + c) * T + t) * OH + y) * OW + x) = v;
 }
 
+// Same sampling when the source is smaller than the fragment canvas (fallback_type == "upsample", fusion_datasets.py:
+// 43-50): the frame is first enlarged with F.interpolate(video / 255, scale_factor = 1 / ratio, mode = "bilinear")
+// (align_corners = False: src = (dst + 0.5) * rscale - 0.5 clamped at 0, rscale = float(1 / scale_factor)) and scaled
+// back by 255; the cell grid and the offsets keep using the ORIGINAL resolution (:64-71).  The enlarged frame is never
+// materialised: each output pixel interpolates its four source pixels.  One thread per output pixel (rare path).
+__global__ void __launch_bounds__(256)
+fragment_gather_upsample_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ offsets,
+                                float* __restrict__ out, int T, int Hs, int Ws, int fh, int fw, int fs, int aligned,
+                                float rscale, float m0, float m1, float m2, float is0, float is1, float is2,
+                                long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int OW = fw * fs, OH = fh * fs;
+  const int x = static_cast<int>(idx % OW);
+  const int y = static_cast<int>((idx / OW) % OH);
+  const int t = static_cast<int>((idx / (static_cast<long long>(OW) * OH)) % T);
+  const int c = static_cast<int>((idx / (static_cast<long long>(OW) * OH * T)) % 3);
+  const int b = static_cast<int>(idx / (static_cast<long long>(OW) * OH * T * 3));
+  const int i = y / fs, dy = y - i * fs, j = x / fs, dx = x - j * fs;
+  const int nt = T / aligned, tc = t / aligned;
+  int hg = (Hs / fh) * i; if (hg > Hs - fs) hg = Hs - fs;
+  int wg = (Ws / fw) * j; if (wg > Ws - fs) wg = Ws - fs;
+  const int32_t* off = offsets + static_cast<size_t>(b) * 2 * fh * fw * nt;
+  const int uy = hg + off[(i * fw + j) * nt + tc] + dy;                       // pixel of the enlarged frame
+  const int ux = wg + off[fh * fw * nt + (i * fw + j) * nt + tc] + dx;
+  float sy = rscale * (static_cast<float>(uy) + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+  float sx = rscale * (static_cast<float>(ux) + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+  int y0 = static_cast<int>(sy); if (y0 > Hs - 1) y0 = Hs - 1;
+  int x0 = static_cast<int>(sx); if (x0 > Ws - 1) x0 = Ws - 1;
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+  const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
+  const uint8_t* src = frames + ((static_cast<size_t>(b) * T + t) * 3 + c) * Hs * Ws;
+  const float inv255 = 1.0f / 255.0f;   // (the reference divides; the difference is below 1 ulp of the product)
+  const float a = __fdiv_rn(static_cast<float>(src[y0 * Ws + x0]), 255.0f), bq = __fdiv_rn(static_cast<float>(src[y0 * Ws + x1]), 255.0f);
+  const float cq = __fdiv_rn(static_cast<float>(src[y1 * Ws + x0]), 255.0f), d = __fdiv_rn(static_cast<float>(src[y1 * Ws + x1]), 255.0f);
+  (void)inv255;
+  const float top = __fadd_rn(__fmul_rn(1.0f - lx, a), __fmul_rn(lx, bq));
+  const float bot = __fadd_rn(__fmul_rn(1.0f - lx, cq), __fmul_rn(lx, d));
+  const float v = __fmul_rn(__fadd_rn(__fmul_rn(1.0f - ly, top), __fmul_rn(ly, bot)), 255.0f);
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+  const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
+  out[(((static_cast<size_t>(b) * 3 + c) * T + t) * OH + y) * OW + x] = (v - mean) * istd;
+}
+
 // channels-first fp32 [B, C, tokens] -> token rows fp16 [B*tokens, C] (input side of a stand-alone VQAHead)
 __global__ void __launch_bounds__(256)
 cf_to_rows_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int tokens) {
@@ -365,9 +411,22 @@ int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, flo
               "fragment_gather: bad geometry (fsize must be a multiple of 4)");
   KVQ_REQUIRE(aligned > 0 && T % aligned == 0, KVQ_ERR_BAD_SHAPE,
               "fragment_gather: T=%d is not a multiple of aligned=%d (fusion_datasets.py:59)", T, aligned);
-  KVQ_REQUIRE(Hs >= fh * fs && Ws >= fw * fs, KVQ_ERR_BAD_SHAPE,
-              "fragment_gather: %dx%d source is smaller than the %dx%d target; the bilinear upsample fallback "
-              "(fusion_datasets.py:43-50) is not on the B200 path", Hs, Ws, fh * fs, fw * fs);
+  KVQ_REQUIRE(Hs >= fs && Ws >= fs, KVQ_ERR_BAD_SHAPE, "fragment_gather: %dx%d source is smaller than one %dx%d patch",
+              Hs, Ws, fs, fs);
+  if (Hs < fh * fs || Ws < fw * fs) {
+    // fallback_type == "upsample" (:43-50): ratio and scale factor are Python floats (doubles) in the reference
+    const double ratio = std::min(static_cast<double>(Hs) / (fh * fs), static_cast<double>(Ws) / (fw * fs));
+    const double scale = 1.0 / ratio;
+    const float rscale = static_cast<float>(1.0 / scale);
+    const long long tot = static_cast<long long>(B) * 3 * T * (fh * fs) * (fw * fs);
+    const long long g = (tot + 255) / 256;
+    KVQ_REQUIRE(g < (1ll << 31), KVQ_ERR_BAD_SHAPE, "fragment_gather: grid too large");
+    fragment_gather_upsample_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(
+        frames, offsets, out, T, Hs, Ws, fh, fw, fs, aligned, rscale, mean[0], mean[1], mean[2], 1.0f / stdv[0],
+        1.0f / stdv[1], 1.0f / stdv[2], tot);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "fragment_gather_upsample_kernel launch");
+  }
   const long long total = static_cast<long long>(B) * 3 * T * (fh * fs) * (fw * fs / 4);
   const long long grid = (total + 255) / 256;
   KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "fragment_gather: grid too large");

@@ -165,3 +165,24 @@ def test_mlp_fused(M, C):
     err = (xd.cpu() - ref).abs().max().item()
     assert torch.isfinite(xd).all()
     assert err < 2e-3, err      # hidden fp16 rounding differences (erf approximation 1.5e-7) x 4C-term dot product
+
+
+@pytest.mark.parametrize("Hs,Ws,fh,fw", [(60, 90, 3, 3), (100, 70, 4, 3), (224, 200, 7, 7)])
+def test_fragment_gather_upsample_fallback(Hs, Ws, fh, fw):
+    """Source smaller than the fragment canvas: get_spatial_fragments enlarges the frame bilinearly first
+    (fusion_datasets.py:43-50).  The oracle (pinned to the reference golden fragments_upsample_*) runs F.interpolate;
+    the kernel interpolates on the fly."""
+    from kvq_b200 import ops
+    from oracle import fragments
+    B, T, fs, al = 2, 4, 32, 2
+    g = torch.Generator().manual_seed(11)
+    frames = torch.randint(0, 256, (B, T, 3, Hs, Ws), generator=g, dtype=torch.uint8)
+    offs = []
+    for _ in range(B):
+        rh, rw = fragments.draw_offsets(Hs, Ws, T, fh, fw, fs, fs, al, generator=g)
+        offs.append(torch.stack([rh, rw]))
+    offs = torch.stack(offs).int()
+    ref = fragments.fragment_clip(frames, offs, fh, fw, fs, al)
+    out = ops.fragment_gather_u8(frames.to(_dev()), offs.to(_dev()), fh, fw, fs, al).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() < 1e-4, (out - ref).abs().max().item()
