@@ -36,5 +36,6 @@ class SyntheticFragmentDataset(torch.utils.data.Dataset):
             torch.zeros(self.fh, self.fw, nt, dtype=torch.int64)
         return {"frames": frames, "offsets": torch.stack([rnd_h, rnd_w]).int(),
                 "num_clips": {"technical": self.num_clips}, "video_name": f"synthetic_{i:04d}",
+                "label": torch.rand((), generator=g) * 4.0 + 1.0,        # stand-in MOS in [1, 5] (inferece_val)
                 "fragment_opts": {"fragments_h": self.fh, "fragments_w": self.fw, "fsize": self.fs,
                                   "aligned": self.aligned}}

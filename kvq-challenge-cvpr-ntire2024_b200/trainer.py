@@ -105,3 +105,30 @@ class Trainer:
         return list(zip(names, allscores))
 
     inferece_test = inferece
+
+    @staticmethod
+    def rescale(pr, gt=None):
+        """trainer.py:356-361: z-score the predictions, optionally onto the labels' mean / std."""
+        import numpy as np
+        pr = np.asarray(pr, dtype=np.float64)
+        pr = (pr - np.mean(pr)) / np.std(pr)
+        if gt is not None:
+            pr = pr * np.std(gt) + np.mean(gt)
+        return pr
+
+    def inferece_val(self):
+        """trainer.py:251-296: scores of the labelled validation set -> SRCC / PLCC / KRCC / RMSE after `rescale`."""
+        import numpy as np
+        from scipy.stats import kendalltau, pearsonr, spearmanr
+        loader = torch.utils.data.DataLoader(self.val_dataset, batch_size=1, num_workers=self.config.get("num_workers", 0),
+                                             pin_memory=True)
+        preds, labels = [], []
+        for data in loader:
+            preds.append(float(score_video(self.model, data, self.key_list, self.device)))
+            labels.append(float(data["label"].reshape(-1)[0]))
+        labels = np.asarray(labels, dtype=np.float64)
+        preds = self.rescale(preds, labels)
+        s, p, k = spearmanr(labels, preds)[0], pearsonr(labels, preds)[0], kendalltau(labels, preds)[0]
+        r = float(np.sqrt(((labels - preds) ** 2).mean()))
+        print("SRCC{}PLCC{}KRCC{}RMSE{}".format(s, p, k, r))
+        return {"SRCC": float(s), "PLCC": float(p), "KRCC": float(k), "RMSE": r}

@@ -103,6 +103,12 @@ def test_trainer_inferece_writes_reference_format(tmp_path):
         got = float(line.split(",")[1])
         assert abs(got - ref) <= 1e-3, (i, got, ref)
         assert abs(res[i][1] - got) < 1e-6
+    # labelled validation flow (trainer.py:251-296): correlations of the rescaled predictions with the labels
+    cfg["data"]["val"]["args"]["num_videos"] = 4
+    t4 = tr.Trainer(types.SimpleNamespace(gpu_id="0"), cfg)
+    m = t4.inferece_val()
+    assert set(m) == {"SRCC", "PLCC", "KRCC", "RMSE"} and all(v == v for v in m.values())      # finite numbers
+    assert -1.0 <= m["SRCC"] <= 1.0 and -1.0 <= m["PLCC"] <= 1.0 and m["RMSE"] >= 0.0
 
 
 def test_cuda_graph_replay_matches_eager():

@@ -178,3 +178,17 @@ def test_pack_conv_weight_layouts():
     cols = cols.permute(0, 2, 4, 5, 3, 1).reshape(-1, 48)                       # rows (t,h,w), K = (dt, c)
     got = (cols @ w2.t()).reshape(1, 5, 2, 2, 4).permute(0, 4, 1, 2, 3)
     assert torch.allclose(ref, got, atol=1e-5)
+
+
+def test_trainer_rescale_matches_reference_formula():
+    """trainer.py:356-361."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("kvq_trainer_cpu", os.path.join(PKG, "trainer.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    pr, gt = np.array([0.2, 0.9, 0.4, 0.7]), np.array([1.0, 4.5, 2.0, 3.0])
+    z = tr.Trainer.rescale(pr)
+    assert abs(z.mean()) < 1e-12 and abs(z.std() - 1.0) < 1e-12
+    r = tr.Trainer.rescale(pr, gt)
+    assert abs(r.mean() - gt.mean()) < 1e-12 and abs(r.std() - gt.std()) < 1e-12
