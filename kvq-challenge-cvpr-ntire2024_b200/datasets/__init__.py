@@ -3,6 +3,7 @@
 Video decoding (decord / cv2) and the KVQ annotation files are outside the B200 hot path, so the only
 dataset shipped is a synthetic one that produces the same item dict as ViewDecompositionDataset_KVQ
 (datasets/fusion_datasets.py:930-1050).  Register real datasets with `datasets.register(cls)`."""
+from .features import load_motion_features  # noqa: F401
 from .synthetic import SyntheticFragmentDataset  # noqa: F401
 
 

@@ -2,6 +2,7 @@
 reference holds no fixture for this path) and of the host-side pieces of the drop-in."""
 import ctypes
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -85,3 +86,18 @@ def test_video_clip_schedule():
     assert clips[1][9, 0, 0, 0] == 39 and clips[1][31, 0, 0, 0] == 61
     c = sf.video_clips(frames[:50], 30)[0]
     assert c[31, 0, 0, 0] == 31
+
+
+def test_feature_files_round_trip(tmp_path):
+    """SlowFast_features.py:196-197 writes what fusion_datasets.py:859-890 reads: [1,2048,1,1,1] / [1,256,1,1,1] per clip
+    -> feat [8, 2304] (slow then fast)."""
+    import SlowFast_features as sf
+    import datasets
+    s = torch.randn(8, 2048, 1, 1, 1)
+    f = torch.randn(8, 256, 1, 1, 1)
+    sf.save_clip_features(str(tmp_path / "vid"), s, f)
+    assert np.load(tmp_path / "vid" / "feature_7_fast_feature.npy").shape == (1, 256, 1, 1, 1)
+    feat = datasets.load_motion_features(str(tmp_path / "vid"))
+    assert feat.shape == (8, 2304)
+    assert torch.equal(feat[:, :2048], s.view(8, 2048)) and torch.equal(feat[:, 2048:], f.view(8, 256))
+    assert datasets.load_motion_features(str(tmp_path / "vid"), "Fast").shape == (8, 256)
