@@ -1,10 +1,10 @@
 """Dataset registry of the drop-in (`getattr(datasets, cfg['data']['val']['type'])(args, None)`, trainer.py:117).
 
-Video decoding (decord / cv2) and the KVQ annotation files are outside the B200 hot path, so the only
-dataset shipped is a synthetic one that produces the same item dict as ViewDecompositionDataset_KVQ
-(datasets/fusion_datasets.py:930-1050).  Register real datasets with `datasets.register(cls)`."""
+Video decoding (decord / cv2) and the KVQ annotation files are outside the B200 hot path, so the
+datasets shipped are synthetic ones producing the same item dicts as ViewDecompositionDataset_KVQ
+(datasets/fusion_datasets.py:930-1050) and ViewDecompositionDataset_add_forSimpleVQA (:780-930).  Register real datasets with `datasets.register(cls)`."""
 from .features import load_motion_features  # noqa: F401
-from .synthetic import SyntheticFragmentDataset  # noqa: F401
+from .synthetic import SyntheticFragmentDataset, SyntheticSimpleVQADataset  # noqa: F401
 
 
 def register(cls, name=None):

@@ -39,3 +39,25 @@ class SyntheticFragmentDataset(torch.utils.data.Dataset):
                 "label": torch.rand((), generator=g) * 4.0 + 1.0,        # stand-in MOS in [1, 5] (inferece_val)
                 "fragment_opts": {"fragments_h": self.fh, "fragments_w": self.fw, "fsize": self.fs,
                                   "aligned": self.aligned}}
+
+
+class SyntheticSimpleVQADataset(torch.utils.data.Dataset):
+    """Stand-in for ViewDecompositionDataset_add_forSimpleVQA (datasets/fusion_datasets.py:780-930): `clip_len` frames
+    resized / centre-cropped to `crop` and ImageNet-normalised (`simpleVQA` [3,T,crop,crop]) plus the pre-extracted
+    SlowFast features of the video (`feat` [T, 2304], see datasets.load_motion_features)."""
+
+    def __init__(self, opt, _unused=None):
+        st = opt["sample_types"]["simpleVQA"]
+        self.crop, self.clip_len, self.num_clips = st.get("crop", 448), st.get("clip_len", 8), st.get("num_clips", 1)
+        self.n, self.seed = opt.get("num_videos", 4), opt.get("seed", 7)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed + i)
+        T = self.clip_len * self.num_clips
+        return {"simpleVQA": torch.randn((3, T, self.crop, self.crop), generator=g),
+                "feat": torch.randn((T, 2304), generator=g).abs(),
+                "num_clips": {"simpleVQA": self.num_clips}, "video_name": f"synthetic_{i:04d}",
+                "label": torch.rand((), generator=g) * 4.0 + 1.0}

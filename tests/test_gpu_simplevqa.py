@@ -89,3 +89,32 @@ def test_full_size_determinism_and_frame_independence():
                for t in range(8)]
     assert torch.equal(s1, s2)
     assert (torch.stack(per).mean(dim=0) - s1).abs().max().item() < 1e-4
+
+
+def test_trainer_flow_with_the_simplevqa_yaml(tmp_path):
+    """BASELINE config 1 literally: config/kwai_simpleVQA_test.yml -> Trainer -> inferece() -> output.txt, checked
+    against the CPU oracle on the same synthetic items (224^2 crop here to keep the oracle quick)."""
+    import importlib.util
+    import types
+    import yaml
+    from conftest import PKG
+    spec = importlib.util.spec_from_file_location("kvq_trainer_sv", os.path.join(PKG, "trainer.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    with open(os.path.join(PKG, "config", "kwai_simpleVQA_test.yml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg["data"]["val"]["args"]["num_videos"] = 2
+    cfg["data"]["val"]["args"]["sample_types"]["simpleVQA"]["crop"] = 224
+    sd = synth.simplevqa_network_state_dict(51)
+    ckpt = tmp_path / "ckpt.pth"
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}}, ckpt)
+    cfg["load_path"] = str(ckpt)
+    t = tr.Trainer(types.SimpleNamespace(gpu_id="0"), cfg)
+    assert t.key_list == ["simpleVQA"]
+    res = t.inferece(str(tmp_path / "output.txt"))
+    lines = (tmp_path / "output.txt").read_text().strip().split("\n")
+    assert [l.split(",")[0] for l in lines] == ["synthetic_0000", "synthetic_0001"]
+    for i, (name, score) in enumerate(res):
+        item = t.val_dataset[i]
+        _, ref = simplevqa.simplevqa_forward(item["simpleVQA"][None], item["feat"][None], sd)
+        assert abs(score - float(ref.reshape(-1)[0])) < 1e-3, (i, score, float(ref.reshape(-1)[0]))
