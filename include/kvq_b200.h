@@ -133,6 +133,15 @@ int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float*
                            int fragments_h, int fragments_w, int fsize, int aligned, const float mean[3],
                            const float std[3], void* stream);
 
+/* First piece of the literal KSVQE key: quality-aware region selection, RegionNet_CLIP.forward eval
+ * branch (models/backbones/patchnet.py:461-550) + obtain_keyframes grouping (KSVQE_model.py:1352-1376), without the
+ * reference's per-frame .item() host syncs (graph-capturable).
+ *   fragment f32 [B,3,T,H,W] (H = W = g*anchor), cls_attn f32 [B*n_key, L] (n_key = 4 key frames, L = l*l CLIP patch
+ *   tokens) -> region_out i32 [B, n_key] (arg-max of the mean score over every region_patches^2 window of the
+ *   nearest-resized g x g score map) and x_sel_out f32 [B,3,T,anchor*region_patches,anchor*region_patches] */
+int kvq_qrs_select_gather(const float* fragment, const float* cls_attn, float* x_sel_out, int32_t* region_out, int B,
+                          int T, int H, int W, int n_key, int L, int anchor, int region_patches, void* stream);
+
 /* ---- SimpleVQA spatial branch (config/kwai_simpleVQA_test.yml): ResNet-50 per frame + mean/std pools + head ---- */
 typedef struct KvqResNetConfig {
   int32_t layers[4];   /* 3,4,6,3 Bottleneck blocks (models/backbones/simpleVQA_model.py:276 resnet50) */

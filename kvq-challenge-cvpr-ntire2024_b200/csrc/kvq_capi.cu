@@ -128,6 +128,12 @@ int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float*
                                    std, static_cast<cudaStream_t>(stream));
 }
 
+int kvq_qrs_select_gather(const float* fragment, const float* cls_attn, float* x_sel_out, int32_t* region_out, int B,
+                          int T, int H, int W, int n_key, int L, int anchor, int region_patches, void* stream) {
+  return launch_qrs_select_gather(fragment, cls_attn, x_sel_out, region_out, B, T, H, W, n_key, L, anchor, region_patches,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 size_t kvq_vqa_head_workspace_bytes(int B, int C, int tokens) {
   return align_up(static_cast<size_t>(B) * tokens * C * 2 + 128 * 3072 * 2, 256) +
          align_up(static_cast<size_t>(B) * tokens * 4, 256);

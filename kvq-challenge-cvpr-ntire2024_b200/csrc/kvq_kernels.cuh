@@ -201,6 +201,9 @@ int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cuda
 int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float* out, int B, int T, int Hs, int Ws,
                               int fh, int fw, int fs, int aligned, const float mean[3], const float stdv[3],
                               cudaStream_t stream);
+// KSVQE quality-aware region selection + gather (RegionNet_CLIP eval branch, patchnet.py:461-550)
+int launch_qrs_select_gather(const float* fragment, const float* score, float* out, int32_t* region, int B, int T, int H,
+                             int W, int n_key, int L, int anchor, int ks, cudaStream_t stream);
 // fp32 [B, C, tokens] -> fp16 [B*tokens, C]
 int launch_cf_to_rows(const float* in, __half* out, int B, int C, int tokens, cudaStream_t stream);
 int launch_pack_split(const float* in, __half* out, int rows, int K, cudaStream_t stream);

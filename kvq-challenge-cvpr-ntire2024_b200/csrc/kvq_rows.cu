@@ -299,6 +299,57 @@ fragment_gather_upsample_kernel(const uint8_t* __restrict__ frames, const int32_
   out[(((static_cast<size_t>(b) * 3 + c) * T + t) * OH + y) * OW + x] = (v - mean) * istd;
 }
 
+// ---- QRS: quality-aware region selection of KSVQE (RegionNet_CLIP.forward eval branch, patchnet.py:461-550) ----
+// score [B*n_key, L] = cos(CLS, patch) of each key frame on an l x l grid (l*l = L).  Per key frame: nearest-neighbour
+// resize to the g x g fragment grid (F.interpolate(scale_factor = g/l, mode="nearest"): src = floor(dst * float(l/g))),
+// mean over every ks x ks window (F.unfold, stride 1), arg-max (min_max_norm is monotone; HardTopK(1) keeps the
+// first maximum) -> region[b, key] = ry * (g - ks + 1) + rx.  One thread per key frame; the map is at most 16 x 16.
+__global__ void __launch_bounds__(128)
+qrs_select_kernel(const float* __restrict__ score, int32_t* __restrict__ region, int n, int l, int g, int ks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* s = score + static_cast<size_t>(i) * l * l;
+  const float rs = 1.0f / (static_cast<float>(g) / static_cast<float>(l));   // ATen: scale = 1 / scale_factor (fp32)
+  const int nr = g - ks + 1;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int ry = 0; ry < nr; ++ry)
+    for (int rx = 0; rx < nr; ++rx) {
+      float acc = 0.f;
+      for (int dy = 0; dy < ks; ++dy) {
+        int sy = static_cast<int>(floorf(static_cast<float>(ry + dy) * rs)); if (sy > l - 1) sy = l - 1;
+        for (int dx = 0; dx < ks; ++dx) {
+          int sx = static_cast<int>(floorf(static_cast<float>(rx + dx) * rs)); if (sx > l - 1) sx = l - 1;
+          acc += s[sy * l + sx];
+        }
+      }
+      acc /= static_cast<float>(ks * ks);
+      if (acc > best) { best = acc; arg = ry * nr + rx; }
+    }
+  region[i] = arg;
+}
+
+// x_sel[b, c, t] = fragment[b, c, t, a*ry : a*ry + a*ks, a*rx : a*rx + a*ks] with (ry, rx) = region of frame t's key-frame
+// group (obtain_keyframes, KSVQE_model.py:1352-1376: groups change at t = T/4 - 1, T/2 - 1, 3T/4 - 1).  float4 per thread.
+__global__ void __launch_bounds__(256)
+qrs_gather_kernel(const float* __restrict__ frag, const int32_t* __restrict__ region, float* __restrict__ out, int T,
+                  int H, int W, int n_key, int anchor, int ks, int nr, long long total4) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int S = anchor * ks, S4 = S >> 2;
+  const int x4 = static_cast<int>(idx % S4);
+  const int y = static_cast<int>((idx / S4) % S);
+  const int t = static_cast<int>((idx / (static_cast<long long>(S4) * S)) % T);
+  const long long bc = idx / (static_cast<long long>(S4) * S * T);
+  const int b = static_cast<int>(bc / 3);
+  int grp = (t >= T / 4 - 1) + (t >= T / 2 - 1) + (t >= T * 3 / 4 - 1);
+  if (grp > n_key - 1) grp = n_key - 1;
+  const int r = region[b * n_key + grp];
+  const int ry = r / nr, rx = r - ry * nr;
+  const float4 v = *reinterpret_cast<const float4*>(frag + ((bc * T + t) * H + (anchor * ry + y)) * W + anchor * rx + 4 * x4);
+  *reinterpret_cast<float4*>(out + ((bc * T + t) * S + y) * S + 4 * x4) = v;
+}
+
 // channels-first fp32 [B, C, tokens] -> token rows fp16 [B*tokens, C] (input side of a stand-alone VQAHead)
 __global__ void __launch_bounds__(256)
 cf_to_rows_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int tokens) {
@@ -435,6 +486,28 @@ int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, flo
       1.0f / stdv[2], total);
   count_launch();
   return check_cuda(cudaGetLastError(), "fragment_gather_kernel launch");
+}
+
+int launch_qrs_select_gather(const float* fragment, const float* score, float* out, int32_t* region, int B, int T, int H,
+                             int W, int n_key, int L, int anchor, int ks, cudaStream_t stream) {
+  int l = 1;
+  while (l * l < L) ++l;
+  KVQ_REQUIRE(fragment && score && out && region, KVQ_ERR_BAD_SHAPE, "qrs: NULL argument");
+  KVQ_REQUIRE(B > 0 && T >= 4 && n_key == 4 && l * l == L && anchor > 0 && anchor % 4 == 0 && ks > 0, KVQ_ERR_BAD_SHAPE,
+              "qrs: B=%d T=%d n_key=%d (4 key frames) L=%d (square) anchor=%d ks=%d", B, T, n_key, L, anchor, ks);
+  KVQ_REQUIRE(H == W && H % anchor == 0 && H / anchor >= ks && W % 4 == 0, KVQ_ERR_BAD_SHAPE,
+              "qrs: fragment %dx%d must be a square grid of %d-pixel patches with at least %d per side", H, W, anchor, ks);
+  const int g = H / anchor, nr = g - ks + 1;
+  qrs_select_kernel<<<(B * n_key + 127) / 128, 128, 0, stream>>>(score, region, B * n_key, l, g, ks);
+  count_launch();
+  KVQ_CUDA(cudaGetLastError());
+  const long long total4 = static_cast<long long>(B) * 3 * T * (anchor * ks) * (anchor * ks / 4);
+  const long long grid = (total4 + 255) / 256;
+  KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "qrs: grid too large");
+  qrs_gather_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(fragment, region, out, T, H, W, n_key, anchor, ks, nr,
+                                                                   total4);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "qrs_gather_kernel launch");
 }
 
 int launch_cf_to_rows(const float* in, __half* out, int B, int C, int tokens, cudaStream_t stream) {

@@ -159,6 +159,22 @@ def fragment_gather_u8(frames, offsets, fragments_h=7, fragments_w=7, fsize=32, 
     return out
 
 
+def qrs_select_gather(fragment, cls_attn, n_key=4, anchor=32, region_patches=7):
+    """KSVQE quality-aware region selection (patchnet.py:461-550, eval): fragment f32 [B,3,T,H,W], cls_attn f32
+    [B*n_key, L] -> (x_sel f32 [B,3,T,anchor*region_patches, anchor*region_patches], region i32 [B, n_key])."""
+    _need_cuda(fragment, cls_attn)
+    if fragment.dtype != torch.float32 or cls_attn.dtype != torch.float32:
+        raise RuntimeError("qrs_select_gather takes float32 tensors")
+    fragment, cls_attn = fragment.contiguous(), cls_attn.contiguous()
+    B, _, T, H, W = fragment.shape
+    S = anchor * region_patches
+    out = torch.empty((B, 3, T, S, S), dtype=torch.float32, device=fragment.device)
+    region = torch.empty((B, n_key), dtype=torch.int32, device=fragment.device)
+    _l.check(_l.load().kvq_qrs_select_gather(_p(fragment), _p(cls_attn), _p(out), _p(region), B, T, H, W, n_key,
+                                             cls_attn.shape[-1], anchor, region_patches, _stream()), "qrs_select_gather")
+    return out, region
+
+
 class SwinWeights:
     """Device-resident packed weights of SwinTransformer3D (+ VQAHead) in the order include/kvq_b200.h documents.
 

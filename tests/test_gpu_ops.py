@@ -186,3 +186,28 @@ def test_fragment_gather_upsample_fallback(Hs, Ws, fh, fw):
     out = ops.fragment_gather_u8(frames.to(_dev()), offs.to(_dev()), fh, fw, fs, al).cpu()
     assert out.shape == ref.shape
     assert (out - ref).abs().max().item() < 1e-4, (out - ref).abs().max().item()
+
+
+def test_qrs_region_selection_matches_the_reference_golden():
+    """First piece of the literal KSVQE key: the REAL reference (tools/make_golden_ksvqe.py) chose region[b, t] from
+    cls_attn on a seeded clip; the kernel must take the same decisions and gather bit-exactly."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from kvq_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "ksvqe_t32_288.npz"))
+    frag = torch.randn((1, 3, 32, 288, 288), generator=torch.Generator().manual_seed(int(g["xseed"])))   # same draw
+    cls_attn = torch.from_numpy(g["cls_attn"])
+    x_sel, region = ops.qrs_select_gather(frag.to(_dev()), cls_attn.to(_dev()))
+    region = region.cpu()
+    want = torch.from_numpy(g["region"])[0]
+    grp = [(t >= 7) + (t >= 15) + (t >= 23) for t in range(32)]
+    assert [int(region[0, k]) for k in grp] == want.tolist()
+    x_sel = x_sel.cpu()
+    for t in (0, 7, 15, 31):
+        ry, rx = divmod(int(want[t]), 3)
+        assert torch.equal(x_sel[0, :, t], frag[0, :, t, 32 * ry:32 * ry + 224, 32 * rx:32 * rx + 224])
+    # 7x7 fragment grid (BASELINE config 5): exactly one candidate region = identity
+    f7 = torch.randn((2, 3, 8, 224, 224), generator=torch.Generator().manual_seed(3)).to(_dev())
+    xs, rg = ops.qrs_select_gather(f7, torch.rand(8, 49, device=_dev()))
+    assert torch.equal(xs, f7) and int(rg.abs().max()) == 0
