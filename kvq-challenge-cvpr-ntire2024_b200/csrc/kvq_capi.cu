@@ -555,7 +555,9 @@ int conv_spatial(const __half* in, int N, int H, int W, int C, int k, int stride
     gp.out = out; gp.ldo = cout;
     gp.relu = relu ? 1 : 0;
     ProfScope ps(PK_CONV_GEMM, stage, st);
-    return launch_conv_implicit(in, N, 1, H, W, C, 1, k, k, 1, stride, stride, 0, pad, pad,
+    // the N frames are the T axis of one "clip": a 128-pixel tile may then span several frames of a small map (7x7 and
+    // 14x14 maps would otherwise waste up to 2.6x of every tile), and a (1,k,k) kernel never mixes frames
+    return launch_conv_implicit(in, 1, N, H, W, C, 1, k, k, 1, stride, stride, 0, pad, pad,
                                 static_cast<const __half*>(w), gp, st);
   }
   const int Ho = conv_out(H, k, stride, pad), Wo = conv_out(W, k, stride, pad);
