@@ -142,6 +142,20 @@ int kvq_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, float*
 int kvq_qrs_select_gather(const float* fragment, const float* cls_attn, float* x_sel_out, int32_t* region_out, int B,
                           int T, int H, int W, int n_key, int L, int anchor, int region_patches, void* stream);
 
+/* Second piece of the literal KSVQE key: the CONTRIQUE distortion encoder (CONTRIQUE_model.forward,
+ * models/backbones/KSVQE_model.py:1622-1665; called on x_sel_ori[:, :, ::2], :1425).
+ *   x f32 [B,3,T,H,W] -> every frame_step-th frame is cut into anchor x anchor patches (order b, t, gy, gx) -> torchvision
+ *   ResNet-50 trunk (children()[:-2]) -> [N,2048] -> F.normalize -> Linear(2048,2048)+BN1d+ReLU -> Linear(2048,128)+BN1d
+ *   z_out f32 [B, T/frame_step, (H/anchor)*(W/anchor), 128]
+ * Weight table (BatchNorm folded as in kvq_simplevqa_forward): conv1 in the stem layout; per layer / block conv1,
+ * conv2, conv3 (+ downsample for block 0); projector.0+projector.1 (fp16 [2048,2048], f32 [2048]);
+ * projector.3+projector.4 (fp16 [128,2048], f32 [128]). */
+int kvq_contrique_num_weights(void);
+size_t kvq_contrique_workspace_bytes(int B, int T, int H, int W, int anchor, int frame_step);
+int kvq_contrique_forward(const void* const* weights, int num_weights, const float* x, int B, int T, int H, int W,
+                          int anchor, int frame_step, float* z_out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* ---- SimpleVQA spatial branch (config/kwai_simpleVQA_test.yml): ResNet-50 per frame + mean/std pools + head ---- */
 typedef struct KvqResNetConfig {
   int32_t layers[4];   /* 3,4,6,3 Bottleneck blocks (models/backbones/simpleVQA_model.py:276 resnet50) */

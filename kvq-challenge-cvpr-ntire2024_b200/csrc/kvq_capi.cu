@@ -571,6 +571,57 @@ int conv_spatial(const __half* in, int N, int H, int W, int C, int k, int stride
   return conv_gemm(col, Kp, w, b, nullptr, 0, out, N * Ho * Wo, cout, Kp, relu, stage, st);
 }
 
+// layer1..layer4 of a torchvision-style Bottleneck ResNet (stride on the 3x3) on N channels-last maps, starting from
+// act[1] = [N, h, w, 64] (after the stem max pool); `on_stage(s, cur, h*w, cout)` runs after each layer.
+extern "C++" {
+template <typename OnStage>
+int resnet_layers(const int32_t layers[4], const void* const* weights, int& wi, __half* const act[5], __half* col, int N,
+                  int h, int w, cudaStream_t st, OnStage on_stage, __half** final_act, int* final_h, int* final_w) {
+  auto W_ = [&]() { return weights[wi++]; };
+  __half* cur = act[1];
+  int ci = 1;  // index of `cur`
+  int cin = 64, rc;
+  for (int s = 0; s < 4; ++s) {
+    const int planes = 64 << s, cout = planes * 4;
+    for (int j = 0; j < layers[s]; ++j) {
+      const int stride = (j == 0 && s > 0) ? 2 : 1;
+      const int ho = conv_out(h, 3, stride, 1), wo = conv_out(w, 3, stride, 1);
+      const int M = N * h * w, Mo = N * ho * wo;
+      __half* t1 = act[(ci + 1) % 5];
+      __half* t2 = act[(ci + 2) % 5];
+      __half* idn = act[(ci + 3) % 5];
+      __half* out = act[(ci + 4) % 5];
+      const void* w1 = W_(); const void* b1 = W_();
+      const void* w2 = W_(); const void* b2 = W_();
+      const void* w3 = W_(); const void* b3 = W_();
+      // Bottleneck.forward (:106-126): 1x1 -> 3x3 (stride here) -> 1x1, + identity / downsample, ReLU
+      rc = conv_gemm(cur, cin, w1, b1, nullptr, 0, t1, M, planes, cin, true, s, st);
+      if (rc != 0) return rc;
+      rc = conv_spatial(t1, N, h, w, planes, 3, stride, 1, w2, b2, t2, planes, true, col, s, st);
+      if (rc != 0) return rc;
+      const __half* resid = cur;
+      if (j == 0) {
+        const void* wd = W_(); const void* bd = W_();
+        if (stride == 2) rc = conv_spatial(cur, N, h, w, cin, 1, 2, 0, wd, bd, idn, cout, false, col, s, st);
+        else rc = conv_gemm(cur, cin, wd, bd, nullptr, 0, idn, Mo, cout, cin, false, s, st);
+        if (rc != 0) return rc;
+        resid = idn;
+      }
+      rc = conv_gemm(t2, planes, w3, b3, resid, cout, out, Mo, cout, planes, true, s, st);
+      if (rc != 0) return rc;
+      cur = out;
+      ci = (ci + 4) % 5;
+      cin = cout;
+      h = ho; w = wo;
+    }
+    rc = on_stage(s, cur, h * w, cout);
+    if (rc != 0) return rc;
+  }
+  if (final_act != nullptr) { *final_act = cur; *final_h = h; *final_w = w; }
+  return KVQ_OK;
+}
+}  // extern "C++"
+
 }  // namespace
 
 int kvq_resnet_num_weights(const KvqResNetConfig* cfg) {
@@ -630,50 +681,19 @@ int kvq_simplevqa_forward(const KvqResNetConfig* cfg, const void* const* weights
   }
   if (rc != 0) return rc;
 
-  __half* cur = act[1];
-  int ci = 1;  // index of `cur`
-  int h = pl.Hp, w = pl.Wp, cin = 64, col_off = 0;
-  for (int s = 0; s < 4; ++s) {
-    const int planes = 64 << s, cout = planes * 4;
-    for (int j = 0; j < cfg->layers[s]; ++j) {
-      const int stride = (j == 0 && s > 0) ? 2 : 1;
-      const int ho = conv_out(h, 3, stride, 1), wo = conv_out(w, 3, stride, 1);
-      const int M = N * h * w, Mo = N * ho * wo;
-      __half* t1 = act[(ci + 1) % 5];
-      __half* t2 = act[(ci + 2) % 5];
-      __half* idn = act[(ci + 3) % 5];
-      __half* out = act[(ci + 4) % 5];
-      const void* w1 = W_(); const void* b1 = W_();
-      const void* w2 = W_(); const void* b2 = W_();
-      const void* w3 = W_(); const void* b3 = W_();
-      // Bottleneck.forward (:106-126): 1x1 -> 3x3 (stride here) -> 1x1, + identity / downsample, ReLU
-      rc = conv_gemm(cur, cin, w1, b1, nullptr, 0, t1, M, planes, cin, true, s, st);
-      if (rc != 0) return rc;
-      rc = conv_spatial(t1, N, h, w, planes, 3, stride, 1, w2, b2, t2, planes, true, col, s, st);
-      if (rc != 0) return rc;
-      const __half* resid = cur;
-      if (j == 0) {
-        const void* wd = W_(); const void* bd = W_();
-        if (stride == 2) rc = conv_spatial(cur, N, h, w, cin, 1, 2, 0, wd, bd, idn, cout, false, col, s, st);
-        else rc = conv_gemm(cur, cin, wd, bd, nullptr, 0, idn, Mo, cout, cin, false, s, st);
-        if (rc != 0) return rc;
-        resid = idn;
-      }
-      rc = conv_gemm(t2, planes, w3, b3, resid, cout, out, Mo, cout, planes, true, s, st);
-      if (rc != 0) return rc;
-      cur = out;
-      ci = (ci + 4) % 5;
-      cin = cout;
-      h = ho; w = wo;
-    }
-    if (s >= 1) {
-      // AdaptiveAvgPool2d(1) + global_std_pool2d of layer2/3/4 (:242-251), concatenated in that order (:252)
-      ProfScope ps(PK_CONV_POOL, s, st);
-      rc = launch_pool_stats(cur, nullptr, feat_out + col_off, feat_out + col_off + cout, N, h * w, cout, fdim, st);
-      if (rc != 0) return rc;
-      col_off += 2 * cout;
-    }
-  }
+  int col_off = 0;
+  rc = resnet_layers(cfg->layers, weights, wi, act, col, N, pl.Hp, pl.Wp, st,
+                     [&](int s, const __half* cur, int hw, int cout) -> int {
+                       if (s < 1) return KVQ_OK;
+                       // AdaptiveAvgPool2d(1) + global_std_pool2d of layer2/3/4 (:242-251), concatenated (:252)
+                       ProfScope ps(PK_CONV_POOL, s, st);
+                       const int r = launch_pool_stats(cur, nullptr, feat_out + col_off, feat_out + col_off + cout, N, hw,
+                                                       cout, fdim, st);
+                       col_off += 2 * cout;
+                       return r;
+                     },
+                     nullptr, nullptr, nullptr);
+  if (rc != 0) return rc;
   if (cfg->feat3d_dim > 0) {
     // torch.cat((x, x_3D_features), dim=1) (:256)
     KVQ_CUDA(cudaMemcpy2DAsync(feat_out + col_off, static_cast<size_t>(fdim) * 4, feat3d,
@@ -690,6 +710,97 @@ int kvq_simplevqa_forward(const KvqResNetConfig* cfg, const void* const* weights
     if (rc != 0) return rc;
   }
   return KVQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CONTRIQUE distortion encoder of KSVQE (KSVQE_model.py:1622-1665): 32x32 patches of every 2nd frame -> torchvision
+// ResNet-50 trunk -> L2 normalise -> Linear + BN1d + ReLU -> Linear + BN1d
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct CqPlan {
+  int N, gh, gw;
+  size_t patch_bytes;
+  ResPlan res;
+  size_t total;
+};
+int make_cq_plan(int B, int T, int H, int W, int anchor, int step, CqPlan* pl) {
+  KVQ_REQUIRE(B >= 1 && T >= 1 && step >= 1 && T % step == 0 && anchor >= 32 && H % anchor == 0 && W % anchor == 0,
+              KVQ_ERR_BAD_SHAPE, "contrique: x %dx3x%dx%dx%d, patch %d, frame step %d", B, T, H, W, anchor, step);
+  pl->gh = H / anchor; pl->gw = W / anchor;
+  const long long n = static_cast<long long>(B) * (T / step) * pl->gh * pl->gw;
+  KVQ_REQUIRE(n < (1 << 24), KVQ_ERR_BAD_SHAPE, "contrique: %lld patches", n);
+  pl->N = static_cast<int>(n);
+  KvqResNetConfig rc{{3, 4, 6, 3}, 0, 0};
+  int r = make_res_plan(&rc, 1, pl->N, anchor, anchor, &pl->res);
+  if (r != 0) return r;
+  pl->patch_bytes = align_up(static_cast<size_t>(pl->N) * 3 * anchor * anchor * 4, 256);
+  pl->total = pl->patch_bytes + pl->res.total;
+  return KVQ_OK;
+}
+}  // namespace
+
+int kvq_contrique_num_weights(void) { return 2 + 2 * (3 * 16 + 4) + 4; }
+
+size_t kvq_contrique_workspace_bytes(int B, int T, int H, int W, int anchor, int frame_step) {
+  CqPlan pl;
+  if (make_cq_plan(B, T, H, W, anchor, frame_step, &pl) != 0) return 0;
+  return pl.total;
+}
+
+int kvq_contrique_forward(const void* const* weights, int num_weights, const float* x, int B, int T, int H, int W,
+                          int anchor, int frame_step, float* z_out, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  CqPlan pl;
+  int rc = make_cq_plan(B, T, H, W, anchor, frame_step, &pl);
+  if (rc != 0) return rc;
+  KVQ_REQUIRE(num_weights == kvq_contrique_num_weights(), KVQ_ERR_BAD_SHAPE, "contrique: %d weight pointers, expected %d",
+              num_weights, kvq_contrique_num_weights());
+  KVQ_REQUIRE(x && z_out && workspace && weights, KVQ_ERR_BAD_SHAPE, "contrique: NULL argument");
+  KVQ_REQUIRE(workspace_bytes >= pl.total, KVQ_ERR_WORKSPACE, "contrique: workspace %zu < %zu bytes", workspace_bytes,
+              pl.total);
+  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, KVQ_ERR_MISALIGNED, "workspace not 256 B aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* wp = static_cast<uint8_t*>(workspace);
+  float* patches = reinterpret_cast<float*>(wp);
+  wp += pl.patch_bytes;
+  __half* col = reinterpret_cast<__half*>(wp);
+  __half* act[5];
+  for (int i = 0; i < 5; ++i) act[i] = reinterpret_cast<__half*>(wp + pl.res.col_bytes + i * pl.res.act_bytes);
+  const int N = pl.N;
+  int wi = 0;
+  rc = launch_patch_split(x, patches, B, T, H, W, anchor, frame_step, st);
+  if (rc != 0) return rc;
+  {   // encoder[0..3]: conv1 + bn1 + relu + maxpool; the N patches are the T axis of one [1,3,N,a,a] "clip"
+    const void* w = weights[wi++]; const void* b = weights[wi++];
+    ProfScope ps(PK_CONV_STEM, 0, st);
+    rc = launch_stem_conv(patches, static_cast<const __half*>(w), static_cast<const float*>(b), act[0], 1, N, anchor,
+                          anchor, 1, 64, st);
+  }
+  if (rc != 0) return rc;
+  rc = launch_maxpool_hw(act[0], act[1], N, pl.res.Hs, pl.res.Ws, 64, st);
+  if (rc != 0) return rc;
+  const int32_t layers[4] = {3, 4, 6, 3};
+  __half* fin = nullptr;
+  int fh = 0, fw = 0;
+  rc = resnet_layers(layers, weights, wi, act, col, N, pl.res.Hp, pl.res.Wp, st,
+                     [](int, const __half*, int, int) -> int { return KVQ_OK; }, &fin, &fh, &fw);
+  if (rc != 0) return rc;
+  KVQ_REQUIRE(fh == 1 && fw == 1, KVQ_ERR_BAD_SHAPE,
+              "contrique: %dx%d patches leave a %dx%d map; h.view(-1, 2048) (:1655) needs 1x1 (32x32 patches)", anchor,
+              anchor, fh, fw);
+  // three free activation buffers: anything but `fin`
+  __half* t[3];
+  for (int i = 0, k = 0; i < 5 && k < 3; ++i)
+    if (act[i] != fin) t[k++] = act[i];
+  rc = launch_row_l2norm(fin, t[0], N, 2048, st);                                          // F.normalize (:1657)
+  if (rc != 0) return rc;
+  const void* w1 = weights[wi++]; const void* b1 = weights[wi++];
+  const void* w2 = weights[wi++]; const void* b2 = weights[wi++];
+  rc = conv_gemm(t[0], 2048, w1, b1, nullptr, 0, t[1], N, 2048, 2048, true, 3, st);         // Linear + BN1d + ReLU
+  if (rc != 0) return rc;
+  rc = conv_gemm(t[1], 2048, w2, b2, nullptr, 0, t[2], N, 128, 2048, false, 3, st);         // Linear + BN1d
+  if (rc != 0) return rc;
+  return launch_f16_to_f32(t[2], z_out, static_cast<size_t>(N) * 128, st);
 }
 
 int kvq_mlp_fused(const void* a_f16, const void* w1_f16, const float* b1, const void* w2_f16, const float* b2, float* x,

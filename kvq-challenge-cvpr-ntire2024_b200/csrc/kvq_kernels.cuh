@@ -204,6 +204,10 @@ int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, flo
 // KSVQE quality-aware region selection + gather (RegionNet_CLIP eval branch, patchnet.py:461-550)
 int launch_qrs_select_gather(const float* fragment, const float* score, float* out, int32_t* region, int B, int T, int H,
                              int W, int n_key, int L, int anchor, int ks, cudaStream_t stream);
+// CONTRIQUE pieces (KSVQE_model.py:1622-1665): patch split of every step-th frame, F.normalize over rows, fp16 -> fp32
+int launch_patch_split(const float* x, float* out, int B, int T, int H, int W, int a, int step, cudaStream_t stream);
+int launch_row_l2norm(const __half* in, __half* out, int rows, int C, cudaStream_t stream);
+int launch_f16_to_f32(const __half* in, float* out, size_t n, cudaStream_t stream);
 // fp32 [B, C, tokens] -> fp16 [B*tokens, C]
 int launch_cf_to_rows(const float* in, __half* out, int B, int C, int tokens, cudaStream_t stream);
 int launch_pack_split(const float* in, __half* out, int rows, int K, cudaStream_t stream);

@@ -350,6 +350,54 @@ qrs_gather_kernel(const float* __restrict__ frag, const int32_t* __restrict__ re
   *reinterpret_cast<float4*>(out + ((bc * T + t) * S + y) * S + 4 * x4) = v;
 }
 
+// CONTRIQUE_model.forward patch split (KSVQE_model.py:1643-1651) of every `step`-th frame:
+// x [B,3,T,H,W] -> patches [N,3,1,a,a], N = B * T/step * (H/a) * (W/a) ordered (b, t, gy, gx); float4 per thread
+__global__ void __launch_bounds__(256)
+patch_split_kernel(const float* __restrict__ x, float* __restrict__ out, int T, int H, int W, int a, int step,
+                   long long total4) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int a4 = a >> 2, gw = W / a, gh = H / a, Ts = T / step;
+  long long r = idx;
+  const int x4 = static_cast<int>(r % a4); r /= a4;
+  const int py = static_cast<int>(r % a); r /= a;
+  const int c = static_cast<int>(r % 3); r /= 3;
+  const int gx = static_cast<int>(r % gw); r /= gw;
+  const int gy = static_cast<int>(r % gh); r /= gh;
+  const int t = static_cast<int>(r % Ts);
+  const long long b = r / Ts;
+  const float4 v = *reinterpret_cast<const float4*>(
+      x + (((b * 3 + c) * T + static_cast<long long>(t) * step) * H + (gy * a + py)) * W + gx * a + 4 * x4);
+  reinterpret_cast<float4*>(out)[idx] = v;
+}
+
+// F.normalize(h, dim=1) (:1657): rows of C halfs, one warp per row, fp32 norm, eps 1e-12
+__global__ void __launch_bounds__(256)
+row_l2norm_kernel(const __half* __restrict__ in, __half* __restrict__ out, int rows, int C) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const __half2* src = reinterpret_cast<const __half2*>(in + static_cast<size_t>(row) * C);
+  float ss = 0.f;
+  for (int i = lane; i < (C >> 1); i += 32) {
+    const float2 f = __half22float2(src[i]);
+    ss += f.x * f.x + f.y * f.y;
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  __half2* dst = reinterpret_cast<__half2*>(out + static_cast<size_t>(row) * C);
+  for (int i = lane; i < (C >> 1); i += 32) {
+    const float2 f = __half22float2(src[i]);
+    dst[i] = __floats2half2_rn(f.x * inv, f.y * inv);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+f16_to_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __half2float(in[i]);
+}
+
 // channels-first fp32 [B, C, tokens] -> token rows fp16 [B*tokens, C] (input side of a stand-alone VQAHead)
 __global__ void __launch_bounds__(256)
 cf_to_rows_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int tokens) {
@@ -486,6 +534,30 @@ int launch_fragment_gather_u8(const uint8_t* frames, const int32_t* offsets, flo
       1.0f / stdv[2], total);
   count_launch();
   return check_cuda(cudaGetLastError(), "fragment_gather_kernel launch");
+}
+
+int launch_patch_split(const float* x, float* out, int B, int T, int H, int W, int a, int step, cudaStream_t stream) {
+  KVQ_REQUIRE(B > 0 && T > 0 && step > 0 && T % step == 0 && a > 0 && a % 4 == 0 && H % a == 0 && W % a == 0,
+              KVQ_ERR_BAD_SHAPE, "patch_split: x %dx3x%dx%dx%d, patch %d, frame step %d", B, T, H, W, a, step);
+  const long long total4 = static_cast<long long>(B) * (T / step) * (H / a) * (W / a) * 3 * a * (a / 4);
+  const long long grid = (total4 + 255) / 256;
+  KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "patch_split: grid too large");
+  patch_split_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(x, out, T, H, W, a, step, total4);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "patch_split_kernel launch");
+}
+
+int launch_row_l2norm(const __half* in, __half* out, int rows, int C, cudaStream_t stream) {
+  KVQ_REQUIRE(rows > 0 && C > 0 && C % 2 == 0, KVQ_ERR_BAD_SHAPE, "row_l2norm: rows=%d C=%d", rows, C);
+  row_l2norm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(in, out, rows, C);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "row_l2norm_kernel launch");
+}
+
+int launch_f16_to_f32(const __half* in, float* out, size_t n, cudaStream_t stream) {
+  f16_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, out, n);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "f16_to_f32_kernel launch");
 }
 
 int launch_qrs_select_gather(const float* fragment, const float* score, float* out, int32_t* region, int B, int T, int H,

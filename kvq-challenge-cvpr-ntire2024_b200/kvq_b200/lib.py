@@ -54,6 +54,10 @@ PROTOTYPES = {
                                        c_int, POINTER(c_float), POINTER(c_float), c_void_p]),
     "kvq_qrs_select_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_void_p]),
+    "kvq_contrique_num_weights": (c_int, []),
+    "kvq_contrique_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "kvq_contrique_forward": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "kvq_resnet_num_weights": (c_int, [POINTER(KvqResNetConfig)]),
     "kvq_resnet_feature_dim": (c_int, [POINTER(KvqResNetConfig)]),
     "kvq_simplevqa_workspace_bytes": (c_size_t, [POINTER(KvqResNetConfig), c_int, c_int, c_int, c_int]),

@@ -786,3 +786,54 @@ class SlowFastWeights:
         so, fo = alloc()
         self._launch(slow, fast, so, fo, ws)
         return so, fo
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CONTRIQUE distortion encoder of KSVQE (KSVQE_model.py:1622-1665)
+# ---------------------------------------------------------------------------------------------------------------
+class ContriqueWeights:
+    """Packed weights of CONTRIQUE_model (torchvision ResNet-50 trunk `encoder.<i>.` + `projector.`); `sd` maps the
+    reference state_dict names (e.g. `distortion_tool.encoder.0.weight`) to tensors."""
+
+    def __init__(self, sd, device, prefix="distortion_tool.", eps=1e-5):
+        self.device = torch.device(device)
+
+        def t(k):
+            return sd[prefix + k].detach().to(self.device, torch.float32)
+
+        def bn(p):
+            return [t(p + "." + leaf) for leaf in ("weight", "bias", "running_mean", "running_var")]
+
+        ts = list(pack_stem_weight(t("encoder.0.weight"), bn("encoder.1"), eps))
+        for li, depth in enumerate((3, 4, 6, 3)):
+            for j in range(depth):
+                b = f"encoder.{4 + li}.{j}."
+                for c in (1, 2, 3):
+                    ts += list(pack_conv_weight(t(b + f"conv{c}.weight"), bn(b + f"bn{c}"), eps))
+                if j == 0:
+                    ts += list(pack_conv_weight(t(b + "downsample.0.weight"), bn(b + "downsample.1"), eps))
+        ts += list(pack_conv_weight(t("projector.0.weight"), bn("projector.1"), eps))
+        ts += list(pack_conv_weight(t("projector.3.weight"), bn("projector.4"), eps))
+        self.tensors = ts
+        n = _l.load().kvq_contrique_num_weights()
+        if n != len(ts):
+            raise RuntimeError(f"kvq_b200: CONTRIQUE weight table has {len(ts)} entries, library expects {n}")
+        self.ptrs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in ts])
+        self._ws = None
+
+    def forward(self, x, anchor=32, frame_step=2):
+        """x f32 [B,3,T,H,W] (x_sel_ori) -> z f32 [B, T/frame_step, (H/anchor)*(W/anchor), 128]."""
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("kvq_b200: CONTRIQUE input must be a float32 CUDA tensor (no CPU fallback exists)")
+        x = x.contiguous()
+        B, _, T, H, W = x.shape
+        need = _l.load().kvq_contrique_workspace_bytes(B, T, H, W, anchor, frame_step)
+        if need == 0:
+            raise RuntimeError(f"kvq_b200: cannot plan a CONTRIQUE forward on {tuple(x.shape)}: {_l.last_error()}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        z = torch.empty((B, T // frame_step, (H // anchor) * (W // anchor), 128), dtype=torch.float32, device=x.device)
+        rc = _l.load().kvq_contrique_forward(self.ptrs, len(self.tensors), _p(x), B, T, H, W, anchor, frame_step, _p(z),
+                                             _p(self._ws), self._ws.numel(), _stream())
+        _l.check(rc, "contrique_forward")
+        return z

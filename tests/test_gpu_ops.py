@@ -211,3 +211,31 @@ def test_qrs_region_selection_matches_the_reference_golden():
     f7 = torch.randn((2, 3, 8, 224, 224), generator=torch.Generator().manual_seed(3)).to(_dev())
     xs, rg = ops.qrs_select_gather(f7, torch.rand(8, 49, device=_dev()))
     assert torch.equal(xs, f7) and int(rg.abs().max()) == 0
+
+
+def test_contrique_encoder_matches_the_reference_golden():
+    """Second piece of the literal KSVQE key.  Chain: seeded fragment + the reference's CLIP cosine map (golden) -> QRS
+    region selection -> CONTRIQUE on every 2nd frame; compared with what the REAL reference produced for the same
+    seeded weights (tools/make_golden_ksvqe.py: distortion_tool output statistics and a slice)."""
+    import json
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from kvq_b200 import ops
+    from tools import synth
+    g = np.load(os.path.join(GOLDEN, "ksvqe_t32_288.npz"))
+    keys = json.load(open(os.path.join(GOLDEN, "state_dict_keys_ksvqe.json")))["KSVQE"]
+    wseed = int(g["wseed"])
+    sd = {k: synth.fill_like("KSVQE_backbone." + k, tuple(v[0]), wseed) for k, v in keys.items()
+          if k.startswith("distortion_tool.") and v[1].startswith("float")}
+    frag = torch.randn((1, 3, 32, 288, 288), generator=torch.Generator().manual_seed(int(g["xseed"])))
+    x_sel, _ = ops.qrs_select_gather(frag.to(_dev()), torch.from_numpy(g["cls_attn"]).to(_dev()))
+    z = ops.ContriqueWeights(sd, _dev()).forward(x_sel).cpu()
+    assert z.shape == (1, 16, 49, 128)
+    ref_slice = torch.from_numpy(g["dist_token_slice"])                    # z[0, 0, :4, :8]
+    got_slice = z[0, 0, :4, :8]
+    st = g["dist_token_stats"]                                             # mean, |mean|, |max|, std of the reference
+    # fp16 storage through 53 layers; z is O(0.1..0.6)
+    assert (got_slice - ref_slice).abs().max().item() < 1e-2, (got_slice, ref_slice)
+    assert abs(z.abs().mean().item() - st[1]) < 2e-3 and abs(z.std().item() - st[3]) < 3e-3
+    assert abs(z.abs().max().item() - st[2]) < 3e-2
