@@ -156,6 +156,31 @@ int kvq_contrique_forward(const void* const* weights, int num_weights, const flo
                           int anchor, int frame_step, float* z_out, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* Third piece of the literal KSVQE key: the CLIP ViT-B/16 visual tower with CLS adapters that KSVQE runs on its four
+ * key frames (CLIP_extractor_addadapter_cls.forward, models/backbones/CLIP_backbone.py:156-202). */
+typedef struct KvqClipConfig {
+  int32_t width;         /* 768 */
+  int32_t heads;         /* 12 (head_dim 64) */
+  int32_t layers;        /* 12 */
+  int32_t patch;         /* 16 */
+  int32_t adapter_from;  /* CLIP_location (8): layers >= this blend the CLS token with its adapter output */
+} KvqClipConfig;
+/*
+ * Weight table: conv1 (f16 [768, 768], K index (ky, kx, c)); class_embedding f32 [768]; positional_embedding f32
+ * [1 + g*g, 768] ALREADY resized to the g x g patch grid (resize_pos_embed2d, bicubic, at load time); ln_pre weight,
+ * bias; then per layer ln_1 weight, bias; attn.in_proj_weight (f16 [2304,768]), in_proj_bias (f32); attn.out_proj
+ * weight (f16), bias; ln_2 weight, bias; mlp.c_fc weight (f16 [3072,768]), bias; mlp.c_proj weight (f16 [768,3072]),
+ * bias; and for layers >= adapter_from the adapter's Linear(768,192) / Linear(192,768) weight, bias in f32.
+ *   images f32 [n_img,3,H,W] (KSVQE: the 4 key frames of each clip, 112x112)
+ *   cls_attn_out f32 [n_img, g*g] = cos(CLS, patch token);  tokens_out f32 [n_img, 1 + g*g, 768] (cls_token = row 0,
+ *   pat_token = rows 1..)
+ */
+int kvq_clip_num_weights(const KvqClipConfig* cfg);
+size_t kvq_clip_workspace_bytes(const KvqClipConfig* cfg, int n_img, int H, int W);
+int kvq_clip_visual_forward(const KvqClipConfig* cfg, const void* const* weights, int num_weights, const float* images,
+                            int n_img, int H, int W, float* cls_attn_out, float* tokens_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* ---- SimpleVQA spatial branch (config/kwai_simpleVQA_test.yml): ResNet-50 per frame + mean/std pools + head ---- */
 typedef struct KvqResNetConfig {
   int32_t layers[4];   /* 3,4,6,3 Bottleneck blocks (models/backbones/simpleVQA_model.py:276 resnet50) */

@@ -72,6 +72,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, erf_as(x * 0.70710678118654752f), hx);
 }
 
+// QuickGELU of OpenAI CLIP (models/backbones/clip/model.py: x * sigmoid(1.702 * x))
+__device__ __forceinline__ float2 quick_gelu2(float2 x) {
+  const float2 e = make_float2(fast_exp2(-1.702f * 1.4426950408889634f * x.x), fast_exp2(-1.702f * 1.4426950408889634f * x.y));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(1.0f + e.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(1.0f + e.y));
+  return fmul2(x, r);
+}
+
 // two GELUs per call on the packed fp32x2 pipe (same formula as gelu_erf)
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 z = fmul2(x, splat2(0.70710678118654752f));
@@ -353,8 +362,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float2 v01 = fadd2(make_float2(__uint_as_float(rc[4 * j]), __uint_as_float(rc[4 * j + 1])), make_float2(bb.x, bb.y));
             float2 v23 = fadd2(make_float2(__uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3])), make_float2(bb.z, bb.w));
             if constexpr (EPI == EPI_GELU_F16) {
-              v01 = gelu_erf2(v01);
-              v23 = gelu_erf2(v23);
+              if (p.quick_gelu) {
+                v01 = quick_gelu2(v01);
+                v23 = quick_gelu2(v23);
+              } else {
+                v01 = gelu_erf2(v01);
+                v23 = gelu_erf2(v23);
+              }
             }
             h[2 * j] = pack_half2(v01.x, v01.y);
             h[2 * j + 1] = pack_half2(v23.x, v23.y);

@@ -126,6 +126,7 @@ struct GemmParams {
   const float* resid;   // EPI_RESID_F32: nullptr = no residual; may alias out
   const __half* resid_h; // EPI_CONV_F16: fp16 residual [M, ldr] or nullptr
   int ldr;
+  int quick_gelu;       // EPI_GELU_F16: x * sigmoid(1.702 x) (CLIP's QuickGELU) instead of the exact erf GELU
   int relu;             // EPI_CONV_F16: apply ReLU
   int nvalid;           // EPI_CONV_F16: columns >= nvalid are padding (not stored); 0 = N
   // EPI_CONV_F16 implicit-GEMM mode (conv.on): A is the channels-last activation [B,T,H,W,C] behind a 5-D tensor map;

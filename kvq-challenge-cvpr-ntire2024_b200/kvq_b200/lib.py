@@ -23,6 +23,11 @@ class KvqSlowFastConfig(ctypes.Structure):
     _fields_ = [("depths", c_int32 * 4), ("alpha", c_int32), ("slow_pool", c_int32 * 3), ("fast_pool", c_int32 * 3)]
 
 
+class KvqClipConfig(ctypes.Structure):
+    _fields_ = [("width", c_int32), ("heads", c_int32), ("layers", c_int32), ("patch", c_int32),
+                ("adapter_from", c_int32)]
+
+
 _I3 = c_int32 * 3
 _F3 = c_float * 3
 
@@ -58,6 +63,10 @@ PROTOTYPES = {
     "kvq_contrique_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "kvq_contrique_forward": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_clip_num_weights": (c_int, [POINTER(KvqClipConfig)]),
+    "kvq_clip_workspace_bytes": (c_size_t, [POINTER(KvqClipConfig), c_int, c_int, c_int]),
+    "kvq_clip_visual_forward": (c_int, [POINTER(KvqClipConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kvq_resnet_num_weights": (c_int, [POINTER(KvqResNetConfig)]),
     "kvq_resnet_feature_dim": (c_int, [POINTER(KvqResNetConfig)]),
     "kvq_simplevqa_workspace_bytes": (c_size_t, [POINTER(KvqResNetConfig), c_int, c_int, c_int, c_int]),

@@ -837,3 +837,77 @@ class ContriqueWeights:
                                              _p(self._ws), self._ws.numel(), _stream())
         _l.check(rc, "contrique_forward")
         return z
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CLIP ViT-B/16 visual tower with CLS adapters (CLIP_backbone.py:156-202)
+# ---------------------------------------------------------------------------------------------------------------
+def resize_pos_embed(pos, src_grid, tgt_grid):
+    """resize_pos_embed2d (CLIP_backbone.py:35-69): bicubic resize of the patch-grid part of positional_embedding
+    [1 + s*s, C] to [1 + t*t, C]; weight preprocessing, done once at load time."""
+    import torch.nn.functional as F
+    if src_grid == tgt_grid:
+        return pos
+    cls, grid = pos[:1], pos[1:]
+    grid = grid.t().reshape(1, -1, src_grid, src_grid)
+    grid = F.interpolate(grid, size=(tgt_grid, tgt_grid), mode="bicubic", align_corners=False)
+    return torch.cat([cls, grid.permute(0, 2, 3, 1).reshape(tgt_grid * tgt_grid, -1)], dim=0)
+
+
+class ClipVisualWeights:
+    """Packed weights of CLIP_extractor_addadapter_cls; `sd` maps the reference names (`CLIP_tool.visual.*`,
+    `CLIP_tool.adapter_layer.*`) to tensors."""
+
+    def __init__(self, sd, device, prefix="CLIP_tool.", image_size=112, adapter_from=8):
+        self.device = torch.device(device)
+
+        def t(k):
+            return sd[prefix + k].detach().to(self.device, torch.float32).contiguous()
+
+        v = "visual."
+        conv = t(v + "conv1.weight")                                   # [768, 3, 16, 16]
+        width, patch = conv.shape[0], conv.shape[-1]
+        layers = 1 + max(int(k[len(prefix + v + "transformer.resblocks."):].split(".")[0]) for k in sd
+                         if k.startswith(prefix + v + "transformer.resblocks."))
+        self.cfg = _l.KvqClipConfig(width, width // 64, layers, patch, adapter_from)
+        self.grid = image_size // patch
+        pos = t(v + "positional_embedding")
+        src = int(round((pos.shape[0] - 1) ** 0.5))
+        ts = [cast_f16(conv.permute(0, 2, 3, 1).reshape(width, -1).contiguous()), t(v + "class_embedding"),
+              resize_pos_embed(pos, src, self.grid).contiguous(), t(v + "ln_pre.weight"), t(v + "ln_pre.bias")]
+        for i in range(layers):
+            b = f"{v}transformer.resblocks.{i}."
+            ts += [t(b + "ln_1.weight"), t(b + "ln_1.bias"), cast_f16(t(b + "attn.in_proj_weight")),
+                   t(b + "attn.in_proj_bias"), cast_f16(t(b + "attn.out_proj.weight")), t(b + "attn.out_proj.bias"),
+                   t(b + "ln_2.weight"), t(b + "ln_2.bias"), cast_f16(t(b + "mlp.c_fc.weight")), t(b + "mlp.c_fc.bias"),
+                   cast_f16(t(b + "mlp.c_proj.weight")), t(b + "mlp.c_proj.bias")]
+            if i >= adapter_from:
+                a = f"adapter_layer.{i - adapter_from}."
+                ts += [t(a + "0.weight"), t(a + "0.bias"), t(a + "2.weight"), t(a + "2.bias")]
+        self.tensors = ts
+        n = _l.load().kvq_clip_num_weights(ctypes.byref(self.cfg))
+        if n != len(ts):
+            raise RuntimeError(f"kvq_b200: CLIP weight table has {len(ts)} entries, library expects {n}")
+        self.ptrs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in ts])
+        self._ws = None
+
+    def forward(self, images):
+        """images f32 [n,3,H,W] -> (cls_attn f32 [n, g*g], tokens f32 [n, 1 + g*g, 768])."""
+        if not images.is_cuda or images.dtype != torch.float32:
+            raise RuntimeError("kvq_b200: CLIP input must be a float32 CUDA tensor (no CPU fallback exists)")
+        images = images.contiguous()
+        n, _, H, W = images.shape
+        if H // self.cfg.patch != self.grid:
+            raise RuntimeError(f"kvq_b200: positional embedding was resized for a {self.grid}x{self.grid} grid")
+        need = _l.load().kvq_clip_workspace_bytes(ctypes.byref(self.cfg), n, H, W)
+        if need == 0:
+            raise RuntimeError(f"kvq_b200: cannot plan a CLIP forward on {tuple(images.shape)}: {_l.last_error()}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        L = 1 + self.grid * self.grid
+        attn = torch.empty((n, L - 1), dtype=torch.float32, device=images.device)
+        tokens = torch.empty((n, L, self.cfg.width), dtype=torch.float32, device=images.device)
+        rc = _l.load().kvq_clip_visual_forward(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(images), n, H, W,
+                                               _p(attn), _p(tokens), _p(self._ws), self._ws.numel(), _stream())
+        _l.check(rc, "clip_visual_forward")
+        return attn, tokens

@@ -239,3 +239,28 @@ def test_contrique_encoder_matches_the_reference_golden():
     assert (got_slice - ref_slice).abs().max().item() < 1e-2, (got_slice, ref_slice)
     assert abs(z.abs().mean().item() - st[1]) < 2e-3 and abs(z.std().item() - st[3]) < 3e-3
     assert abs(z.abs().max().item() - st[2]) < 3e-2
+
+
+def test_clip_visual_tower_matches_the_reference_golden():
+    """Third piece of the literal KSVQE key: CLIP ViT-B/16 + CLS adapters on the four 112x112 key frames; the cosine
+    map cos(CLS, patch) must match what the REAL reference produced for the same seeded weights / frames."""
+    import json
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from kvq_b200 import ops
+    from tools import synth
+    g = np.load(os.path.join(GOLDEN, "ksvqe_t32_288.npz"))
+    keys = json.load(open(os.path.join(GOLDEN, "state_dict_keys_ksvqe.json")))["KSVQE"]
+    wseed = int(g["wseed"])
+    sd = {k: synth.fill_like("KSVQE_backbone." + k, tuple(v[0]), wseed) for k, v in keys.items()
+          if k.startswith("CLIP_tool.") and v[1].startswith("float")}
+    gen = torch.Generator().manual_seed(int(g["xseed"]))
+    torch.randn((1, 3, 32, 288, 288), generator=gen)                       # the fragment view is drawn first
+    revideo = torch.randn((1, 3, 32, 112, 112), generator=gen)
+    key_frames = torch.stack([revideo[0, :, t] for t in (0, 7, 15, 23)])   # obtain_keyframes: t = 0, T/4-1, T/2-1, 3T/4-1
+    attn, tokens = ops.ClipVisualWeights(sd, _dev()).forward(key_frames.to(_dev()))
+    ref = torch.from_numpy(g["cls_attn"])
+    assert attn.shape == ref.shape and tokens.shape == (4, 50, 768)
+    err = (attn.cpu() - ref).abs().max().item()
+    assert err < 5e-3, err

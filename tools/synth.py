@@ -31,7 +31,8 @@ def fill_like(key, shape, seed, dtype=torch.float32):
         t = 0.1 * n
     elif leaf == "weight" and len(shape) == 1:          # LayerNorm / BatchNorm scale
         t = 1.0 + 0.2 * n
-    elif leaf == "weight":                              # Linear / Conv: variance-preserving-ish
+    elif leaf == "weight" or (leaf.endswith("_weight") and len(shape) == 2):   # Linear / Conv / MHA in_proj_weight:
+        # variance-preserving-ish (an O(0.1) in_proj makes the attention logits O(10): a chaotic, near one-hot softmax)
         fan_in = 1
         for s in shape[1:]:
             fan_in *= s
