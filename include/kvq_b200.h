@@ -83,6 +83,16 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
                        int T, int H, int W, float* feat_out, float* score_out, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Same forward with a host callback after every stage (BasicLayer incl. its PatchMerging): `tokens` is the fp32
+ * channels-last activation [rows, channels] (rows = B*D*h*w of the stage output) that the next stage reads, and may be
+ * modified in place by work the hook enqueues on `stream` (KSVQE's cross-gating modulation after stages >= tuning_stage,
+ * models/backbones/KSVQE_model.py:1436-1482).  The hook runs on the calling thread while the forward is being
+ * enqueued (also under CUDA-graph capture); a non-zero return aborts the forward. */
+typedef int (*kvq_stage_hook)(void* arg, int stage, float* tokens, int rows, int channels, void* stream);
+int kvq_swin3d_forward_hooked(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const float* x,
+                              int B, int T, int H, int W, float* feat_out, float* score_out, void* workspace,
+                              size_t workspace_bytes, void* stream, kvq_stage_hook hook, void* hook_arg);
+
 /* ---- weight packing (once per load_state_dict) ---- */
 int kvq_cast_f16(const float* in, void* out_f16, size_t n, void* stream);
 /* fp32 [rows, K] -> fp16 [rows, 2*ceil64(K)] = [hi | 0 | lo | 0] with hi = fp16(w), lo = fp16(w - hi) */

@@ -207,6 +207,13 @@ size_t kvq_swin3d_workspace_bytes(const KvqSwinConfig* cfg, int B, int T, int H,
 int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const float* x, int B,
                        int T, int H, int W, float* feat_out, float* score_out, void* workspace,
                        size_t workspace_bytes, void* stream) {
+  return kvq_swin3d_forward_hooked(cfg, weights, num_weights, x, B, T, H, W, feat_out, score_out, workspace,
+                                   workspace_bytes, stream, nullptr, nullptr);
+}
+
+int kvq_swin3d_forward_hooked(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const float* x,
+                              int B, int T, int H, int W, float* feat_out, float* score_out, void* workspace,
+                              size_t workspace_bytes, void* stream, kvq_stage_hook hook, void* hook_arg) {
   int rc = validate_cfg(cfg);
   if (rc != 0) return rc;
   Plan pl;
@@ -335,6 +342,14 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
       if (rc != 0) return rc;
       std::swap(xcur, xnext);
       // after the first merge the big buffer is free: keep ping-ponging between the two (xa always fits)
+    }
+    if (hook != nullptr) {
+      // BasicLayer output (blocks + downsample), channels-last fp32 tokens: KSVQE modulates it in place after stages
+      // >= tuning_stage (KSVQE_model.py:1436-1482); the hook enqueues its work on the same stream
+      const bool merged = s + 1 < cfg->num_stages;
+      const int h2 = merged ? (sd.H + 1) / 2 : sd.H, w2 = merged ? (sd.W + 1) / 2 : sd.W;
+      rc = hook(hook_arg, s, xcur, B * sd.D * h2 * w2, merged ? 2 * C : C, stream);
+      KVQ_REQUIRE(rc == 0, rc < 0 ? rc : KVQ_ERR_BAD_SHAPE, "stage hook failed after stage %d (code %d)", s, rc);
     }
   }
 

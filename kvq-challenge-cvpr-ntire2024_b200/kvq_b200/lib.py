@@ -28,6 +28,8 @@ class KvqClipConfig(ctypes.Structure):
                 ("adapter_from", c_int32)]
 
 
+STAGE_HOOK = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p)
+
 _I3 = c_int32 * 3
 _F3 = c_float * 3
 
@@ -37,6 +39,8 @@ PROTOTYPES = {
     "kvq_swin3d_workspace_bytes": (c_size_t, [POINTER(KvqSwinConfig), c_int, c_int, c_int, c_int]),
     "kvq_swin3d_forward": (c_int, [POINTER(KvqSwinConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
                                    c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_swin3d_forward_hooked": (c_int, [POINTER(KvqSwinConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
+                                          c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, STAGE_HOOK, c_void_p]),
     "kvq_pack_split_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "kvq_cast_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "kvq_attn_table_len": (c_int, [c_int, c_int, c_int]),

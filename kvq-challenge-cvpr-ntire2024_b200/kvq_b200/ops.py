@@ -267,6 +267,34 @@ class SwinWeights:
                                           _p(feat), _p(score), _p(ws), ws.numel(), _stream())
         _l.check(rc, "swin3d_forward")
 
+    def forward_hooked(self, x, stage_hook, want_feat=True, want_score=True):
+        """Eager forward with `stage_hook(stage, tokens_ptr, rows, channels, stream_ptr) -> int` called after every
+        stage; tokens_ptr is the raw device pointer of the fp32 [rows, channels] stage output, which work enqueued
+        on the stream may modify in place (KSVQE's modulation).  Returns (feat or None, score or None)."""
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("kvq_b200: input clips must be float32 CUDA tensors (no CPU fallback exists)")
+        x = x.contiguous()
+        B, _, T, H, W = x.shape
+        ws, _ = self.workspace(B, T, H, W)
+        feat = torch.empty(self.feat_shape(B, T, H, W), dtype=torch.float32, device=x.device) if want_feat else None
+        score = torch.empty(B, dtype=torch.float32, device=x.device) if want_score and self.cfg.head_hidden else None
+        err = []
+
+        def tramp(_arg, stage, tokens, rows, channels, stream):
+            try:
+                return int(stage_hook(stage, tokens, rows, channels, stream) or 0)
+            except Exception as e:                      # never let an exception cross the C boundary
+                err.append(e)
+                return -1
+
+        cb = _l.STAGE_HOOK(tramp)
+        rc = _l.load().kvq_swin3d_forward_hooked(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(x), B, T, H, W,
+                                                 _p(feat), _p(score), _p(ws), ws.numel(), _stream(), cb, None)
+        if err:
+            raise err[0]
+        _l.check(rc, "swin3d_forward_hooked")
+        return feat, score
+
     def forward(self, x, want_feat=False, want_score=True, score_out=None, graph=None):
         """x f32 [B,3,T,H,W] on this device -> (feat [B,Cf,D,h,w] or None, score [B] or None).
 
