@@ -191,6 +191,26 @@ int kvq_clip_visual_forward(const KvqClipConfig* cfg, const void* const* weights
                             int n_img, int H, int W, float* cls_attn_out, float* tokens_out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* Building blocks of KSVQE's cross-gating modulation (CDM, models/backbones/KSVQE_model.py:1436-1482); the Linears on
+ * token rows are kvq_linear_f16 / kvq_conv_gemm_f16. */
+/* softmax(q k^T * scale) v per (sequence, head), head_dim 64, at most 64 tokens (crossattention1 :1553-1587 with
+ * scale = dim^-0.5; Attention :1508-1551 with scale = 64^-0.5).  Token t of sequence (o, i), o < n_outer, i < n_inner,
+ * is row o*outer_stride + i*inner_stride + t*t_stride of q / k / v / out (f16, row strides ld* halfs). */
+int kvq_mha_f16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                int n_outer, int n_inner, long long outer_stride, long long inner_stride, long long t_stride, int Lq,
+                int Lkv, int heads, float scale, void* stream);
+/* x f32 [rows, C] in place: (a1 * (sigmoid(gd_pre[b]) * x + bd[b]) + a2 * (gs * x + bs)) / 2 with the per-token
+ * gs = sigmoid(<es, wg> + bg), bs = <es, wb> + bb (Semantic_Transformation2 :817-835), the per-clip, per-channel
+ * gd_pre / bd f32 [B, C] (Dist_Transformation3 :934-960 before its sigmoid) and the mix of :1482 */
+int kvq_cdm_mix(float* x, const void* es_f16, const float* wg, const float* bg, const float* wb, const float* bb,
+                const float* gd_pre, const float* bd, const float* a1, const float* a2, int rows, int C,
+                int rows_per_clip, void* stream);
+/* out f32 [M, N] = x f32 [M, K] * w f32 [N, K]^T + b (tiny M: per-clip statistics) */
+int kvq_small_linear_f32(const float* x, const float* w, const float* b, float* out, int M, int N, int K, void* stream);
+/* wa * a (f16) + wb * z (f32) -> f16 and / or f32 (dist_token = 0.2 * dist_adapter(z) + 0.8 * z, :1426) */
+int kvq_blend_f16_f32(const void* a_f16, const float* z, float wa, float wb, void* out_f16, float* out_f32, size_t n,
+                      void* stream);
+
 /* ---- SimpleVQA spatial branch (config/kwai_simpleVQA_test.yml): ResNet-50 per frame + mean/std pools + head ---- */
 typedef struct KvqResNetConfig {
   int32_t layers[4];   /* 3,4,6,3 Bottleneck blocks (models/backbones/simpleVQA_model.py:276 resnet50) */

@@ -71,6 +71,11 @@ PROTOTYPES = {
     "kvq_clip_workspace_bytes": (c_size_t, [POINTER(KvqClipConfig), c_int, c_int, c_int]),
     "kvq_clip_visual_forward": (c_int, [POINTER(KvqClipConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_mha_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                            ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_float, c_void_p]),
+    "kvq_cdm_mix": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_void_p]),
+    "kvq_small_linear_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kvq_blend_f16_f32": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kvq_resnet_num_weights": (c_int, [POINTER(KvqResNetConfig)]),
     "kvq_resnet_feature_dim": (c_int, [POINTER(KvqResNetConfig)]),
     "kvq_simplevqa_workspace_bytes": (c_size_t, [POINTER(KvqResNetConfig), c_int, c_int, c_int, c_int]),

@@ -1,0 +1,301 @@
+"""KSVQE backbone (reference models/backbones/KSVQE_model.py:1024-1500) with the reference's parameter names; the
+modules are parameter containers and `forward` is a host-side sequence of libkvq_b200.so calls:
+
+    key frames -> CLIP ViT-B/16 + CLS adapters (kvq_clip_visual_forward)           CLIP_backbone.py:156-202
+    cos(CLS, patch) -> QRS region selection + gather (kvq_qrs_select_gather)       patchnet.py:461-550
+    every 2nd frame -> CONTRIQUE encoder (kvq_contrique_forward) + dist_adapter    KSVQE_model.py:1622-1665, :1425-1426
+    Swin3D-GRPB stages (kvq_swin3d_forward_hooked); after stages >= tuning_stage the stage output is modulated in place
+    by the cross-gating module: semantic branch (CLIP tokens -> adapter -> cross-attention -> per-token gate) and
+    distortion branch (CONTRIQUE tokens -> adapter -> cross-attention -> temporal self-attention -> per-channel gate),
+    mixed with a1 / a2                                                               :1436-1482
+    final LayerNorm (+ VQAHead when called through VQA_Network)                      :1484-1486, head.py:60-68
+
+There is no CPU / eager fallback.  The one value computed with torch ops (on the device) is the second output,
+`distortion_contrastive_supervised` (:1666-1691): a training loss that inference discards (trainer.py:323-325)."""
+import collections
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from kvq_b200 import lib as _l
+from kvq_b200 import ops
+
+from .swin_backbone import SwinTransformer3D
+
+__all__ = ["KSVQE"]
+
+
+def _adapter(cin, hid, cout):
+    return nn.Sequential(nn.Linear(cin, hid), nn.ReLU(inplace=True), nn.Linear(hid, cout), nn.ReLU(inplace=True))
+
+
+class _ResidualAttentionBlock(nn.Module):            # clip/model.py ResidualAttentionBlock (parameter container)
+    def __init__(self, width, heads):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(width, heads)
+        self.ln_1 = nn.LayerNorm(width)
+        self.mlp = nn.Sequential(collections.OrderedDict([("c_fc", nn.Linear(width, width * 4)), ("gelu", nn.Identity()),
+                                                          ("c_proj", nn.Linear(width * 4, width))]))
+        self.ln_2 = nn.LayerNorm(width)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, width, layers, heads):
+        super().__init__()
+        self.width = width
+        self.resblocks = nn.Sequential(*[_ResidualAttentionBlock(width, heads) for _ in range(layers)])
+
+
+class _VisionTransformer(nn.Module):                 # clip/model.py VisionTransformer, ViT-B/16 at 224
+    def __init__(self, input_resolution=224, patch_size=16, width=768, layers=12, heads=12, output_dim=512):
+        super().__init__()
+        self.grid_size = input_resolution // patch_size
+        self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(self.grid_size ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = _Transformer(width, layers, heads)
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+
+class _ClipTool(nn.Module):                          # CLIP_extractor_addadapter_cls (CLIP_backbone.py:117-153)
+    def __init__(self, CLIP_location, cls_use):
+        super().__init__()
+        self.visual = _VisionTransformer()
+        self.CLIP_location, self.cls_use = CLIP_location, cls_use
+        if cls_use:
+            self.adapter_layer = nn.ModuleList([_adapter(768, 192, 768) for _ in range(11 - CLIP_location + 1)])
+
+
+class _Contrique(nn.Module):                         # CONTRIQUE_model (:1622-1641)
+    def __init__(self):
+        super().__init__()
+        import torchvision
+        self.encoder = nn.Sequential(*list(torchvision.models.resnet50(weights=None).children())[:-2])
+        self.projector = nn.Sequential(nn.Linear(2048, 2048, bias=False), nn.BatchNorm1d(2048), nn.ReLU(),
+                                       nn.Linear(2048, 128, bias=False), nn.BatchNorm1d(128))
+
+
+class _SemanticMod(nn.Module):                       # Semantic_Transformation2 (:817-835)
+    def __init__(self, c):
+        super().__init__()
+        self.conv_gama = nn.Conv2d(c, 1, 1)
+        self.conv_beta = nn.Conv2d(c, 1, 1)
+
+
+class _DistMod(nn.Module):                           # Dist_Transformation3 (:934-960)
+    def __init__(self, c):
+        super().__init__()
+        self.get_gamma = nn.Linear(c, c)
+        self.get_beta = nn.Linear(c, c)
+
+
+class _Cross(nn.Module):                             # crossattention1 (:1553-1587)
+    def __init__(self, dim):
+        super().__init__()
+        self.fc_q, self.fc_k, self.fc_v = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+
+
+class _SelfAttn(nn.Module):                          # Attention (:1508-1551)
+    def __init__(self, dim):
+        super().__init__()
+        self.to_qkv = nn.Linear(dim, dim * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(dim, dim), nn.Dropout(0.0))
+
+
+def _pad_rows(w, b, mult=64):
+    """[N,K] weight (+ bias) -> fp16 [ceil_mult(N), K], fp32 [ceil_mult(N)] for kvq_conv_gemm_f16 (N % 64 == 0)."""
+    n = w.shape[0]
+    npad = (n + mult - 1) // mult * mult
+    wp = torch.zeros((npad, w.shape[1]), dtype=torch.float32, device=w.device)
+    wp[:n] = w
+    bp = torch.zeros(npad, dtype=torch.float32, device=w.device)
+    if b is not None:
+        bp[:n] = b
+    return ops.cast_f16(wp.contiguous()), bp.contiguous(), n
+
+
+class KSVQE(SwinTransformer3D):
+    def __init__(self, pretrained=None, pretrained2d=False, num_samples=500, sample_type="topkpertubation",
+                 CLIP_location=10, cls_use=True, tuning_stage=2, a1=1, a2=0, **kwargs):
+        super().__init__(pretrained=None, **kwargs)
+        if tuple(self.depths) != (2, 2, 6, 2) or self.embed_dim != 96:
+            raise NotImplementedError("kvq_b200: KSVQE is built on the Swin-T backbone (depths 2,2,6,2, embed 96)")
+        if sample_type not in ("topkpertubation", "gumbel", "multinomial"):
+            raise NotImplementedError("kvq_b200: QRS eval branch takes the arg-max region; 'random' sampling is not built")
+        self.tuning_stage = tuning_stage
+        self.CLIP_tool = _ClipTool(CLIP_location, cls_use)
+        self.distortion_tool = _Contrique()
+        self.dist_adapter = _adapter(128, 32, 128)
+        n_mod = len(self.depths) - tuning_stage
+        self.a1 = nn.Parameter(torch.zeros(n_mod, 1) + a1)
+        self.a2 = nn.Parameter(torch.zeros(n_mod, 1) + a2)
+        c = self.num_features                                    # every modulated stage output has 768 channels (:1159-1163)
+        self.semantic_adapter = nn.ModuleList([_adapter(768, 192, c) for _ in range(n_mod)])
+        self.distortion_adapter = nn.ModuleList([_adapter(128, 32, c) for _ in range(n_mod)])
+        self.semantic_mod = nn.ModuleList([_SemanticMod(c) for _ in range(n_mod)])
+        self.distortion_mod = nn.ModuleList([_DistMod(c) for _ in range(n_mod)])
+        self.semantic_cross = nn.ModuleList([_Cross(c) for _ in range(n_mod)])
+        self.distortion_cross = nn.ModuleList([_Cross(c) for _ in range(n_mod)])
+        self.distortion_self = nn.ModuleList([_SelfAttn(c) for _ in range(n_mod)])
+        self._extra = None
+        self._extra_key = None
+
+    # ---- packed device weights of everything around the Swin stages ----
+    def _pack_extras(self, dev):
+        key = self._state_key(list(self.buffers()))
+        if self._extra is not None and self._extra_key == key:
+            return self._extra
+        sd = {k: v for k, v in self.state_dict().items()}
+        ex = {"clip": ops.ClipVisualWeights(sd, dev, prefix="CLIP_tool.", adapter_from=self.CLIP_tool.CLIP_location),
+              "contrique": ops.ContriqueWeights(sd, dev, prefix="distortion_tool.")}
+
+        def f32(k):
+            return sd[k].detach().to(dev, torch.float32).contiguous()
+
+        def lin(prefix, bias=True):
+            return _pad_rows(f32(prefix + ".weight"), f32(prefix + ".bias") if bias else None)
+
+        ex["dist_adapter"] = (lin("dist_adapter.0"), lin("dist_adapter.2"))
+        stages = []
+        for i in range(len(self.depths) - self.tuning_stage):
+            s = {"sem_ad": (lin(f"semantic_adapter.{i}.0"), lin(f"semantic_adapter.{i}.2")),
+                 "dis_ad": (lin(f"distortion_adapter.{i}.0"), lin(f"distortion_adapter.{i}.2")),
+                 "sem_cross": [lin(f"semantic_cross.{i}.fc_{n}") for n in "qkv"],
+                 "dis_cross": [lin(f"distortion_cross.{i}.fc_{n}") for n in "qkv"],
+                 "to_qkv": lin(f"distortion_self.{i}.to_qkv", bias=False), "to_out": lin(f"distortion_self.{i}.to_out.0"),
+                 "wg": f32(f"semantic_mod.{i}.conv_gama.weight").reshape(-1), "bg": f32(f"semantic_mod.{i}.conv_gama.bias"),
+                 "wb": f32(f"semantic_mod.{i}.conv_beta.weight").reshape(-1), "bb": f32(f"semantic_mod.{i}.conv_beta.bias"),
+                 "gw": f32(f"distortion_mod.{i}.get_gamma.weight"), "gb": f32(f"distortion_mod.{i}.get_gamma.bias"),
+                 "bw": f32(f"distortion_mod.{i}.get_beta.weight"), "bbias": f32(f"distortion_mod.{i}.get_beta.bias"),
+                 "a1": f32("a1")[i].contiguous(), "a2": f32("a2")[i].contiguous()}
+            stages.append(s)
+        ex["stages"] = stages
+        self._extra, self._extra_key = ex, key
+        return ex
+
+    def packed(self, head=None):
+        # the Swin part only: the inherited packer reads `patch_embed.*`, `layers.*`, `norm.*` (+ head) by name
+        return super().packed(head)
+
+    # ---- host-side helpers over the C ABI (everything is enqueued on the current stream) ----
+    @staticmethod
+    def _gemm(a, wpack, relu=False, stream=None):
+        w, b, n = wpack
+        M, K = a.shape
+        out = torch.empty((M, n), dtype=torch.float16, device=a.device)
+        rc = _l.load().kvq_conv_gemm_f16(ops._p(a), a.stride(0), ops._p(w), ops._p(b), None, 0, ops._p(out), out.stride(0),
+                                         M, w.shape[0], K, 0 if n == w.shape[0] else n, int(relu), stream)
+        _l.check(rc, "conv_gemm_f16")
+        return out
+
+    def _cdm(self, st, tokens_ptr, rows, C, B, clip16, dist16, stream):
+        """The cross-gating modulation of one stage output (:1436-1482) on the fp32 token matrix at `tokens_ptr`."""
+        L = _l.load()
+        dev = clip16.device
+        frames = rows // 49                       # B * T/2 frames of 7x7 tokens
+        x16 = torch.empty((rows, C), dtype=torch.float16, device=dev)
+        _l.check(L.kvq_cast_f16(ctypes.c_void_p(tokens_ptr), ops._p(x16), rows * C, stream), "cast_f16")
+
+        def mha(q, k, v, n_outer, n_inner, outer, inner, tstride, Lq, Lkv, scale):
+            out = torch.empty((rows, C), dtype=torch.float16, device=dev)
+            _l.check(L.kvq_mha_f16(ops._p(q), q.stride(0), ops._p(k), k.stride(0), ops._p(v), v.stride(0), ops._p(out), C,
+                                   n_outer, n_inner, outer, inner, tstride, Lq, Lkv, C // 64, scale, stream), "mha_f16")
+            return out
+
+        g = lambda a, w, relu=False: self._gemm(a, w, relu, stream)
+        # semantic branch: CLIP tokens -> adapter -> cross-attention (scale dim^-0.5, :1579)
+        sa = g(g(clip16, st["sem_ad"][0], True), st["sem_ad"][1], True)
+        es = mha(g(x16, st["sem_cross"][0]), g(sa, st["sem_cross"][1]), g(sa, st["sem_cross"][2]), frames, 1, 49, 0, 1,
+                 49, 49, 1.0 / math.sqrt(C))
+        # distortion branch: CONTRIQUE tokens -> adapter -> cross-attention -> temporal self-attention over the frames
+        da = g(g(dist16, st["dis_ad"][0], True), st["dis_ad"][1], True)
+        od = mha(g(x16, st["dis_cross"][0]), g(da, st["dis_cross"][1]), g(da, st["dis_cross"][2]), frames, 1, 49, 0, 1,
+                 49, 49, 1.0 / math.sqrt(C))
+        qkv = g(od, st["to_qkv"])
+        T2 = frames // B
+        at = mha(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, 49, T2 * 49, 1, 49, T2, T2, 0.125)
+        ed = g(at, st["to_out"])
+        mean, std = ops.pool_stats_f16(ed.view(B, T2 * 49, C))                     # Dist_Transformation3 statistics
+        gd = torch.empty((B, C), dtype=torch.float32, device=dev)
+        bd = torch.empty((B, C), dtype=torch.float32, device=dev)
+        _l.check(L.kvq_small_linear_f32(ops._p(std), ops._p(st["gw"]), ops._p(st["gb"]), ops._p(gd), B, C, C, stream), "small_linear")
+        _l.check(L.kvq_small_linear_f32(ops._p(mean), ops._p(st["bw"]), ops._p(st["bbias"]), ops._p(bd), B, C, C, stream), "small_linear")
+        _l.check(L.kvq_cdm_mix(ctypes.c_void_p(tokens_ptr), ops._p(es), ops._p(st["wg"]), ops._p(st["bg"]), ops._p(st["wb"]),
+                               ops._p(st["bb"]), ops._p(gd), ops._p(bd), ops._p(st["a1"]), ops._p(st["a2"]), rows, C,
+                               T2 * 49, stream), "cdm_mix")
+        self._keep += [x16, sa, es, da, od, qkv, at, ed, mean, std, gd, bd]        # alive until the stream has run them
+
+    @staticmethod
+    def _contrastive_loss(z, dis_label):
+        """distortion_contrastive_supervised (:1666-1691) with torch ops on the device: discarded at inference."""
+        b, t, n, _ = z.shape
+        f = torch.nn.functional.normalize(z.reshape(b * t * n, -1), p=2, dim=1)
+        same = (dis_label.unsqueeze(1).repeat(1, b) == dis_label).float().to(z.device)
+        labels = same.repeat(1, t * n).view(b * t * n, -1)
+        sim = f @ f.t() / 0.1
+        pos = (labels @ labels.t()).fill_diagonal_(0)
+        off = torch.ones_like(sim).fill_diagonal_(0)
+        return torch.mean(torch.log(torch.sum(torch.exp(sim) * off, dim=1)) - torch.sum(sim * pos, dim=1) / pos.sum(dim=1))
+
+    def _run(self, x, head, want_feat=True):
+        if self.training:
+            raise RuntimeError("kvq_b200: inference path only -- call model.eval()")
+        revideo, fragment, dis_label = x["resize_video"], x["fragment"], x["dis_label"]
+        self._require_cuda(fragment)
+        dev = fragment.device
+        with torch.cuda.device(dev), torch.no_grad():
+            ex = self._pack_extras(dev)
+            B, _, T, H, W = fragment.shape
+            if H // 32 < 7 or T % 4 != 0:
+                raise RuntimeError(f"kvq_b200: KSVQE needs at least a 7x7 fragment grid and T % 4 == 0, got {tuple(fragment.shape)}")
+            stream = ops._stream()
+            self._keep = []
+            # key frames t = 0, T/4-1, T/2-1, 3T/4-1 and the frame -> key-frame group map (obtain_keyframes :1352-1376)
+            kt = [0, T // 4 - 1, T // 2 - 1, T * 3 // 4 - 1]
+            key_frames = revideo.to(dev, torch.float32)[:, :, kt].permute(0, 2, 1, 3, 4).reshape(B * 4, 3, *revideo.shape[-2:])
+            cls_attn, tokens = ex["clip"].forward(key_frames.contiguous())
+            x_sel, _ = ops.qrs_select_gather(fragment.to(torch.float32), cls_attn)
+            z = ex["contrique"].forward(x_sel)                                     # [B, T/2, 49, 128]
+            rows = B * (T // 2) * 49
+            z16 = ops.cast_f16(z.view(rows, 128))
+            w0, w2 = ex["dist_adapter"]
+            ad = self._gemm(self._gemm(z16, w0, True, stream), w2, True, stream)
+            dist16 = torch.empty((rows, 128), dtype=torch.float16, device=dev)
+            dist32 = torch.empty((B, T // 2, 49, 128), dtype=torch.float32, device=dev)
+            _l.check(_l.load().kvq_blend_f16_f32(ops._p(ad), ops._p(z), 0.2, 0.8, ops._p(dist16), ops._p(dist32), rows * 128,
+                                                 stream), "blend")
+            # CLIP patch tokens of every 2nd frame, through the frame's key-frame group (extend_fullcls_attn :1378-1386)
+            grp = torch.tensor([(t >= kt[1]) + (t >= kt[2]) + (t >= kt[3]) for t in range(0, T, 2)], device=dev)
+            pat = tokens.view(B, 4, 50, 768)[:, :, 1:]                              # [B,4,49,768]
+            clip16 = ops.cast_f16(pat[:, grp].reshape(rows, 768).contiguous())
+
+            def hook(stage, tokens_ptr, nrows, channels, stream_ptr):
+                if stage >= self.tuning_stage:
+                    if nrows != rows or channels != self.num_features:
+                        raise RuntimeError(f"kvq_b200: KSVQE stage {stage} output is [{nrows},{channels}], expected "
+                                           f"[{rows},{self.num_features}] (fragment region must be 224x224)")
+                    self._cdm(ex["stages"][stage - self.tuning_stage], tokens_ptr, nrows, channels, B, clip16, dist16,
+                              ctypes.c_void_p(stream_ptr))
+                return 0
+
+            feat, score = self.packed(head).forward_hooked(x_sel, hook, want_feat=want_feat, want_score=head is not None)
+            loss = self._contrastive_loss(dist32, dis_label.to(dev))
+            self._keep = []
+        return feat, score, loss
+
+    def forward(self, x, multi=False, layer=-1, adaptive_window_size=False):
+        """x: {'resize_video' [B,3,T,112,112], 'fragment' [B,3,T,288,288], 'dis_label' [B]} -> (feat, loss)  (:1389-1500)."""
+        if multi or layer > -1 or adaptive_window_size:
+            raise NotImplementedError("kvq_b200: multi / layer / adaptive_window_size outputs are not on the B200 path")
+        feat, _, loss = self._run(x, None)
+        return feat, loss
+
+    def forward_with_head(self, x, head, want_feat=False, graph=None):
+        feat, score, loss = self._run(x, head, want_feat=want_feat)
+        self.last_dis_contra_loss = loss
+        return feat, score.reshape(-1, 1)

@@ -10,6 +10,7 @@ import torch.nn as nn
 
 from .backbones.swin_backbone import SwinTransformer3D as VideoBackbone
 from .backbones.swin_backbone import swin_3d_small, swin_3d_tiny
+from .backbones.KSVQE_model import KSVQE as KSVQE_Backbone
 from .backbones.simpleVQA_model import resnet50 as simpleVQA_Backbone
 from .head import VQAHead, simpleVQAHead
 
@@ -39,6 +40,12 @@ class VQA_Network(nn.Module):
                 backbone = swin_3d_small(**hypers.get("backbone", {}))
             elif key == "simpleVQA":
                 backbone = simpleVQA_Backbone(pretrained=True)                              # model.py:52-55
+            elif key == "KSVQE":                                                            # model.py:56-68
+                hb = hypers["backbone"]
+                backbone = KSVQE_Backbone(num_samples=hb["num_samples"], sample_type=hb["sample_type"],
+                                          CLIP_location=hb["CLIP_location"], cls_use=hb["cls_use"],
+                                          tuning_stage=hb["tuning_stage"], a1=hb["a1"], a2=hb["a2"],
+                                          frozen_stages=hb["frozen_stages"])
             else:
                 raise NotImplementedError(
                     f"kvq_b200: model key '{key}' is not on the B200 hot path yet (DESIGN.md, out-of-scope table)")
@@ -51,16 +58,19 @@ class VQA_Network(nn.Module):
                 pooled=False, clip_return=False, **kwargs):
         if self.training:
             raise RuntimeError("kvq_b200: inference path only -- call model.eval() (trainer.py:305)")
-        scores, feats = [], {}
+        scores, feats, dis_contra_loss = [], {}, None
         for key in self.key_names:
             backbone, head = getattr(self, key + "_backbone"), getattr(self, key + "_head")
-            x = inputs if key == "simpleVQA" else inputs["technical"]   # the ResNet reads batch['simpleVQA'] + ['feat']
+            # the ResNet reads batch['simpleVQA'] + ['feat'], KSVQE 'fragment' / 'resize_video' / 'dis_label'
+            x = inputs if key in ("simpleVQA", "KSVQE") else inputs["technical"]
             feat, score = backbone.forward_with_head(x, head, want_feat=return_pooled_feats, graph=self.use_cuda_graph)
+            if key == "KSVQE":
+                dis_contra_loss = backbone.last_dis_contra_loss
             scores.append(score)
             if return_pooled_feats:
                 feats[key] = feat
         if reduce_scores:
             scores = reduce(lambda a, b: a + b, scores) if len(scores) > 1 else scores[0]
-        if return_pooled_feats:
-            return scores, feats
-        return scores
+        if return_pooled_feats:                                     # model.py:109-121
+            return (scores, feats, dis_contra_loss) if dis_contra_loss is not None else (scores, feats)
+        return (scores, dis_contra_loss) if dis_contra_loss is not None else scores

@@ -1,0 +1,66 @@
+"""The literal `KSVQE` key (config/Kwai_KSVQE_test.yml: CLIP ViT-B/16 + adapters, QRS, CONTRIQUE, CDM, Swin3D-GRPB,
+VQAHead) through the drop-in VQA_Network -> libkvq_b200.so, against golden vectors the REAL reference produced on the
+same seeded weights / inputs (tools/make_golden_ksvqe.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"model": {"type": "KSVQE", "args": {"KSVQE": {
+    "backbone": {"num_samples": 1, "sample_type": "topkpertubation", "CLIP_location": 8, "cls_use": True,
+                 "tuning_stage": 2, "a1": 1.0, "a2": 1.0, "frozen_stages": -1},
+    "head": {"in_channels": 768, "hidden_channels": 64}}}}}
+
+
+def _network(g):
+    import models
+    net = models.VQA_Network(CFG)
+    keys = json.load(open(os.path.join(GOLDEN, "state_dict_keys_ksvqe.json")))["KSVQE"]
+    wseed = int(g["wseed"])
+    sd = {}
+    for k, v in keys.items():
+        if not v[1].startswith("float"):
+            continue
+        t = synth.fill_like("KSVQE_backbone." + k, tuple(v[0]), wseed)
+        if k in ("a1", "a2"):
+            t = torch.ones(tuple(v[0]))
+        sd["KSVQE_backbone." + k] = t
+    for k, v in net.KSVQE_head.state_dict().items():
+        sd["KSVQE_head." + k] = synth.fill_like("KSVQE_head." + k, tuple(v.shape), wseed)
+    missing = net.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    assert all("num_batches_tracked" in k or "relative_position_index" in k for k in missing.missing_keys), missing.missing_keys
+    return net.to("cuda:0").eval()
+
+
+def test_ksvqe_network_matches_the_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "ksvqe_t32_288.npz"))
+    net = _network(g)
+    gen = torch.Generator().manual_seed(int(g["xseed"]))
+    x = {"fragment": torch.randn((1, 3, 32, 288, 288), generator=gen).cuda(),
+         "resize_video": torch.randn((1, 3, 32, 112, 112), generator=gen).cuda(),
+         "dis_label": torch.zeros(1, dtype=torch.long).cuda()}
+    with torch.no_grad():
+        (score, feats, loss) = net(inputs=x, reduce_scores=True, return_pooled_feats=True)
+    feat = feats["KSVQE"].cpu()
+    assert feat.shape == (1, 768, 16, 7, 7) and score.shape == (1, 1)
+    ref_stats = g["feat_stats"]
+    mine = np.array([feat.mean().item(), feat.abs().mean().item(), feat.abs().max().item(), feat.std().item()])
+    ferr = (feat[0, :8, 0] - torch.from_numpy(g["feat_slice"])).abs().max().item()
+    serr = abs(float(score.cpu().reshape(-1)[0]) - float(g["score"].reshape(-1)[0]))
+    print("ksvqe: score", float(score.cpu().reshape(-1)[0]), "ref", float(g["score"].reshape(-1)[0]), "feat slice err", ferr,
+          "stats", mine, ref_stats, "loss", float(loss), float(g["loss"]))
+    assert serr < 1e-3, serr
+    assert ferr < 3e-2 and np.abs(mine - ref_stats)[[0, 1, 3]].max() < 3e-3
+    assert abs(float(loss) - float(g["loss"])) < 1e-2
+    # the (scores, loss) contract of the KSVQE key (model.py:118-121, trainer.py:323-325)
+    with torch.no_grad():
+        out = net(inputs=x, reduce_scores=True)
+    assert isinstance(out, tuple) and len(out) == 2 and torch.equal(out[0], score)

@@ -26,8 +26,18 @@ def test_ksvqe_golden_has_the_reference_structure():
     assert sum(int(np.prod(v[0])) for v in keys.values()) > 150e6          # ~158 M parameters + buffers
 
 
-def test_ksvqe_key_fails_loudly_on_the_product_path():
+def test_ksvqe_dropin_has_the_reference_state_dict_and_refuses_cpu():
+    import torch
     import models
-    cfg = {"model": {"type": "KSVQE", "args": {"KSVQE": {"backbone": {}, "head": {"in_channels": 768, "hidden_channels": 64}}}}}
-    with pytest.raises(NotImplementedError, match="KSVQE"):
-        models.VQA_Network(cfg)
+    cfg = {"model": {"type": "KSVQE", "args": {"KSVQE": {
+        "backbone": {"num_samples": 1, "sample_type": "topkpertubation", "CLIP_location": 8, "cls_use": True,
+                     "tuning_stage": 2, "a1": 1.0, "a2": 1.0, "frozen_stages": -1},
+        "head": {"in_channels": 768, "hidden_channels": 64}}}}}
+    net = models.VQA_Network(cfg)
+    keys = json.load(open(os.path.join(GOLDEN, "state_dict_keys_ksvqe.json")))["KSVQE"]
+    mine = {k: list(v.shape) for k, v in net.KSVQE_backbone.state_dict().items()}
+    assert mine == {k: v[0] for k, v in keys.items()}                  # 759 tensors, names and shapes of the reference
+    x = {"fragment": torch.zeros(1, 3, 32, 288, 288), "resize_video": torch.zeros(1, 3, 32, 112, 112),
+         "dis_label": torch.zeros(1, dtype=torch.long)}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net.eval()(inputs=x, reduce_scores=True)

@@ -101,6 +101,14 @@ def main():
              m.distortion_tool.register_forward_hook(lambda mod, i, o: cap.__setitem__("dist_token", o))]
     for l, layer in enumerate(m.layers):
         hooks.append(layer.register_forward_hook(lambda mod, i, o, l=l: cap.__setitem__(f"stage{l}", o)))
+    # CDM internals of both modulated stages (bring-up checkpoints for the B200 path)
+    first = lambda o: o[0] if isinstance(o, (tuple, list)) else o
+    for name in ("semantic_adapter", "semantic_cross", "semantic_mod", "distortion_adapter", "distortion_cross",
+                 "distortion_self", "distortion_mod"):
+        for i in range(2):
+            hooks.append(getattr(m, name)[i].register_forward_hook(
+                lambda mod, inp, o, k=f"{name}{i}": cap.__setitem__(k, first(o))))
+    hooks.append(m.dist_adapter.register_forward_hook(lambda mod, i, o: cap.__setitem__("dist_adapter", o)))
     with torch.no_grad():
         feat, loss = m(x)
         score = head(feat)
@@ -122,6 +130,12 @@ def main():
            "wseed": WSEED, "xseed": XSEED}
     for l in range(4):
         out[f"stage{l}_stats"] = stats(cap[f"stage{l}"])
+    for k, v in cap.items():
+        if k[:-1] in ("semantic_adapter", "semantic_cross", "semantic_mod", "distortion_adapter", "distortion_cross",
+                      "distortion_self", "distortion_mod") or k == "dist_adapter":
+            out[k + "_stats"] = stats(v)
+            out[k + "_slice"] = v.detach().float().reshape(-1, v.shape[-1])[:3, :6].numpy()
+            out[k + "_shape"] = np.array(v.shape)
     np.savez_compressed(os.path.join(GOLD, "ksvqe_t32_288.npz"), **out)
     spec = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in m.state_dict().items()}
     with open(os.path.join(GOLD, "state_dict_keys_ksvqe.json"), "w") as f:
