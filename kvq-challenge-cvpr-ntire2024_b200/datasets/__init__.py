@@ -4,7 +4,7 @@ Video decoding (decord / cv2) and the KVQ annotation files are outside the B200 
 datasets shipped are synthetic ones producing the same item dicts as ViewDecompositionDataset_KVQ
 (datasets/fusion_datasets.py:930-1050) and ViewDecompositionDataset_add_forSimpleVQA (:780-930).  Register real datasets with `datasets.register(cls)`."""
 from .features import load_motion_features  # noqa: F401
-from .synthetic import SyntheticFragmentDataset, SyntheticSimpleVQADataset  # noqa: F401
+from .synthetic import SyntheticFragmentDataset, SyntheticKSVQEDataset, SyntheticSimpleVQADataset  # noqa: F401
 
 
 def register(cls, name=None):

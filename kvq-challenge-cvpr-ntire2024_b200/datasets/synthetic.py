@@ -61,3 +61,30 @@ class SyntheticSimpleVQADataset(torch.utils.data.Dataset):
                 "feat": torch.randn((T, 2304), generator=g).abs(),
                 "num_clips": {"simpleVQA": self.num_clips}, "video_name": f"synthetic_{i:04d}",
                 "label": torch.rand((), generator=g) * 4.0 + 1.0}
+
+
+class SyntheticKSVQEDataset(torch.utils.data.Dataset):
+    """Stand-in for ViewDecompositionDataset_KVQ in the KSVQE configuration (datasets/fusion_datasets.py:930-1050,
+    config/Kwai_KSVQE_test.yml): `fragment` = num_clips * clip_len frames of a fragments_h x fragments_w grid of fsize
+    patches, ImageNet-normalised; `resize_video` = the same frames resized to size_h x size_w, CLIP-normalised;
+    `dis_label` = the distortion class of the video.  (As in the reference, the clips of a video stay concatenated on
+    the T axis: trainer.py never splits them for this key.)"""
+
+    def __init__(self, opt, _unused=None):
+        st = opt["sample_types"]["technical"]
+        self.fh, self.fw, self.fs = st.get("fragments_h", 9), st.get("fragments_w", 9), st.get("fsize_h", 32)
+        self.rh, self.rw = st.get("size_h", 112), st.get("size_w", 112)
+        self.T = st.get("clip_len", 32) * st.get("num_clips", 3)
+        self.num_clips = st.get("num_clips", 3)
+        self.n, self.seed = opt.get("num_videos", 4), opt.get("seed", 11)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed + i)
+        frag = torch.randn((3, self.T, self.fh * self.fs, self.fw * self.fs), generator=g)
+        return {"technical": frag, "fragment": frag, "resize_video": torch.randn((3, self.T, self.rh, self.rw), generator=g),
+                "dis_label": torch.tensor(int(torch.randint(0, 5, (1,), generator=g))),
+                "num_clips": {"technical": self.num_clips}, "video_name": f"synthetic_{i:04d}",
+                "label": torch.rand((), generator=g) * 4.0 + 1.0}

@@ -39,6 +39,12 @@ def score_video(model, data, key_list, device=None):
         data["technical"] = ops.fragment_gather_u8(frames.contiguous(), offsets.to(device).int().contiguous(),
                                                    g(fo["fragments_h"]), g(fo["fragments_w"]), g(fo["fsize"]),
                                                    g(fo["aligned"]))
+    if "KSVQE" in key_list and device is not None:
+        # nn.DataParallel scatters these in the reference (trainer.py:61); 'KSVQE' is not a key of the data dict, so
+        # the clip reshape below never applies to them (the 96 frames of a video go through as one clip)
+        for k in ("fragment", "resize_video", "dis_label"):
+            if k in data and torch.is_tensor(data[k]):
+                data[k] = data[k].to(device, non_blocking=True)
     for key in key_list:
         if key in data:
             if device is not None:

@@ -84,17 +84,28 @@ def stats(t):
     return np.array([t.mean().item(), t.abs().mean().item(), t.abs().max().item(), t.std().item()], dtype=np.float64)
 
 
+# (file name, clips, frames, input seed, dis_label): one 32-frame clip (the training geometry), a batch of two clips with
+# different distortion labels, and one 96-frame item (what inferece_test feeds: trainer.py never splits the KSVQE views
+# into clips because 'KSVQE' is not a key of the data dict)
+CASES = [("ksvqe_t32_288", 1, 32, XSEED, [0]), ("ksvqe_b2_t32_288", 2, 32, XSEED + 1, [0, 3]),
+         ("ksvqe_t96_288", 1, 96, XSEED + 2, [0])]
+
+
 def main():
     m, head = build_reference_ksvqe()
     seed_weights(m, "KSVQE_backbone.", WSEED)
     seed_weights(head, "KSVQE_head.", WSEED)
     m.eval()
     head.eval()
-    g = torch.Generator().manual_seed(XSEED)
-    B = 1
-    x = {"fragment": torch.randn((B, 3, 32, 288, 288), generator=g),          # 9x9 grid of 32x32 patches, normalised
-         "resize_video": torch.randn((B, 3, 32, 112, 112), generator=g),      # CLIP-normalised 112x112 view
-         "dis_label": torch.zeros(B, dtype=torch.long)}
+    for i, case in enumerate(CASES):
+        run_case(m, head, *case, write_keys=(i == 0))
+
+
+def run_case(m, head, name, B, T, xseed, labels, write_keys):
+    g = torch.Generator().manual_seed(xseed)
+    x = {"fragment": torch.randn((B, 3, T, 288, 288), generator=g),           # 9x9 grid of 32x32 patches, normalised
+         "resize_video": torch.randn((B, 3, T, 112, 112), generator=g),       # CLIP-normalised 112x112 view
+         "dis_label": torch.tensor(labels, dtype=torch.long)}
     cap = {}
     hooks = [m.CLIP_tool.register_forward_hook(lambda mod, i, o: cap.__setitem__("clip", o)),
              m.spa_patchnet.register_forward_hook(lambda mod, i, o: cap.__setitem__("x_sel_ori", o)),
@@ -103,11 +114,11 @@ def main():
         hooks.append(layer.register_forward_hook(lambda mod, i, o, l=l: cap.__setitem__(f"stage{l}", o)))
     # CDM internals of both modulated stages (bring-up checkpoints for the B200 path)
     first = lambda o: o[0] if isinstance(o, (tuple, list)) else o
-    for name in ("semantic_adapter", "semantic_cross", "semantic_mod", "distortion_adapter", "distortion_cross",
-                 "distortion_self", "distortion_mod"):
+    for mod_name in ("semantic_adapter", "semantic_cross", "semantic_mod", "distortion_adapter", "distortion_cross",
+                     "distortion_self", "distortion_mod"):
         for i in range(2):
-            hooks.append(getattr(m, name)[i].register_forward_hook(
-                lambda mod, inp, o, k=f"{name}{i}": cap.__setitem__(k, first(o))))
+            hooks.append(getattr(m, mod_name)[i].register_forward_hook(
+                lambda mod, inp, o, k=f"{mod_name}{i}": cap.__setitem__(k, first(o))))
     hooks.append(m.dist_adapter.register_forward_hook(lambda mod, i, o: cap.__setitem__("dist_adapter", o)))
     with torch.no_grad():
         feat, loss = m(x)
@@ -118,16 +129,16 @@ def main():
     x_sel = cap["x_sel_ori"]                                                   # [B,3,32,224,224] selected 7x7 region
     # which of the 3x3 candidate regions each frame took: compare against the nine crops of the 9x9 fragment grid
     frag = x["fragment"]
-    region = np.zeros((B, 32), dtype=np.int64)
+    region = np.zeros((B, T), dtype=np.int64)
     for b in range(B):
-        for t in range(32):
+        for t in range(T):
             hit = [(ry, rx) for ry in range(3) for rx in range(3)
                    if torch.equal(frag[b, :, t, 32 * ry:32 * ry + 224, 32 * rx:32 * rx + 224], x_sel[b, :, t])]
             region[b, t] = hit[0][0] * 3 + hit[0][1] if hit else -1
     out = {"score": score.numpy(), "loss": np.array(float(loss)), "feat_stats": stats(feat),
            "feat_slice": feat[0, :8, 0, :, :].numpy(), "cls_attn": cls_attn.numpy(), "region": region,
            "dist_token_stats": stats(cap["dist_token"]), "dist_token_slice": cap["dist_token"][0, 0, :4, :8].numpy(),
-           "wseed": WSEED, "xseed": XSEED}
+           "wseed": WSEED, "xseed": xseed, "B": B, "T": T, "labels": np.array(labels)}
     for l in range(4):
         out[f"stage{l}_stats"] = stats(cap[f"stage{l}"])
     for k, v in cap.items():
@@ -136,10 +147,11 @@ def main():
             out[k + "_stats"] = stats(v)
             out[k + "_slice"] = v.detach().float().reshape(-1, v.shape[-1])[:3, :6].numpy()
             out[k + "_shape"] = np.array(v.shape)
-    np.savez_compressed(os.path.join(GOLD, "ksvqe_t32_288.npz"), **out)
-    spec = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in m.state_dict().items()}
-    with open(os.path.join(GOLD, "state_dict_keys_ksvqe.json"), "w") as f:
-        json.dump({"KSVQE": spec}, f, indent=0, sort_keys=True)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    if write_keys:
+        spec = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in m.state_dict().items()}
+        with open(os.path.join(GOLD, "state_dict_keys_ksvqe.json"), "w") as f:
+            json.dump({"KSVQE": spec}, f, indent=0, sort_keys=True)
     print("score", score.flatten().tolist(), "loss", float(loss), "feat", out["feat_stats"], "regions", region[0].tolist())
     print("cls_attn", tuple(cls_attn.shape), "dist_token", tuple(cap["dist_token"].shape), out["dist_token_stats"])
     for l in range(4):
