@@ -1,0 +1,65 @@
+"""oracle/views.py against the golden vectors the REAL reference produced (tools/make_golden_views.py ran
+datasets/fusion_datasets.get_resized_video / get_resizecrop_video / UnifiedFrameSampler and the datasets' normalisation
+lines): uint8 views and normalised float32 views bit-exact, frame indices equal under the same numpy seed."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import views
+
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "views_resize*.npz")))
+
+
+def golden_frames(g):
+    """the generator's frames: [T,H,W,3] u8 from the seeded torch generator, viewed as [3,T,H,W]"""
+    T, H, W = (int(v) for v in g["shape"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    return torch.randint(0, 256, (T, H, W, 3), generator=gen, dtype=torch.uint8).permute(3, 0, 1, 2)
+
+
+def golden_view(g, video):
+    if str(g["kind"]) == "resize":
+        out = views.resized_video(video, size_h=int(g["size_h"]), size_w=int(g["size_w"]))
+        return out, views.normalise(out, views.CLIP_MEAN, views.CLIP_STD, 255.0)
+    out = views.resizecrop_video(video, resize=int(g["resize"]), crop=int(g["crop"]))
+    return out, views.normalise(out, views.IMAGENET_MEAN, views.IMAGENET_STD)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_views_match_reference_golden(path):
+    g = np.load(path)
+    out, norm = golden_view(g, golden_frames(g).numpy())
+    np.testing.assert_array_equal(out, g["out"])
+    assert sha(out) == str(g["out_sha256"])
+    assert sha(norm) == str(g["norm_sha256"])                       # every float32 of the normalised view
+    np.testing.assert_array_equal(norm[:, :, ::7, ::5], g["norm_sample"])
+
+
+def test_frame_sampler_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "views_frame_sampler.npz"))
+    for i, (fsize_t, fragments_t, interval, num_clips, total, seed) in enumerate(g["cases"]):
+        np.random.seed(int(seed))
+        inds = views.frame_indices(int(total), int(fsize_t), int(fragments_t), int(interval), int(num_clips))
+        assert inds.dtype == np.int32
+        np.testing.assert_array_equal(inds, g[f"inds_{i}"])
+
+
+def test_aa_weights_properties():
+    for n_in, n_out in [(1920, 112), (1080, 520), (64, 112), (7, 7), (5, 1), (1, 3)]:
+        xmin, xsize, w = views.aa_weights(n_in, n_out)
+        assert (xmin >= 0).all() and (xmin + xsize <= n_in).all() and (xsize >= 1).all()
+        assert (np.diff(xmin) >= 0).all() and (np.diff(xmin + xsize) >= 0).all()      # windows move monotonically
+        np.testing.assert_allclose(w.sum(1), 1.0, atol=2e-6)
+        assert w.shape[1] == views.aa_taps(n_in, n_out) and (xsize <= w.shape[1]).all()
+    xmin, xsize, w = views.aa_weights(9, 9)                          # identity resize: one tap of weight 1 ... or 3 taps
+    ident = views.interpolate_bilinear_aa(np.arange(81, dtype=np.float32).reshape(9, 9), 9, 9)
+    np.testing.assert_array_equal(ident, np.arange(81, dtype=np.float32).reshape(9, 9))
