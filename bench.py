@@ -102,6 +102,11 @@ WORKLOADS = {
                           "in a host callback)",
               "metric": "clips/sec KSVQE (CLIP + QRS + CONTRIQUE + CDM + Swin3D) 32x288x288", "batch": 8,
               "gflop_per_clip": 175.53 + 170.0},
+    "views": {"workload": "KSVQE view pipeline (SURVEY 8f-3): decoder-order uint8 frames [B,32,3,1080,1920] -> "
+                          "resize_video (torchvision Resize 112x112, CLIP-normalised f32) + fragment view (9x9 grid of "
+                          "32x32 patches, aligned 8, ImageNet-normalised f32 288x288), batch 4 clips per GPU",
+              "metric": "clips/sec KSVQE view pipeline 32x1080x1920 -> 112x112 + 288x288", "batch": 4,
+              "gflop_per_clip": 0.0},
     "fragment": {"workload": "Fragment-sampled KSVQE: uint8 frames [B,32,3,448,448] -> 7x7 grid of 32x32 patches "
                              "(aligned 8) + normalise -> Swin3D-GRPB + VQAHead, batch 8 per GPU",
                  "metric": "clips/sec fragment-sampled KSVQE Swin3D 7x7x32", "batch": 8,
@@ -301,6 +306,8 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "the literal KSVQE key has no CPU restatement; its parity "
                           "is pinned by golden vectors of the real reference (tests/golden/ksvqe_*.npz)"}), flush=True)
         return
+    if args.workload == "views":
+        return run_reference_views(args, wl)
     sd = synth_model_state()
     torch.set_num_threads(os.cpu_count() or 1)
     host_inputs = reference_inputs(args.workload)
@@ -325,6 +332,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_views(args, wl):
+    """Reference arm of --workload views: what the reference's dataset worker executes per clip on the host cores --
+    torchvision.transforms.Resize((112, 112)) on the uint8 clip (the third-party arithmetic of get_resized_video, installed
+    in this image) + the CLIP normalisation lines, and the Grid Mini-patch Sampling loop + normalisation
+    (oracle/fragments.py, pinned to get_spatial_fragments goldens).  One 32-frame 1080x1920 clip per step."""
+    import torch
+    import torchvision
+    from oracle import fragments as ofr
+    from oracle import views as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    T, _, Hs, Ws = VIEW_SRC
+    op = torchvision.transforms.Resize((112, 112))
+    mean = torch.tensor(O.CLIP_MEAN).view(3, 1, 1, 1)
+    std = torch.tensor(O.CLIP_STD).view(3, 1, 1, 1)
+
+    def one(seed):
+        g = torch.Generator().manual_seed(seed)
+        frames = torch.randint(0, 256, (1,) + VIEW_SRC, generator=g, dtype=torch.uint8)
+        offs = torch.stack([torch.randint(Hs // 9 - 32, (1, 9, 9, T // 8), generator=g),
+                            torch.randint(Ws // 9 - 32, (1, 9, 9, T // 8), generator=g)], dim=1)
+        t0 = time.perf_counter()
+        video = frames[0].permute(1, 0, 2, 3)                                   # [3,T,H,W] as the reference holds it
+        rv = op(video.permute(1, 0, 2, 3)).permute(1, 0, 2, 3)
+        rv = (rv / 255.0 - mean) / std
+        fr = ofr.fragment_clip(frames, offs, 9, 9, 32, 8)
+        return time.perf_counter() - t0, float(rv.sum()) + float(fr.sum())
+
+    for i in range(args.warmup):
+        one(1000 + i)
+    dt = sum(one(2000 + i)[0] for i in range(args.steps))                      # input synthesis is outside the clock
+    v = args.steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": wl["metric"], "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 -> f32", "data": "synthetic",
+            "config": {"workload": wl["workload"], "per_step": f"1 clip sample of the {wl['batch']}-clip batch (CPU)"},
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} clips, one per step: torchvision Resize (the reference's own third-party "
+                                       f"kernel) + oracle/fragments.py on {cores} host threads"},
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def reference_inputs(name):
     """One-clip host inputs of a workload, without touching CUDA."""
     import torch
@@ -342,6 +393,160 @@ def reference_inputs(name):
         offs = torch.randint(64 - 32, (1, 2, 7, 7, 4), generator=g).to(torch.int32)
         return [frames, offs]
     return host
+
+
+VIEW_SRC = (32, 3, 1080, 1920)      # one decoded clip, decoder order [T,3,H,W]
+
+
+def run_views(args):
+    """--workload views: the step BEFORE the models.  HBM-bound byte work: the roofline is the achieved
+    algorithmic bytes/s of kvq_resize_view_u8 (u8 source read once + f32 view written once) against the measured copy
+    bandwidth.  No collective: clips are independent, every rank converts its own clips."""
+    import torch
+    import torch.distributed as dist
+    from datasets import views as V
+    from kvq_b200 import ops as kops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS["views"]
+    B = args.batch or wl["batch"]
+    T, _, Hs, Ws = VIEW_SRC
+    fh = fw = 9
+
+    def device_inputs(seed):
+        g = torch.Generator(device=dev).manual_seed(seed + rank)
+        frames = torch.randint(0, 256, (B,) + VIEW_SRC, generator=g, dtype=torch.uint8, device=dev)
+        offs = torch.stack([torch.randint(Hs // fh - 32, (B, fh, fw, T // 8), generator=g, device=dev),
+                            torch.randint(Ws // fw - 32, (B, fh, fw, T // 8), generator=g, device=dev)], dim=1)
+        return [frames, offs.to(torch.int32).contiguous()]
+
+    x = device_inputs(3)                                      # 796 MB of frames at B = 4: far beyond the 126 MB L2
+    frag = torch.empty((B, 3, T, fh * 32, fw * 32), dtype=torch.float32, device=dev)
+    need = kops._l.load().kvq_resize_view_workspace_bytes(B, T, Hs, Ws, 112, 112, 0, 0, 0, 0)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+
+    def resize(t):
+        return kops.resize_view_u8(t[0], 112, 112, mean=V.CLIP_MEAN, std=V.CLIP_STD, divisor=255.0, workspace=ws)[1]
+
+    def step(t):
+        rv = resize(t)
+        kops.fragment_gather_u8(t[0], t[1], fh, fw, 32, 8, out=frag)
+        return torch.stack([rv.sum(dim=(1, 2, 3, 4)), frag.sum(dim=(1, 2, 3, 4))], dim=1)    # [B,2] checksums
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for _ in range(n):
+            fn(x)
+        ev1.record()
+        sync_all()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        out = step(x)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = kops.kernel_launches()
+    ms = timed(step, args.steps)
+    launches = kops.kernel_launches() - launches0
+    ms_resize = timed(resize, args.steps)                     # the dominant kernels alone (tables + rows + columns)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1000.0)
+
+    # end to end: pinned host frames -> H2D -> both views -> checksums D2H
+    xh = [[t.cpu().pin_memory() for t in device_inputs(50 + i)] for i in range(2)]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in x)
+    res = torch.empty((B, 2), dtype=torch.float32).pin_memory()
+
+    def e2e(n):
+        tot = 0.0
+        for i in range(n):
+            for d, h in zip(x, xh[i % 2]):
+                d.copy_(h, non_blocking=True)
+            res.copy_(step(x), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            tot += float(res[0, 0])
+        return tot
+
+    e2e(1)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e(args.steps)
+    sync_all()
+    t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+
+    if rank == 0:
+        pk = peaks()
+        planes = B * 3 * T
+        alg = planes * (Hs * Ws + 112 * 112 * 4)
+        achieved = alg / (ms_resize / args.steps * 1e-3) / 1e9
+        roof = {"kernel": "resize_rows_kernel + resize_cols_kernel (one kvq_resize_view_u8 call, chunks of 66 planes)",
+                "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "avg_launch_ms": ms_resize / args.steps,
+                "peak_source": pk["src"] + " copy bandwidth (MEASURED_PEAKS.json)",
+                "algorithmic": f"{Hs * Ws} B u8 read + {112 * 112 * 4} B f32 written per plane x {planes} planes per call"}
+        cpu, delta = None, None
+        if world == 1 and not args.no_cpu:
+            import numpy as np
+            import torchvision
+            from oracle import views as O
+            sample = x[0][0, :2].permute(1, 0, 2, 3).contiguous().cpu()                  # [3,2,H,W]: 2 frames of clip 0
+            t0 = time.perf_counter()
+            ref = O.normalise(O.resized_video(sample.numpy(), 112, 112), O.CLIP_MEAN, O.CLIP_STD, 255.0)
+            dt = time.perf_counter() - t0
+            got = resize(x)[0, :, :2].cpu().numpy()
+            delta = float(np.abs(got - ref).max())                                       # bit-exact path: 0.0
+            torch.set_num_threads(os.cpu_count() or 1)
+            clip = x[0][0].permute(1, 0, 2, 3).contiguous().cpu()                         # [3,32,H,W]
+            op = torchvision.transforms.Resize((112, 112))
+            op(clip.permute(1, 0, 2, 3))
+            t0 = time.perf_counter()
+            for _ in range(3):
+                op(clip.permute(1, 0, 2, 3))
+            tv = 3.0 / (time.perf_counter() - t0)
+            cpu = {"value": 2.0 / 32.0 / dt, "unit": "clips/s", "cores": 1, "kind": "port",
+                   "sample": "2 frames of 1080x1920 -> 112x112 + normalise, oracle/views.py (numpy, 1 thread), scaled to "
+                             "32-frame clips; the resize view only",
+                   "torchvision_resize_clips_per_s": tv, "torchvision_threads": torch.get_num_threads()}
+        line = {"metric": wl["metric"], "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8 -> f32", "data": "synthetic",
+                "config": {"workload": wl["workload"], "global_batch": world * B,
+                           "parallelism": f"clip-sharded x{world}, no collective",
+                           "l2": f"inputs ({h2d_bytes / 1e6:.0f} MB/GPU) exceed the 126 MB L2"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": B * 2 * 4},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "score_delta_vs_oracle": delta,
+                "breakdown": [{"kernel": "kvq_resize_view_u8 (112x112 CLIP view)", "ms_per_step": ms_resize / args.steps},
+                              {"kernel": "kvq_fragment_gather_u8 (9x9x32 fragment view) + checksums",
+                               "ms_per_step": (ms - ms_resize) / args.steps}]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ours(args):
@@ -570,6 +775,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "views":
+        run_views(args)
     else:
         run_ours(args)
 

@@ -332,6 +332,28 @@ int kvq_pool_stats_f16(const void* in_f16, const float* weights, float* out_mean
 int kvq_rowdot_mean_f32(const float* x, const float* w, const float* b, float* score, int rows, int K, int group,
                         void* stream);
 
+/* ---- view pipeline in front of the models ----
+ * torchvision.transforms.Resize((out_h, out_w)) on uint8 frames as the reference's get_resized_video
+ * (datasets/fusion_datasets.py:229-252) and get_resizecrop_video (:299-316, test phase: centre crop) apply it, fused with
+ * the datasets' normalisation lines (:1017-1027: (v - mean) / std for fragments, (v / 255 - clip_mean) / clip_std for the
+ * CLIP view; :902-905 SimpleVQA).  Resize on uint8 = float32 anti-aliased bilinear interpolate (W axis, then H axis) ->
+ * round half to even -> uint8; the kernels keep ATen's order of roundings, so out_u8 equals the reference byte for byte
+ * and out_f32 float for float.
+ *   frames u8: layout 0 = [B,T,3,Hs,Ws] (decoder order, as kvq_fragment_gather_u8), 1 = [B,3,T,Hs,Ws] (the argument
+ *   order of the reference functions); outputs [B,3,T,crop_h,crop_w]: out_u8 (resized bytes) and / or out_f32 =
+ *   ((v / divisor) - mean[c]) / std[c] (divisor 1 skips the first division), either may be NULL.
+ *   crop window = rows [crop_y, crop_y+crop_h) x columns [crop_x, crop_x+crop_w) of the resized frame; crop_h = crop_w
+ *   = 0 keeps the whole frame.  Only the source rows / output columns the window needs are computed.
+ * kvq_resize_aa_taps / kvq_resize_aa_weights: the per-axis tap windows and weights (host, no GPU needed):
+ *   xmin, xsize i32 [out_size], weights f32 [out_size, taps] */
+int kvq_resize_aa_taps(int in_size, int out_size);
+int kvq_resize_aa_weights(int in_size, int out_size, int32_t* xmin, int32_t* xsize, float* weights);
+size_t kvq_resize_view_workspace_bytes(int B, int T, int Hs, int Ws, int out_h, int out_w, int crop_y, int crop_x,
+                                       int crop_h, int crop_w);
+int kvq_resize_view_u8(const uint8_t* frames, int layout, int B, int T, int Hs, int Ws, int out_h, int out_w, int crop_y,
+                       int crop_x, int crop_h, int crop_w, float divisor, const float mean[3], const float std[3],
+                       uint8_t* out_u8, float* out_f32, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py): kernels launched so far by this process, and optional CUDA-event timing of
  * every kernel of kvq_swin3d_forward grouped by (kind, stage).  Timing is OFF unless enabled. ---- */
 long long kvq_launch_count(void);

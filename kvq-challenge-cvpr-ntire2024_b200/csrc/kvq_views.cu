@@ -1,0 +1,370 @@
+// The view pipeline in front of the models: torchvision Resize on uint8 frames (get_resized_video,
+// datasets/fusion_datasets.py:244-252; get_resizecrop_video + centre crop, :299-316) fused with the datasets'
+// normalisation lines (:1017-1027 KVQ, :902-905 SimpleVQA).
+//
+// Resize on a uint8 tensor = float32 F.interpolate(mode="bilinear", antialias=True) -> round half to even -> uint8; the
+// interpolate is ATen's separable anti-aliased filter (aten/src/ATen/native/cpu/UpSampleKernel.cpp): W axis first, H
+// axis second, float32 in between.  The kernels below keep ATen's ORDER OF ROUNDINGS so that every byte of the resized
+// view (and every float of the normalised view) equals the reference's: per output the accumulation is
+// t = v0*w0; then for tap k = 1..n-1 the first ((n-1)/4)*4 taps are a rounded product followed by a rounded add and the
+// remaining (n-1)%4 taps are fused multiply-adds (what the x86 build executes -- measured by tools/make_golden_views.py
+// and restated in oracle/views.py, which is pinned to goldens of the real reference).
+//
+// Byte work bound by HBM: algorithmic bytes per source plane = Hs*Ws (u8 read) + oh*ow*4 (f32 write) [+ oh*ow u8].
+//   pass 0  aa_tables_kernel   per-axis tap windows and normalised triangle weights, computed on the device (no host
+//                              upload, graph-capturable); ~2 us
+//   pass 1  resize_rows_kernel u8 rows -> f32 [planes, rows needed by the crop, cropped columns]; a CTA stages R whole
+//                              source rows in shared memory as f32 (coalesced 4 B loads, conflict-free float4 stores),
+//                              one thread per output column x 4 rows walks its tap window
+//   pass 2  resize_cols_kernel f32 rows -> round -> u8 -> ((v / divisor) - mean[c]) / std[c] with IEEE divisions
+// Planes are processed in chunks whose float32 intermediate stays L2-resident (32 MB) between pass 1 and pass 2.
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/kvq_b200.h"
+#include "kvq_common.cuh"
+#include "kvq_kernels.cuh"
+
+namespace kvq {
+namespace {
+
+constexpr int kRowsPerThread = 4;
+constexpr size_t kChunkBytes = 32u << 20;
+constexpr size_t kRowTileBytes = 64u << 10;
+constexpr size_t kRowTileMaxBytes = 200u << 10;
+
+struct AxisGeom {
+  float scale, support, invscale;
+  int taps;
+};
+
+// HelperInterpBase::_compute_indices_min_size_weights_aa with scalar_t = float, interp_size = 2 (bilinear): the mixed
+// float / double expression types of the C++ source are kept (oracle/views.py:aa_weights walks the same lines)
+__host__ __device__ inline AxisGeom axis_geom(int in_size, int out_size) {
+  AxisGeom g;
+  g.scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  g.support = g.scale >= 1.0f ? g.scale : 1.0f;
+  g.invscale = g.scale >= 1.0f ? static_cast<float>(1.0 / static_cast<double>(g.scale)) : 1.0f;
+  g.taps = static_cast<int>(ceilf(g.support)) * 2 + 1;
+  return g;
+}
+
+__host__ __device__ inline void axis_window(const AxisGeom& g, int in_size, int i, int* x0, int* n, float* center_out) {
+  const float center = static_cast<float>(static_cast<double>(g.scale) * (static_cast<double>(i) + 0.5));
+  const float flo = center - g.support, fhi = center + g.support;
+  const long long lo = static_cast<long long>(static_cast<double>(flo) + 0.5);
+  const long long hi = static_cast<long long>(static_cast<double>(fhi) + 0.5);
+  const long long xmin = lo > 0 ? lo : 0;
+  long long xs = (hi < in_size ? hi : in_size) - xmin;
+  if (xs < 0) xs = 0;
+  if (xs > g.taps) xs = g.taps;
+  *x0 = static_cast<int>(xmin);
+  *n = static_cast<int>(xs);
+  *center_out = center;
+}
+
+// weights of output index i written with stride `stride` (w[k * stride]); returns the window through x0 / n
+__host__ __device__ inline void axis_weights(const AxisGeom& g, int in_size, int i, int* x0, int* n, float* w,
+                                             long long stride) {
+  float center;
+  axis_window(g, in_size, i, x0, n, &center);
+  float total = 0.0f;
+  for (int j = 0; j < *n; ++j) {
+    const float d = static_cast<float>(j + *x0) - center;
+    const float x = fabsf(static_cast<float>((static_cast<double>(d) + 0.5) * static_cast<double>(g.invscale)));
+    const float v = x < 1.0f ? 1.0f - x : 0.0f;
+    w[j * stride] = v;
+    total = total + v;
+  }
+  if (total != 0.0f)
+    for (int j = 0; j < *n; ++j) w[j * stride] = w[j * stride] / total;
+  for (int j = *n; j < g.taps; ++j) w[j * stride] = 0.0f;
+}
+
+// tables of one axis: xmin i32 [out], xsize i32 [out], weights f32 [taps][out] (tap-major: lanes = consecutive outputs)
+__global__ void __launch_bounds__(128)
+aa_tables_kernel(int in_size, int out_size, int32_t* __restrict__ xmin, int32_t* __restrict__ xsize,
+                 float* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_size) return;
+  const AxisGeom g = axis_geom(in_size, out_size);
+  int x0, n;
+  axis_weights(g, in_size, i, &x0, &n, w + i, out_size);
+  xmin[i] = x0;
+  xsize[i] = n;
+}
+
+// ATen's order of roundings over one tap window (file header)
+#define KVQ_AA_ACCUMULATE(ACC, N, LOADV, LOADW)                                  \
+  do {                                                                           \
+    const int _unfused = (((N) - 1) >> 2) << 2;                                  \
+    int _k = 1;                                                                  \
+    for (; _k <= _unfused; ++_k) {                                               \
+      const float _w = LOADW(_k);                                                \
+      _Pragma("unroll") for (int _r = 0; _r < kRowsPerThread; ++_r)              \
+          ACC[_r] = __fadd_rn(ACC[_r], __fmul_rn(LOADV(_r, _k), _w));            \
+    }                                                                            \
+    for (; _k < (N); ++_k) {                                                     \
+      const float _w = LOADW(_k);                                                \
+      _Pragma("unroll") for (int _r = 0; _r < kRowsPerThread; ++_r)              \
+          ACC[_r] = __fmaf_rn(LOADV(_r, _k), _w, ACC[_r]);                       \
+    }                                                                            \
+  } while (0)
+
+// pass 1: W axis.  One CTA = R consecutive source rows of one plane (contiguous bytes), staged as f32 in shared memory.
+// frames u8: layout 0 = [B,T,3,Hs,Ws] (decoder order), 1 = [B,3,T,Hs,Ws] (the reference functions' argument order).
+// inter f32 [planes in chunk (b,c,t order), Hr, cw].
+__global__ void __launch_bounds__(256)
+resize_rows_kernel(const uint8_t* __restrict__ frames, float* __restrict__ inter, const int32_t* __restrict__ xmin,
+                   const int32_t* __restrict__ xsize, const float* __restrict__ wx, int layout, int T, int Hs, int Ws,
+                   int ow, int cx, int cw, int ry0, int Hr, int R, int tiles_per_plane, int plane0) {
+  extern __shared__ __align__(16) float rows_f32[];
+  const int tile = blockIdx.x % tiles_per_plane;
+  const int pl = blockIdx.x / tiles_per_plane;  // plane inside the chunk
+  const int p_out = plane0 + pl;                // (b*3 + c)*T + t
+  long long p_in = p_out;
+  if (layout == 0) {
+    const int t = p_out % T, c = (p_out / T) % 3, b = p_out / (3 * T);
+    p_in = (static_cast<long long>(b) * T + t) * 3 + c;
+  }
+  const int r0 = tile * R;  // first row of the tile, relative to ry0
+  const int rows = min(R, Hr - r0);
+  const uint8_t* src = frames + (p_in * Hs + ry0 + r0) * static_cast<long long>(Ws);
+  const long long nbytes = static_cast<long long>(rows) * Ws;
+  // shared float j <-> byte (src - head + j): whole aligned words land as one float4
+  const int head = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 3);
+  const long long nwords = (head + nbytes + 3) >> 2;
+  const uint8_t* base = src - head;
+  for (long long w = threadIdx.x; w < nwords; w += blockDim.x) {
+    float4 v;
+    if (w == 0 || w == nwords - 1) {  // partial words: only bytes of the tile are touched
+      float f[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long j = w * 4 + q - head;
+        f[q] = (j >= 0 && j < nbytes) ? static_cast<float>(src[j]) : 0.0f;
+      }
+      v = make_float4(f[0], f[1], f[2], f[3]);
+    } else {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(base) + w);
+      v = make_float4(static_cast<float>(u & 0xff), static_cast<float>((u >> 8) & 0xff),
+                      static_cast<float>((u >> 16) & 0xff), static_cast<float>(u >> 24));
+    }
+    reinterpret_cast<float4*>(rows_f32)[w] = v;
+  }
+  __syncthreads();
+  const float* s = rows_f32 + head;
+  const int groups = (rows + kRowsPerThread - 1) / kRowsPerThread;
+  float* dst = inter + (static_cast<long long>(pl) * Hr + r0) * cw;
+  for (int item = threadIdx.x; item < groups * cw; item += blockDim.x) {
+    const int oc = item % cw, rg = item / cw;
+    const int o = cx + oc;
+    const int n = xsize[o], x0 = xmin[o];
+    const int rbase = rg * kRowsPerThread;
+    float acc[kRowsPerThread];
+    const float* sp[kRowsPerThread];
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+      const int rr = min(rbase + r, rows - 1);  // rows past the tile repeat the last one (never stored)
+      sp[r] = s + static_cast<long long>(rr) * Ws + x0;
+      acc[r] = 0.0f;
+    }
+    if (n > 0) {
+      const float w0 = wx[o];
+#pragma unroll
+      for (int r = 0; r < kRowsPerThread; ++r) acc[r] = __fmul_rn(sp[r][0], w0);
+#define KVQ_LV(r, k) sp[r][k]
+#define KVQ_LW(k) wx[static_cast<long long>(k) * ow + o]
+      KVQ_AA_ACCUMULATE(acc, n, KVQ_LV, KVQ_LW);
+#undef KVQ_LV
+#undef KVQ_LW
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r)
+      if (rbase + r < rows) dst[static_cast<long long>(rbase + r) * cw + oc] = acc[r];
+  }
+}
+
+// pass 2: H axis + round + normalise.  One thread per output pixel x 4 consecutive output rows would re-read taps; the
+// intermediate is L2-resident, so one thread per pixel (lanes = consecutive columns, weights broadcast) is enough.
+// out_u8 [B,3,T,ch,cw] (may be NULL), out_f32 [B,3,T,ch,cw] (may be NULL)
+__global__ void __launch_bounds__(256)
+resize_cols_kernel(const float* __restrict__ inter, const int32_t* __restrict__ ymin, const int32_t* __restrict__ ysize,
+                   const float* __restrict__ wy, uint8_t* __restrict__ out_u8, float* __restrict__ out_f32, int T, int oh,
+                   int cy, int ch, int cw, int ry0, int Hr, int plane0, long long total, float divisor, float m0, float m1,
+                   float m2, float s0, float s1, float s2) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % cw);
+  const int oyc = static_cast<int>((idx / cw) % ch);
+  const int pl = static_cast<int>(idx / (static_cast<long long>(cw) * ch));
+  const int oy = cy + oyc;
+  const int n = ysize[oy], y0 = ymin[oy] - ry0;
+  const float* col = inter + (static_cast<long long>(pl) * Hr + y0) * cw + ox;
+  float t = 0.0f;
+  if (n > 0) {
+    t = __fmul_rn(col[0], wy[oy]);
+    const int unfused = ((n - 1) >> 2) << 2;
+    int k = 1;
+    for (; k <= unfused; ++k)
+      t = __fadd_rn(t, __fmul_rn(col[static_cast<long long>(k) * cw], wy[static_cast<long long>(k) * oh + oy]));
+    for (; k < n; ++k) t = __fmaf_rn(col[static_cast<long long>(k) * cw], wy[static_cast<long long>(k) * oh + oy], t);
+  }
+  const float v = fminf(fmaxf(rintf(t), 0.0f), 255.0f);  // torch.round (half to even) + uint8 cast
+  const int p_out = plane0 + pl;
+  const long long o = (static_cast<long long>(p_out) * ch + oyc) * cw + ox;
+  if (out_u8) out_u8[o] = static_cast<uint8_t>(v);
+  if (out_f32) {
+    const int c = (p_out / T) % 3;
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+    const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    float x = v;
+    if (divisor != 1.0f) x = __fdiv_rn(x, divisor);
+    out_f32[o] = __fdiv_rn(__fsub_rn(x, mean), sd);
+  }
+}
+
+struct ViewPlan {
+  int oh, ow, cy, cx, ch, cw;
+  int taps_x, taps_y, ry0, Hr;
+  int R;                  // source rows per pass-1 CTA
+  size_t smem;            // dynamic shared memory of pass 1
+  long long planes, chunk_planes;
+  size_t off_xmin, off_xsize, off_wx, off_ymin, off_ysize, off_wy, off_inter, total;
+};
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+int make_plan(ViewPlan* p, int B, int T, int Hs, int Ws, int out_h, int out_w, int crop_y, int crop_x, int crop_h,
+              int crop_w) {
+  KVQ_REQUIRE(B > 0 && T > 0 && Hs > 0 && Ws > 0 && out_h > 0 && out_w > 0, KVQ_ERR_BAD_SHAPE,
+              "resize_view: frames %dx%dx3x%dx%d -> %dx%d", B, T, Hs, Ws, out_h, out_w);
+  if (crop_h <= 0 && crop_w <= 0) {
+    crop_y = crop_x = 0;
+    crop_h = out_h;
+    crop_w = out_w;
+  }
+  KVQ_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_h > 0 && crop_w > 0 && crop_y + crop_h <= out_h &&
+                  crop_x + crop_w <= out_w,
+              KVQ_ERR_BAD_SHAPE, "resize_view: crop window (%d,%d)+(%d,%d) leaves the %dx%d resized frame", crop_y, crop_x,
+              crop_h, crop_w, out_h, out_w);
+  p->oh = out_h; p->ow = out_w; p->cy = crop_y; p->cx = crop_x; p->ch = crop_h; p->cw = crop_w;
+  const AxisGeom gx = axis_geom(Ws, out_w), gy = axis_geom(Hs, out_h);
+  p->taps_x = gx.taps;
+  p->taps_y = gy.taps;
+  int x0, n;
+  float c;
+  axis_window(gy, Hs, crop_y, &x0, &n, &c);
+  p->ry0 = x0;
+  axis_window(gy, Hs, crop_y + crop_h - 1, &x0, &n, &c);
+  p->Hr = std::max(x0 + n - p->ry0, 1);  // windows move monotonically: the last output row ends the range
+  const size_t row_bytes = static_cast<size_t>(Ws) * 4;
+  KVQ_REQUIRE(row_bytes * kRowsPerThread + 16 <= kRowTileMaxBytes, KVQ_ERR_BAD_SHAPE,
+              "resize_view: source rows of %d pixels do not fit the shared-memory row tile", Ws);
+  int R = static_cast<int>(kRowTileBytes / row_bytes) / kRowsPerThread * kRowsPerThread;
+  R = std::min(std::max(R, kRowsPerThread), 16);
+  R = std::min(R, (p->Hr + kRowsPerThread - 1) / kRowsPerThread * kRowsPerThread);
+  p->R = R;
+  p->smem = static_cast<size_t>(R) * row_bytes + 32;
+  p->planes = static_cast<long long>(B) * 3 * T;
+  const size_t plane_bytes = static_cast<size_t>(p->Hr) * crop_w * 4;
+  p->chunk_planes = std::min<long long>(p->planes, std::max<long long>(1, static_cast<long long>(kChunkBytes / plane_bytes)));
+  size_t off = 0;
+  p->off_xmin = off;  off += align256(static_cast<size_t>(out_w) * 4);
+  p->off_xsize = off; off += align256(static_cast<size_t>(out_w) * 4);
+  p->off_wx = off;    off += align256(static_cast<size_t>(out_w) * p->taps_x * 4);
+  p->off_ymin = off;  off += align256(static_cast<size_t>(out_h) * 4);
+  p->off_ysize = off; off += align256(static_cast<size_t>(out_h) * 4);
+  p->off_wy = off;    off += align256(static_cast<size_t>(out_h) * p->taps_y * 4);
+  p->off_inter = off; off += align256(plane_bytes * static_cast<size_t>(p->chunk_planes));
+  p->total = off;
+  return KVQ_OK;
+}
+
+}  // namespace
+}  // namespace kvq
+
+using namespace kvq;
+
+extern "C" {
+
+int kvq_resize_aa_taps(int in_size, int out_size) {
+  KVQ_REQUIRE(in_size > 0 && out_size > 0, KVQ_ERR_BAD_SHAPE, "resize_aa_taps: %d -> %d", in_size, out_size);
+  return axis_geom(in_size, out_size).taps;
+}
+
+int kvq_resize_aa_weights(int in_size, int out_size, int32_t* xmin, int32_t* xsize, float* weights) {
+  KVQ_REQUIRE(in_size > 0 && out_size > 0 && xmin && xsize && weights, KVQ_ERR_BAD_SHAPE,
+              "resize_aa_weights: %d -> %d or NULL table", in_size, out_size);
+  const AxisGeom g = axis_geom(in_size, out_size);
+  for (int i = 0; i < out_size; ++i) {
+    int x0, n;
+    axis_weights(g, in_size, i, &x0, &n, weights + static_cast<size_t>(i) * g.taps, 1);
+    xmin[i] = x0;
+    xsize[i] = n;
+  }
+  return KVQ_OK;
+}
+
+size_t kvq_resize_view_workspace_bytes(int B, int T, int Hs, int Ws, int out_h, int out_w, int crop_y, int crop_x,
+                                       int crop_h, int crop_w) {
+  ViewPlan p;
+  if (make_plan(&p, B, T, Hs, Ws, out_h, out_w, crop_y, crop_x, crop_h, crop_w) != KVQ_OK) return 0;
+  return p.total;
+}
+
+int kvq_resize_view_u8(const uint8_t* frames, int layout, int B, int T, int Hs, int Ws, int out_h, int out_w, int crop_y,
+                       int crop_x, int crop_h, int crop_w, float divisor, const float mean[3], const float std[3],
+                       uint8_t* out_u8, float* out_f32, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  KVQ_REQUIRE(frames && workspace && (out_u8 || out_f32), KVQ_ERR_BAD_SHAPE, "resize_view: NULL argument");
+  KVQ_REQUIRE(layout == 0 || layout == 1, KVQ_ERR_BAD_SHAPE, "resize_view: layout %d (0 = [B,T,3,H,W], 1 = [B,3,T,H,W])",
+              layout);
+  KVQ_REQUIRE(!out_f32 || (mean && std && divisor > 0.0f), KVQ_ERR_BAD_SHAPE,
+              "resize_view: the normalised view needs mean, std and a positive divisor");
+  KVQ_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, KVQ_ERR_MISALIGNED,
+              "resize_view: workspace must be 256-byte aligned");
+  ViewPlan p;
+  int rc = make_plan(&p, B, T, Hs, Ws, out_h, out_w, crop_y, crop_x, crop_h, crop_w);
+  if (rc != KVQ_OK) return rc;
+  KVQ_REQUIRE(workspace_bytes >= p.total, KVQ_ERR_WORKSPACE, "resize_view: workspace %zu < %zu bytes", workspace_bytes,
+              p.total);
+  char* ws = static_cast<char*>(workspace);
+  int32_t* xmin = reinterpret_cast<int32_t*>(ws + p.off_xmin);
+  int32_t* xsize = reinterpret_cast<int32_t*>(ws + p.off_xsize);
+  float* wx = reinterpret_cast<float*>(ws + p.off_wx);
+  int32_t* ymin = reinterpret_cast<int32_t*>(ws + p.off_ymin);
+  int32_t* ysize = reinterpret_cast<int32_t*>(ws + p.off_ysize);
+  float* wy = reinterpret_cast<float*>(ws + p.off_wy);
+  float* inter = reinterpret_cast<float*>(ws + p.off_inter);
+
+  aa_tables_kernel<<<(out_w + 127) / 128, 128, 0, stream>>>(Ws, out_w, xmin, xsize, wx);
+  count_launch();
+  aa_tables_kernel<<<(out_h + 127) / 128, 128, 0, stream>>>(Hs, out_h, ymin, ysize, wy);
+  count_launch();
+  KVQ_CUDA(cudaGetLastError());
+  if (p.smem > (48u << 10))
+    KVQ_CUDA(cudaFuncSetAttribute(resize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kRowTileMaxBytes + 64)));
+  const int tiles = (p.Hr + p.R - 1) / p.R;
+  const float m0 = mean ? mean[0] : 0.f, m1 = mean ? mean[1] : 0.f, m2 = mean ? mean[2] : 0.f;
+  const float s0 = std ? std[0] : 1.f, s1 = std ? std[1] : 1.f, s2 = std ? std[2] : 1.f;
+  for (long long plane0 = 0; plane0 < p.planes; plane0 += p.chunk_planes) {
+    const long long np = std::min(p.chunk_planes, p.planes - plane0);
+    const long long g1 = np * tiles;
+    const long long total = np * p.ch * p.cw;
+    const long long g2 = (total + 255) / 256;
+    KVQ_REQUIRE(g1 < (1ll << 31) && g2 < (1ll << 31), KVQ_ERR_BAD_SHAPE, "resize_view: grid too large");
+    resize_rows_kernel<<<static_cast<unsigned>(g1), 256, p.smem, stream>>>(
+        frames, inter, xmin, xsize, wx, layout, T, Hs, Ws, p.ow, p.cx, p.cw, p.ry0, p.Hr, p.R, tiles,
+        static_cast<int>(plane0));
+    count_launch();
+    resize_cols_kernel<<<static_cast<unsigned>(g2), 256, 0, stream>>>(
+        inter, ymin, ysize, wy, out_u8, out_f32, T, p.oh, p.cy, p.ch, p.cw, p.ry0, p.Hr, static_cast<int>(plane0), total,
+        divisor, m0, m1, m2, s0, s1, s2);
+    count_launch();
+  }
+  return check_cuda(cudaGetLastError(), "resize_view kernels");
+}
+
+}  // extern "C"

@@ -106,6 +106,11 @@ PROTOTYPES = {
     "kvq_maxpool_hw_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "kvq_pool_stats_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "kvq_rowdot_mean_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kvq_resize_aa_taps": (c_int, [c_int, c_int]),
+    "kvq_resize_aa_weights": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "kvq_resize_view_workspace_bytes": (c_size_t, [c_int] * 10),
+    "kvq_resize_view_u8": (c_int, [c_void_p] + [c_int] * 11 + [c_float, POINTER(c_float), POINTER(c_float), c_void_p,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "kvq_launch_count": (ctypes.c_longlong, []),
     "kvq_profile_enable": (None, [c_int]),
     "kvq_profile_num_categories": (c_int, []),

@@ -1,0 +1,130 @@
+"""View pipeline through the C ABI (kvq_resize_view_u8) against the golden vectors the REAL reference
+produced (tools/make_golden_views.py: get_resized_video / get_resizecrop_video + the datasets' normalisation lines) and
+against oracle/views.py on seeded inputs.  The bar is BIT-EXACT: every uint8 of the resized view, every float32 of the
+normalised view."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "views_resize*.npz")))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _golden_frames(g):
+    T, H, W = (int(v) for v in g["shape"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    return torch.randint(0, 256, (T, H, W, 3), generator=gen, dtype=torch.uint8)      # decoder order [T,H,W,3]
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_views_match_reference_golden(path):
+    from datasets import views as V
+    from kvq_b200 import ops
+    g = np.load(path)
+    thwc = _golden_frames(g)
+    video = thwc.permute(3, 0, 1, 2).contiguous().cuda()                              # the reference's [3,T,H,W]
+    if str(g["kind"]) == "resize":
+        out = V.get_resized_video(video, size_h=int(g["size_h"]), size_w=int(g["size_w"]))
+        bt3hw = thwc.permute(0, 3, 1, 2).contiguous().unsqueeze(0).cuda()             # [1,T,3,H,W]
+        norm = V.resized_video_normalised(bt3hw, int(g["size_h"]), int(g["size_w"]))[0]
+    else:
+        out = V.get_resizecrop_video(video, resize=int(g["resize"]), crop=int(g["crop"]), phase="test")
+        bt3hw = thwc.permute(0, 3, 1, 2).contiguous().unsqueeze(0).cuda()
+        norm = V.resizecrop_video_normalised(bt3hw, int(g["resize"]), int(g["crop"]))[0]
+    out, norm = out.cpu().numpy(), norm.cpu().numpy()
+    assert out.dtype == np.uint8 and norm.dtype == np.float32
+    np.testing.assert_array_equal(out, g["out"])
+    assert _sha(out) == str(g["out_sha256"])
+    np.testing.assert_array_equal(norm[:, :, ::7, ::5], g["norm_sample"])
+    assert _sha(norm) == str(g["norm_sha256"])                                        # every float32
+    # both outputs of one call agree with the two separate calls
+    lo_n = V.centre_crop_window(int(g["resize"]), int(g["crop"])) if str(g["kind"]) != "resize" else None
+    u8, f32 = ops.resize_view_u8(video.unsqueeze(0), out.shape[-2] if lo_n is None else int(g["resize"]),
+                                 out.shape[-1] if lo_n is None else int(g["resize"]),
+                                 crop=None if lo_n is None else (lo_n[0], lo_n[0], lo_n[1], lo_n[1]),
+                                 mean=V.CLIP_MEAN if lo_n is None else V.IMAGENET_MEAN,
+                                 std=V.CLIP_STD if lo_n is None else V.IMAGENET_STD,
+                                 divisor=255.0 if lo_n is None else 1.0, layout="B3THW", want_u8=True)
+    np.testing.assert_array_equal(u8[0].cpu().numpy(), out)
+    np.testing.assert_array_equal(f32[0].cpu().numpy(), norm)
+
+
+@pytest.mark.parametrize("B,T,Hs,Ws,oh,ow,crop", [
+    (2, 3, 135, 241, 112, 112, None),            # KSVQE resize_video geometry, odd source, unaligned row starts
+    (1, 2, 540, 960, 112, 112, None),            # 8.6x / 4.8x down-scaling: tap windows of 19 / 11
+    (1, 2, 67, 45, 80, 90, None),                # enlargement on both axes (support 1, 3 taps)
+    (2, 2, 131, 77, 52, 52, (4, 6, 44, 40)),     # rectangular crop window off the centre
+    (1, 1, 9, 1030, 5, 3, None),                 # rows wider than one CTA pass, 2-row plane, 687-tap windows
+    (1, 1, 33, 17, 33, 17, None),                # identity size: exact copy
+])
+def test_views_match_oracle_seeded(B, T, Hs, Ws, oh, ow, crop):
+    from kvq_b200 import ops
+    from oracle import views as O
+    gen = torch.Generator().manual_seed(1000 + Hs * 7 + Ws)
+    frames = torch.randint(0, 256, (B, T, 3, Hs, Ws), generator=gen, dtype=torch.uint8)
+    u8, f32 = ops.resize_view_u8(frames.cuda(), oh, ow, crop=crop, divisor=255.0, mean=ops.CLIP_MEAN, std=ops.CLIP_STD,
+                                 want_u8=True)
+    ref = O.resize_u8(frames.permute(0, 2, 1, 3, 4).numpy(), oh, ow)                   # [B,3,T,oh,ow]
+    if crop is not None:
+        y, x, h, w = crop
+        ref = ref[..., y:y + h, x:x + w]
+    np.testing.assert_array_equal(u8.cpu().numpy(), ref)
+    refn = np.stack([O.normalise(r, O.CLIP_MEAN, O.CLIP_STD, 255.0) for r in ref])
+    np.testing.assert_array_equal(f32.cpu().numpy(), refn)
+    if (oh, ow) == (Hs, Ws):
+        np.testing.assert_array_equal(u8.cpu().numpy(), frames.permute(0, 2, 1, 3, 4).numpy())
+
+
+def test_views_full_size_properties():
+    """KSVQE's resize_video view at a decoder-sized source (8 frames of 1080x1920 -> 112x112): size-independent checks --
+    a constant frame stays constant (the weights of every window sum to 1 within rounding: |v - c| <= 1 is the bound, 0
+    is what ATen gives), frames are independent of their neighbours in the batch, layouts agree, and a horizontal /
+    vertical flip of the source flips the view (the filter is symmetric) up to the last-bit order of summation."""
+    from kvq_b200 import ops
+    T, Hs, Ws = 8, 1080, 1920
+    gen = torch.Generator().manual_seed(77)
+    frames = torch.randint(0, 256, (1, T, 3, Hs, Ws), generator=gen, dtype=torch.uint8).cuda()
+    u8, f32 = ops.resize_view_u8(frames, 112, 112, divisor=255.0, mean=ops.CLIP_MEAN, std=ops.CLIP_STD, want_u8=True)
+    assert tuple(u8.shape) == (1, 3, T, 112, 112) and tuple(f32.shape) == (1, 3, T, 112, 112)
+    # normalisation is the stated function of the bytes
+    m = torch.tensor(ops.CLIP_MEAN, device="cuda").view(1, 3, 1, 1, 1)
+    s = torch.tensor(ops.CLIP_STD, device="cuda").view(1, 3, 1, 1, 1)
+    assert torch.equal(f32, (u8.float() / torch.full((1,), 255.0, device="cuda") - m) / s)   # tensor divisor: true division
+    # layout B3THW on the permuted frames gives the same bytes
+    u8b, _ = ops.resize_view_u8(frames.permute(0, 2, 1, 3, 4).contiguous(), 112, 112, layout="B3THW", want_u8=True,
+                                want_f32=False)
+    assert torch.equal(u8, u8b)
+    # a sub-batch gives the same frames
+    u8c, _ = ops.resize_view_u8(frames[:, 2:5].contiguous(), 112, 112, want_u8=True, want_f32=False)
+    assert torch.equal(u8[:, :, 2:5], u8c)
+    # constants are preserved
+    const = torch.full((1, 2, 3, Hs, Ws), 201, dtype=torch.uint8, device="cuda")
+    uc, _ = ops.resize_view_u8(const, 112, 112, want_u8=True, want_f32=False)
+    assert int(uc.min()) == 201 and int(uc.max()) == 201
+    # noise averaged over a 17x10 footprint: mean close to 127.5, far smaller spread than the source
+    assert abs(float(u8.float().mean()) - 127.5) < 1.0 and float(u8.float().std()) < 15.0
+    # symmetric filter: flipping the source flips the view within one grey level
+    uf, _ = ops.resize_view_u8(frames.flip(-1).contiguous(), 112, 112, want_u8=True, want_f32=False)
+    assert int((uf.flip(-1).int() - u8.int()).abs().max()) <= 1
+
+
+def test_views_error_paths():
+    from kvq_b200 import ops
+    frames = torch.zeros((1, 2, 3, 16, 16), dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="crop window"):
+        ops.resize_view_u8(frames, 8, 8, crop=(4, 4, 8, 8))
+    with pytest.raises(RuntimeError, match="uint8"):
+        ops.resize_view_u8(frames.float(), 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        ops.resize_view_u8(frames.cpu(), 8, 8)

@@ -192,3 +192,42 @@ def test_trainer_rescale_matches_reference_formula():
     assert abs(z.mean()) < 1e-12 and abs(z.std() - 1.0) < 1e-12
     r = tr.Trainer.rescale(pr, gt)
     assert abs(r.mean() - gt.mean()) < 1e-12 and abs(r.std() - gt.std()) < 1e-12
+
+
+def test_view_host_entry_points():
+    """View pipeline, host side only: the library's tap windows / weights equal the golden-pinned oracle
+    bit for bit, the plan sizes the workspace for the crop window only, bad geometry is reported not crashed, and the
+    drop-in UnifiedFrameSampler reproduces the reference's indices under the same numpy seed."""
+    import numpy as np
+    from kvq_b200 import lib
+    from oracle import views as O
+    L = lib.load()
+    for n_in, n_out in [(1920, 112), (1080, 112), (1080, 520), (1920, 520), (64, 112), (7, 7), (5, 1), (1, 3),
+                        (608, 224), (270, 224), (90, 70), (70, 90), (3840, 112), (2160, 448), (1030, 3)]:
+        xmin, xsize, w = O.aa_weights(n_in, n_out)
+        taps = L.kvq_resize_aa_taps(n_in, n_out)
+        assert taps == w.shape[1] == O.aa_taps(n_in, n_out)
+        a, b, c = np.zeros(n_out, np.int32), np.zeros(n_out, np.int32), np.zeros((n_out, taps), np.float32)
+        assert L.kvq_resize_aa_weights(n_in, n_out, a.ctypes.data, b.ctypes.data, c.ctypes.data) == 0
+        np.testing.assert_array_equal(a, xmin)
+        np.testing.assert_array_equal(b, xsize)
+        np.testing.assert_array_equal(c.view(np.uint32), w.view(np.uint32))
+    assert L.kvq_resize_aa_taps(0, 4) < 0 and "resize_aa_taps" in lib.last_error()
+    # workspace: tables + an L2-sized chunk of the float32 intermediate; a crop window shrinks rows and columns
+    full = L.kvq_resize_view_workspace_bytes(1, 1, 1080, 1920, 520, 520, 0, 0, 0, 0)
+    crop = L.kvq_resize_view_workspace_bytes(1, 1, 1080, 1920, 520, 520, 36, 36, 448, 448)
+    assert 3 * 1080 * 520 * 4 <= full < 3 * 1080 * 520 * 4 + (1 << 20)
+    assert crop < full * 0.8
+    big = L.kvq_resize_view_workspace_bytes(8, 32, 1080, 1920, 112, 112, 0, 0, 0, 0)
+    assert big < (34 << 20)                                        # chunked: never the whole batch's intermediate
+    assert L.kvq_resize_view_workspace_bytes(1, 1, 16, 16, 8, 8, 4, 4, 8, 8) == 0 and "crop window" in lib.last_error()
+    assert L.kvq_resize_view_workspace_bytes(1, 1, 4, 60000, 8, 8, 0, 0, 0, 0) == 0 and "row tile" in lib.last_error()
+
+    from datasets.views import UnifiedFrameSampler, centre_crop_window
+    g = np.load(os.path.join(GOLDEN, "views_frame_sampler.npz"))
+    for i, (fsize_t, fragments_t, interval, num_clips, total, seed) in enumerate(g["cases"]):
+        np.random.seed(int(seed))
+        inds = UnifiedFrameSampler(int(fsize_t), int(fragments_t), int(interval), int(num_clips))(int(total))
+        assert inds.dtype == np.int32
+        np.testing.assert_array_equal(inds, g[f"inds_{i}"])
+    assert centre_crop_window(520, 448) == (36, 448) and centre_crop_window(91, 45) == O.centre_crop_window(91, 45)
