@@ -77,14 +77,32 @@ class SyntheticKSVQEDataset(torch.utils.data.Dataset):
         self.T = st.get("clip_len", 32) * st.get("num_clips", 3)
         self.num_clips = st.get("num_clips", 3)
         self.n, self.seed = opt.get("num_videos", 4), opt.get("seed", 11)
+        self.aligned = st.get("aligned", 8)
+        # raw_frames: the item carries decoded uint8 frames [T,3,src_h,src_w] and the fragment offsets; the Trainer
+        # builds `fragment` and `resize_video` with the view kernels after the H2D copy
+        self.raw = bool(opt.get("raw_frames", False))
+        self.src_h, self.src_w = opt.get("src_h", 540), opt.get("src_w", 960)
 
     def __len__(self):
         return self.n
 
     def __getitem__(self, i):
         g = torch.Generator().manual_seed(self.seed + i)
+        common = {"num_clips": {"technical": self.num_clips}, "video_name": f"synthetic_{i:04d}"}
+        if self.raw:
+            frames = torch.randint(0, 256, (self.T, 3, self.src_h, self.src_w), generator=g, dtype=torch.uint8)
+            hl, wl, nt = self.src_h // self.fh, self.src_w // self.fw, self.T // self.aligned
+            # reference draw order: rnd_h then rnd_w (fusion_datasets.py:87-98)
+            rnd_h = torch.randint(hl - self.fs, (self.fh, self.fw, nt), generator=g)
+            rnd_w = torch.randint(wl - self.fs, (self.fh, self.fw, nt), generator=g)
+            return dict(common, frames=frames, offsets=torch.stack([rnd_h, rnd_w]).int(),
+                        fragment_opts={"fragments_h": self.fh, "fragments_w": self.fw, "fsize": self.fs,
+                                       "aligned": self.aligned},
+                        resize_opts={"size_h": self.rh, "size_w": self.rw},
+                        dis_label=torch.tensor(int(torch.randint(0, 5, (1,), generator=g))),
+                        label=torch.rand((), generator=g) * 4.0 + 1.0)
         frag = torch.randn((3, self.T, self.fh * self.fs, self.fw * self.fs), generator=g)
-        return {"technical": frag, "fragment": frag, "resize_video": torch.randn((3, self.T, self.rh, self.rw), generator=g),
-                "dis_label": torch.tensor(int(torch.randint(0, 5, (1,), generator=g))),
-                "num_clips": {"technical": self.num_clips}, "video_name": f"synthetic_{i:04d}",
-                "label": torch.rand((), generator=g) * 4.0 + 1.0}
+        return dict(common, technical=frag, fragment=frag,
+                    resize_video=torch.randn((3, self.T, self.rh, self.rw), generator=g),
+                    dis_label=torch.tensor(int(torch.randint(0, 5, (1,), generator=g))),
+                    label=torch.rand((), generator=g) * 4.0 + 1.0)

@@ -28,7 +28,7 @@ def strip_module_prefix(state_dict):
 
 def score_video(model, data, key_list, device=None):
     """Body of the inferece_test loop (trainer.py:306-329) for one loader item; returns the video's mean score."""
-    if "frames" in data and "technical" not in data:                    # raw frames: fragment kernel on the GPU
+    if "frames" in data and "technical" not in data:                    # raw frames: the view kernels on the GPU
         fo = data["fragment_opts"]
         frames = data["frames"].to(device, non_blocking=True)
         if frames.dim() == 4:
@@ -36,9 +36,17 @@ def score_video(model, data, key_list, device=None):
         else:
             offsets = data["offsets"]
         g = lambda v: int(v[0]) if torch.is_tensor(v) else int(v)         # DataLoader collates ints into tensors
-        data["technical"] = ops.fragment_gather_u8(frames.contiguous(), offsets.to(device).int().contiguous(),
+        frames = frames.contiguous()
+        data["technical"] = ops.fragment_gather_u8(frames, offsets.to(device).int().contiguous(),
                                                    g(fo["fragments_h"]), g(fo["fragments_w"]), g(fo["fsize"]),
                                                    g(fo["aligned"]))
+        if "KSVQE" in key_list:
+            # the two views of ViewDecompositionDataset_KVQ (fusion_datasets.py:1017-1027): the normalised fragment grid
+            # and the frames resized to size_h x size_w, CLIP-normalised -- both from the same decoded frames
+            from datasets import views
+            ro = data["resize_opts"]
+            data["fragment"] = data["technical"]
+            data["resize_video"] = views.resized_video_normalised(frames, g(ro["size_h"]), g(ro["size_w"]))
     if "KSVQE" in key_list and device is not None:
         # nn.DataParallel scatters these in the reference (trainer.py:61); 'KSVQE' is not a key of the data dict, so
         # the clip reshape below never applies to them (the 96 frames of a video go through as one clip)

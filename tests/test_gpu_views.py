@@ -128,3 +128,49 @@ def test_views_error_paths():
         ops.resize_view_u8(frames.float(), 8, 8)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         ops.resize_view_u8(frames.cpu(), 8, 8)
+
+
+def test_ksvqe_from_raw_frames_matches_cpu_views():
+    """Decoded uint8 frames -> (fragment kernel + resize kernel on the device) -> literal KSVQE key, against the same
+    network fed with the views the golden-pinned CPU restatements build (oracle/fragments.py, oracle/views.py): the
+    resized view is bit-exact, the fragment view within one ulp of the normalisation, the score unchanged."""
+    import importlib.util
+    import models
+    from conftest import PKG
+    from datasets import SyntheticKSVQEDataset
+    from oracle import fragments as ofr
+    from oracle import views as O
+    from tools import synth
+    spec = importlib.util.spec_from_file_location("kvq_trainer_views", os.path.join(PKG, "trainer.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    cfg = {"model": {"type": "KSVQE", "args": {"KSVQE": {
+        "backbone": {"num_samples": 1, "sample_type": "topkpertubation", "CLIP_location": 8, "cls_use": True,
+                     "tuning_stage": 2, "a1": 1.0, "a2": 1.0, "frozen_stages": -1},
+        "head": {"in_channels": 768, "hidden_channels": 64}}}}}
+    net = models.VQA_Network(cfg)
+    sd = {k: (torch.ones(tuple(v.shape)) if k.endswith((".a1", ".a2")) else synth.fill_like(k, tuple(v.shape), 61))
+          for k, v in net.state_dict().items() if v.is_floating_point()}
+    net.load_state_dict(sd, strict=False)
+    net = net.to("cuda:0").eval()
+    st = {"fragments_h": 9, "fragments_w": 9, "fsize_h": 32, "fsize_w": 32, "size_h": 112, "size_w": 112, "aligned": 8,
+          "clip_len": 32, "num_clips": 1}
+    ds = SyntheticKSVQEDataset({"num_videos": 1, "raw_frames": True, "src_h": 360, "src_w": 640,
+                                "sample_types": {"technical": st}})
+    item = ds[0]
+    assert item["frames"].shape == (32, 3, 360, 640) and item["frames"].dtype == torch.uint8
+    dev = torch.device("cuda:0")
+    data1 = next(iter(torch.utils.data.DataLoader(ds, batch_size=1)))                 # as Trainer.inferece feeds it
+    s1 = float(tr.score_video(net, data1, ["KSVQE"], dev))
+
+    frames = item["frames"][None]                                                     # [1,T,3,H,W]
+    frag = ofr.fragment_clip(frames, item["offsets"][None], 9, 9, 32, 8)              # f32 [1,3,T,288,288]
+    rv = O.normalise(O.resized_video(frames[0].permute(1, 0, 2, 3).numpy(), 112, 112), O.CLIP_MEAN, O.CLIP_STD, 255.0)
+    np.testing.assert_array_equal(data1["resize_video"][0].cpu().numpy(), rv)
+    assert tuple(data1["fragment"].shape) == (1, 3, 32, 288, 288)
+    np.testing.assert_allclose(data1["fragment"].cpu().numpy(), frag.numpy(), rtol=0, atol=1e-6)
+    data2 = {"fragment": frag, "resize_video": torch.from_numpy(rv)[None], "dis_label": item["dis_label"][None],
+             "num_clips": item["num_clips"], "video_name": item["video_name"]}
+    s2 = float(tr.score_video(net, data2, ["KSVQE"], dev))
+    print("ksvqe raw-frame score", s1, "cpu-view score", s2)
+    assert np.isfinite(s1) and abs(s1 - s2) < 1e-4
