@@ -20,6 +20,7 @@
 // Planes are processed in chunks whose float32 intermediate stays L2-resident (32 MB) between pass 1 and pass 2.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "../../include/kvq_b200.h"
 #include "kvq_common.cuh"
@@ -29,6 +30,7 @@ namespace kvq {
 namespace {
 
 constexpr int kRowsPerThread = 4;
+constexpr int kDefaultVariant = 2;  // 2 = resize_rows_kernel, 3 = resize_rows_paired_kernel when eligible
 constexpr size_t kChunkBytes = 32u << 20;
 constexpr size_t kRowTileBytes = 64u << 10;
 constexpr size_t kRowTileMaxBytes = 200u << 10;
@@ -204,6 +206,114 @@ resize_rows_kernel(const uint8_t* __restrict__ frames, float* __restrict__ inter
   }
 }
 
+// pass 1, paired rows (source rows of whole 4-byte words: Ws % 4 == 0 and a 4-byte aligned frame pointer -- every real
+// video size).  Two source rows are interleaved in shared memory as float2 [R/2][Ws], so one 8-byte shared load feeds one
+// packed fp32x2 instruction (mul.rn.f32x2 for the unfused taps, fma.rn.f32x2 for the fused tail: IEEE per lane, same
+// roundings as the scalar form): half the shared loads and two thirds of the arithmetic issue slots of
+// resize_rows_kernel per tap.
+constexpr int kPairBatch = 8;  // items (one word of each row of a pair) in flight per thread = 16 loads
+
+__global__ void __launch_bounds__(256)
+resize_rows_paired_kernel(const uint8_t* __restrict__ frames, float* __restrict__ inter,
+                          const int32_t* __restrict__ xmin, const int32_t* __restrict__ xsize,
+                          const float* __restrict__ wx, int layout, int T, int Hs, int Ws, int ow, int cx, int cw, int ry0,
+                          int Hr, int R, int tiles_per_plane, int plane0) {
+  extern __shared__ __align__(16) float rows_f32[];
+  const int tile = blockIdx.x % tiles_per_plane;
+  const int pl = blockIdx.x / tiles_per_plane;
+  const int p_out = plane0 + pl;
+  long long p_in = p_out;
+  if (layout == 0) {
+    const int t = p_out % T, c = (p_out / T) % 3, b = p_out / (3 * T);
+    p_in = (static_cast<long long>(b) * T + t) * 3 + c;
+  }
+  const int r0 = tile * R;
+  const int rows = min(R, Hr - r0);
+  const uint32_t* src32 =
+      reinterpret_cast<const uint32_t*>(frames + (p_in * Hs + ry0 + r0) * static_cast<long long>(Ws));
+  const int wpr = Ws >> 2;  // words per source row
+  const int pairs = (rows + 1) >> 1;
+  const int nitems = pairs * wpr;
+  float4* s4 = reinterpret_cast<float4*>(rows_f32);
+  for (int i0 = threadIdx.x; i0 < nitems; i0 += 256 * kPairBatch) {
+    uint32_t ua[kPairBatch], ub[kPairBatch];
+#pragma unroll
+    for (int q = 0; q < kPairBatch; ++q) {
+      const int i = i0 + q * 256;
+      ua[q] = ub[q] = 0u;
+      if (i < nitems) {
+        const int rp = i / wpr, xw = i - rp * wpr;
+        const int rb = min(2 * rp + 1, rows - 1);  // an odd last row pairs with itself (never stored)
+        ua[q] = __ldg(src32 + (2 * rp) * wpr + xw);
+        ub[q] = __ldg(src32 + rb * wpr + xw);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kPairBatch; ++q) {
+      const int i = i0 + q * 256;
+      if (i < nitems) {  // floats (rp*Ws + 4*xw)*2 .. +8  =  float4 2*i, 2*i + 1
+        s4[2 * i] = make_float4(byte_to_float(ua[q], 0), byte_to_float(ub[q], 0), byte_to_float(ua[q], 1),
+                                byte_to_float(ub[q], 1));
+        s4[2 * i + 1] = make_float4(byte_to_float(ua[q], 2), byte_to_float(ub[q], 2), byte_to_float(ua[q], 3),
+                                    byte_to_float(ub[q], 3));
+      }
+    }
+  }
+  __syncthreads();
+  const float2* s2 = reinterpret_cast<const float2*>(rows_f32);
+  const int groups = (rows + kRowsPerThread - 1) / kRowsPerThread;
+  float* dst = inter + (static_cast<long long>(pl) * Hr + r0) * cw;
+  for (int item = threadIdx.x; item < groups * cw; item += blockDim.x) {
+    const int oc = item % cw, rg = item / cw;
+    const int o = cx + oc;
+    const int n = xsize[o], x0 = xmin[o];
+    const int rbase = rg * kRowsPerThread;
+    const float2* spa = s2 + (2 * rg) * Ws + x0;
+    const float2* spb = s2 + min(2 * rg + 1, pairs - 1) * Ws + x0;
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+    if (n > 0) {
+      const float* wp = wx + o;
+      const float2 w0 = splat2(wp[0]);
+      acc0 = fmul2(spa[0], w0);
+      acc1 = fmul2(spb[0], w0);
+      const int unfused = ((n - 1) >> 2) << 2;
+      int k = 1;
+      for (; k <= unfused; k += 4) {
+        float wk[4];
+        float2 va[4], vb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wk[e] = wp[static_cast<long long>(k + e) * ow];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          va[e] = spa[k + e];
+          vb[e] = spb[k + e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // packed products, SCALAR sums: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (checked in SASS),
+          // which would change the roundings; FMUL2 + FADD stays unfused
+          const float2 w2 = splat2(wk[e]);
+          const float2 pa = fmul2(va[e], w2), pb = fmul2(vb[e], w2);
+          acc0.x = __fadd_rn(acc0.x, pa.x);
+          acc0.y = __fadd_rn(acc0.y, pa.y);
+          acc1.x = __fadd_rn(acc1.x, pb.x);
+          acc1.y = __fadd_rn(acc1.y, pb.y);
+        }
+      }
+      for (; k < n; ++k) {
+        const float2 w2 = splat2(wp[static_cast<long long>(k) * ow]);
+        acc0 = ffma2(spa[k], w2, acc0);
+        acc1 = ffma2(spb[k], w2, acc1);
+      }
+    }
+    float* d = dst + static_cast<long long>(rbase) * cw + oc;
+    if (rbase + 0 < rows) d[0] = acc0.x;
+    if (rbase + 1 < rows) d[cw] = acc0.y;
+    if (rbase + 2 < rows) d[2 * static_cast<long long>(cw)] = acc1.x;
+    if (rbase + 3 < rows) d[3 * static_cast<long long>(cw)] = acc1.y;
+  }
+}
+
 // pass 2: H axis + round + normalise.  One thread per output pixel x 4 consecutive output rows would re-read taps; the
 // intermediate is L2-resident, so one thread per pixel (lanes = consecutive columns, weights broadcast) is enough.
 // out_u8 [B,3,T,ch,cw] (may be NULL), out_f32 [B,3,T,ch,cw] (may be NULL)
@@ -282,6 +392,10 @@ int make_plan(ViewPlan* p, int B, int T, int Hs, int Ws, int out_h, int out_w, i
               "resize_view: source rows of %d pixels do not fit the shared-memory row tile", Ws);
   int R = static_cast<int>(kRowTileBytes / row_bytes) / kRowsPerThread * kRowsPerThread;
   R = std::min(std::max(R, kRowsPerThread), 16);
+  if (const char* e = std::getenv("KVQ_VIEWS_ROWS")) {  // tuning knob (tools/views_timing.py): source rows per CTA
+    const int v = std::atoi(e);
+    if (v >= kRowsPerThread && v % kRowsPerThread == 0 && v <= 64 && v * row_bytes + 64 <= kRowTileMaxBytes) R = v;
+  }
   R = std::min(R, (p->Hr + kRowsPerThread - 1) / kRowsPerThread * kRowsPerThread);
   p->R = R;
   p->smem = static_cast<size_t>(R) * row_bytes + 32;
@@ -362,9 +476,16 @@ int kvq_resize_view_u8(const uint8_t* frames, int layout, int B, int T, int Hs, 
   aa_tables_kernel<<<(out_h + 127) / 128, 128, 0, stream>>>(Hs, out_h, ymin, ysize, wy);
   count_launch();
   KVQ_CUDA(cudaGetLastError());
-  if (p.smem > (48u << 10))
+  // rows of whole aligned words take the paired-row kernel (KVQ_VIEWS_VARIANT=2 forces the generic one)
+  const char* variant = std::getenv("KVQ_VIEWS_VARIANT");
+  const int want = variant ? std::atoi(variant) : kDefaultVariant;
+  const bool paired = want == 3 && Ws % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 3) == 0;
+  if (p.smem > (48u << 10)) {
     KVQ_CUDA(cudaFuncSetAttribute(resize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kRowTileMaxBytes + 64)));
+    KVQ_CUDA(cudaFuncSetAttribute(resize_rows_paired_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kRowTileMaxBytes + 64)));
+  }
   const int tiles = (p.Hr + p.R - 1) / p.R;
   const float m0 = mean ? mean[0] : 0.f, m1 = mean ? mean[1] : 0.f, m2 = mean ? mean[2] : 0.f;
   const float s0 = std ? std[0] : 1.f, s1 = std ? std[1] : 1.f, s2 = std ? std[2] : 1.f;
@@ -374,9 +495,14 @@ int kvq_resize_view_u8(const uint8_t* frames, int layout, int B, int T, int Hs, 
     const long long total = np * p.ch * p.cw;
     const long long g2 = (total + 255) / 256;
     KVQ_REQUIRE(g1 < (1ll << 31) && g2 < (1ll << 31), KVQ_ERR_BAD_SHAPE, "resize_view: grid too large");
-    resize_rows_kernel<<<static_cast<unsigned>(g1), 256, p.smem, stream>>>(
-        frames, inter, xmin, xsize, wx, layout, T, Hs, Ws, p.ow, p.cx, p.cw, p.ry0, p.Hr, p.R, tiles,
-        static_cast<int>(plane0));
+    if (paired)
+      resize_rows_paired_kernel<<<static_cast<unsigned>(g1), 256, p.smem, stream>>>(
+          frames, inter, xmin, xsize, wx, layout, T, Hs, Ws, p.ow, p.cx, p.cw, p.ry0, p.Hr, p.R, tiles,
+          static_cast<int>(plane0));
+    else
+      resize_rows_kernel<<<static_cast<unsigned>(g1), 256, p.smem, stream>>>(
+          frames, inter, xmin, xsize, wx, layout, T, Hs, Ws, p.ow, p.cx, p.cw, p.ry0, p.Hr, p.R, tiles,
+          static_cast<int>(plane0));
     count_launch();
     resize_cols_kernel<<<static_cast<unsigned>(g2), 256, 0, stream>>>(
         inter, ymin, ysize, wy, out_u8, out_f32, T, p.oh, p.cy, p.ch, p.cw, p.ry0, p.Hr, static_cast<int>(plane0), total,

@@ -86,6 +86,36 @@ def test_views_match_oracle_seeded(B, T, Hs, Ws, oh, ow, crop):
         np.testing.assert_array_equal(u8.cpu().numpy(), frames.permute(0, 2, 1, 3, 4).numpy())
 
 
+@pytest.mark.parametrize("variant", ["2", "3"])
+@pytest.mark.parametrize("B,T,Hs,Ws,oh,ow,crop", [
+    (1, 2, 135, 240, 112, 112, None),            # odd row count: the last row pair of a tile is half empty
+    (2, 1, 37, 64, 20, 24, (3, 2, 15, 20)),      # tiles of one, two and three rows; crop window
+    (1, 1, 50, 1920, 9, 112, None),              # decoder-wide rows, 37-tap windows, 8-row tiles
+    (1, 2, 30, 44, 45, 66, None),                # enlargement (3 taps: the fused tail only)
+])
+def test_views_row_kernels_agree_with_oracle(variant, B, T, Hs, Ws, oh, ow, crop, monkeypatch):
+    """Both W-axis kernels (KVQ_VIEWS_VARIANT=2: generic rows; 3: paired rows + packed fp32x2, rows of whole words) give
+    the oracle's bytes and floats; KVQ_VIEWS_ROWS changes the tile height only."""
+    from kvq_b200 import ops
+    from oracle import views as O
+    monkeypatch.setenv("KVQ_VIEWS_VARIANT", variant)
+    gen = torch.Generator().manual_seed(4000 + Hs + Ws)
+    frames = torch.randint(0, 256, (B, T, 3, Hs, Ws), generator=gen, dtype=torch.uint8)
+    ref = O.resize_u8(frames.permute(0, 2, 1, 3, 4).numpy(), oh, ow)
+    if crop is not None:
+        y, x, h, w = crop
+        ref = ref[..., y:y + h, x:x + w]
+    refn = np.stack([O.normalise(r, O.IMAGENET_MEAN, O.IMAGENET_STD) for r in ref])
+    for rows in (None, "4", "12"):
+        if rows is None:
+            monkeypatch.delenv("KVQ_VIEWS_ROWS", raising=False)
+        else:
+            monkeypatch.setenv("KVQ_VIEWS_ROWS", rows)
+        u8, f32 = ops.resize_view_u8(frames.cuda(), oh, ow, crop=crop, want_u8=True)
+        np.testing.assert_array_equal(u8.cpu().numpy(), ref)
+        np.testing.assert_array_equal(f32.cpu().numpy(), refn)
+
+
 def test_views_full_size_properties():
     """KSVQE's resize_video view at a decoder-sized source (8 frames of 1080x1920 -> 112x112): size-independent checks --
     a constant frame stays constant (the weights of every window sum to 1 within rounding: |v - c| <= 1 is the bound, 0

@@ -2,6 +2,7 @@
 # One GPU-box visit: parity suite, view-pipeline bench + ncu capture, smoke, default bench.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 timeout 90 python -m pytest tests -m gpu -x -q > gpurun_out/final_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/final_pytest.log
+timeout 40 python tools/views_timing.py 4 > gpurun_out/views_timing.jsonl 2>&1; echo "timing rc=$?"; cat gpurun_out/views_timing.jsonl | cut -c1-160
 timeout 40 python bench.py --workload views --steps 10 > gpurun_out/b_views.json 2> gpurun_out/b_views.err; echo "views rc=$?"
 python - <<'PY'
 import json
@@ -12,5 +13,7 @@ except Exception as e:
     print("views parse failed", e)
 PY
 timeout 45 ncu --profile-from-start off --set full --clock-control none --import-source on -f -o gpurun_out/views_full python tools/views_profile.py 1 > gpurun_out/views_ncu.log 2>&1; echo "ncu rc=$?"
+if [ "$1" = "full" ]; then
 timeout 30 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 45 python bench.py --steps 10 > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/final_bench.json
+fi
