@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box visit: parity suite, view-pipeline bench + ncu capture, smoke, default bench.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
-timeout 90 python -m pytest tests -m gpu -x -q > gpurun_out/final_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/final_pytest.log
+timeout 90 python -m pytest tests -m gpu -q > gpurun_out/final_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/final_pytest.log
 timeout 40 python tools/views_timing.py 4 > gpurun_out/views_timing.jsonl 2>&1; echo "timing rc=$?"; cat gpurun_out/views_timing.jsonl | cut -c1-160
 timeout 40 python bench.py --workload views --steps 10 > gpurun_out/b_views.json 2> gpurun_out/b_views.err; echo "views rc=$?"
 python - <<'PY'
