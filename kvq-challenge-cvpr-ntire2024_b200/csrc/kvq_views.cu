@@ -30,7 +30,7 @@ namespace kvq {
 namespace {
 
 constexpr int kRowsPerThread = 4;
-constexpr int kDefaultVariant = 2;  // 2 = resize_rows_kernel, 3 = resize_rows_paired_kernel when eligible
+constexpr int kDefaultVariant = 2;  // 2 = resize_rows_kernel, 3 = resize_rows_paired_kernel when eligible, 4 = resize_rows_bytes_kernel
 constexpr size_t kChunkBytes = 32u << 20;
 constexpr size_t kRowTileBytes = 64u << 10;
 constexpr size_t kRowTileMaxBytes = 200u << 10;
@@ -314,6 +314,145 @@ resize_rows_paired_kernel(const uint8_t* __restrict__ frames, float* __restrict_
   }
 }
 
+// pass 1, raw bytes in shared memory (any width / alignment).  ncu on resize_rows_kernel showed the shared-memory pipe as
+// the bound (76 % L1/TEX, 2-way conflicts: float32 staging moves 12 B of shared traffic per source byte).  Here the tile
+// stays uint8 (a quarter of the shared bytes, 16 B vector copies, up to 8 CTAs per SM in flight) and every shared load
+// fetches FOUR taps of a row: the aligned word pair around the window is funnelled with one PRMT (selector = byte phase
+// of the window start) and the four bytes are converted with the 2^23 trick.  Roundings as in the other kernels.
+constexpr int kVecBatch = 8;  // 16 B loads in flight per thread while a tile is staged
+
+__global__ void __launch_bounds__(256)
+resize_rows_bytes_kernel(const uint8_t* __restrict__ frames, float* __restrict__ inter, const int32_t* __restrict__ xmin,
+                         const int32_t* __restrict__ xsize, const float* __restrict__ wx, int layout, int T, int Hs, int Ws,
+                         int ow, int cx, int cw, int ry0, int Hr, int R, int tiles_per_plane, int plane0) {
+  extern __shared__ __align__(16) float rows_f32[];
+  uint4* s16 = reinterpret_cast<uint4*>(rows_f32);
+  const int tile = blockIdx.x % tiles_per_plane;
+  const int pl = blockIdx.x / tiles_per_plane;
+  const int p_out = plane0 + pl;
+  long long p_in = p_out;
+  if (layout == 0) {
+    const int t = p_out % T, c = (p_out / T) % 3, b = p_out / (3 * T);
+    p_in = (static_cast<long long>(b) * T + t) * 3 + c;
+  }
+  const int r0 = tile * R;
+  const int rows = min(R, Hr - r0);
+  const uint8_t* src = frames + (p_in * Hs + ry0 + r0) * static_cast<long long>(Ws);
+  const int nbytes = rows * Ws;
+  // shared byte j <-> source byte (src - head + j): aligned 16 B vectors are copied whole
+  const int head = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15);
+  const int nvec = (head + nbytes + 15) >> 4;
+  const uint4* base = reinterpret_cast<const uint4*>(src - head);
+  for (int v0 = threadIdx.x; v0 <= nvec; v0 += 256 * kVecBatch) {
+    uint4 u[kVecBatch];
+#pragma unroll
+    for (int q = 0; q < kVecBatch; ++q) {
+      const int v = v0 + q * 256;
+      u[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (v > 0 && v < nvec - 1) u[q] = __ldg(base + v);  // whole vectors of the tile only
+    }
+#pragma unroll
+    for (int q = 0; q < kVecBatch; ++q) {
+      const int v = v0 + q * 256;
+      if (v <= nvec) s16[v] = u[q];  // vector nvec = zero padding for the funnel's look-ahead word
+    }
+  }
+  __syncthreads();
+  // first and last vector: only bytes of the tile are read (they may sit at the ends of the allocation)
+  uint8_t* sb = reinterpret_cast<uint8_t*>(rows_f32);
+  const int first_end = min(16 - head, nbytes);
+  for (int j = threadIdx.x; j < first_end; j += 256) sb[head + j] = src[j];
+  if (nvec > 1) {
+    const int last0 = (nvec - 1) * 16 - head;  // tile byte of the last vector's first byte (> 0)
+    for (int j = last0 + threadIdx.x; j < nbytes; j += 256) sb[head + j] = src[j];
+  }
+  __syncthreads();
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(rows_f32);
+  const int groups = (rows + kRowsPerThread - 1) / kRowsPerThread;
+  float* dst = inter + (static_cast<long long>(pl) * Hr + r0) * cw;
+  for (int item = threadIdx.x; item < groups * cw; item += blockDim.x) {
+    const int oc = item % cw, rg = item / cw;
+    const int o = cx + oc;
+    const int n = xsize[o], x0 = xmin[o];
+    const int rbase = rg * kRowsPerThread;
+    float acc[kRowsPerThread];
+    uint32_t lo[kRowsPerThread], sel[kRowsPerThread], b4[kRowsPerThread];
+    int wi[kRowsPerThread];
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+      const int rr = min(rbase + r, rows - 1);  // rows past the tile repeat the last one (never stored)
+      const int bo = head + rr * Ws + x0;       // shared byte of tap 0
+      wi[r] = bo >> 2;
+      sel[r] = 0x3210u + 0x1111u * (bo & 3);    // bytes (bo&3) .. (bo&3)+3 of the word pair {lo, hi}
+      lo[r] = sw[wi[r]];
+      acc[r] = 0.0f;
+    }
+    if (n > 0) {
+      const float* wp = wx + o;
+      const int m = (n - 1) >> 2;  // taps 1 .. 4m: rounded product + rounded add; taps 4m+1 .. n-1: fused
+      float w[4];
+      // ---- group 0: taps 0..3
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = e < n ? wp[static_cast<long long>(e) * ow] : 0.0f;
+#pragma unroll
+      for (int r = 0; r < kRowsPerThread; ++r) {
+        const uint32_t hi = sw[wi[r] + 1];
+        b4[r] = __byte_perm(lo[r], hi, sel[r]);
+        lo[r] = hi;
+        acc[r] = __fmul_rn(byte_to_float(b4[r], 0), w[0]);
+      }
+      if (m == 0) {
+#pragma unroll
+        for (int e = 1; e < 4; ++e)
+          if (e < n) {
+#pragma unroll
+            for (int r = 0; r < kRowsPerThread; ++r) acc[r] = __fmaf_rn(byte_to_float(b4[r], e), w[e], acc[r]);
+          }
+      } else {
+#pragma unroll
+        for (int e = 1; e < 4; ++e)
+#pragma unroll
+          for (int r = 0; r < kRowsPerThread; ++r)
+            acc[r] = __fadd_rn(acc[r], __fmul_rn(byte_to_float(b4[r], e), w[e]));
+        // ---- groups 1 .. m-1: four unfused taps each
+        for (int g = 1; g < m; ++g) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = wp[static_cast<long long>(4 * g + e) * ow];
+#pragma unroll
+          for (int r = 0; r < kRowsPerThread; ++r) {
+            const uint32_t hi = sw[wi[r] + g + 1];
+            b4[r] = __byte_perm(lo[r], hi, sel[r]);
+            lo[r] = hi;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int r = 0; r < kRowsPerThread; ++r)
+              acc[r] = __fadd_rn(acc[r], __fmul_rn(byte_to_float(b4[r], e), w[e]));
+        }
+        // ---- group m: tap 4m unfused, taps 4m+1 .. n-1 fused
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = 4 * m + e < n ? wp[static_cast<long long>(4 * m + e) * ow] : 0.0f;
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) {
+          const uint32_t hi = sw[wi[r] + m + 1];
+          b4[r] = __byte_perm(lo[r], hi, sel[r]);
+          acc[r] = __fadd_rn(acc[r], __fmul_rn(byte_to_float(b4[r], 0), w[0]));
+        }
+#pragma unroll
+        for (int e = 1; e < 4; ++e)
+          if (4 * m + e < n) {
+#pragma unroll
+            for (int r = 0; r < kRowsPerThread; ++r) acc[r] = __fmaf_rn(byte_to_float(b4[r], e), w[e], acc[r]);
+          }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r)
+      if (rbase + r < rows) dst[static_cast<long long>(rbase + r) * cw + oc] = acc[r];
+  }
+}
+
 // pass 2: H axis + round + normalise.  One thread per output pixel x 4 consecutive output rows would re-read taps; the
 // intermediate is L2-resident, so one thread per pixel (lanes = consecutive columns, weights broadcast) is enough.
 // out_u8 [B,3,T,ch,cw] (may be NULL), out_f32 [B,3,T,ch,cw] (may be NULL)
@@ -356,6 +495,7 @@ resize_cols_kernel(const float* __restrict__ inter, const int32_t* __restrict__ 
 struct ViewPlan {
   int oh, ow, cy, cx, ch, cw;
   int taps_x, taps_y, ry0, Hr;
+  int variant;            // W-axis kernel (2, 3 or 4)
   int R;                  // source rows per pass-1 CTA
   size_t smem;            // dynamic shared memory of pass 1
   long long planes, chunk_planes;
@@ -387,10 +527,16 @@ int make_plan(ViewPlan* p, int B, int T, int Hs, int Ws, int out_h, int out_w, i
   p->ry0 = x0;
   axis_window(gy, Hs, crop_y + crop_h - 1, &x0, &n, &c);
   p->Hr = std::max(x0 + n - p->ry0, 1);  // windows move monotonically: the last output row ends the range
-  const size_t row_bytes = static_cast<size_t>(Ws) * 4;
-  KVQ_REQUIRE(row_bytes * kRowsPerThread + 16 <= kRowTileMaxBytes, KVQ_ERR_BAD_SHAPE,
+  // W-axis kernel: 2 = float32 rows in shared memory, 3 = paired rows (when the launch finds whole aligned words),
+  // 4 = raw bytes in shared memory (KVQ_VIEWS_VARIANT, tools/views_timing.py)
+  const char* variant = std::getenv("KVQ_VIEWS_VARIANT");
+  p->variant = variant ? std::atoi(variant) : kDefaultVariant;
+  if (p->variant < 2 || p->variant > 4) p->variant = kDefaultVariant;
+  const size_t px_bytes = p->variant == 4 ? 1 : 4;  // shared-memory bytes per staged source pixel
+  const size_t row_bytes = static_cast<size_t>(Ws) * px_bytes;
+  KVQ_REQUIRE(row_bytes * kRowsPerThread + 64 <= kRowTileMaxBytes, KVQ_ERR_BAD_SHAPE,
               "resize_view: source rows of %d pixels do not fit the shared-memory row tile", Ws);
-  int R = static_cast<int>(kRowTileBytes / row_bytes) / kRowsPerThread * kRowsPerThread;
+  int R = static_cast<int>((kRowTileBytes / 4 * px_bytes) / row_bytes) / kRowsPerThread * kRowsPerThread;
   R = std::min(std::max(R, kRowsPerThread), 16);
   if (const char* e = std::getenv("KVQ_VIEWS_ROWS")) {  // tuning knob (tools/views_timing.py): source rows per CTA
     const int v = std::atoi(e);
@@ -398,7 +544,7 @@ int make_plan(ViewPlan* p, int B, int T, int Hs, int Ws, int out_h, int out_w, i
   }
   R = std::min(R, (p->Hr + kRowsPerThread - 1) / kRowsPerThread * kRowsPerThread);
   p->R = R;
-  p->smem = static_cast<size_t>(R) * row_bytes + 32;
+  p->smem = static_cast<size_t>(R) * row_bytes + 64;  // + alignment head / look-ahead vector
   p->planes = static_cast<long long>(B) * 3 * T;
   const size_t plane_bytes = static_cast<size_t>(p->Hr) * crop_w * 4;
   p->chunk_planes = std::min<long long>(p->planes, std::max<long long>(1, static_cast<long long>(kChunkBytes / plane_bytes)));
@@ -476,14 +622,14 @@ int kvq_resize_view_u8(const uint8_t* frames, int layout, int B, int T, int Hs, 
   aa_tables_kernel<<<(out_h + 127) / 128, 128, 0, stream>>>(Hs, out_h, ymin, ysize, wy);
   count_launch();
   KVQ_CUDA(cudaGetLastError());
-  // rows of whole aligned words take the paired-row kernel (KVQ_VIEWS_VARIANT=2 forces the generic one)
-  const char* variant = std::getenv("KVQ_VIEWS_VARIANT");
-  const int want = variant ? std::atoi(variant) : kDefaultVariant;
-  const bool paired = want == 3 && Ws % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 3) == 0;
+  const bool bytes = p.variant == 4;
+  const bool paired = p.variant == 3 && Ws % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 3) == 0;
   if (p.smem > (48u << 10)) {
     KVQ_CUDA(cudaFuncSetAttribute(resize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kRowTileMaxBytes + 64)));
     KVQ_CUDA(cudaFuncSetAttribute(resize_rows_paired_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kRowTileMaxBytes + 64)));
+    KVQ_CUDA(cudaFuncSetAttribute(resize_rows_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kRowTileMaxBytes + 64)));
   }
   const int tiles = (p.Hr + p.R - 1) / p.R;
@@ -495,7 +641,11 @@ int kvq_resize_view_u8(const uint8_t* frames, int layout, int B, int T, int Hs, 
     const long long total = np * p.ch * p.cw;
     const long long g2 = (total + 255) / 256;
     KVQ_REQUIRE(g1 < (1ll << 31) && g2 < (1ll << 31), KVQ_ERR_BAD_SHAPE, "resize_view: grid too large");
-    if (paired)
+    if (bytes)
+      resize_rows_bytes_kernel<<<static_cast<unsigned>(g1), 256, p.smem, stream>>>(
+          frames, inter, xmin, xsize, wx, layout, T, Hs, Ws, p.ow, p.cx, p.cw, p.ry0, p.Hr, p.R, tiles,
+          static_cast<int>(plane0));
+    else if (paired)
       resize_rows_paired_kernel<<<static_cast<unsigned>(g1), 256, p.smem, stream>>>(
           frames, inter, xmin, xsize, wx, layout, T, Hs, Ws, p.ow, p.cx, p.cw, p.ry0, p.Hr, p.R, tiles,
           static_cast<int>(plane0));

@@ -86,16 +86,19 @@ def test_views_match_oracle_seeded(B, T, Hs, Ws, oh, ow, crop):
         np.testing.assert_array_equal(u8.cpu().numpy(), frames.permute(0, 2, 1, 3, 4).numpy())
 
 
-@pytest.mark.parametrize("variant", ["2", "3"])
+@pytest.mark.parametrize("variant", ["2", "3", "4"])
 @pytest.mark.parametrize("B,T,Hs,Ws,oh,ow,crop", [
     (1, 2, 135, 240, 112, 112, None),            # odd row count: the last row pair of a tile is half empty
     (2, 1, 37, 64, 20, 24, (3, 2, 15, 20)),      # tiles of one, two and three rows; crop window
     (1, 1, 50, 1920, 9, 112, None),              # decoder-wide rows, 37-tap windows, 8-row tiles
     (1, 2, 30, 44, 45, 66, None),                # enlargement (3 taps: the fused tail only)
+    (1, 3, 21, 75, 10, 15, None),                # odd width: every row starts at another byte phase; 11-tap windows
+    (2, 2, 19, 17, 7, 1, None),                  # one output column: the window is the whole 17-byte row
 ])
 def test_views_row_kernels_agree_with_oracle(variant, B, T, Hs, Ws, oh, ow, crop, monkeypatch):
-    """Both W-axis kernels (KVQ_VIEWS_VARIANT=2: generic rows; 3: paired rows + packed fp32x2, rows of whole words) give
-    the oracle's bytes and floats; KVQ_VIEWS_ROWS changes the tile height only."""
+    """All W-axis kernels (KVQ_VIEWS_VARIANT=2: float32 rows in shared memory; 3: paired rows + packed fp32x2, rows of
+    whole words; 4: raw bytes in shared memory, four taps per shared load) give the oracle's bytes and floats;
+    KVQ_VIEWS_ROWS changes the tile height only."""
     from kvq_b200 import ops
     from oracle import views as O
     monkeypatch.setenv("KVQ_VIEWS_VARIANT", variant)

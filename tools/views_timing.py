@@ -22,8 +22,8 @@ def main():
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     alg = B * 96 * (1080 * 1920 + 112 * 112 * 4)
     ref = None
-    for variant in ("2", "3"):
-        for rows in ("4", "8", "12", "16"):
+    for variant in ("2", "3", "4"):
+        for rows in ("4", "8", "16", "32"):
             os.environ["KVQ_VIEWS_VARIANT"], os.environ["KVQ_VIEWS_ROWS"] = variant, rows
 
             def call():
