@@ -30,7 +30,7 @@ namespace kvq {
 namespace {
 
 constexpr int kRowsPerThread = 4;
-constexpr int kDefaultVariant = 2;  // 2 = resize_rows_kernel, 3 = resize_rows_paired_kernel when eligible, 4 = resize_rows_bytes_kernel
+constexpr int kDefaultVariant = 4;  // 2 = resize_rows_kernel, 3 = resize_rows_paired_kernel when eligible, 4 = resize_rows_bytes_kernel
 constexpr size_t kChunkBytes = 32u << 20;
 constexpr size_t kRowTileBytes = 64u << 10;
 constexpr size_t kRowTileMaxBytes = 200u << 10;
@@ -536,7 +536,9 @@ int make_plan(ViewPlan* p, int B, int T, int Hs, int Ws, int out_h, int out_w, i
   const size_t row_bytes = static_cast<size_t>(Ws) * px_bytes;
   KVQ_REQUIRE(row_bytes * kRowsPerThread + 64 <= kRowTileMaxBytes, KVQ_ERR_BAD_SHAPE,
               "resize_view: source rows of %d pixels do not fit the shared-memory row tile", Ws);
-  int R = static_cast<int>((kRowTileBytes / 4 * px_bytes) / row_bytes) / kRowsPerThread * kRowsPerThread;
+  // tile budget: 64 KB of float32 rows (3 CTAs per SM) or 32 KB of raw bytes (measured sweep, tools/views_timing.py)
+  const size_t tile_budget = p->variant == 4 ? (32u << 10) : kRowTileBytes;
+  int R = static_cast<int>(tile_budget / row_bytes) / kRowsPerThread * kRowsPerThread;
   R = std::min(std::max(R, kRowsPerThread), 16);
   if (const char* e = std::getenv("KVQ_VIEWS_ROWS")) {  // tuning knob (tools/views_timing.py): source rows per CTA
     const int v = std::atoi(e);
