@@ -502,9 +502,13 @@ def run_views(args):
         planes = B * 3 * T
         alg = planes * (Hs * Ws + 112 * 112 * 4)
         achieved = alg / (ms_resize / args.steps * 1e-3) / 1e9
-        roof = {"kernel": "resize_rows_kernel + resize_cols_kernel (one kvq_resize_view_u8 call, chunks of 66 planes)",
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (resize_rows_bytes_kernel, 77 % of
+        # the call) per 69-plane launch from the ncu --set full capture in profiles/r01_views_ncu_full_bytes_kernel.csv
+        # (143.1 MB read = the algorithmic source bytes of 69 planes, 20.7 MB of the L2-resident intermediate written back)
+        roof = {"kernel": "one kvq_resize_view_u8 call = chunks of <= 69 planes x (resize_rows_bytes_kernel + "
+                          "resize_cols_kernel) + 2 aa_tables_kernel",
                 "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "avg_launch_ms": ms_resize / args.steps,
+                "frac": achieved / pk["hbm_gbs"], "traffic": 163.8e6, "avg_launch_ms": ms_resize / args.steps,
                 "peak_source": pk["src"] + " copy bandwidth (MEASURED_PEAKS.json)",
                 "algorithmic": f"{Hs * Ws} B u8 read + {112 * 112 * 4} B f32 written per plane x {planes} planes per call"}
         cpu, delta = None, None
