@@ -11,13 +11,18 @@
 // and restated in oracle/views.py, which is pinned to goldens of the real reference).
 //
 // Byte work bound by HBM: algorithmic bytes per source plane = Hs*Ws (u8 read) + oh*ow*4 (f32 write) [+ oh*ow u8].
-//   pass 0  aa_tables_kernel   per-axis tap windows and normalised triangle weights, computed on the device (no host
-//                              upload, graph-capturable); ~2 us
-//   pass 1  resize_rows_kernel u8 rows -> f32 [planes, rows needed by the crop, cropped columns]; a CTA stages R whole
-//                              source rows in shared memory as f32 (coalesced 4 B loads, conflict-free float4 stores),
-//                              one thread per output column x 4 rows walks its tap window
-//   pass 2  resize_cols_kernel f32 rows -> round -> u8 -> ((v / divisor) - mean[c]) / std[c] with IEEE divisions
+//   pass 0  aa_tables_kernel          per-axis tap windows and normalised triangle weights, computed on the device (no
+//                                     host upload, graph-capturable); ~6 us
+//   pass 1  resize_rows_bytes_kernel  W axis: u8 rows -> f32 [planes, rows needed by the crop, cropped columns].  A CTA
+//                                     copies R whole source rows into shared memory as raw bytes (16 B vectors, 8 in flight
+//                                     per thread); one thread per output column x 4 rows walks its tap window, four taps per
+//                                     shared load (PRMT funnel + 2^23 byte->float trick).  Default (KVQ_VIEWS_VARIANT=4).
+//           resize_rows_kernel        the same pass with the rows staged as float32 (variant 2; shared-memory-pipe bound)
+//           resize_rows_paired_kernel variant 2 on float2-interleaved row pairs with packed fp32x2 products (variant 3)
+//   pass 2  resize_cols_kernel        H axis from the intermediate -> round -> u8 -> ((v / divisor) - mean[c]) / std[c]
+//                                     with IEEE divisions
 // Planes are processed in chunks whose float32 intermediate stays L2-resident (32 MB) between pass 1 and pass 2.
+// Measurements and the ncu findings behind the three W-axis kernels: DESIGN.md section 10, profiles/r01_summary.md.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
