@@ -115,6 +115,24 @@ def resized_video(video, size_h=224, size_w=224, **_):
     return resize_u8(video, size_h, size_w)
 
 
+def resize_hw(size_h, size_w, src_h, src_w, arp=False):
+    """get_resize_function (fusion_datasets.py:229-241) as get_resized_video calls it (:247-249): with arp the target
+    ratio is src_h / src_w and the LONGER side is recomputed from the other one (int() truncation)."""
+    ratio = src_h / src_w if arp else 1
+    if ratio > 1:
+        size_h = int(ratio * size_w)
+    elif ratio < 1:
+        size_w = int(size_h / ratio)
+    return size_h, size_w
+
+
+def train_crop_window(resize, crop, rng):
+    """get_resizecrop_video, train phase (fusion_datasets.py:308-311): rows then columns, random.randrange(res - crop)."""
+    y = rng.randrange(resize - crop)
+    x = rng.randrange(resize - crop)
+    return y, x
+
+
 def centre_crop_window(resize, crop):
     """fusion_datasets.py:313-315: rows / columns [resize//2 - crop//2, resize//2 + crop//2)."""
     lo = resize // 2 - crop // 2

@@ -163,6 +163,14 @@ def test_views_error_paths():
         ops.resize_view_u8(frames.cpu(), 8, 8)
 
 
+def test_arp_and_train_crop_match_reference_golden():
+    """get_resized_video(arp=True) and get_resizecrop_video(phase='train') of the REAL reference (views_geometry.npz)
+    through the C ABI; the same body runs on CPU with an oracle-backed kernel (tests/test_host_cpu.py)."""
+    from datasets import views as V
+    import views_cases
+    views_cases.check_geometry(V, "cuda")
+
+
 def test_ksvqe_from_raw_frames_matches_cpu_views():
     """Decoded uint8 frames -> (fragment kernel + resize kernel on the device) -> literal KSVQE key, against the same
     network fed with the views the golden-pinned CPU restatements build (oracle/fragments.py, oracle/views.py): the

@@ -231,3 +231,48 @@ def test_view_host_entry_points():
         assert inds.dtype == np.int32
         np.testing.assert_array_equal(inds, g[f"inds_{i}"])
     assert centre_crop_window(520, 448) == (36, 448) and centre_crop_window(91, 45) == O.centre_crop_window(91, 45)
+
+
+def test_view_functions_host_logic_with_oracle_backed_kernel(monkeypatch):
+    """datasets/views.py (target sizes incl. arp, crop windows, train-phase draw order, [3,T,H,W] / [B,3,T,H,W] handling,
+    the fused normalised variants) checked on CPU: ops.resize_view_u8 is replaced by a stand-in built on the golden-pinned
+    oracle, so only the host logic is under test here (the kernel itself is tests/test_gpu_views.py)."""
+    import glob
+    import numpy as np
+    from datasets import views as V
+    from kvq_b200 import ops
+    from oracle import views as O
+    import views_cases
+
+    def fake(frames, out_h, out_w, crop=None, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, divisor=1.0, layout="BT3HW",
+             want_u8=False, want_f32=True, workspace=None):
+        x = frames.numpy()
+        if layout == "BT3HW":
+            x = x.transpose(0, 2, 1, 3, 4)
+        r = O.resize_u8(x, out_h, out_w)
+        if crop is not None:
+            y, x0, h, w = crop
+            r = r[..., y:y + h, x0:x0 + w]
+        u8 = torch.from_numpy(np.ascontiguousarray(r)) if want_u8 else None
+        f32 = torch.from_numpy(np.stack([O.normalise(c, mean, std, divisor) for c in r])) if want_f32 else None
+        return u8, f32
+
+    monkeypatch.setattr(ops, "resize_view_u8", fake)
+    views_cases.check_geometry(V, "cpu")
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "views_resize*.npz"))):
+        g = np.load(path)
+        T, H, W = (int(v) for v in g["shape"])
+        video = views_cases.golden_video(T, H, W, g["seed"])
+        bt3hw = video.permute(1, 0, 2, 3).contiguous().unsqueeze(0)
+        if str(g["kind"]) == "resize":
+            out = V.get_resized_video(video.contiguous(), size_h=int(g["size_h"]), size_w=int(g["size_w"]))
+            norm = V.resized_video_normalised(bt3hw, int(g["size_h"]), int(g["size_w"]))[0]
+        else:
+            out = V.get_resizecrop_video(video.contiguous(), resize=int(g["resize"]), crop=int(g["crop"]), phase="test")
+            norm = V.resizecrop_video_normalised(bt3hw, int(g["resize"]), int(g["crop"]))[0]
+        np.testing.assert_array_equal(out.numpy(), g["out"])
+        np.testing.assert_array_equal(norm.numpy()[:, :, ::7, ::5], g["norm_sample"])
+    with pytest.raises(NotImplementedError):
+        V.get_resized_video(torch.zeros((3, 1, 8, 8), dtype=torch.uint8), random_crop=True)
+    with pytest.raises(RuntimeError, match="uint8"):
+        V.get_resized_video(torch.zeros((1, 8, 8), dtype=torch.uint8))

@@ -63,3 +63,23 @@ def test_aa_weights_properties():
     xmin, xsize, w = views.aa_weights(9, 9)                          # identity resize: one tap of weight 1 ... or 3 taps
     ident = views.interpolate_bilinear_aa(np.arange(81, dtype=np.float32).reshape(9, 9), 9, 9)
     np.testing.assert_array_equal(ident, np.arange(81, dtype=np.float32).reshape(9, 9))
+
+
+def test_arp_and_train_crop_match_reference_golden():
+    """get_resized_video(arp=True) (aspect-ratio-preserving target size, fusion_datasets.py:229-241) and
+    get_resizecrop_video(phase='train') (random.randrange rows, then columns, :308-311) of the REAL reference."""
+    import random
+    g = np.load(os.path.join(GOLDEN, "views_geometry.npz"))
+    for i, (T, H, W, sh, sw, seed) in enumerate(g["arp_cases"]):
+        gen = torch.Generator().manual_seed(int(seed))
+        video = torch.randint(0, 256, (int(T), int(H), int(W), 3), generator=gen, dtype=torch.uint8).permute(3, 0, 1, 2)
+        oh, ow = views.resize_hw(int(sh), int(sw), int(H), int(W), arp=True)
+        np.testing.assert_array_equal(views.resize_u8(video.numpy(), oh, ow), g[f"arp_out_{i}"])
+    for i, (T, H, W, rs, cr, seed, rseed) in enumerate(g["train_cases"]):
+        gen = torch.Generator().manual_seed(int(seed))
+        video = torch.randint(0, 256, (int(T), int(H), int(W), 3), generator=gen, dtype=torch.uint8).permute(3, 0, 1, 2)
+        random.seed(int(rseed))
+        y, x = views.train_crop_window(int(rs), int(cr), random)
+        assert [y, x] == g[f"train_yx_{i}"].tolist()
+        np.testing.assert_array_equal(views.resize_u8(video.numpy(), int(rs), int(rs))[..., y:y + int(cr), x:x + int(cr)],
+                                      g[f"train_out_{i}"])

@@ -37,6 +37,12 @@ SAMPLER_CASES = [
 ]
 
 
+# get_resized_video(arp=True): (T, H, W, size_h, size_w, seed);  get_resizecrop_video(phase='train'): (T, H, W, resize, crop,
+# frame seed, `random` seed)
+ARP_CASES = [(2, 60, 90, 32, 32, 81), (2, 90, 60, 32, 32, 82), (1, 50, 50, 24, 40, 83), (1, 1080 // 8, 608 // 8, 28, 28, 84)]
+TRAIN_CROP_CASES = [(2, 70, 110, 40, 28, 91, 5), (1, 64, 64, 33, 20, 92, 6), (2, 40, 30, 48, 47, 93, 7)]
+
+
 def seeded_frames(T, H, W, seed):
     """decord-like frames [T,H,W,3] u8 stacked and permuted exactly as spatial_temporal_view_decomposition does."""
     g = torch.Generator().manual_seed(seed)
@@ -82,6 +88,27 @@ def main():
                             norm_sha256=np.array(sha(n)), norm_sample=n[:, :, ::7, ::5], kind=np.array(kind),
                             shape=np.array([T, H, W]), seed=seed, **{k: np.array(v) for k, v in kw.items()})
         print(name, tuple(out.shape), "mean", float(o.mean()), "float32 interpolate bit-exact, u8 exact, norm exact")
+    import random
+    geo = {"arp_cases": np.array(ARP_CASES), "train_cases": np.array(TRAIN_CROP_CASES)}
+    for i, (T, H, W, sh, sw, seed) in enumerate(ARP_CASES):
+        video = seeded_frames(T, H, W, seed)
+        out = fd.get_resized_video(video, size_h=sh, size_w=sw, arp=True).contiguous().numpy()
+        oh, ow = views.resize_hw(sh, sw, H, W, arp=True)
+        assert out.shape[-2:] == (oh, ow), (out.shape, oh, ow)
+        assert np.array_equal(out, views.resize_u8(video.numpy(), oh, ow))
+        geo[f"arp_out_{i}"] = out
+        print("arp", (T, H, W, sh, sw), "->", out.shape)
+    for i, (T, H, W, rs, cr, seed, rseed) in enumerate(TRAIN_CROP_CASES):
+        video = seeded_frames(T, H, W, seed)
+        random.seed(rseed)
+        out = fd.get_resizecrop_video(video, resize=rs, crop=cr, phase="train").contiguous().numpy()
+        random.seed(rseed)
+        y, x = views.train_crop_window(rs, cr, random)
+        assert np.array_equal(out, views.resize_u8(video.numpy(), rs, rs)[..., y:y + cr, x:x + cr])
+        geo[f"train_out_{i}"] = out
+        geo[f"train_yx_{i}"] = np.array([y, x])
+        print("train crop", (T, H, W, rs, cr), "window", (y, x), "->", out.shape)
+    np.savez_compressed(os.path.join(GOLD, "views_geometry.npz"), **geo)
     rows = []
     for fsize_t, fragments_t, interval, num_clips, total, seed in SAMPLER_CASES:
         sampler = fd.UnifiedFrameSampler(fsize_t, fragments_t, interval, num_clips)
