@@ -276,3 +276,24 @@ def test_view_functions_host_logic_with_oracle_backed_kernel(monkeypatch):
         V.get_resized_video(torch.zeros((3, 1, 8, 8), dtype=torch.uint8), random_crop=True)
     with pytest.raises(RuntimeError, match="uint8"):
         V.get_resized_video(torch.zeros((1, 8, 8), dtype=torch.uint8))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, no
+    CUDA needed; under torchrun only rank 0 prints.  The view-pipeline workload keeps the run to a few seconds."""
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "views", "--steps", "1",
+           "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="0"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["steps"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"] and "model" not in d["config"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
