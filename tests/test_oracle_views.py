@@ -83,3 +83,63 @@ def test_arp_and_train_crop_match_reference_golden():
         assert [y, x] == g[f"train_yx_{i}"].tolist()
         np.testing.assert_array_equal(views.resize_u8(video.numpy(), int(rs), int(rs))[..., y:y + int(cr), x:x + int(cr)],
                                       g[f"train_out_{i}"])
+
+
+def _byte_perm(lo, hi, sel):
+    b = [(lo >> (8 * i)) & 255 for i in range(4)] + [(hi >> (8 * i)) & 255 for i in range(4)]
+    return sum(b[(sel >> (4 * e)) & 7] << (8 * e) for e in range(4))
+
+
+def _emulate_rows_bytes_kernel(tile, head, out_w):
+    """Python walk of resize_rows_bytes_kernel (csrc/kvq_views.cu): raw bytes at a 16 B phase `head` in shared memory,
+    aligned word pairs funnelled by PRMT, taps taken four at a time in three rounding regimes (product; 4*((n-1)//4)
+    rounded product + rounded add; fused tail)."""
+    F = np.float32
+    rows, Ws = tile.shape
+    xmin, xsize, wts = views.aa_weights(Ws, out_w)
+    nbytes = rows * Ws
+    nvec = (head + nbytes + 15) >> 4
+    sb = np.zeros((nvec + 1) * 16, np.uint8)
+    sb[head:head + nbytes] = tile.reshape(-1)
+    sw = sb.view("<u4")
+    fma = lambda t, v, w: F(np.float64(t) + np.float64(v) * np.float64(w))
+    out = np.zeros((rows, out_w), F)
+    for r in range(rows):
+        for o in range(out_w):
+            n, x0 = int(xsize[o]), int(xmin[o])
+            bo = head + r * Ws + x0
+            wi, sel = bo >> 2, 0x3210 + 0x1111 * (bo & 3)
+            m = (n - 1) >> 2
+            b4 = _byte_perm(int(sw[wi]), int(sw[wi + 1]), sel)
+            byte = lambda e: F((b4 >> (8 * e)) & 255)
+            acc = F(byte(0) * wts[o, 0])
+            if m == 0:
+                for e in range(1, 4):
+                    if e < n:
+                        acc = fma(acc, byte(e), wts[o, e])
+            else:
+                for e in range(1, 4):
+                    acc = F(acc + F(byte(e) * wts[o, e]))
+                for g in range(1, m):
+                    b4 = _byte_perm(int(sw[wi + g]), int(sw[wi + g + 1]), sel)
+                    for e in range(4):
+                        acc = F(acc + F(byte(e) * wts[o, 4 * g + e]))
+                b4 = _byte_perm(int(sw[wi + m]), int(sw[wi + m + 1]), sel)
+                acc = F(acc + F(byte(0) * wts[o, 4 * m]))
+                for e in range(1, 4):
+                    if 4 * m + e < n:
+                        acc = fma(acc, byte(e), wts[o, 4 * m + e])
+            out[r, o] = acc
+    return out
+
+
+@pytest.mark.parametrize("rows,Ws,out_w,head", [(5, 75, 15, 3), (4, 64, 24, 0), (3, 17, 1, 9), (6, 44, 66, 15),
+                                               (2, 240, 14, 7), (3, 100, 33, 1), (2, 37, 37, 2)])
+def test_byte_funnel_tap_order_equals_oracle(rows, Ws, out_w, head):
+    """The index / funnel / rounding-regime logic of the default W-axis kernel, walked in Python, gives the oracle's
+    float32 bits for any byte phase of the tile and of the rows (the kernel itself: tests/test_gpu_views.py)."""
+    rng = np.random.default_rng(rows * 1000 + Ws)
+    tile = rng.integers(0, 256, (rows, Ws), dtype=np.uint8)
+    ref = views.reduce_last_axis(tile.astype(np.float32), out_w)
+    got = _emulate_rows_bytes_kernel(tile, head, out_w)
+    np.testing.assert_array_equal(ref.view(np.uint32), got.view(np.uint32))
