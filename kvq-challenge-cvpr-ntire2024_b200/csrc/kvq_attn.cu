@@ -777,7 +777,8 @@ int debug_attn_timers(unsigned long long* out16, int reset) {
 }
 
 int attn_table_len(int bd, int bh, int bw) {
-  return compact_len(bd, bh, bw) + (is_fast_window(bd, bh, bw) ? FAST_TAB_LEN : 0);
+  // float2 entries per head: compact | conflict-free fast layout | paired float4 layout (two float2 per entry)
+  return compact_len(bd, bh, bw) + (is_fast_window(bd, bh, bw) ? FAST_TAB_LEN + 2 * ATT3_PAIR_LEN : 0);
 }
 
 float attn_qscale() { return 0.17677669529663687f * LOG2E; }  // head_dim^-0.5 (:191), log2 domain
@@ -794,11 +795,14 @@ int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, in
   const int n = heads * (Lp + (fast ? FAST_TAB_LEN : 0));
   pack_bias_kernel<<<(n + 255) / 256, 256, 0, stream>>>(rel, frag, reinterpret_cast<float2*>(out), L, Lp, heads, fast);
   count_launch();
-  return check_cuda(cudaGetLastError(), "pack_bias_kernel launch");
+  KVQ_CUDA(cudaGetLastError());
+  if (fast) return launch_pack_bias_pair(rel, frag, out + static_cast<size_t>(n) * 2, heads, stream);
+  return KVQ_OK;
 }
 
 static int resolve_variant(int variant) {
-  // 5 (default) = two-CTA flash-style kernel (kvq_attn2.cu) for full (8,7,7) windows; tuning knob
+  // 6 = third generation (kvq_attn3.cu: one-pass softmax, three tile slots per SM) for full (8,7,7) windows;
+  // 5 = two-CTA flash-style kernel (kvq_attn2.cu); tuning knob
   // KVQ_ATTN_VARIANT: 1 = first-generation persistent kernel, 2 = generic kernel everywhere
   if (variant != 0) return variant;
   static int env_variant = -1;
@@ -816,7 +820,9 @@ static bool full_window(const WinGeom& g, const int base_win[3]) {
 }
 
 int window_attn_pitch(const WinGeom& g, const int base_win[3], int variant) {
-  return (resolve_variant(variant) == 5 && full_window(g, base_win)) ? ATT2_PITCH : ATT_SLAB;
+  const int v = resolve_variant(variant);
+  if (!full_window(g, base_win)) return ATT_SLAB;
+  return v == 6 ? ATT3_PITCH : v == 5 ? ATT2_PITCH : ATT_SLAB;
 }
 
 int launch_window_attn(const AttnParams& p_in, cudaStream_t stream) {
@@ -825,6 +831,7 @@ int launch_window_attn(const AttnParams& p_in, cudaStream_t stream) {
   const WinGeom& g = p.geom;
   {
     const int bw[3] = {p.base_wd, p.base_wh, p.base_ww};
+    if (p.variant == 6 && full_window(g, bw) && p.heads <= num_sms()) return launch_window_attn3(p, stream);
     if (p.variant == 5 && full_window(g, bw) && 2 * p.heads <= 2 * num_sms()) return launch_window_attn2(p, stream);
   }
   KVQ_REQUIRE(p.C == p.heads * ATT_HD, KVQ_ERR_BAD_SHAPE, "attn: C=%d must be heads(%d) x 32", p.C, p.heads);

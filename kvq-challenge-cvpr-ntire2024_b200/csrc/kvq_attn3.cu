@@ -1,0 +1,564 @@
+// Fused 3-D window attention, third generation for the (8,7,7) window (WindowAttention3D.forward,
+// swin_backbone.py:245-326; compute_mask :560-586; global_position_index :22-50).
+//
+// The second generation (kvq_attn2.cu) was latency-bound in its scalar softmax path: two TMEM round trips per logit,
+// MMA and softmax serialised inside a CTA, eight softmax warps per SM.  This kernel is organised around the per-logit
+// instruction count instead:
+//   * ONE persistent CTA per SM, 16 warps: warp 0 loads (cp.async.bulk), warps 1..3 each issue the tcgen05.mma of one
+//     tile slot, warps 4..15 are three softmax warpgroups (one per slot; thread = query row = TMEM lane).
+//     The three slots work on the three 128-row tiles of the same (window, head) unit, sharing its K | V image.
+//   * keys are ordered (h, w, d) with d fastest: slot = h*64 + w*8 + d, one 56-key chunk (+8 zero pad slots) per
+//     window row h.  A chunk is S = Q K_c^T (M128 x N64 x K32), read ONCE into registers; bias, running-max test, exp2
+//     and the fp16 pack all happen there; P_c goes back to TMEM and O += P_c V_c is a TS-form MMA.
+//   * the two temporal neighbours (d = 2k, 2k+1) of a key position sit in adjacent TMEM columns and share the GRPB
+//     gate fg = |dfh| + |dfw| (it does not depend on d), so the bias is ONE LDS.128 + FFMA2 + FADD2 per two logits:
+//     table entry {t0[e], t0[e-1], t1[e], t1[e-1]} with e = d_i - 2k, conflict-free strides (15, 201).
+//   * lazy row max (as in FlashAttention-4): P = exp2(v - m_ref) with m_ref the max of an EARLIER chunk; it is only
+//     raised (and O, L rescaled in TMEM) when a chunk's max exceeds m_ref by more than 8, so P <= 256 in fp16 and
+//     the result is exact up to rounding because the row sum uses the same m_ref.
+//   * the row sum L = sum_j P_j comes from the tensor core as well: one more MMA per K step against an all-ones B
+//     tile (N = 16), so the normalisation uses exactly the fp16 P the PV product saw and costs no CUDA-core work.
+//   * the SW-MSA region mask is folded into QK^T: a third K step contracts [a_d 1 a_h 1 a_w 1] (query region bits,
+//     zeroed for dims this window does not mask) with (-100 log2e / 2) * [(1-2b_d) b_d (1-2b_h) b_h (1-2b_w) b_w]
+//     (key region bits, static); the second 8-half K chunk aliases the first (LBO = 0), hence the factor 1/2.
+//     -100 per differing dim instead of -100 once: exp(-100) and exp(-300) are both 0 next to an unmasked logit.
+//   * the 8 tail rows (384..391) are replicated into all lane groups (SBO = 0, as in the second generation); warp q
+//     takes the chunks c = q (mod 4) and writes zero P elsewhere; the four partial (m, L, O) are merged in smem.
+// TMEM per slot: S 64 | P 32 | O 32 | L 16 = 144 columns, 432 of 512.
+#include <cstdlib>
+
+#include "kvq_common.cuh"
+#include "kvq_kernels.cuh"
+
+namespace kvq {
+
+namespace {
+
+constexpr int A3_THREADS = 512;
+constexpr int NSLOT = 3;
+constexpr int NCHUNK3 = 7;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float TAU = 8.0f;                       // lazy-max slack (log2 units): P <= 2^TAU
+
+// shared memory map (bytes)
+constexpr int S3_TAB = 0;
+constexpr int S3_TAB_BYTES = (ATT3_PAIR_LEN * 16 + 255) / 256 * 256;        // 45 056
+constexpr int S3_KV = S3_TAB + S3_TAB_BYTES;                               // 2 x (K | V)
+constexpr int S3_Q = S3_KV + 2 * 2 * ATT3_KV_BYTES;                        // 3 slots x 2 x 8192
+constexpr int S3_KAUG = S3_Q + NSLOT * 2 * 8192;                           // 448 x 16
+constexpr int S3_SCR = S3_KAUG + ATT3_KV_ROWS * 16;                        // per slot: Qaug (2048) / tail merge (3264)
+constexpr int SCR_BYTES = 3328;
+constexpr int S3_ONES = S3_SCR + NSLOT * SCR_BYTES;                        // 512
+constexpr int S3_BARS = S3_ONES + 512;                                     // 512
+constexpr int S3_SMEM = S3_BARS + 512 + 128;
+static_assert(S3_SMEM <= 227 * 1024, "attn3 shared memory exceeds the SM");
+
+// TMEM columns of a slot
+constexpr int T3_SLOT = 144, T3_S = 0, T3_P = 64, T3_O = 96, T3_L = 128;
+
+struct Bars3 {
+  uint64_t tab, kv[2], kvfree[2];
+  uint64_t q[NSLOT][2], qfree[NSLOT][2];
+  uint64_t s[NSLOT], sc[NSLOT], p[NSLOT], pv[NSLOT], of[NSLOT], qa[NSLOT];
+  uint32_t tmem_slot;
+};
+static_assert(sizeof(Bars3) <= 512, "Bars3 overflows its slot");
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+template <int REGS>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+// fragment coordinate of window-local row/col k (global_position_index :22-50: nearest-resized fragment index of the
+// rolled position)
+__device__ __forceinline__ float frag_coord(int base, int k, int shift, int size) {
+  int o = base + k + shift;
+  if (o >= size) o -= size;
+  int f = static_cast<int>(floorf(static_cast<float>(o) * (7.0f / static_cast<float>(size))));
+  return static_cast<float>(f > 6 ? 6 : f);
+}
+
+struct UnitInfo {
+  int win_g, wdi, whi, wwi;
+  bool md, mh, mw;     // dims whose SW-MSA region mask applies in this window
+};
+__device__ __forceinline__ UnitInfo unit_info(const AttnParams& p, int unit) {
+  const WinGeom& g = p.geom;
+  UnitInfo u;
+  u.win_g = unit / p.heads;
+  const int win = u.win_g % g.nW;
+  u.wdi = win / (g.nwh * g.nww);
+  u.whi = (win / g.nww) % g.nwh;
+  u.wwi = win % g.nww;
+  u.md = g.sd != 0 && u.wdi == g.nwd - 1;
+  u.mh = g.sh != 0 && u.whi == g.nwh - 1;
+  u.mw = g.sw != 0 && u.wwi == g.nww - 1;
+  return u;
+}
+
+__global__ void __launch_bounds__(A3_THREADS, 1)
+window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int units) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
+  Bars3& bars = *reinterpret_cast<Bars3*>(smem + S3_BARS);
+
+  const WinGeom& g = p.geom;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x;                     // multiple of heads: a CTA keeps one head's table
+  const int head = blockIdx.x % p.heads;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(p.img);
+
+  if (tid == 0) {
+    mbar_init(&bars.tab, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.kv[i], 1);
+      mbar_init(&bars.kvfree[i], NSLOT);
+    }
+    for (int s = 0; s < NSLOT; ++s) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars.q[s][i], 1);
+        mbar_init(&bars.qfree[s][i], 1);
+      }
+      mbar_init(&bars.s[s], 1);
+      mbar_init(&bars.sc[s], 4);
+      mbar_init(&bars.p[s], 4);
+      mbar_init(&bars.pv[s], 1);
+      mbar_init(&bars.of[s], 4);
+      mbar_init(&bars.qa[s], 4);
+    }
+    mbar_fence_init();
+    // the bias table is a weight: fetch it while the previous kernel (the QKV GEMM) may still be draining
+    mbar_expect_tx(&bars.tab, ATT3_PAIR_LEN * 16);
+    bulk_load_1d(smem + S3_TAB, tabs + static_cast<size_t>(head) * ATT3_PAIR_LEN, ATT3_PAIR_LEN * 16, &bars.tab);
+  }
+  // static operands: all-ones B tile of the row-sum MMA, key side of the folded region mask
+  if (tid < 128) reinterpret_cast<uint32_t*>(smem + S3_ONES)[tid] = 0x3C003C00u;   // half2(1, 1)
+  for (int r = tid; r < ATT3_KV_ROWS; r += A3_THREADS) {
+    const int hj = r >> 6, wj = (r >> 3) & 7, dj = r & 7;
+    const float mh = -50.0f * LOG2E;           // half of -100 log2(e): the aliased second K chunk doubles it
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (wj < 7) {
+      const float bd = dj >= 4 ? 1.f : 0.f, bh = hj >= 4 ? 1.f : 0.f, bw = wj >= 4 ? 1.f : 0.f;
+      v[0] = mh * (1.f - 2.f * bd); v[1] = mh * bd;
+      v[2] = mh * (1.f - 2.f * bh); v[3] = mh * bh;
+      v[4] = mh * (1.f - 2.f * bw); v[5] = mh * bw;
+    }
+    uint4 w;
+    w.x = pack_half2(v[0], v[1]); w.y = pack_half2(v[2], v[3]); w.z = pack_half2(v[4], v[5]); w.w = 0u;
+    *reinterpret_cast<uint4*>(smem + S3_KAUG + r * 16) = w;
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) {
+    tmem_alloc(&bars.tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_slot;
+  if (tmem_base != 0) {   // one CTA per SM owns all 512 columns: the MMA issuers rely on base 0 (uniform operands)
+    if (tid == 0) printf("kvq attn3: unexpected TMEM base %u\n", tmem_base);
+    __trap();
+  }
+  pdl_wait();   // the operand images are the previous kernel's output; nothing is written before this point
+
+  const int n_units = (units - static_cast<int>(blockIdx.x) + G - 1) / G;   // units of this CTA: blockIdx.x + n*G
+
+  if (warp < 4) {
+    reg_dec<64>();
+    if (warp == 0) {
+      // =============================== loader ===============================
+      if (lane == 0) {
+        uint32_t k_item[NSLOT] = {0, 0, 0};
+        for (int n = 0; n < n_units; ++n) {
+          const int unit = blockIdx.x + n * G;
+          const uint8_t* src = img + static_cast<size_t>(unit) * ATT3_UNIT_BYTES;
+          const int b = n & 1;
+          if (n >= 2) mbar_wait(&bars.kvfree[b], ((n >> 1) - 1) & 1);
+          mbar_expect_tx(&bars.kv[b], 2 * ATT3_KV_BYTES);
+          bulk_load_1d(smem + S3_KV + b * 2 * ATT3_KV_BYTES, src + ATT_IMG_BYTES, 2 * ATT3_KV_BYTES, &bars.kv[b]);
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s) {
+            const int items = (n % NSLOT == s) ? 2 : 1;
+            for (int it = 0; it < items; ++it) {
+              const uint32_t k = k_item[s]++;
+              const int qb = k & 1;
+              if (k >= 2) mbar_wait(&bars.qfree[s][qb], ((k >> 1) - 1) & 1);
+              uint8_t* dst = smem + S3_Q + (s * 2 + qb) * 8192;
+              if (it == 0) {
+                mbar_expect_tx(&bars.q[s][qb], 8192);
+                bulk_load_1d(dst, src + s * 8192, 8192, &bars.q[s][qb]);
+              } else {   // the 8 tail rows: one 512 B row group; the MMA descriptor replicates it with SBO = 0
+                mbar_expect_tx(&bars.q[s][qb], 512);
+                bulk_load_1d(dst, src + 48 * 512, 512, &bars.q[s][qb]);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      // =============================== MMA issuer of slot `warp - 1` ===============================
+      // The whole warp runs this loop with warp-uniform control flow and operands (TMEM base 0: this CTA owns all 512
+      // columns; descriptors derived from uniform shared-memory offsets and loop counters), one elected lane issues:
+      // ptxas then keeps the descriptors in uniform registers and a small MMA costs ~20-75 cycles of issue instead of
+      // the ~130 of a per-lane R2UR waterfall (tools/ubench/mma_lat.cu).
+      const int s = warp - 1;
+      const uint32_t tS = s * T3_SLOT + T3_S, tP = s * T3_SLOT + T3_P;
+      const uint32_t tO = s * T3_SLOT + T3_O, tL = s * T3_SLOT + T3_L;
+      const uint32_t sbase = smem_u32(smem);
+      const uint32_t aOnes = sbase + S3_ONES, aKaug = sbase + S3_KAUG;
+      const uint32_t aQaug = sbase + S3_SCR + s * SCR_BYTES;
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 64, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, 32, 0, 1);
+      constexpr uint32_t idesc_l = umma_idesc_f16(128, 16, 0, 1);
+      const uint64_t d_ones = umma_smem_desc(aOnes, 256, 128, UMMA_SW_NONE);
+      auto wait_all = [&](uint64_t* bar, uint32_t parity) {   // one lane polls, the warp follows
+        if (lane == 0) mbar_wait(bar, parity);
+        __syncwarp();
+      };
+      uint32_t gc = 0, k = 0, n_qa = 0;
+      for (int n = 0; n < n_units; ++n) {
+        const int unit = blockIdx.x + n * G;
+        const UnitInfo u = unit_info(p, unit);
+        const bool masked = u.md || u.mh || u.mw;
+        const int b = n & 1;
+        const uint32_t aK = sbase + S3_KV + b * 2 * ATT3_KV_BYTES, aV = aK + ATT3_KV_BYTES;
+        wait_all(&bars.kv[b], (n >> 1) & 1);
+        const int items = (n % NSLOT == s) ? 2 : 1;
+        for (int it = 0; it < items; ++it, ++k) {
+          const bool tail = it == 1;
+          const int qb = k & 1;
+          const uint32_t aQ = sbase + S3_Q + (s * 2 + qb) * 8192;
+          const uint32_t q_sbo = tail ? 0u : 512u, qa_sbo = tail ? 0u : 128u;
+          auto issue_s = [&](int c) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t dq = umma_smem_desc(aQ + ks * 256, 128, q_sbo, UMMA_SW_NONE);
+              const uint64_t dk = umma_smem_desc(aK + c * 4096 + ks * 256, 128, 512, UMMA_SW_NONE);
+              umma_f16_ss(tS, dq, dk, idesc_s, ks);
+            }
+            if (masked) {
+              const uint64_t dq = umma_smem_desc(aQaug, 0, qa_sbo, UMMA_SW_NONE);
+              const uint64_t dk = umma_smem_desc(aKaug + c * 1024, 0, 128, UMMA_SW_NONE);
+              umma_f16_ss(tS, dq, dk, idesc_s, 1u);
+            }
+            umma_commit(&bars.s[s]);
+          };
+          wait_all(&bars.q[s][qb], (k >> 1) & 1);
+          if (masked) {
+            wait_all(&bars.qa[s], n_qa & 1);
+            ++n_qa;
+          }
+          tc_fence_after();
+          if (elect_one()) issue_s(0);
+          __syncwarp();
+#pragma unroll 1
+          for (int c = 0; c < NCHUNK3; ++c, ++gc) {
+            wait_all(&bars.sc[s], gc & 1);             // S_c is in registers: its columns may be overwritten
+            tc_fence_after();
+            if (elect_one()) {
+              if (c + 1 < NCHUNK3) issue_s(c + 1);
+              else umma_commit(&bars.qfree[s][qb]);    // every S MMA of this item has read the Q tile
+            }
+            __syncwarp();
+            wait_all(&bars.p[s], gc & 1);              // P_c written
+            if (c == 0 && k > 0) wait_all(&bars.of[s], (k - 1) & 1);   // previous item's O / L were read
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t acc0 = c > 0 ? 1u : 0u;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t dv = umma_smem_desc(aV + (c * 4 + ks) * 1024, 512, 128, UMMA_SW_NONE);
+                umma_f16_ts(tO, tP + 8 * ks, dv, idesc_pv, ks > 0 ? 1u : acc0);
+                umma_f16_ts(tL, tP + 8 * ks, d_ones, idesc_l, ks > 0 ? 1u : acc0);
+              }
+              umma_commit(&bars.pv[s]);
+            }
+            __syncwarp();
+          }
+        }
+        if (elect_one()) umma_commit(&bars.kvfree[b]);   // all MMAs of this slot on unit n are complete
+        __syncwarp();
+      }
+    }
+  } else {
+    reg_inc<144>();
+    // =============================== softmax warps: one thread per query row ===============================
+    const int s = (warp - 4) >> 2, q = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + s * T3_SLOT + T3_S, tP = tmem_base + lane_off + s * T3_SLOT + T3_P;
+    const uint32_t tO = tmem_base + lane_off + s * T3_SLOT + T3_O, tL = tmem_base + lane_off + s * T3_SLOT + T3_L;
+    uint8_t* scr = smem + S3_SCR + s * SCR_BYTES;
+    const uint32_t stab = smem_u32(smem + S3_TAB);
+    uint32_t gc = 0, k = 0;
+    mbar_wait(&bars.tab, 0);
+    for (int n = 0; n < n_units; ++n) {
+      const int unit = blockIdx.x + n * G;
+      const UnitInfo u = unit_info(p, unit);
+      const bool masked = u.md || u.mh || u.mw;
+      const int items = (n % NSLOT == s) ? 2 : 1;
+#pragma unroll 1
+      for (int it = 0; it < items; ++it, ++k) {
+        const bool tail = it == 1;
+        const int ri = tail ? 384 + (lane & 7) : s * 128 + q * 32 + lane;
+        const int d_i = ri / 49, hw_i = ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
+        if (masked) {
+          // query side of the folded mask: [a_d 1 a_h 1 a_w 1 0 0], a pair zeroed when its dim is not masked here
+          const float ad = d_i >= 4 ? 1.f : 0.f, ah = h_i >= 4 ? 1.f : 0.f, aw = w_i >= 4 ? 1.f : 0.f;
+          uint4 w;
+          w.x = u.md ? pack_half2(ad, 1.f) : 0u;
+          w.y = u.mh ? pack_half2(ah, 1.f) : 0u;
+          w.z = u.mw ? pack_half2(aw, 1.f) : 0u;
+          w.w = 0u;
+          const int row = q * 32 + lane;
+          if (!tail || row < 8) *reinterpret_cast<uint4*>(scr + row * 16) = w;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.qa[s]);
+        }
+        const float fh_i = frag_coord(u.whi * 7, h_i, g.sh, g.Hp), fw_i = frag_coord(u.wwi * 7, w_i, g.sw, g.Wp);
+        float Aw[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) Aw[j] = fabsf(fw_i - frag_coord(u.wwi * 7, j, g.sw, g.Wp));
+        const uint32_t trow0 = stab + 16u * static_cast<uint32_t>((d_i + 6) * ATT3_SD + (h_i + 6) * ATT3_SH + (w_i + 6));
+
+        float m_ref = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK3; ++c, ++gc) {
+          const bool own = !tail || (c & 3) == q;
+          uint32_t r[56];
+          mbar_wait(&bars.s[s], gc & 1);
+          __syncwarp();
+          tc_fence_after();
+          if (own) {
+            tmem_ld_x32(tS, r);
+            tmem_ld_x16(tS + 32, r + 32);
+            tmem_ld_x8(tS + 48, r + 48);
+          }
+          const uint32_t tb = trow0 - 16u * static_cast<uint32_t>(c * ATT3_SH);
+          float4 e[2][4];
+          if (own) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) e[0][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD));
+            tmem_wait_ld();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.sc[s]);     // S_c is in registers (or not needed)
+          if (own) {
+            // ---- bias: v = s + t0 + fg * t1 for the two temporal neighbours at once; chunk max ----
+            const float Ah = fabsf(fh_i - frag_coord(u.whi * 7, c, g.sh, g.Hp));
+            float gmax = -INFINITY;
+#pragma unroll
+            for (int wj = 0; wj < 7; ++wj) {
+              if (wj < 6) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) e[(wj + 1) & 1][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD + wj + 1));
+              }
+              const float2 fg2 = splat2(Ah + Aw[wj]);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const float4 t = e[wj & 1][kk];
+                const int j = wj * 8 + 2 * kk;
+                const float2 v = fadd2(ffma2(fg2, make_float2(t.z, t.w),
+                                             make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]))),
+                                       make_float2(t.x, t.y));
+                gmax = fmax3(gmax, v.x, v.y);
+                r[j] = __float_as_uint(v.x);
+                r[j + 1] = __float_as_uint(v.y);
+              }
+            }
+            // P buffer free / O, L stable: PV of the previous chunk has completed (it was issued a chunk ago)
+            if (gc > 0) mbar_wait(&bars.pv[s], (gc - 1) & 1);
+            tc_fence_after();
+            // ---- lazy row max ----
+            const bool need = gmax > m_ref + TAU;
+            if (__any_sync(0xffffffffu, need)) {
+              const float m_new = need ? gmax : m_ref;
+              if (c > 0) {
+                const float alpha = need ? fast_exp2(m_ref - m_new) : 1.0f;     // 0 while m_ref is still -inf
+                uint32_t o[32], l1[1];
+                tmem_ld_x32(tO, o);
+                tmem_ld_x1(tL, l1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+                l1[0] = __float_as_uint(__uint_as_float(l1[0]) * alpha);
+                tmem_st_x32(tO, o);
+                tmem_st_x1(tL, l1);
+              }
+              m_ref = m_new;
+            }
+            // ---- P = exp2(v - m_ref), fp16 pairs; 8 zero pad slots complete the fourth K step ----
+            const float2 negm2 = splat2(-m_ref);
+            uint32_t h[32];
+#pragma unroll
+            for (int j = 0; j < 28; ++j) {
+              const float2 x = fadd2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), negm2);
+              h[j] = pack_half2(fast_exp2(x.x), fast_exp2(x.y));
+            }
+            h[28] = h[29] = h[30] = h[31] = 0u;
+            tmem_st_x32(tP, h);
+          } else {
+            if (gc > 0) mbar_wait(&bars.pv[s], (gc - 1) & 1);
+            tc_fence_after();
+            uint32_t z[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = 0u;
+            tmem_st_x32(tP, z);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.p[s]);
+        }
+
+        // ---- epilogue: O / L -> global ----
+        mbar_wait(&bars.pv[s], (gc - 1) & 1);
+        __syncwarp();
+        tc_fence_after();
+        uint32_t o[32], l1[1];
+        tmem_ld_x32(tO, o);
+        tmem_ld_x1(tL, l1);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.of[s]);
+        if (!tail) {
+          const float inv = 1.0f / __uint_as_float(l1[0]);
+          __half* dst = p.out + (static_cast<size_t>(u.win_g) * 392 + ri) * p.C + head * ATT_HD;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+            v.y = pack_half2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+            v.z = pack_half2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+            v.w = pack_half2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + j) = v;
+          }
+        } else {
+          // four partial softmaxes per row (one per warp), each against its own m_ref: merge like split-K
+          float* sc = reinterpret_cast<float*>(scr);
+          if (q > 0 && lane < 8) {
+            float* d = sc + ((q - 1) * 8 + lane) * 34;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(o[j]);
+            d[32] = __uint_as_float(l1[0]);
+            d[33] = m_ref;
+          }
+          named_bar_sync(1 + s, 128);
+          if (q == 0 && lane < 8) {
+            float mq[4], wq[4];
+            mq[0] = m_ref;
+#pragma unroll
+            for (int j = 1; j < 4; ++j) mq[j] = sc[((j - 1) * 8 + lane) * 34 + 33];
+            const float M = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wq[j] = fast_exp2(mq[j] - M);
+            float L = wq[0] * __uint_as_float(l1[0]);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) L = fmaf(wq[j], sc[((j - 1) * 8 + lane) * 34 + 32], L);
+            const float inv = 1.0f / L;
+            __half* dst = p.out + (static_cast<size_t>(u.win_g) * 392 + 384 + lane) * p.C + head * ATT_HD;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float a = wq[0] * __uint_as_float(o[j + i]);
+#pragma unroll
+                for (int w = 1; w < 4; ++w) a = fmaf(wq[w], sc[((w - 1) * 8 + lane) * 34 + j + i], a);
+                v[i] = a * inv;
+              }
+              uint4 pk;
+              pk.x = pack_half2(v[0], v[1]);
+              pk.y = pack_half2(v[2], v[3]);
+              pk.z = pack_half2(v[4], v[5]);
+              pk.w = pack_half2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(dst + j) = pk;
+            }
+          }
+          named_bar_sync(1 + s, 128);   // the merge scratch aliases the next masked item's Qaug rows
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// [L, heads] fp32 tables -> paired layout [heads][ATT3_PAIR_LEN] float4 {t0[e], t0[e-1], t1[e], t1[e-1]} (log2 domain),
+// index (e + 6) * SD + (dh + 6) * SH + (dw + 6), e in [-6, 7], bias = t0 + fg * t1
+__global__ void pack_bias_pair_kernel(const float* __restrict__ rel, const float* __restrict__ frag,
+                                      float4* __restrict__ out, int heads) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= heads * ATT3_PAIR_LEN) return;
+  const int h = i / ATT3_PAIR_LEN, f = i - h * ATT3_PAIR_LEN;
+  const int ee = f / ATT3_SD, rem = f - ee * ATT3_SD, dh = rem / ATT3_SH, dw = rem - dh * ATT3_SH;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ee < 14 && dh < 13 && dw < 13) {
+    // relative_position_index (:214-231): (dd + 7) * 169 + (dh + 6) * 13 + (dw + 6) with d = query - key
+    const int ia = (ee + 1) * 169 + dh * 13 + dw;    // dd = e      = ee - 6
+    const int ib = ee * 169 + dh * 13 + dw;          // dd = e - 1
+    const float ra = rel[ia * heads + h], rb = rel[ib * heads + h];
+    if (frag != nullptr) {
+      const float fa = frag[ia * heads + h], fb = frag[ib * heads + h];
+      v = make_float4(fa * LOG2E, fb * LOG2E, (ra - fa) * LOG2E, (rb - fb) * LOG2E);
+    } else {
+      v = make_float4(ra * LOG2E, rb * LOG2E, 0.f, 0.f);
+    }
+  }
+  out[i] = v;
+}
+
+}  // namespace
+
+int launch_pack_bias_pair(const float* rel, const float* frag, float* out, int heads, cudaStream_t stream) {
+  const int n = heads * ATT3_PAIR_LEN;
+  pack_bias_pair_kernel<<<(n + 255) / 256, 256, 0, stream>>>(rel, frag, reinterpret_cast<float4*>(out), heads);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "pack_bias_pair_kernel launch");
+}
+
+int launch_window_attn3(const AttnParams& p, cudaStream_t stream) {
+  const WinGeom& g = p.geom;
+  KVQ_REQUIRE(g.wd == 8 && g.wh == 7 && g.ww == 7 && p.base_wd == 8 && p.base_wh == 7 && p.base_ww == 7,
+              KVQ_ERR_BAD_SHAPE, "attn3: built for the (8,7,7) window");
+  KVQ_REQUIRE((g.sd == 0 || g.sd == 4) && (g.sh == 0 || g.sh == 3) && (g.sw == 0 || g.sw == 3), KVQ_ERR_BAD_SHAPE,
+              "attn3: shift must be (4,3,3) or clamped to 0 per dim");
+  KVQ_REQUIRE(p.C == p.heads * ATT_HD, KVQ_ERR_BAD_SHAPE, "attn3: C=%d must be heads(%d) x 32", p.C, p.heads);
+  const long long units = static_cast<long long>(p.B) * g.nW * p.heads;
+  KVQ_REQUIRE(units > 0 && units < (1ll << 31), KVQ_ERR_BAD_SHAPE, "attn3: %lld units", units);
+  KVQ_REQUIRE(p.heads <= num_sms(), KVQ_ERR_BAD_SHAPE, "attn3: %d heads exceed the SM count", p.heads);
+  int dev = 0;
+  KVQ_CUDA(cudaGetDevice(&dev));
+  static bool attr[64] = {};
+  if (dev < 64 && !attr[dev]) {
+    KVQ_CUDA(cudaFuncSetAttribute(window_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM));
+    attr[dev] = true;
+  }
+  int grid = num_sms() / p.heads * p.heads;   // multiple of heads so a CTA keeps one head's table
+  if (grid > units) grid = static_cast<int>(units);
+  count_launch();
+  const float* tab3 = p.packed_tab + static_cast<size_t>(p.heads) * (2536 + 4336) * 2;   // after compact + fast sections
+  return launch_pdl(window_attn3_kernel, dim3(grid), dim3(A3_THREADS), S3_SMEM, stream, p,
+                    reinterpret_cast<const float4*>(tab3), static_cast<int>(units));
+}
+
+}  // namespace kvq

@@ -568,10 +568,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int i = row - win_g * ntok;
         const int slab = i / p.geom.SL;
         const int pitch = p.att_pitch;
-        const int kv_rows = 8 * pitch;                         // 400 or 416 key slots
+        // pitch 50 / 52: slab-padded key slots d*pitch + h*7 + w; pitch 64 (third generation): h*64 + w*8 + d
+        const bool hwd = pitch == ATT3_PITCH;
+        const int kv_rows = hwd ? ATT3_KV_ROWS : 8 * pitch;    // 400, 416 or 448 key slots
         const int kv_bytes = kv_rows * ATT_HD * 2;
         const size_t unit_bytes = static_cast<size_t>(ATT_IMG_BYTES) + 2 * kv_bytes;
-        const int kv_row = slab * pitch + (i - slab * p.geom.SL);
+        const int pos = i - slab * p.geom.SL;
+        const int kv_row = hwd ? (pos / 7) * ATT3_PITCH + (pos % 7) * 8 + slab : slab * pitch + pos;
         constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
         if (n_blk != bias_nblk) {     // bias slice of this warp's chunks -> private smem, once per n-block
           __syncwarp();
@@ -616,8 +619,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               st_global_v4(dst + att_img_offset(rimg, kc0 + j), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
             // the last token of a slab also zeroes the padded K/V key slots behind it (P is 0 there, but 0 * NaN
             // from uninitialised workspace would poison PV); the last token of the window zeroes all the rest
-            if (which != 0 && (i - slab * p.geom.SL) == p.geom.SL - 1) {
-              const int end = (i == ntok - 1) ? kv_rows : (slab + 1) * pitch;
+            const bool pad_owner = hwd ? (slab == 7 && pos % 7 == 6) : (pos == p.geom.SL - 1);
+            if (which != 0 && pad_owner) {
+              const int end = hwd ? kv_row + 9 : (i == ntok - 1) ? kv_rows : (slab + 1) * pitch;
               for (int rz = kv_row + 1; rz < end; ++rz) {
 #pragma unroll
                 for (int j = 0; j < CW / 8; ++j) st_global_v4(dst + att_img_offset(rz, kc0 + j), 0u, 0u, 0u, 0u);

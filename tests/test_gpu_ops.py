@@ -74,9 +74,10 @@ def _block_params(C, heads, frag, seed):
     return synth.synth_state_dict(shapes, seed)
 
 
-# attention kernel generations: 0 = library default (two-CTA flash-style kernel for full (8,7,7) windows, generic
-# kernel otherwise), 1 = first-generation persistent kernel, 2 = generic kernel everywhere
-@pytest.mark.parametrize("variant", [0, 1, 2])
+# attention kernel generations: 0 = library default, 1 = first-generation persistent kernel, 2 = generic kernel
+# everywhere, 5 = two-CTA flash-style kernel, 6 = third generation (one-pass softmax, three tile slots per SM);
+# 5 / 6 fall back to the generic kernel for clamped windows
+@pytest.mark.parametrize("variant", [0, 1, 2, 5, 6])
 @pytest.mark.parametrize("geom", GEOMS, ids=[f"D{g[1]}H{g[2]}W{g[3]}C{g[4]}s{g[6][0]}{g[6][1]}{g[6][2]}" for g in GEOMS])
 def test_ln_window_and_attention(geom, variant):
     from kvq_b200 import ops
