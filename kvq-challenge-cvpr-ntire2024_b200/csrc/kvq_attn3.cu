@@ -3,28 +3,31 @@
 //
 // The second generation (kvq_attn2.cu) was latency-bound in its scalar softmax path: two TMEM round trips per logit,
 // MMA and softmax serialised inside a CTA, eight softmax warps per SM.  This kernel is organised around the per-logit
-// instruction count instead:
+// instruction count and around keeping the LDS, MUFU and tensor pipes busy at the same time:
 //   * ONE persistent CTA per SM, 16 warps: warp 0 loads (cp.async.bulk), warps 1..3 each issue the tcgen05.mma of one
 //     tile slot, warps 4..15 are three softmax warpgroups (one per slot; thread = query row = TMEM lane).
 //     The three slots work on the three 128-row tiles of the same (window, head) unit, sharing its K | V image.
-//   * keys are ordered (h, w, d) with d fastest: slot = h*64 + w*8 + d, one 56-key chunk (+8 zero pad slots) per
-//     window row h.  A chunk is S = Q K_c^T (M128 x N64 x K32), read ONCE into registers; bias, running-max test, exp2
-//     and the fp16 pack all happen there; P_c goes back to TMEM and O += P_c V_c is a TS-form MMA.
+//   * keys are ordered (h, w, d) with d fastest: slot = h*56 + w*8 + d, one 56-key chunk per window row h.  A chunk is
+//     S = Q K_c^T (M128 x N64 x K32: the 8 columns past the chunk are the next chunk's keys and are never read),
+//     double-buffered in TMEM, read ONCE into registers; bias, exp2 and the fp16 pack happen there in a single fused
+//     pass, P_c is written in place over S_c and O += P_c V_c is a TS-form MMA (K = 64: the 8 pad columns of P are 0).
 //   * the two temporal neighbours (d = 2k, 2k+1) of a key position sit in adjacent TMEM columns and share the GRPB
 //     gate fg = |dfh| + |dfw| (it does not depend on d), so the bias is ONE LDS.128 + FFMA2 + FADD2 per two logits:
 //     table entry {t0[e], t0[e-1], t1[e], t1[e-1]} with e = d_i - 2k, conflict-free strides (15, 201).
-//   * lazy row max (as in FlashAttention-4): P = exp2(v - m_ref) with m_ref the max of an EARLIER chunk; it is only
-//     raised (and O, L rescaled in TMEM) when a chunk's max exceeds m_ref by more than 8, so P <= 256 in fp16 and
-//     the result is exact up to rounding because the row sum uses the same m_ref.
-//   * the row sum L = sum_j P_j comes from the tensor core as well: one more MMA per K step against an all-ones B
-//     tile (N = 16), so the normalisation uses exactly the fp16 P the PV product saw and costs no CUDA-core work.
+//   * lazy row max (as in FlashAttention-4): P = exp2(v - m_ref) with m_ref the exact max of the row's FIRST chunk;
+//     later chunks run the fused pass against that m_ref and only when a logit exceeds it by more than 15 (P would
+//     leave fp16 range) is the chunk redone in two passes, m_ref raised and O, l rescaled.  The result is exact up to
+//     rounding because the row sum uses the same m_ref.
 //   * the SW-MSA region mask is folded into QK^T: a third K step contracts [a_d 1 a_h 1 a_w 1] (query region bits,
 //     zeroed for dims this window does not mask) with (-100 log2e / 2) * [(1-2b_d) b_d (1-2b_h) b_h (1-2b_w) b_w]
 //     (key region bits, static); the second 8-half K chunk aliases the first (LBO = 0), hence the factor 1/2.
 //     -100 per differing dim instead of -100 once: exp(-100) and exp(-300) are both 0 next to an unmasked logit.
 //   * the 8 tail rows (384..391) are replicated into all lane groups (SBO = 0, as in the second generation); warp q
-//     takes the chunks c = q (mod 4) and writes zero P elsewhere; the four partial (m, L, O) are merged in smem.
-// TMEM per slot: S 64 | P 32 | O 32 | L 16 = 144 columns, 432 of 512.
+//     takes the chunks c = q (mod 4) and writes zero P elsewhere; the four partial (m, l, O) are merged in smem.
+//   * the MMA issuers run warp-uniform code with uniform operands (TMEM base 0, descriptors from uniform offsets) and
+//     one elected lane: a per-lane `if (lane == 0)` issue path makes ptxas emit an R2UR waterfall of ~130 cycles per
+//     MMA (tools/ubench/mma_lat.cu: 27 cycles for a TS N=32 MMA, 75 for an SS N=64 one when issued uniformly).
+// TMEM per slot: S/P buffer 0 (64) | S/P buffer 1 (64) | O (32) = 160 columns, 480 of 512.
 #include <cstdlib>
 
 #include "kvq_common.cuh"
@@ -38,28 +41,28 @@ constexpr int A3_THREADS = 512;
 constexpr int NSLOT = 3;
 constexpr int NCHUNK3 = 7;
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr float TAU = 8.0f;                       // lazy-max slack (log2 units): P <= 2^TAU
+constexpr float TAU = 15.0f;                      // lazy-max slack (log2 units): P <= 2^15 stays inside fp16
 
 // shared memory map (bytes)
 constexpr int S3_TAB = 0;
 constexpr int S3_TAB_BYTES = (ATT3_PAIR_LEN * 16 + 255) / 256 * 256;        // 45 056
 constexpr int S3_KV = S3_TAB + S3_TAB_BYTES;                               // 2 x (K | V)
 constexpr int S3_Q = S3_KV + 2 * 2 * ATT3_KV_BYTES;                        // 3 slots x 2 x 8192
-constexpr int S3_KAUG = S3_Q + NSLOT * 2 * 8192;                           // 448 x 16
-constexpr int S3_SCR = S3_KAUG + ATT3_KV_ROWS * 16;                        // per slot: Qaug (2048) / tail merge (3264)
-constexpr int SCR_BYTES = 3328;
-constexpr int S3_ONES = S3_SCR + NSLOT * SCR_BYTES;                        // 512
-constexpr int S3_BARS = S3_ONES + 512;                                     // 512
+constexpr int S3_KAUG = S3_Q + NSLOT * 2 * 8192;                           // 400 x 16
+constexpr int S3_QAUG = S3_KAUG + ATT3_KV_ROWS * 16;                       // 3 slots x 128 x 16
+constexpr int S3_SCR = S3_QAUG + NSLOT * 2048;                             // 3 slots x tail merge scratch
+constexpr int SCR_BYTES = 3328;                                            // 3 warps x 8 rows x 34 floats = 3264
+constexpr int S3_BARS = S3_SCR + NSLOT * SCR_BYTES;                        // 512
 constexpr int S3_SMEM = S3_BARS + 512 + 128;
 static_assert(S3_SMEM <= 227 * 1024, "attn3 shared memory exceeds the SM");
 
 // TMEM columns of a slot
-constexpr int T3_SLOT = 144, T3_S = 0, T3_P = 64, T3_O = 96, T3_L = 128;
+constexpr int T3_SLOT = 160, T3_O = 128;
 
 struct Bars3 {
   uint64_t tab, kv[2], kvfree[2];
   uint64_t q[NSLOT][2], qfree[NSLOT][2];
-  uint64_t s[NSLOT], sc[NSLOT], p[NSLOT], pv[NSLOT], of[NSLOT], qa[NSLOT];
+  uint64_t s[NSLOT][2], p[NSLOT][2], pv[NSLOT][2], of[NSLOT], qa[NSLOT];
   uint32_t tmem_slot;
 };
 static_assert(sizeof(Bars3) <= 512, "Bars3 overflows its slot");
@@ -80,16 +83,16 @@ template <int REGS>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 // fragment coordinate of window-local row/col k (global_position_index :22-50: nearest-resized fragment index of the
-// rolled position)
-__device__ __forceinline__ float frag_coord(int base, int k, int shift, int size) {
+// rolled position); inv = 7 / size
+__device__ __forceinline__ float frag_coord(int base, int k, int shift, int size, float inv) {
   int o = base + k + shift;
   if (o >= size) o -= size;
-  int f = static_cast<int>(floorf(static_cast<float>(o) * (7.0f / static_cast<float>(size))));
+  int f = static_cast<int>(floorf(static_cast<float>(o) * inv));
   return static_cast<float>(f > 6 ? 6 : f);
 }
 
 struct UnitInfo {
-  int win_g, wdi, whi, wwi;
+  int win_g, whi, wwi;
   bool md, mh, mw;     // dims whose SW-MSA region mask applies in this window
 };
 __device__ __forceinline__ UnitInfo unit_info(const AttnParams& p, int unit) {
@@ -97,13 +100,44 @@ __device__ __forceinline__ UnitInfo unit_info(const AttnParams& p, int unit) {
   UnitInfo u;
   u.win_g = unit / p.heads;
   const int win = u.win_g % g.nW;
-  u.wdi = win / (g.nwh * g.nww);
+  const int wdi = win / (g.nwh * g.nww);
   u.whi = (win / g.nww) % g.nwh;
   u.wwi = win % g.nww;
-  u.md = g.sd != 0 && u.wdi == g.nwd - 1;
+  u.md = g.sd != 0 && wdi == g.nwd - 1;
   u.mh = g.sh != 0 && u.whi == g.nwh - 1;
   u.mw = g.sw != 0 && u.wwi == g.nww - 1;
   return u;
+}
+
+// walks the (unit, item, chunk) sequence of one slot: slot s takes tile s of every unit and the tail of units n = s (mod 3)
+struct Cursor {
+  int n, it, c;
+  uint32_t k;          // item ordinal of this slot
+  __device__ __forceinline__ void advance(int s) {
+    if (++c == NCHUNK3) {
+      c = 0;
+      ++k;
+      if (++it == ((n % NSLOT == s) ? 2 : 1)) {
+        it = 0;
+        ++n;
+      }
+    }
+  }
+};
+
+// bias for one key position (8 logits = 4 temporal pairs): r <- s + t0 + fg * t1; running max
+__device__ __forceinline__ void bias_pos(uint32_t (&r)[56], const int wj, const float4 (&e)[4], const float2 fg2,
+                                         float& gmax) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const float4 t = e[kk];
+    const int j = wj * 8 + 2 * kk;
+    const float2 v = fadd2(ffma2(fg2, make_float2(t.z, t.w), make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]))),
+                           make_float2(t.x, t.y));
+    gmax = fmax3(gmax, v.x, v.y);
+    r[j] = __float_as_uint(v.x);
+    r[j + 1] = __float_as_uint(v.y);
+  }
 }
 
 __global__ void __launch_bounds__(A3_THREADS, 1)
@@ -129,11 +163,10 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars.q[s][i], 1);
         mbar_init(&bars.qfree[s][i], 1);
+        mbar_init(&bars.s[s][i], 1);
+        mbar_init(&bars.p[s][i], 4);
+        mbar_init(&bars.pv[s][i], 1);
       }
-      mbar_init(&bars.s[s], 1);
-      mbar_init(&bars.sc[s], 4);
-      mbar_init(&bars.p[s], 4);
-      mbar_init(&bars.pv[s], 1);
       mbar_init(&bars.of[s], 4);
       mbar_init(&bars.qa[s], 4);
     }
@@ -142,20 +175,17 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
     mbar_expect_tx(&bars.tab, ATT3_PAIR_LEN * 16);
     bulk_load_1d(smem + S3_TAB, tabs + static_cast<size_t>(head) * ATT3_PAIR_LEN, ATT3_PAIR_LEN * 16, &bars.tab);
   }
-  // static operands: all-ones B tile of the row-sum MMA, key side of the folded region mask
-  if (tid < 128) reinterpret_cast<uint32_t*>(smem + S3_ONES)[tid] = 0x3C003C00u;   // half2(1, 1)
+  // static operand: key side of the folded region mask
   for (int r = tid; r < ATT3_KV_ROWS; r += A3_THREADS) {
-    const int hj = r >> 6, wj = (r >> 3) & 7, dj = r & 7;
+    const int hj = r / 56, wj = (r % 56) >> 3, dj = r & 7;
     const float mh = -50.0f * LOG2E;           // half of -100 log2(e): the aliased second K chunk doubles it
-    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (wj < 7) {
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (r < 392) {
       const float bd = dj >= 4 ? 1.f : 0.f, bh = hj >= 4 ? 1.f : 0.f, bw = wj >= 4 ? 1.f : 0.f;
-      v[0] = mh * (1.f - 2.f * bd); v[1] = mh * bd;
-      v[2] = mh * (1.f - 2.f * bh); v[3] = mh * bh;
-      v[4] = mh * (1.f - 2.f * bw); v[5] = mh * bw;
+      w.x = pack_half2(mh * (1.f - 2.f * bd), mh * bd);
+      w.y = pack_half2(mh * (1.f - 2.f * bh), mh * bh);
+      w.z = pack_half2(mh * (1.f - 2.f * bw), mh * bw);
     }
-    uint4 w;
-    w.x = pack_half2(v[0], v[1]); w.y = pack_half2(v[2], v[3]); w.z = pack_half2(v[4], v[5]); w.w = 0u;
     *reinterpret_cast<uint4*>(smem + S3_KAUG + r * 16) = w;
   }
   fence_proxy_async_smem();
@@ -209,87 +239,81 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       }
     } else {
       // =============================== MMA issuer of slot `warp - 1` ===============================
-      // The whole warp runs this loop with warp-uniform control flow and operands (TMEM base 0: this CTA owns all 512
-      // columns; descriptors derived from uniform shared-memory offsets and loop counters), one elected lane issues:
-      // ptxas then keeps the descriptors in uniform registers and a small MMA costs ~20-75 cycles of issue instead of
-      // the ~130 of a per-lane R2UR waterfall (tools/ubench/mma_lat.cu).
+      // Warp-uniform control flow and operands; one elected lane issues (see the header comment).
       const int s = warp - 1;
-      const uint32_t tS = s * T3_SLOT + T3_S, tP = s * T3_SLOT + T3_P;
-      const uint32_t tO = s * T3_SLOT + T3_O, tL = s * T3_SLOT + T3_L;
+      const uint32_t tB = s * T3_SLOT, tO = s * T3_SLOT + T3_O;
       const uint32_t sbase = smem_u32(smem);
-      const uint32_t aOnes = sbase + S3_ONES, aKaug = sbase + S3_KAUG;
-      const uint32_t aQaug = sbase + S3_SCR + s * SCR_BYTES;
+      const uint32_t aKaug = sbase + S3_KAUG, aQaug = sbase + S3_QAUG + s * 2048;
       constexpr uint32_t idesc_s = umma_idesc_f16(128, 64, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 32, 0, 1);
-      constexpr uint32_t idesc_l = umma_idesc_f16(128, 16, 0, 1);
-      const uint64_t d_ones = umma_smem_desc(aOnes, 256, 128, UMMA_SW_NONE);
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {   // one lane polls, the warp follows
         if (lane == 0) mbar_wait(bar, parity);
         __syncwarp();
       };
-      uint32_t gc = 0, k = 0, n_qa = 0;
-      for (int n = 0; n < n_units; ++n) {
-        const int unit = blockIdx.x + n * G;
-        const UnitInfo u = unit_info(p, unit);
+      uint32_t n_qa = 0;
+      // S_j = Q K_c^T of the chunk at cursor x into buffer j & 1 (waits for the operands of a new item / unit first)
+      auto issue_s = [&](const Cursor& x, uint32_t j) {
+        const UnitInfo u = unit_info(p, blockIdx.x + x.n * G);
         const bool masked = u.md || u.mh || u.mw;
-        const int b = n & 1;
-        const uint32_t aK = sbase + S3_KV + b * 2 * ATT3_KV_BYTES, aV = aK + ATT3_KV_BYTES;
-        wait_all(&bars.kv[b], (n >> 1) & 1);
-        const int items = (n % NSLOT == s) ? 2 : 1;
-        for (int it = 0; it < items; ++it, ++k) {
-          const bool tail = it == 1;
-          const int qb = k & 1;
-          const uint32_t aQ = sbase + S3_Q + (s * 2 + qb) * 8192;
-          const uint32_t q_sbo = tail ? 0u : 512u, qa_sbo = tail ? 0u : 128u;
-          auto issue_s = [&](int c) {
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t dq = umma_smem_desc(aQ + ks * 256, 128, q_sbo, UMMA_SW_NONE);
-              const uint64_t dk = umma_smem_desc(aK + c * 4096 + ks * 256, 128, 512, UMMA_SW_NONE);
-              umma_f16_ss(tS, dq, dk, idesc_s, ks);
-            }
-            if (masked) {
-              const uint64_t dq = umma_smem_desc(aQaug, 0, qa_sbo, UMMA_SW_NONE);
-              const uint64_t dk = umma_smem_desc(aKaug + c * 1024, 0, 128, UMMA_SW_NONE);
-              umma_f16_ss(tS, dq, dk, idesc_s, 1u);
-            }
-            umma_commit(&bars.s[s]);
-          };
-          wait_all(&bars.q[s][qb], (k >> 1) & 1);
+        const bool tail = x.it == 1;
+        const int qb = x.k & 1;
+        if (x.c == 0) {
+          if (x.it == 0) wait_all(&bars.kv[x.n & 1], (x.n >> 1) & 1);
+          wait_all(&bars.q[s][qb], (x.k >> 1) & 1);
           if (masked) {
             wait_all(&bars.qa[s], n_qa & 1);
             ++n_qa;
           }
           tc_fence_after();
-          if (elect_one()) issue_s(0);
-          __syncwarp();
-#pragma unroll 1
-          for (int c = 0; c < NCHUNK3; ++c, ++gc) {
-            wait_all(&bars.sc[s], gc & 1);             // S_c is in registers: its columns may be overwritten
-            tc_fence_after();
-            if (elect_one()) {
-              if (c + 1 < NCHUNK3) issue_s(c + 1);
-              else umma_commit(&bars.qfree[s][qb]);    // every S MMA of this item has read the Q tile
-            }
-            __syncwarp();
-            wait_all(&bars.p[s], gc & 1);              // P_c written
-            if (c == 0 && k > 0) wait_all(&bars.of[s], (k - 1) & 1);   // previous item's O / L were read
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t acc0 = c > 0 ? 1u : 0u;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t dv = umma_smem_desc(aV + (c * 4 + ks) * 1024, 512, 128, UMMA_SW_NONE);
-                umma_f16_ts(tO, tP + 8 * ks, dv, idesc_pv, ks > 0 ? 1u : acc0);
-                umma_f16_ts(tL, tP + 8 * ks, d_ones, idesc_l, ks > 0 ? 1u : acc0);
-              }
-              umma_commit(&bars.pv[s]);
-            }
-            __syncwarp();
-          }
         }
-        if (elect_one()) umma_commit(&bars.kvfree[b]);   // all MMAs of this slot on unit n are complete
+        const uint32_t aK = sbase + S3_KV + (x.n & 1) * 2 * ATT3_KV_BYTES + x.c * (56 * 64);
+        const uint32_t aQ = sbase + S3_Q + (s * 2 + qb) * 8192;
+        const uint32_t q_sbo = tail ? 0u : 512u, qa_sbo = tail ? 0u : 128u;
+        const uint32_t tS = tB + (j & 1) * 64;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t dq = umma_smem_desc(aQ + ks * 256, 128, q_sbo, UMMA_SW_NONE);
+            const uint64_t dk = umma_smem_desc(aK + ks * 256, 128, 512, UMMA_SW_NONE);
+            umma_f16_ss(tS, dq, dk, idesc_s, ks);
+          }
+          if (masked) {
+            const uint64_t dq = umma_smem_desc(aQaug, 0, qa_sbo, UMMA_SW_NONE);
+            const uint64_t dk = umma_smem_desc(aKaug + x.c * (56 * 16), 0, 128, UMMA_SW_NONE);
+            umma_f16_ss(tS, dq, dk, idesc_s, 1u);
+          }
+          umma_commit(&bars.s[s][j & 1]);
+          if (x.c == NCHUNK3 - 1) umma_commit(&bars.qfree[s][qb]);   // every S MMA of this item has read the Q tile
+        }
         __syncwarp();
+      };
+      Cursor cur = {0, 0, 0, 0}, ahead = {0, 0, 0, 0};
+      if (ahead.n < n_units) { issue_s(ahead, 0); ahead.advance(s); }
+      if (ahead.n < n_units) { issue_s(ahead, 1); ahead.advance(s); }
+#pragma unroll 1
+      for (uint32_t j = 0; cur.n < n_units; ++j) {
+        // P_j written over S_j.  One barrier per buffer: a warp can run at most two chunks ahead of its slowest
+        // sibling (S_{j+2} is only issued once phase j completed), so its arrivals for chunks j and j+1 never mix
+        wait_all(&bars.p[s][j & 1], (j >> 1) & 1);
+        if (cur.c == 0 && cur.k > 0) wait_all(&bars.of[s], (cur.k - 1) & 1);   // previous item's O was read
+        tc_fence_after();
+        const uint32_t aV = sbase + S3_KV + (cur.n & 1) * 2 * ATT3_KV_BYTES + ATT3_KV_BYTES + cur.c * (56 * 64);
+        const uint32_t tP = tB + (j & 1) * 64;
+        const bool last_of_unit = cur.c == NCHUNK3 - 1 && cur.it == ((cur.n % NSLOT == s) ? 1 : 0);
+        if (elect_one()) {
+          const uint32_t acc0 = cur.c > 0 ? 1u : 0u;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t dv = umma_smem_desc(aV + ks * 1024, 512, 128, UMMA_SW_NONE);
+            umma_f16_ts(tO, tP + 8 * ks, dv, idesc_pv, ks > 0 ? 1u : acc0);
+          }
+          umma_commit(&bars.pv[s][j & 1]);
+          if (last_of_unit) umma_commit(&bars.kvfree[cur.n & 1]);     // all MMAs of this slot on the unit are complete
+        }
+        __syncwarp();
+        // the buffer P_j lives in is free once PV_j has run: the tensor pipe executes in issue order
+        if (ahead.n < n_units) { issue_s(ahead, j + 2); ahead.advance(s); }
+        cur.advance(s);
       }
     }
   } else {
@@ -297,68 +321,108 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
     // =============================== softmax warps: one thread per query row ===============================
     const int s = (warp - 4) >> 2, q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + s * T3_SLOT + T3_S, tP = tmem_base + lane_off + s * T3_SLOT + T3_P;
-    const uint32_t tO = tmem_base + lane_off + s * T3_SLOT + T3_O, tL = tmem_base + lane_off + s * T3_SLOT + T3_L;
-    uint8_t* scr = smem + S3_SCR + s * SCR_BYTES;
+    const uint32_t tB = lane_off + s * T3_SLOT, tO = lane_off + s * T3_SLOT + T3_O;
+    float* scr = reinterpret_cast<float*>(smem + S3_SCR + s * SCR_BYTES);
+    uint8_t* qaug = smem + S3_QAUG + s * 2048;
     const uint32_t stab = smem_u32(smem + S3_TAB);
-    uint32_t gc = 0, k = 0;
-    mbar_wait(&bars.tab, 0);
-    for (int n = 0; n < n_units; ++n) {
-      const int unit = blockIdx.x + n * G;
-      const UnitInfo u = unit_info(p, unit);
-      const bool masked = u.md || u.mh || u.mw;
-      const int items = (n % NSLOT == s) ? 2 : 1;
-#pragma unroll 1
-      for (int it = 0; it < items; ++it, ++k) {
-        const bool tail = it == 1;
-        const int ri = tail ? 384 + (lane & 7) : s * 128 + q * 32 + lane;
-        const int d_i = ri / 49, hw_i = ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
-        if (masked) {
-          // query side of the folded mask: [a_d 1 a_h 1 a_w 1 0 0], a pair zeroed when its dim is not masked here
-          const float ad = d_i >= 4 ? 1.f : 0.f, ah = h_i >= 4 ? 1.f : 0.f, aw = w_i >= 4 ? 1.f : 0.f;
-          uint4 w;
-          w.x = u.md ? pack_half2(ad, 1.f) : 0u;
-          w.y = u.mh ? pack_half2(ah, 1.f) : 0u;
-          w.z = u.mw ? pack_half2(aw, 1.f) : 0u;
-          w.w = 0u;
-          const int row = q * 32 + lane;
-          if (!tail || row < 8) *reinterpret_cast<uint4*>(scr + row * 16) = w;
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.qa[s]);
-        }
-        const float fh_i = frag_coord(u.whi * 7, h_i, g.sh, g.Hp), fw_i = frag_coord(u.wwi * 7, w_i, g.sw, g.Wp);
-        float Aw[7];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) Aw[j] = fabsf(fw_i - frag_coord(u.wwi * 7, j, g.sw, g.Wp));
-        const uint32_t trow0 = stab + 16u * static_cast<uint32_t>((d_i + 6) * ATT3_SD + (h_i + 6) * ATT3_SH + (w_i + 6));
+    const float invH = 7.0f / static_cast<float>(g.Hp), invW = 7.0f / static_cast<float>(g.Wp);
 
-        float m_ref = -INFINITY;
+    // query side of the folded mask for the item at cursor x: [a_d 1 a_h 1 a_w 1 0 0] per row, a pair zeroed when its
+    // dim is not masked in that window.  Written one item ahead (see the call sites), consumed by the S MMAs.
+    auto write_qaug = [&](const Cursor& x) {
+      const UnitInfo u = unit_info(p, blockIdx.x + x.n * G);
+      if (!(u.md || u.mh || u.mw)) return;
+      const bool tail = x.it == 1;
+      const int row = q * 32 + lane;
+      const int ri = tail ? 384 + (lane & 7) : s * 128 + row;
+      const int d_i = ri / 49, hw_i = ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
+      uint4 w;
+      w.x = u.md ? pack_half2(d_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
+      w.y = u.mh ? pack_half2(h_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
+      w.z = u.mw ? pack_half2(w_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
+      w.w = 0u;
+      if (!tail || row < 8) *reinterpret_cast<uint4*>(qaug + row * 16) = w;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.qa[s]);
+    };
+
+    Cursor cur = {0, 0, 0, 0};
+    uint32_t j = 0;                            // chunk ordinal of this slot
+    mbar_wait(&bars.tab, 0);
+    if (cur.n < n_units) write_qaug(cur);
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK3; ++c, ++gc) {
-          const bool own = !tail || (c & 3) == q;
-          uint32_t r[56];
-          mbar_wait(&bars.s[s], gc & 1);
-          __syncwarp();
-          tc_fence_after();
-          if (own) {
+    while (cur.n < n_units) {
+      // ---------------- one item: a 128-row tile or the replicated tail rows ----------------
+      const int unit = blockIdx.x + cur.n * G;
+      const UnitInfo u = unit_info(p, unit);
+      const bool tail = cur.it == 1;
+      const int ri = tail ? 384 + (lane & 7) : s * 128 + q * 32 + lane;
+      const int d_i = ri / 49, hw_i = ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
+      const float fh_i = frag_coord(u.whi * 7, h_i, g.sh, g.Hp, invH), fw_i = frag_coord(u.wwi * 7, w_i, g.sw, g.Wp, invW);
+      float Aw[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) Aw[i] = fabsf(fw_i - frag_coord(u.wwi * 7, i, g.sw, g.Wp, invW));
+      const uint32_t trow0 = stab + 16u * static_cast<uint32_t>((d_i + 6) * ATT3_SD + (h_i + 6) * ATT3_SH + (w_i + 6));
+      Cursor next = cur;
+      next.c = NCHUNK3 - 1;
+      next.advance(s);                         // first chunk of the next item of this slot
+
+      float m_ref = -INFINITY, l_run = 0.f;
+      bool fresh = true;                       // no chunk of this row processed yet (warp-uniform)
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK3; ++c, ++j) {
+        const bool own = !tail || (c & 3) == q;
+        const uint32_t tS = tB + (j & 1) * 64;
+        mbar_wait(&bars.s[s][j & 1], (j >> 1) & 1);
+        __syncwarp();
+        tc_fence_after();
+        // every S MMA of this item has completed once its last chunk is visible: the next item's Qaug rows may go in
+        if (c == NCHUNK3 - 1 && next.n < n_units) write_qaug(next);
+        if (own) {
+          uint32_t r[56], h[32];
+          const uint32_t tb = trow0 - 16u * static_cast<uint32_t>(c * ATT3_SH);
+          const float Ah = fabsf(fh_i - frag_coord(u.whi * 7, c, g.sh, g.Hp, invH));
+          float4 e[2][4];
+          bool redo = fresh;                   // the row's first chunk fixes m_ref: two passes
+          if (!redo) {
+            // ---- fused pass against the standing m_ref: bias, exp2, pack, row sum, chunk max ----
             tmem_ld_x32(tS, r);
             tmem_ld_x16(tS + 32, r + 32);
             tmem_ld_x8(tS + 48, r + 48);
-          }
-          const uint32_t tb = trow0 - 16u * static_cast<uint32_t>(c * ATT3_SH);
-          float4 e[2][4];
-          if (own) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) e[0][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD));
             tmem_wait_ld();
+            float gmax = -INFINITY;
+            const float2 negm2 = splat2(-m_ref);
+            float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int wj = 0; wj < 7; ++wj) {
+              if (wj < 6) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) e[(wj + 1) & 1][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD + wj + 1));
+              }
+              bias_pos(r, wj, e[wj & 1], splat2(Ah + Aw[wj]), gmax);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const int i = wj * 8 + 2 * kk;
+                const float2 x = fadd2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), negm2);
+                const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                sum2 = fadd2(sum2, pe);
+                h[i >> 1] = pack_half2(pe.x, pe.y);
+              }
+            }
+            redo = __any_sync(0xffffffffu, gmax > m_ref + TAU);
+            if (!redo) l_run += sum2.x + sum2.y;
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.sc[s]);     // S_c is in registers (or not needed)
-          if (own) {
-            // ---- bias: v = s + t0 + fg * t1 for the two temporal neighbours at once; chunk max ----
-            const float Ah = fabsf(fh_i - frag_coord(u.whi * 7, c, g.sh, g.Hp));
+          if (redo) {
+            // ---- two passes: bias + exact chunk max, raise m_ref (rescaling O and l), then exp2 ----
+            tmem_ld_x32(tS, r);
+            tmem_ld_x16(tS + 32, r + 32);
+            tmem_ld_x8(tS + 48, r + 48);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) e[0][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD));
+            tmem_wait_ld();
             float gmax = -INFINITY;
 #pragma unroll
             for (int wj = 0; wj < 7; ++wj) {
@@ -366,132 +430,116 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) e[(wj + 1) & 1][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD + wj + 1));
               }
-              const float2 fg2 = splat2(Ah + Aw[wj]);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const float4 t = e[wj & 1][kk];
-                const int j = wj * 8 + 2 * kk;
-                const float2 v = fadd2(ffma2(fg2, make_float2(t.z, t.w),
-                                             make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]))),
-                                       make_float2(t.x, t.y));
-                gmax = fmax3(gmax, v.x, v.y);
-                r[j] = __float_as_uint(v.x);
-                r[j + 1] = __float_as_uint(v.y);
-              }
+              bias_pos(r, wj, e[wj & 1], splat2(Ah + Aw[wj]), gmax);
             }
-            // P buffer free / O, L stable: PV of the previous chunk has completed (it was issued a chunk ago)
-            if (gc > 0) mbar_wait(&bars.pv[s], (gc - 1) & 1);
-            tc_fence_after();
-            // ---- lazy row max ----
-            const bool need = gmax > m_ref + TAU;
-            if (__any_sync(0xffffffffu, need)) {
-              const float m_new = need ? gmax : m_ref;
-              if (c > 0) {
-                const float alpha = need ? fast_exp2(m_ref - m_new) : 1.0f;     // 0 while m_ref is still -inf
-                uint32_t o[32], l1[1];
-                tmem_ld_x32(tO, o);
-                tmem_ld_x1(tL, l1);
-                tmem_wait_ld();
+            const float m_new = fmaxf(m_ref, gmax);
+            const float alpha = fast_exp2(m_ref - m_new);             // 0 while m_ref is still -inf
+            if (!fresh) {
+              // O holds this item's partial sums against the old m_ref; PV of the previous chunk must have landed
+              // (one barrier per buffer parity: a single one could still be a phase behind and alias the parity test)
+              mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
+              tc_fence_after();
+              uint32_t o[32];
+              tmem_ld_x32(tO, o);
+              tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-                l1[0] = __float_as_uint(__uint_as_float(l1[0]) * alpha);
-                tmem_st_x32(tO, o);
-                tmem_st_x1(tL, l1);
-              }
-              m_ref = m_new;
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x32(tO, o);
+              l_run *= alpha;
             }
-            // ---- P = exp2(v - m_ref), fp16 pairs; 8 zero pad slots complete the fourth K step ----
+            m_ref = m_new;
             const float2 negm2 = splat2(-m_ref);
-            uint32_t h[32];
+            float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 28; ++j) {
-              const float2 x = fadd2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), negm2);
-              h[j] = pack_half2(fast_exp2(x.x), fast_exp2(x.y));
+            for (int i = 0; i < 28; ++i) {
+              const float2 x = fadd2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), negm2);
+              const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+              sum2 = fadd2(sum2, pe);
+              h[i] = pack_half2(pe.x, pe.y);
             }
-            h[28] = h[29] = h[30] = h[31] = 0u;
-            tmem_st_x32(tP, h);
-          } else {
-            if (gc > 0) mbar_wait(&bars.pv[s], (gc - 1) & 1);
-            tc_fence_after();
-            uint32_t z[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) z[j] = 0u;
-            tmem_st_x32(tP, z);
+            l_run += sum2.x + sum2.y;
           }
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.p[s]);
+          fresh = false;
+          h[28] = h[29] = h[30] = h[31] = 0u;  // 8 zero pad slots complete the fourth K step
+          tmem_st_x32(tS, h);                  // P_c in place over S_c
+        } else {
+          uint32_t z[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) z[i] = 0u;
+          tmem_st_x32(tS, z);
         }
-
-        // ---- epilogue: O / L -> global ----
-        mbar_wait(&bars.pv[s], (gc - 1) & 1);
-        __syncwarp();
-        tc_fence_after();
-        uint32_t o[32], l1[1];
-        tmem_ld_x32(tO, o);
-        tmem_ld_x1(tL, l1);
-        tmem_wait_ld();
+        tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.of[s]);
-        if (!tail) {
-          const float inv = 1.0f / __uint_as_float(l1[0]);
-          __half* dst = p.out + (static_cast<size_t>(u.win_g) * 392 + ri) * p.C + head * ATT_HD;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 v;
-            v.x = pack_half2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
-            v.y = pack_half2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
-            v.z = pack_half2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
-            v.w = pack_half2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + j) = v;
-          }
-        } else {
-          // four partial softmaxes per row (one per warp), each against its own m_ref: merge like split-K
-          float* sc = reinterpret_cast<float*>(scr);
-          if (q > 0 && lane < 8) {
-            float* d = sc + ((q - 1) * 8 + lane) * 34;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(o[j]);
-            d[32] = __uint_as_float(l1[0]);
-            d[33] = m_ref;
-          }
-          named_bar_sync(1 + s, 128);
-          if (q == 0 && lane < 8) {
-            float mq[4], wq[4];
-            mq[0] = m_ref;
-#pragma unroll
-            for (int j = 1; j < 4; ++j) mq[j] = sc[((j - 1) * 8 + lane) * 34 + 33];
-            const float M = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) wq[j] = fast_exp2(mq[j] - M);
-            float L = wq[0] * __uint_as_float(l1[0]);
-#pragma unroll
-            for (int j = 1; j < 4; ++j) L = fmaf(wq[j], sc[((j - 1) * 8 + lane) * 34 + 32], L);
-            const float inv = 1.0f / L;
-            __half* dst = p.out + (static_cast<size_t>(u.win_g) * 392 + 384 + lane) * p.C + head * ATT_HD;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float a = wq[0] * __uint_as_float(o[j + i]);
-#pragma unroll
-                for (int w = 1; w < 4; ++w) a = fmaf(wq[w], sc[((w - 1) * 8 + lane) * 34 + j + i], a);
-                v[i] = a * inv;
-              }
-              uint4 pk;
-              pk.x = pack_half2(v[0], v[1]);
-              pk.y = pack_half2(v[2], v[3]);
-              pk.z = pack_half2(v[4], v[5]);
-              pk.w = pack_half2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(dst + j) = pk;
-            }
-          }
-          named_bar_sync(1 + s, 128);   // the merge scratch aliases the next masked item's Qaug rows
-        }
+        if (lane == 0) mbar_arrive(&bars.p[s][j & 1]);
       }
+
+      // ---- epilogue: O / l -> global ----
+      mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld_x32(tO, o);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.of[s]);
+      if (!tail) {
+        const float inv = 1.0f / l_run;
+        __half* dst = p.out + (static_cast<size_t>(u.win_g) * 392 + ri) * p.C + head * ATT_HD;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_half2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          v.y = pack_half2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          v.z = pack_half2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          v.w = pack_half2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + i) = v;
+        }
+      } else {
+        // four partial softmaxes per row (one per warp), each against its own m_ref: merge like split-K
+        if (q > 0 && lane < 8) {
+          float* d = scr + ((q - 1) * 8 + lane) * 34;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(o[i]);
+          d[32] = l_run;
+          d[33] = m_ref;
+        }
+        named_bar_sync(1 + s, 128);
+        if (q == 0 && lane < 8) {
+          float mq[4], wq[4];
+          mq[0] = m_ref;
+#pragma unroll
+          for (int i = 1; i < 4; ++i) mq[i] = scr[((i - 1) * 8 + lane) * 34 + 33];
+          const float M = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wq[i] = fast_exp2(mq[i] - M);
+          float L = wq[0] * l_run;
+#pragma unroll
+          for (int i = 1; i < 4; ++i) L = fmaf(wq[i], scr[((i - 1) * 8 + lane) * 34 + 32], L);
+          const float inv = 1.0f / L;
+          __half* dst = p.out + (static_cast<size_t>(u.win_g) * 392 + 384 + lane) * p.C + head * ATT_HD;
+#pragma unroll
+          for (int i0 = 0; i0 < 32; i0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a = wq[0] * __uint_as_float(o[i0 + i]);
+#pragma unroll
+              for (int w = 1; w < 4; ++w) a = fmaf(wq[w], scr[((w - 1) * 8 + lane) * 34 + i0 + i], a);
+              v[i] = a * inv;
+            }
+            uint4 pk;
+            pk.x = pack_half2(v[0], v[1]);
+            pk.y = pack_half2(v[2], v[3]);
+            pk.z = pack_half2(v[4], v[5]);
+            pk.w = pack_half2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(dst + i0) = pk;
+          }
+        }
+        named_bar_sync(1 + s, 128);   // the scratch is rewritten by this slot's next tail item
+      }
+      cur = next;
     }
   }
 
@@ -549,9 +597,9 @@ int launch_window_attn3(const AttnParams& p, cudaStream_t stream) {
   int dev = 0;
   KVQ_CUDA(cudaGetDevice(&dev));
   static bool attr[64] = {};
-  if (dev < 64 && !attr[dev]) {
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
     KVQ_CUDA(cudaFuncSetAttribute(window_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM));
-    attr[dev] = true;
+    if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   int grid = num_sms() / p.heads * p.heads;   // multiple of heads so a CTA keeps one head's table
   if (grid > units) grid = static_cast<int>(units);

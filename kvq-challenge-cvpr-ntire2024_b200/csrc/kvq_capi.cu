@@ -61,7 +61,7 @@ int make_plan(const KvqSwinConfig* cfg, int B, int T, int H, int W, Plan* pl) {
     const size_t rows = static_cast<size_t>(B) * g.tokens;
     KVQ_REQUIRE(rows_w < (1ull << 31), KVQ_ERR_BAD_SHAPE, "stage %d has %zu window rows (int32 overflow)", s, rows_w);
     max_a16 = std::max(max_a16, rows_w * C * 2);
-    max_img = std::max(max_img, static_cast<size_t>(B) * g.nW * cfg->num_heads[s] * ATT3_UNIT_BYTES);
+    max_img = std::max(max_img, static_cast<size_t>(B) * g.nW * cfg->num_heads[s] * ATT2_UNIT_BYTES);
     max_hid = std::max(max_hid, rows * 4 * C * 2);
     if (s + 1 < cfg->num_stages) {
       const int H2 = (Hh + 1) / 2, W2 = (Ww + 1) / 2;
@@ -839,7 +839,7 @@ int kvq_ln_window(const float* x, void* out_f16, const float* gamma, const float
 size_t kvq_window_attention_workspace_bytes(int B, int D, int H, int W, int C, const int32_t window[3],
                                             const int32_t shift[3]) {
   const WinGeom g = make_geom(D, H, W, window, shift);
-  return static_cast<size_t>(B) * g.nW * (C / 32) * ATT3_UNIT_BYTES;
+  return static_cast<size_t>(B) * g.nW * (C / 32) * ATT2_UNIT_BYTES;
 }
 
 int kvq_window_attention(const void* xw_f16, const void* qkv_w_f16, const float* qkv_b, const float* packed_table,
@@ -849,7 +849,7 @@ int kvq_window_attention(const void* xw_f16, const void* qkv_w_f16, const float*
   KVQ_REQUIRE(window[0] <= 8 && window[1] <= 7 && window[2] <= 7, KVQ_ERR_BAD_SHAPE, "window exceeds (8,7,7)");
   KVQ_REQUIRE(heads * 32 == C, KVQ_ERR_BAD_SHAPE, "heads=%d x 32 != C=%d", heads, C);
   const WinGeom g = make_geom(D, H, W, window, shift);
-  const size_t need = static_cast<size_t>(B) * g.nW * heads * ATT3_UNIT_BYTES;
+  const size_t need = static_cast<size_t>(B) * g.nW * heads * ATT2_UNIT_BYTES;
   KVQ_REQUIRE(workspace != nullptr && workspace_bytes >= need, KVQ_ERR_WORKSPACE, "workspace %zu B < required %zu B",
               workspace_bytes, need);
   return run_attention(static_cast<const __half*>(xw_f16), static_cast<const __half*>(qkv_w_f16), qkv_b,

@@ -568,9 +568,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int i = row - win_g * ntok;
         const int slab = i / p.geom.SL;
         const int pitch = p.att_pitch;
-        // pitch 50 / 52: slab-padded key slots d*pitch + h*7 + w; pitch 64 (third generation): h*64 + w*8 + d
+        // pitch 50 / 52: slab-padded key slots d*pitch + h*7 + w; pitch 56 (third generation): h*56 + w*8 + d
         const bool hwd = pitch == ATT3_PITCH;
-        const int kv_rows = hwd ? ATT3_KV_ROWS : 8 * pitch;    // 400, 416 or 448 key slots
+        const int kv_rows = hwd ? ATT3_KV_ROWS : 8 * pitch;    // 400 or 416 key slots
         const int kv_bytes = kv_rows * ATT_HD * 2;
         const size_t unit_bytes = static_cast<size_t>(ATT_IMG_BYTES) + 2 * kv_bytes;
         const int pos = i - slab * p.geom.SL;
@@ -619,7 +619,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               st_global_v4(dst + att_img_offset(rimg, kc0 + j), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
             // the last token of a slab also zeroes the padded K/V key slots behind it (P is 0 there, but 0 * NaN
             // from uninitialised workspace would poison PV); the last token of the window zeroes all the rest
-            const bool pad_owner = hwd ? (slab == 7 && pos % 7 == 6) : (pos == p.geom.SL - 1);
+            const bool pad_owner = hwd ? (slab == 7 && pos == 48) : (pos == p.geom.SL - 1);
             if (which != 0 && pad_owner) {
               const int end = hwd ? kv_row + 9 : (i == ntok - 1) ? kv_rows : (slab + 1) * pitch;
               for (int rz = kv_row + 1; rz < end; ++rz) {

@@ -100,13 +100,13 @@ constexpr int ATT2_KV_BYTES = ATT2_KV_ROWS * ATT_HD * 2;   // 26 624
 constexpr int ATT2_Q_BYTES = ATT_IMG_BYTES;                // 25 600
 constexpr int ATT2_UNIT_BYTES = ATT2_Q_BYTES + 2 * ATT2_KV_BYTES;   // 78 848
 
-// third-generation layout (kvq_attn3.cu): keys ordered (h, w, d) with d fastest, one 64-slot chunk per window row h
-// (56 keys + 8 zero pad slots): slot = h*64 + w*8 + d; unit = Q (400 rows, natural order) | K (448 rows) | V (448 rows).
+// third-generation layout (kvq_attn3.cu): keys ordered (h, w, d) with d fastest, one 56-key chunk per window row h:
+// slot = h*56 + w*8 + d, 392 keys + 8 zero rows; unit = Q (400 rows, natural order) | K (400 rows) | V (400 rows).
 // Its bias table is the paired layout float4 {t0[e], t0[e-1], t1[e], t1[e-1]} at (e+6)*SD + (dh+6)*SH + (dw+6).
-constexpr int ATT3_PITCH = 64;
-constexpr int ATT3_KV_ROWS = 7 * ATT3_PITCH;               // 448
-constexpr int ATT3_KV_BYTES = ATT3_KV_ROWS * ATT_HD * 2;   // 28 672
-constexpr int ATT3_UNIT_BYTES = ATT_IMG_BYTES + 2 * ATT3_KV_BYTES;   // 82 944
+constexpr int ATT3_PITCH = 56;
+constexpr int ATT3_KV_ROWS = 400;
+constexpr int ATT3_KV_BYTES = ATT3_KV_ROWS * ATT_HD * 2;   // 25 600
+constexpr int ATT3_UNIT_BYTES = ATT_IMG_BYTES + 2 * ATT3_KV_BYTES;   // 76 800
 constexpr int ATT3_SH = 15, ATT3_SD = 201;                 // bank-conflict-free strides for LDS.128 (16 B entries)
 constexpr int ATT3_PAIR_LEN = 13 * ATT3_SD + 12 * ATT3_SH + 13;      // 2806 float4 per head
 
