@@ -239,81 +239,103 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       }
     } else {
       // =============================== MMA issuer of slot `warp - 1` ===============================
-      // Warp-uniform control flow and operands; one elected lane issues (see the header comment).
+      // Warp-uniform control flow and operands; one elected lane issues (see the header comment).  The per-chunk
+      // path is kept to a barrier wait plus the MMAs: everything item-dependent (unit decode, descriptor bases) is
+      // computed once per item, the chunk loop is unrolled so descriptor offsets are immediates.
       const int s = warp - 1;
       const uint32_t tB = s * T3_SLOT, tO = s * T3_SLOT + T3_O;
       const uint32_t sbase = smem_u32(smem);
-      const uint32_t aKaug = sbase + S3_KAUG, aQaug = sbase + S3_QAUG + s * 2048;
       constexpr uint32_t idesc_s = umma_idesc_f16(128, 64, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 32, 0, 1);
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {   // one lane polls, the warp follows
         if (lane == 0) mbar_wait(bar, parity);
         __syncwarp();
       };
-      uint32_t n_qa = 0;
-      // S_j = Q K_c^T of the chunk at cursor x into buffer j & 1 (waits for the operands of a new item / unit first)
-      auto issue_s = [&](const Cursor& x, uint32_t j) {
-        const UnitInfo u = unit_info(p, blockIdx.x + x.n * G);
-        const bool masked = u.md || u.mh || u.mw;
-        const bool tail = x.it == 1;
-        const int qb = x.k & 1;
-        if (x.c == 0) {
-          if (x.it == 0) wait_all(&bars.kv[x.n & 1], (x.n >> 1) & 1);
-          wait_all(&bars.q[s][qb], (x.k >> 1) & 1);
-          if (masked) {
-            wait_all(&bars.qa[s], n_qa & 1);
-            ++n_qa;
-          }
-          tc_fence_after();
-        }
-        const uint32_t aK = sbase + S3_KV + (x.n & 1) * 2 * ATT3_KV_BYTES + x.c * (56 * 64);
-        const uint32_t aQ = sbase + S3_Q + (s * 2 + qb) * 8192;
-        const uint32_t q_sbo = tail ? 0u : 512u, qa_sbo = tail ? 0u : 128u;
-        const uint32_t tS = tB + (j & 1) * 64;
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t dq = umma_smem_desc(aQ + ks * 256, 128, q_sbo, UMMA_SW_NONE);
-            const uint64_t dk = umma_smem_desc(aK + ks * 256, 128, 512, UMMA_SW_NONE);
-            umma_f16_ss(tS, dq, dk, idesc_s, ks);
-          }
-          if (masked) {
-            const uint64_t dq = umma_smem_desc(aQaug, 0, qa_sbo, UMMA_SW_NONE);
-            const uint64_t dk = umma_smem_desc(aKaug + x.c * (56 * 16), 0, 128, UMMA_SW_NONE);
-            umma_f16_ss(tS, dq, dk, idesc_s, 1u);
-          }
-          umma_commit(&bars.s[s][j & 1]);
-          if (x.c == NCHUNK3 - 1) umma_commit(&bars.qfree[s][qb]);   // every S MMA of this item has read the Q tile
-        }
-        __syncwarp();
+      // descriptors of one item: advancing the start-address field by (bytes >> 4) walks chunks / K steps
+      struct ItemDesc {
+        uint64_t dq, dk, dqa, dka, dv;
+        bool masked;
+        int qb, nb;
       };
-      Cursor cur = {0, 0, 0, 0}, ahead = {0, 0, 0, 0};
-      if (ahead.n < n_units) { issue_s(ahead, 0); ahead.advance(s); }
-      if (ahead.n < n_units) { issue_s(ahead, 1); ahead.advance(s); }
-#pragma unroll 1
-      for (uint32_t j = 0; cur.n < n_units; ++j) {
-        // P_j written over S_j.  One barrier per buffer: a warp can run at most two chunks ahead of its slowest
-        // sibling (S_{j+2} is only issued once phase j completed), so its arrivals for chunks j and j+1 never mix
-        wait_all(&bars.p[s][j & 1], (j >> 1) & 1);
-        if (cur.c == 0 && cur.k > 0) wait_all(&bars.of[s], (cur.k - 1) & 1);   // previous item's O was read
+      uint32_t n_qa = 0;
+      // waits for the operands of the item at cursor x and builds its descriptors
+      auto open_item = [&](const Cursor& x) {
+        const UnitInfo u = unit_info(p, blockIdx.x + x.n * G);
+        ItemDesc d;
+        d.masked = u.md || u.mh || u.mw;
+        const bool tail = x.it == 1;
+        d.qb = x.k & 1;
+        d.nb = x.n & 1;
+        if (x.it == 0) wait_all(&bars.kv[d.nb], (x.n >> 1) & 1);
+        wait_all(&bars.q[s][d.qb], (x.k >> 1) & 1);
+        if (d.masked) {
+          wait_all(&bars.qa[s], n_qa & 1);
+          ++n_qa;
+        }
         tc_fence_after();
-        const uint32_t aV = sbase + S3_KV + (cur.n & 1) * 2 * ATT3_KV_BYTES + ATT3_KV_BYTES + cur.c * (56 * 64);
-        const uint32_t tP = tB + (j & 1) * 64;
-        const bool last_of_unit = cur.c == NCHUNK3 - 1 && cur.it == ((cur.n % NSLOT == s) ? 1 : 0);
-        if (elect_one()) {
-          const uint32_t acc0 = cur.c > 0 ? 1u : 0u;
+        const uint32_t aK = sbase + S3_KV + d.nb * 2 * ATT3_KV_BYTES;
+        d.dq = umma_smem_desc(sbase + S3_Q + (s * 2 + d.qb) * 8192, 128, tail ? 0u : 512u, UMMA_SW_NONE);
+        d.dk = umma_smem_desc(aK, 128, 512, UMMA_SW_NONE);
+        d.dqa = umma_smem_desc(sbase + S3_QAUG + s * 2048, 0, tail ? 0u : 128u, UMMA_SW_NONE);
+        d.dka = umma_smem_desc(sbase + S3_KAUG, 0, 128, UMMA_SW_NONE);
+        d.dv = umma_smem_desc(aK + ATT3_KV_BYTES, 512, 128, UMMA_SW_NONE);
+        return d;
+      };
+      // S_c of item d into S/P buffer `buf` (called by the elected lane only)
+      auto issue_s = [&](const ItemDesc& d, int c, uint32_t buf) {
+        const uint32_t tS = tB + buf * 64;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t dv = umma_smem_desc(aV + ks * 1024, 512, 128, UMMA_SW_NONE);
-            umma_f16_ts(tO, tP + 8 * ks, dv, idesc_pv, ks > 0 ? 1u : acc0);
-          }
-          umma_commit(&bars.pv[s][j & 1]);
-          if (last_of_unit) umma_commit(&bars.kvfree[cur.n & 1]);     // all MMAs of this slot on the unit are complete
+        for (int ks = 0; ks < 2; ++ks)
+          umma_f16_ss(tS, d.dq + ((ks * 256) >> 4), d.dk + ((c * (56 * 64) + ks * 256) >> 4), idesc_s, ks);
+        if (d.masked) umma_f16_ss(tS, d.dqa, d.dka + ((c * (56 * 16)) >> 4), idesc_s, 1u);
+        umma_commit(&bars.s[s][buf]);
+        if (c == NCHUNK3 - 1) umma_commit(&bars.qfree[s][d.qb]);   // every S MMA of this item has read the Q tile
+      };
+      Cursor cur = {0, 0, 0, 0};
+      uint32_t j = 0;
+      ItemDesc d;
+      if (cur.n < n_units) {
+        d = open_item(cur);
+        if (elect_one()) {
+          issue_s(d, 0, 0);
+          issue_s(d, 1, 1);
         }
         __syncwarp();
-        // the buffer P_j lives in is free once PV_j has run: the tensor pipe executes in issue order
-        if (ahead.n < n_units) { issue_s(ahead, j + 2); ahead.advance(s); }
-        cur.advance(s);
+      }
+#pragma unroll 1
+      while (cur.n < n_units) {
+        const bool last_item = cur.it == ((cur.n % NSLOT == s) ? 1 : 0);
+#pragma unroll
+        for (int c = 0; c < NCHUNK3; ++c, ++j) {
+          const uint32_t buf = j & 1;
+          // P_c written over S_c.  One barrier per buffer: a warp can run at most two chunks ahead of its slowest
+          // sibling (S_{j+2} is only issued once phase j completed), so its arrivals for chunks j and j+1 never mix
+          wait_all(&bars.p[s][buf], (j >> 1) & 1);
+          if (c == 0 && cur.k > 0) wait_all(&bars.of[s], (cur.k - 1) & 1);   // previous item's O was read
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t tP = tB + buf * 64;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16_ts(tO, tP + 8 * ks, d.dv + ((c * (56 * 64) + ks * 1024) >> 4), idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&bars.pv[s][buf]);
+            if (c == NCHUNK3 - 1 && last_item) umma_commit(&bars.kvfree[d.nb]);   // this slot is done with the unit
+            // the buffer P_c lives in is free once PV_c has run: the tensor pipe executes in issue order
+            if (c + 2 < NCHUNK3) issue_s(d, c + 2, buf);
+          }
+          __syncwarp();
+        }
+        for (int c = 0; c < NCHUNK3; ++c) cur.advance(s);
+        if (cur.n < n_units) {
+          // the next item's first two chunks (its Q tile / K | V image / Qaug rows were produced long ago; S_0 runs
+          // under the softmax warps' epilogue of the item that just ended)
+          d = open_item(cur);
+          if (elect_one()) {
+            issue_s(d, 0, j & 1);
+            issue_s(d, 1, (j + 1) & 1);
+          }
+          __syncwarp();
+        }
       }
     }
   } else {
