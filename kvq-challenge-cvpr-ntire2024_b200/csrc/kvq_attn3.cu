@@ -349,46 +349,67 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
     const uint32_t stab = smem_u32(smem + S3_TAB);
     const float invH = 7.0f / static_cast<float>(g.Hp), invW = 7.0f / static_cast<float>(g.Wp);
 
-    // query side of the folded mask for the item at cursor x: [a_d 1 a_h 1 a_w 1 0 0] per row, a pair zeroed when its
-    // dim is not masked in that window.  Written one item ahead (see the call sites), consumed by the S MMAs.
-    auto write_qaug = [&](const Cursor& x) {
-      const UnitInfo u = unit_info(p, blockIdx.x + x.n * G);
-      if (!(u.md || u.mh || u.mw)) return;
-      const bool tail = x.it == 1;
-      const int row = q * 32 + lane;
-      const int ri = tail ? 384 + (lane & 7) : s * 128 + row;
-      const int d_i = ri / 49, hw_i = ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
-      uint4 w;
-      w.x = u.md ? pack_half2(d_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
-      w.y = u.mh ? pack_half2(h_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
-      w.z = u.mw ? pack_half2(w_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
-      w.w = 0u;
-      if (!tail || row < 8) *reinterpret_cast<uint4*>(qaug + row * 16) = w;
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.qa[s]);
+    // per-item thread state: which query row this thread owns and everything derived from the window position
+    struct Item {
+      int win_g, ri;
+      bool tail, md, mh, mw;
+      float fval;          // this LANE's fragment coordinate: lanes 0..6 rows h = lane, lanes 8..14 cols w = lane - 8
+      float fh_i, fw_i;    // the thread's own row / column fragment coordinates
+      float Aw[7];         // |fw_i - fw(w)|: the w part of the GRPB gate
+      uint32_t trow0;      // table address of (d_i, h_i, w_i) against key (0, 0, 0)
+    };
+    const int win_g0 = static_cast<int>(blockIdx.x) / p.heads, win_step = G / p.heads;   // G is a multiple of heads
+    const float rcp_nW = 1.0f / static_cast<float>(g.nW), rcp_hw = 1.0f / static_cast<float>(g.nwh * g.nww),
+                rcp_w = 1.0f / static_cast<float>(g.nww);
+    auto fdiv = [](int x, float rcp) { return __float2int_rz((static_cast<float>(x) + 0.5f) * rcp); };   // exact for x < 2^20
+    auto open_item = [&](const Cursor& x) {
+      Item it;
+      it.win_g = win_g0 + x.n * win_step;
+      const int win = it.win_g - fdiv(it.win_g, rcp_nW) * g.nW;
+      const int wdi = fdiv(win, rcp_hw), rem = win - wdi * (g.nwh * g.nww);
+      const int whi = fdiv(rem, rcp_w), wwi = rem - whi * g.nww;
+      it.md = g.sd != 0 && wdi == g.nwd - 1;
+      it.mh = g.sh != 0 && whi == g.nwh - 1;
+      it.mw = g.sw != 0 && wwi == g.nww - 1;
+      it.tail = x.it == 1;
+      it.ri = it.tail ? 384 + (lane & 7) : s * 128 + q * 32 + lane;
+      const int d_i = it.ri / 49, hw_i = it.ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
+      it.fval = (lane & 8) ? frag_coord(wwi * 7, lane & 7, g.sw, g.Wp, invW) : frag_coord(whi * 7, lane & 7, g.sh, g.Hp, invH);
+      it.fh_i = __shfl_sync(0xffffffffu, it.fval, h_i);
+      it.fw_i = __shfl_sync(0xffffffffu, it.fval, 8 + w_i);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) it.Aw[i] = fabsf(it.fw_i - __shfl_sync(0xffffffffu, it.fval, 8 + i));
+      it.trow0 = stab + 16u * static_cast<uint32_t>((d_i + 6) * ATT3_SD + (h_i + 6) * ATT3_SH + (w_i + 6));
+      // query side of the folded mask: [a_d 1 a_h 1 a_w 1 0 0] per row, a pair zeroed when its dim is not masked in
+      // this window.  Written while no S MMA of the previous item can still read the rows (see the call sites).
+      if (it.md || it.mh || it.mw) {
+        uint4 w;
+        w.x = it.md ? pack_half2(d_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
+        w.y = it.mh ? pack_half2(h_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
+        w.z = it.mw ? pack_half2(w_i >= 4 ? 1.f : 0.f, 1.f) : 0u;
+        w.w = 0u;
+        const int row = q * 32 + lane;
+        if (!it.tail || row < 8) *reinterpret_cast<uint4*>(qaug + row * 16) = w;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.qa[s]);
+      }
+      return it;
     };
 
     Cursor cur = {0, 0, 0, 0};
     uint32_t j = 0;                            // chunk ordinal of this slot
     mbar_wait(&bars.tab, 0);
-    if (cur.n < n_units) write_qaug(cur);
+    Item item;
+    if (cur.n < n_units) item = open_item(cur);
 #pragma unroll 1
     while (cur.n < n_units) {
       // ---------------- one item: a 128-row tile or the replicated tail rows ----------------
-      const int unit = blockIdx.x + cur.n * G;
-      const UnitInfo u = unit_info(p, unit);
-      const bool tail = cur.it == 1;
-      const int ri = tail ? 384 + (lane & 7) : s * 128 + q * 32 + lane;
-      const int d_i = ri / 49, hw_i = ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
-      const float fh_i = frag_coord(u.whi * 7, h_i, g.sh, g.Hp, invH), fw_i = frag_coord(u.wwi * 7, w_i, g.sw, g.Wp, invW);
-      float Aw[7];
-#pragma unroll
-      for (int i = 0; i < 7; ++i) Aw[i] = fabsf(fw_i - frag_coord(u.wwi * 7, i, g.sw, g.Wp, invW));
-      const uint32_t trow0 = stab + 16u * static_cast<uint32_t>((d_i + 6) * ATT3_SD + (h_i + 6) * ATT3_SH + (w_i + 6));
+      const bool tail = item.tail;
       Cursor next = cur;
       next.c = NCHUNK3 - 1;
       next.advance(s);                         // first chunk of the next item of this slot
+      Item nitem;
 
       float m_ref = -INFINITY, l_run = 0.f;
       bool fresh = true;                       // no chunk of this row processed yet (warp-uniform)
@@ -399,23 +420,35 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
         mbar_wait(&bars.s[s][j & 1], (j >> 1) & 1);
         __syncwarp();
         tc_fence_after();
-        // every S MMA of this item has completed once its last chunk is visible: the next item's Qaug rows may go in
-        if (c == NCHUNK3 - 1 && next.n < n_units) write_qaug(next);
         if (own) {
           uint32_t r[56], h[32];
-          const uint32_t tb = trow0 - 16u * static_cast<uint32_t>(c * ATT3_SH);
-          const float Ah = fabsf(fh_i - frag_coord(u.whi * 7, c, g.sh, g.Hp, invH));
+          const uint32_t tb = item.trow0 - 16u * static_cast<uint32_t>(c * ATT3_SH);
+          const float Ah = fabsf(item.fh_i - __shfl_sync(0xffffffffu, item.fval, c));
           float4 e[2][4];
-          bool redo = fresh;                   // the row's first chunk fixes m_ref: two passes
-          if (!redo) {
-            // ---- fused pass against the standing m_ref: bias, exp2, pack, row sum, chunk max ----
-            tmem_ld_x32(tS, r);
-            tmem_ld_x16(tS + 32, r + 32);
-            tmem_ld_x8(tS + 48, r + 48);
+          // ---- fused pass against the standing m_ref: bias, exp2, pack, row sum, chunk max ----
+          tmem_ld_x32(tS, r);
+          tmem_ld_x16(tS + 32, r + 32);
+          tmem_ld_x8(tS + 48, r + 48);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) e[0][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD));
-            tmem_wait_ld();
-            float gmax = -INFINITY;
+          for (int kk = 0; kk < 4; ++kk) e[0][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD));
+          tmem_wait_ld();
+          if (fresh) {
+            // the row's first chunk: take the max over its first key position (8 logits) as m_ref.  Any later logit
+            // more than 15 above it triggers the two-pass redo below, so the estimate only has to be in the right range
+            const float2 fg2 = splat2(Ah + item.Aw[0]);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const float4 t = e[0][kk];
+              const float2 v = fadd2(ffma2(fg2, make_float2(t.z, t.w),
+                                           make_float2(__uint_as_float(r[2 * kk]), __uint_as_float(r[2 * kk + 1]))),
+                                     make_float2(t.x, t.y));
+              mx = fmax3(mx, v.x, v.y);
+            }
+            m_ref = mx;
+          }
+          float gmax = -INFINITY;
+          {
             const float2 negm2 = splat2(-m_ref);
             float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -424,7 +457,7 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) e[(wj + 1) & 1][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD + wj + 1));
               }
-              bias_pos(r, wj, e[wj & 1], splat2(Ah + Aw[wj]), gmax);
+              bias_pos(r, wj, e[wj & 1], splat2(Ah + item.Aw[wj]), gmax);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 const int i = wj * 8 + 2 * kk;
@@ -434,52 +467,54 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
                 h[i >> 1] = pack_half2(pe.x, pe.y);
               }
             }
-            redo = __any_sync(0xffffffffu, gmax > m_ref + TAU);
-            if (!redo) l_run += sum2.x + sum2.y;
-          }
-          if (redo) {
-            // ---- two passes: bias + exact chunk max, raise m_ref (rescaling O and l), then exp2 ----
-            tmem_ld_x32(tS, r);
-            tmem_ld_x16(tS + 32, r + 32);
-            tmem_ld_x8(tS + 48, r + 48);
+            const bool redo = __any_sync(0xffffffffu, gmax > m_ref + TAU);
+            if (!redo) {
+              l_run += sum2.x + sum2.y;
+            } else {
+              // ---- rare: a logit left the fp16-safe range of m_ref.  Two passes: bias + exact chunk max, raise m_ref
+              // (rescaling O and l), then exp2 ----
+              tmem_ld_x32(tS, r);
+              tmem_ld_x16(tS + 32, r + 32);
+              tmem_ld_x8(tS + 48, r + 48);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) e[0][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD));
-            tmem_wait_ld();
-            float gmax = -INFINITY;
-#pragma unroll
-            for (int wj = 0; wj < 7; ++wj) {
-              if (wj < 6) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) e[(wj + 1) & 1][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD + wj + 1));
-              }
-              bias_pos(r, wj, e[wj & 1], splat2(Ah + Aw[wj]), gmax);
-            }
-            const float m_new = fmaxf(m_ref, gmax);
-            const float alpha = fast_exp2(m_ref - m_new);             // 0 while m_ref is still -inf
-            if (!fresh) {
-              // O holds this item's partial sums against the old m_ref; PV of the previous chunk must have landed
-              // (one barrier per buffer parity: a single one could still be a phase behind and alias the parity test)
-              mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
-              tc_fence_after();
-              uint32_t o[32];
-              tmem_ld_x32(tO, o);
+              for (int kk = 0; kk < 4; ++kk) e[0][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD));
               tmem_wait_ld();
+              gmax = -INFINITY;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_x32(tO, o);
-              l_run *= alpha;
-            }
-            m_ref = m_new;
-            const float2 negm2 = splat2(-m_ref);
-            float2 sum2 = make_float2(0.f, 0.f);
+              for (int wj = 0; wj < 7; ++wj) {
+                if (wj < 6) {
 #pragma unroll
-            for (int i = 0; i < 28; ++i) {
-              const float2 x = fadd2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), negm2);
-              const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-              sum2 = fadd2(sum2, pe);
-              h[i] = pack_half2(pe.x, pe.y);
+                  for (int kk = 0; kk < 4; ++kk) e[(wj + 1) & 1][kk] = lds_f4(tb - 16u * (2 * kk * ATT3_SD + wj + 1));
+                }
+                bias_pos(r, wj, e[wj & 1], splat2(Ah + item.Aw[wj]), gmax);
+              }
+              const float m_new = fmaxf(m_ref, gmax);
+              const float alpha = fast_exp2(m_ref - m_new);
+              if (!fresh) {
+                // O holds this item's partial sums against the old m_ref; PV of the previous chunk must have landed
+                // (one barrier per buffer parity: a single one could still be a phase behind and alias the parity test)
+                mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+                uint32_t o[32];
+                tmem_ld_x32(tO, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_x32(tO, o);
+                l_run *= alpha;
+              }
+              m_ref = m_new;
+              const float2 negm2b = splat2(-m_ref);
+              sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 28; ++i) {
+                const float2 x = fadd2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), negm2b);
+                const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                sum2 = fadd2(sum2, pe);
+                h[i] = pack_half2(pe.x, pe.y);
+              }
+              l_run += sum2.x + sum2.y;
             }
-            l_run += sum2.x + sum2.y;
           }
           fresh = false;
           h[28] = h[29] = h[30] = h[31] = 0u;  // 8 zero pad slots complete the fourth K step
@@ -495,6 +530,9 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.p[s][j & 1]);
       }
+      // every S MMA of this item has completed (its last chunk was visible): the next item's Qaug rows may go in, and
+      // the rest of its set-up runs while the MMA issuer finishes PV of the last chunk
+      if (next.n < n_units) nitem = open_item(next);
 
       // ---- epilogue: O / l -> global ----
       mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
@@ -508,7 +546,7 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       if (lane == 0) mbar_arrive(&bars.of[s]);
       if (!tail) {
         const float inv = 1.0f / l_run;
-        __half* dst = p.out + (static_cast<size_t>(u.win_g) * 392 + ri) * p.C + head * ATT_HD;
+        __half* dst = p.out + (static_cast<size_t>(item.win_g) * 392 + item.ri) * p.C + head * ATT_HD;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 v;
@@ -540,7 +578,7 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
 #pragma unroll
           for (int i = 1; i < 4; ++i) L = fmaf(wq[i], scr[((i - 1) * 8 + lane) * 34 + 32], L);
           const float inv = 1.0f / L;
-          __half* dst = p.out + (static_cast<size_t>(u.win_g) * 392 + 384 + lane) * p.C + head * ATT_HD;
+          __half* dst = p.out + (static_cast<size_t>(item.win_g) * 392 + 384 + lane) * p.C + head * ATT_HD;
 #pragma unroll
           for (int i0 = 0; i0 < 32; i0 += 8) {
             float v[8];
@@ -562,6 +600,7 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
         named_bar_sync(1 + s, 128);   // the scratch is rewritten by this slot's next tail item
       }
       cur = next;
+      item = nitem;
     }
   }
 

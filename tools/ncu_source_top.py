@@ -27,3 +27,22 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def segments(path, marks=("LDTM", "STTM", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "SYNCS.ARRIVE", "BAR.SYNC", "STG", "VOTE", "UTCHMMA", "UTCBAR", "USETMAXREG", "UBLKCP")):
+    """samples / executed instructions between landmark instructions, in program order"""
+    with open(path, newline="") as f:
+        lines = f.readlines()
+    start = next(i for i, ln in enumerate(lines) if ln.startswith('"Address"'))
+    rows = list(csv.DictReader(lines[start:]))
+    seg = ex = 0
+    segstart = 0
+    for i, r in enumerate(rows):
+        s = int(r["# Samples"] or 0)
+        if any(m in r["Source"] for m in marks):
+            print(f"  [{seg:6d} samp {ex:10d} exec {i - segstart:4d} instrs] -> {r['Address'][-5:]} {r['Source'][:70]} ({s} samp, {r['Instructions Executed']} exec)")
+            seg = ex = 0
+            segstart = i
+        seg += s
+        ex += int(r["Instructions Executed"] or 0)
+    print(f"  [{seg:6d} samp {ex:10d} exec] tail")
