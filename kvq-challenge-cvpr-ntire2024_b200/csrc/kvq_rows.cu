@@ -242,8 +242,12 @@ fragment_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __rest
   int hg = (Hs / fh) * i; if (hg > Hs - fs) hg = Hs - fs;
   int wg = (Ws / fw) * j; if (wg > Ws - fs) wg = Ws - fs;
   const int32_t* off = offsets + static_cast<size_t>(b) * 2 * fh * fw * nt;
-  const int oh = off[(i * fw + j) * nt + tc];
-  const int ow = off[fh * fw * nt + (i * fw + j) * nt + tc];
+  // offsets live on the device and cannot be validated by the launcher: clamp them so a bad offset tensor (negative,
+  // beyond the cell, drawn for another source size) reads inside the frame instead of out of bounds
+  int oh = off[(i * fw + j) * nt + tc];
+  int ow = off[fh * fw * nt + (i * fw + j) * nt + tc];
+  oh = oh < 0 ? 0 : (oh > Hs - fs - hg ? Hs - fs - hg : oh);
+  ow = ow < 0 ? 0 : (ow > Ws - fs - wg ? Ws - fs - wg : ow);
   const uint8_t* src = frames + (((static_cast<size_t>(b) * T + t) * 3 + c) * Hs + (hg + oh + dy)) * Ws + (wg + ow + dx);
   const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
   const float istd = c == 0 ? is0 : (c == 1 ? is1 : is2);
@@ -278,8 +282,11 @@ fragment_gather_upsample_kernel(const uint8_t* __restrict__ frames, const int32_
   int hg = (Hs / fh) * i; if (hg > Hs - fs) hg = Hs - fs;
   int wg = (Ws / fw) * j; if (wg > Ws - fs) wg = Ws - fs;
   const int32_t* off = offsets + static_cast<size_t>(b) * 2 * fh * fw * nt;
-  const int uy = hg + off[(i * fw + j) * nt + tc] + dy;                       // pixel of the enlarged frame
-  const int ux = wg + off[fh * fw * nt + (i * fw + j) * nt + tc] + dx;
+  int oh = off[(i * fw + j) * nt + tc], ow = off[fh * fw * nt + (i * fw + j) * nt + tc];
+  oh = oh < 0 ? 0 : oh;                                                       // (the source reads below are clamped)
+  ow = ow < 0 ? 0 : ow;
+  const int uy = hg + oh + dy;                                                // pixel of the enlarged frame
+  const int ux = wg + ow + dx;
   float sy = rscale * (static_cast<float>(uy) + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
   float sx = rscale * (static_cast<float>(ux) + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
   int y0 = static_cast<int>(sy); if (y0 > Hs - 1) y0 = Hs - 1;

@@ -93,8 +93,11 @@ class SyntheticKSVQEDataset(torch.utils.data.Dataset):
             frames = torch.randint(0, 256, (self.T, 3, self.src_h, self.src_w), generator=g, dtype=torch.uint8)
             hl, wl, nt = self.src_h // self.fh, self.src_w // self.fw, self.T // self.aligned
             # reference draw order: rnd_h then rnd_w (fusion_datasets.py:87-98)
-            rnd_h = torch.randint(hl - self.fs, (self.fh, self.fw, nt), generator=g)
-            rnd_w = torch.randint(wl - self.fs, (self.fh, self.fw, nt), generator=g)
+            # a grid cell exactly fsize wide leaves no room to jitter: zero offsets (fusion_datasets.py:88-98)
+            rnd_h = torch.randint(hl - self.fs, (self.fh, self.fw, nt), generator=g) if hl > self.fs else \
+                torch.zeros((self.fh, self.fw, nt), dtype=torch.int64)
+            rnd_w = torch.randint(wl - self.fs, (self.fh, self.fw, nt), generator=g) if wl > self.fs else \
+                torch.zeros((self.fh, self.fw, nt), dtype=torch.int64)
             return dict(common, frames=frames, offsets=torch.stack([rnd_h, rnd_w]).int(),
                         fragment_opts={"fragments_h": self.fh, "fragments_w": self.fw, "fsize": self.fs,
                                        "aligned": self.aligned},

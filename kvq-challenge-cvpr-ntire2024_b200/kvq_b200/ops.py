@@ -682,20 +682,25 @@ class SimpleVQAWeights:
                     torch.empty(B, dtype=torch.float32, device=x.device) if self.cfg.head else None)
 
         if graph:
-            key = (x.data_ptr(), feat3d.data_ptr() if feat3d is not None else 0, tuple(x.shape), ws.data_ptr())
+            # the SlowFast features are copied into a graph-owned staging buffer, so a fresh batch['feat'] tensor per video
+            # neither re-captures the graph nor pins the old tensor
+            key = (x.data_ptr(), tuple(x.shape), ws.data_ptr())
             entry = self._graphs.get(key)
             if entry is None:
                 feats, score = alloc()
-                self._launch(x, feat3d, feats, score, ws)
+                stage = feat3d.clone() if feat3d is not None else None
+                self._launch(x, stage, feats, score, ws)
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 n0 = _l.load().kvq_launch_count()
                 with torch.cuda.graph(g):
-                    self._launch(x, feat3d, feats, score, ws)
+                    self._launch(x, stage, feats, score, ws)
                 nodes = int(_l.load().kvq_launch_count() - n0)
                 if len(self._graphs) >= 8:
                     self._graphs.pop(next(iter(self._graphs)))
-                entry = self._graphs[key] = (g, feats, score, nodes, feat3d)
+                entry = self._graphs[key] = (g, feats, score, nodes, stage)
+            if entry[4] is not None:
+                entry[4].copy_(feat3d)
             entry[0].replay()
             global GRAPH_KERNEL_LAUNCHES
             GRAPH_KERNEL_LAUNCHES += entry[3]

@@ -132,16 +132,19 @@ class SwinTransformer3D(nn.Module):
         fragment table where the checkpoint has none, drop shape-mismatched keys."""
         sd = ckpt.get("state_dict", ckpt)
         own = self.state_dict()
-        out = {}
+        clean = {}
         for k, v in sd.items():
             for pre in ("module.", "backbone."):
                 if k.startswith(pre):
                     k = k[len(pre):]
-            if k in own and own[k].shape == v.shape:
-                out[k] = v
-                fk = k.replace("relative_position_bias_table", "fragment_position_bias_table")
-                if fk != k and fk in own and fk not in sd:
-                    out[fk] = v
+            clean[k] = v
+        # second pass over the CLEANED keys: a fragment table the checkpoint really contains always wins over the fork
+        # (reference :945-952 never overwrites an existing fragment_position_bias_table, whatever the key order)
+        for k in [k for k in clean if "relative_position_bias_table" in k]:
+            fk = k.replace("relative_position_bias_table", "fragment_position_bias_table")
+            if fk in own and fk not in clean:
+                clean[fk] = clean[k]
+        out = {k: v for k, v in clean.items() if k in own and own[k].shape == v.shape}
         return self.load_state_dict(out, strict=strict)
 
     # ---- packed device weights, rebuilt only when a parameter changed ----

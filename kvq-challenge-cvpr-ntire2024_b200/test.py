@@ -22,7 +22,13 @@ def main():
     with open(args.opt) as f:
         opt = yaml.safe_load(f)
     if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+        import torch
         import torch.distributed as dist
+        # bind the device BEFORE NCCL initialises: --gpu_id defaults to "0", and every rank on cuda:0 fails with a
+        # duplicate-GPU error (Trainer applies the same rule)
+        gpus = [int(i) for i in str(args.gpu_id).split(",")]
+        local, lws = int(os.environ["LOCAL_RANK"]), int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        torch.cuda.set_device(gpus[local] if len(gpus) >= lws else local)
         dist.init_process_group("nccl")
     trainer = Trainer(args, opt)
     for name, score in trainer.inferece(args.output):

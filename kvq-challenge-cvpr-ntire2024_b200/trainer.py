@@ -58,7 +58,13 @@ def score_video(model, data, key_list, device=None):
             if device is not None:
                 data[key] = data[key].to(device)
             nc = data["num_clips"][key]
-            data[key] = split_clips(data[key], int(nc[0]) if torch.is_tensor(nc) else int(nc)).contiguous()
+            nc = int(nc[0]) if torch.is_tensor(nc) else int(nc)
+            data[key] = split_clips(data[key], nc).contiguous()
+            if key == "simpleVQA" and "feat" in data and torch.is_tensor(data["feat"]):
+                # the SlowFast features ride with the frames: one device copy, split into the same clips (the reference
+                # head flattens them with view(-1, 2304), head.py:24, so any clip split of [b, T, 2304] is equivalent)
+                f = data["feat"].to(device if device is not None else data[key].device, torch.float32)
+                data["feat"] = f.reshape(data[key].shape[0], data[key].shape[2], f.shape[-1]).contiguous()
     with torch.no_grad():
         pred = model(inputs=data, reduce_scores=True)
         if isinstance(pred, tuple):            # KSVQE key returns (scores, dis_contra_loss)  (trainer.py:323-325)
@@ -71,7 +77,16 @@ class Trainer:
         self.args, self.config = args, config
         self.gpu_list = [int(i) for i in str(args.gpu_id).split(",")]
         local = int(os.environ.get("LOCAL_RANK", "0"))
-        gpu = self.gpu_list[local % len(self.gpu_list)] if "LOCAL_RANK" in os.environ else self.gpu_list[0]
+        if "LOCAL_RANK" in os.environ:
+            # one process per GPU under torchrun: with fewer --gpu_id entries than local ranks (test.py defaults to
+            # "0") every rank would land on the same device, so fall back to cuda:LOCAL_RANK
+            lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+            gpu = self.gpu_list[local] if len(self.gpu_list) >= lws else local
+            if gpu >= torch.cuda.device_count():
+                raise RuntimeError(f"kvq_b200: local rank {local} has no GPU (visible devices: {torch.cuda.device_count()}, "
+                                   f"--gpu_id {args.gpu_id})")
+        else:
+            gpu = self.gpu_list[0]
         self.device = torch.device("cuda", gpu)
         torch.cuda.set_device(self.device)
         self.key_list = ["technical"] if any(k.startswith("swin") for k in config["model"]["args"]) \

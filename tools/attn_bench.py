@@ -11,6 +11,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "kvq-challenge-cvpr-ntire2024_b200"))
 import torch  # noqa: E402
 from kvq_b200 import lib, ops  # noqa: E402
+if os.environ.get("KVQ_LIB"):          # A/B builds: point the loader at another libkvq_b200.so
+    lib.LIB_PATH = os.environ["KVQ_LIB"]
 from tools import synth  # noqa: E402
 
 GEOMS = [("s0", 8, 16, 56, 56, 96, 3), ("s1", 8, 16, 28, 28, 192, 6), ("s2", 8, 16, 14, 14, 384, 12),
