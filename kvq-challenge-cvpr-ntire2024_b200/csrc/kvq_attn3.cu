@@ -4,8 +4,8 @@
 // The second generation (kvq_attn2.cu) was latency-bound in its scalar softmax path: two TMEM round trips per logit,
 // MMA and softmax serialised inside a CTA, eight softmax warps per SM.  This kernel is organised around the per-logit
 // instruction count and around keeping the LDS, MUFU and tensor pipes busy at the same time:
-//   * ONE persistent CTA per SM, 16 warps: warps 0..11 are three softmax warpgroups (one per tile slot; thread = query
-//     row = TMEM lane), warp 12 loads (cp.async.bulk), warps 13..15 each issue the tcgen05.mma of one slot.
+//   * ONE persistent CTA per SM, 16 warps: warp 0 loads (cp.async.bulk), warps 1..3 each issue the tcgen05.mma of one
+//     tile slot, warps 4..15 are three softmax warpgroups (one per slot; thread = query row = TMEM lane).
 //     The three slots work on the three 128-row tiles of the same (window, head) unit, sharing its K | V image.
 //   * keys are ordered (h, w, d) with d fastest: slot = h*56 + w*8 + d, one 56-key chunk per window row h.  A chunk is
 //     S = Q K_c^T (M128 x N64 x K32: the 8 columns past the chunk are the next chunk's keys and are never read),
@@ -189,7 +189,7 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
     *reinterpret_cast<uint4*>(smem + S3_KAUG + r * 16) = w;
   }
   fence_proxy_async_smem();
-  if (warp == 13) {
+  if (warp == 1) {
     tmem_alloc(&bars.tmem_slot, 512);
     tmem_relinquish();
   }
@@ -205,11 +205,9 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
 
   const int n_units = (units - static_cast<int>(blockIdx.x) + G - 1) / G;   // units of this CTA: blockIdx.x + n*G
 
-  if (warp >= 12) {
-    // aux warps carry the HIGHEST warp ids: the issue arbiter favours high ids, and an MMA issuer that waits behind
-    // twelve issue-hungry softmax warps delays every S / PV handoff
-    reg_dec<56>();
-    if (warp == 12) {
+  if (warp < 4) {
+    reg_dec<64>();
+    if (warp == 0) {
       // =============================== loader ===============================
       if (lane == 0) {
         uint32_t k_item[NSLOT] = {0, 0, 0};
@@ -240,11 +238,11 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
         }
       }
     } else {
-      // =============================== MMA issuer of slot `warp - 13` ===============================
+      // =============================== MMA issuer of slot `warp - 1` ===============================
       // Warp-uniform control flow and operands; one elected lane issues (see the header comment).  The per-chunk
       // path is kept to a barrier wait plus the MMAs: everything item-dependent (unit decode, descriptor bases) is
       // computed once per item, the chunk loop is unrolled so descriptor offsets are immediates.
-      const int s = warp - 13;
+      const int s = warp - 1;
       const uint32_t tB = s * T3_SLOT, tO = s * T3_SLOT + T3_O;
       const uint32_t sbase = smem_u32(smem);
       constexpr uint32_t idesc_s = umma_idesc_f16(128, 64, 0, 0);
@@ -260,6 +258,29 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
         int qb, nb;
       };
       uint32_t n_qa = 0;
+      // waits for the operands of the item at cursor x and builds its descriptors
+      auto open_item = [&](const Cursor& x) {
+        const UnitInfo u = unit_info(p, blockIdx.x + x.n * G);
+        ItemDesc d;
+        d.masked = u.md || u.mh || u.mw;
+        const bool tail = x.it == 1;
+        d.qb = x.k & 1;
+        d.nb = x.n & 1;
+        if (x.it == 0) wait_all(&bars.kv[d.nb], (x.n >> 1) & 1);
+        wait_all(&bars.q[s][d.qb], (x.k >> 1) & 1);
+        if (d.masked) {
+          wait_all(&bars.qa[s], n_qa & 1);
+          ++n_qa;
+        }
+        tc_fence_after();
+        const uint32_t aK = sbase + S3_KV + d.nb * 2 * ATT3_KV_BYTES;
+        d.dq = umma_smem_desc(sbase + S3_Q + (s * 2 + d.qb) * 8192, 128, tail ? 0u : 512u, UMMA_SW_NONE);
+        d.dk = umma_smem_desc(aK, 128, 512, UMMA_SW_NONE);
+        d.dqa = umma_smem_desc(sbase + S3_QAUG + s * 2048, 0, tail ? 0u : 128u, UMMA_SW_NONE);
+        d.dka = umma_smem_desc(sbase + S3_KAUG, 0, 128, UMMA_SW_NONE);
+        d.dv = umma_smem_desc(aK + ATT3_KV_BYTES, 512, 128, UMMA_SW_NONE);
+        return d;
+      };
       // S_c of item d into S/P buffer `buf` (called by the elected lane only)
       auto issue_s = [&](const ItemDesc& d, int c, uint32_t buf) {
         const uint32_t tS = tB + buf * 64;
@@ -270,38 +291,11 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
         umma_commit(&bars.s[s][buf]);
         if (c == NCHUNK3 - 1) umma_commit(&bars.qfree[s][d.qb]);   // every S MMA of this item has read the Q tile
       };
-      // operand waits and descriptors are split so the descriptors of the NEXT item can be built while this issuer idles
-      // in the middle of the current item; the waits (long satisfied by then) happen right before its first S
-      auto item_desc = [&](const Cursor& x) {
-        const UnitInfo u = unit_info(p, blockIdx.x + x.n * G);
-        ItemDesc d;
-        d.masked = u.md || u.mh || u.mw;
-        const bool tail = x.it == 1;
-        d.qb = x.k & 1;
-        d.nb = x.n & 1;
-        const uint32_t aK = sbase + S3_KV + d.nb * 2 * ATT3_KV_BYTES;
-        d.dq = umma_smem_desc(sbase + S3_Q + (s * 2 + d.qb) * 8192, 128, tail ? 0u : 512u, UMMA_SW_NONE);
-        d.dk = umma_smem_desc(aK, 128, 512, UMMA_SW_NONE);
-        d.dqa = umma_smem_desc(sbase + S3_QAUG + s * 2048, 0, tail ? 0u : 128u, UMMA_SW_NONE);
-        d.dka = umma_smem_desc(sbase + S3_KAUG, 0, 128, UMMA_SW_NONE);
-        d.dv = umma_smem_desc(aK + ATT3_KV_BYTES, 512, 128, UMMA_SW_NONE);
-        return d;
-      };
-      auto item_wait = [&](const Cursor& x, const ItemDesc& d) {
-        if (x.it == 0) wait_all(&bars.kv[d.nb], (x.n >> 1) & 1);
-        wait_all(&bars.q[s][d.qb], (x.k >> 1) & 1);
-        if (d.masked) {
-          wait_all(&bars.qa[s], n_qa & 1);
-          ++n_qa;
-        }
-        tc_fence_after();
-      };
       Cursor cur = {0, 0, 0, 0};
       uint32_t j = 0;
-      ItemDesc d, dn;
+      ItemDesc d;
       if (cur.n < n_units) {
-        d = item_desc(cur);
-        item_wait(cur, d);
+        d = open_item(cur);
         if (elect_one()) {
           issue_s(d, 0, 0);
           issue_s(d, 1, 1);
@@ -311,14 +305,9 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
 #pragma unroll 1
       while (cur.n < n_units) {
         const bool last_item = cur.it == ((cur.n % NSLOT == s) ? 1 : 0);
-        Cursor nxt = cur;
-        nxt.c = NCHUNK3 - 1;
-        nxt.advance(s);
-        const bool has_next = nxt.n < n_units;
 #pragma unroll
         for (int c = 0; c < NCHUNK3; ++c, ++j) {
           const uint32_t buf = j & 1;
-          if (c == 3 && has_next) dn = item_desc(nxt);                       // idle time: build the next descriptors
           // P_c written over S_c.  One barrier per buffer: a warp can run at most two chunks ahead of its slowest
           // sibling (S_{j+2} is only issued once phase j completed), so its arrivals for chunks j and j+1 never mix
           wait_all(&bars.p[s][buf], (j >> 1) & 1);
@@ -335,22 +324,24 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
             if (c + 2 < NCHUNK3) issue_s(d, c + 2, buf);
           }
           __syncwarp();
-          if (c + 2 >= NCHUNK3 && has_next) {
-            // first two chunks of the next item: its Q tile / K | V image arrived long ago, its Qaug rows are written
-            // by the softmax warps when they pick up the current item's last chunk
-            if (c + 2 == NCHUNK3) item_wait(nxt, dn);
-            if (elect_one()) issue_s(dn, c + 2 - NCHUNK3, buf);
-            __syncwarp();
-          }
         }
-        cur = nxt;
-        d = dn;
+        for (int c = 0; c < NCHUNK3; ++c) cur.advance(s);
+        if (cur.n < n_units) {
+          // the next item's first two chunks (its Q tile / K | V image / Qaug rows were produced long ago; S_0 runs
+          // under the softmax warps' epilogue of the item that just ended)
+          d = open_item(cur);
+          if (elect_one()) {
+            issue_s(d, 0, j & 1);
+            issue_s(d, 1, (j + 1) & 1);
+          }
+          __syncwarp();
+        }
       }
     }
   } else {
-    reg_inc<152>();
+    reg_inc<144>();
     // =============================== softmax warps: one thread per query row ===============================
-    const int s = warp >> 2, q = warp & 3;
+    const int s = (warp - 4) >> 2, q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tB = lane_off + s * T3_SLOT, tO = lane_off + s * T3_SLOT + T3_O;
     float* scr = reinterpret_cast<float*>(smem + S3_SCR + s * SCR_BYTES);
@@ -408,15 +399,6 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
 
     Cursor cur = {0, 0, 0, 0};
     uint32_t j = 0;                            // chunk ordinal of this slot
-#ifdef A3_TIMING
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long t_begin = clock64();
-#define A3_T0() const long long t0_ = clock64()
-#define A3_T1(k) tacc[k] += clock64() - t0_
-#else
-#define A3_T0()
-#define A3_T1(k)
-#endif
     mbar_wait(&bars.tab, 0);
     Item item;
     if (cur.n < n_units) item = open_item(cur);
@@ -435,16 +417,9 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       for (int c = 0; c < NCHUNK3; ++c, ++j) {
         const bool own = !tail || (c & 3) == q;
         const uint32_t tS = tB + (j & 1) * 64;
-        {
-          A3_T0();
-          mbar_wait(&bars.s[s][j & 1], (j >> 1) & 1);
-          A3_T1(tail ? 3 : (c == 0 ? 0 : (c == 1 ? 1 : 2)));
-        }
+        mbar_wait(&bars.s[s][j & 1], (j >> 1) & 1);
         __syncwarp();
         tc_fence_after();
-#ifdef A3_TIMING
-        const long long t_chunk = clock64();
-#endif
         if (own) {
           uint32_t r[56], h[32];
           const uint32_t tb = item.trow0 - 16u * static_cast<uint32_t>(c * ATT3_SH);
@@ -554,20 +529,13 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.p[s][j & 1]);
-#ifdef A3_TIMING
-        if (own) tacc[tail ? 6 : 5] += clock64() - t_chunk;
-#endif
       }
       // every S MMA of this item has completed (its last chunk was visible): the next item's Qaug rows may go in, and
       // the rest of its set-up runs while the MMA issuer finishes PV of the last chunk
       if (next.n < n_units) nitem = open_item(next);
 
       // ---- epilogue: O / l -> global ----
-      {
-        A3_T0();
-        mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
-        A3_T1(4);
-      }
+      mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
       __syncwarp();
       tc_fence_after();
       uint32_t o[32];
@@ -634,16 +602,11 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       cur = next;
       item = nitem;
     }
-#ifdef A3_TIMING
-    if (blockIdx.x == 5 && lane == 0)
-      printf("A3T warp %2d slot %d q %d: total %lld | Swait c0 %lld c1 %lld c2+ %lld tail %lld | pvwait %lld | own full %lld tail %lld\n", warp, s, q,
-             clock64() - t_begin, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6]);
-#endif
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -125,26 +125,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Busy-polling wait (mbarrier.test_wait, no hardware suspend): for handoffs on a critical path where the wake-up
-// latency of the suspending try_wait form is visible.  Same trap-on-timeout guard.
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!ok && ++spins > (1u << 28)) {
-      printf("kvq: mbarrier spin wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  } while (!ok);
-}
-
 // ---- proxies / fences ----
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -7,7 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "kvq-challenge-cvpr-ntire2024_b200"))
 import torch  # noqa: E402
-from kvq_b200 import ops  # noqa: E402
+from kvq_b200 import lib, ops  # noqa: E402
+if os.environ.get("KVQ_LIB"):
+    lib.LIB_PATH = os.environ["KVQ_LIB"]
 from tools import synth  # noqa: E402
 from tools.attn_bench import GEOMS  # noqa: E402
 
