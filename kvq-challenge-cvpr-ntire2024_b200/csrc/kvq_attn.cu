@@ -801,15 +801,15 @@ int launch_pack_bias(const float* rel, const float* frag, float* out, int bd, in
 }
 
 static int resolve_variant(int variant) {
-  // 6 = third generation (kvq_attn3.cu: one-pass softmax, three tile slots per SM) for full (8,7,7) windows;
-  // 5 = two-CTA flash-style kernel (kvq_attn2.cu); tuning knob
+  // 6 (default) = third generation (kvq_attn3.cu: one-pass softmax, three tile slots per SM) for full (8,7,7)
+  // windows; 5 = two-CTA flash-style kernel (kvq_attn2.cu); tuning knob
   // KVQ_ATTN_VARIANT: 1 = first-generation persistent kernel, 2 = generic kernel everywhere
   if (variant != 0) return variant;
   static int env_variant = -1;
   if (env_variant < 0) {
     const char* e = getenv("KVQ_ATTN_VARIANT");
-    env_variant = e ? atoi(e) : 5;
-    if (env_variant == 0) env_variant = 5;
+    env_variant = e ? atoi(e) : 6;
+    if (env_variant == 0) env_variant = 6;
   }
   return env_variant;
 }
