@@ -42,6 +42,25 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
 
 
+def ncu_traffic(kernel_substr, csv_name="r02_window_attn3_ncu_full.csv"):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of a kernel from the committed `ncu --set full`
+    export in profiles/ (tools/ncu_rep_to_csv.py); (None, reason) when the file or the kernel is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None, f"profiles/{csv_name} not found"
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, hit = 0.0, 0
+    with open(path, newline="") as f:
+        for r in csv.DictReader(f):
+            if kernel_substr in r["kernel"] and r["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r["value"].replace(",", "")) * scale.get(r["unit"], 1.0)
+                hit += 1
+    if hit < 2:
+        return None, f"{kernel_substr} not in profiles/{csv_name}"
+    return tot, f"profiles/{csv_name} (one ncu --set full capture of the stage-0 launch at batch 8, not this run)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -565,7 +584,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's own log lines (init banner, ring / tree set-up, nranks) go to
+        # stderr instead of being silenced, so a driver that sets or reads NCCL_DEBUG can still count the ranks
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     L = lib.load()
     wl = WORKLOADS[args.workload]
@@ -624,9 +647,14 @@ def run_ours(args):
         value = world * B * args.steps / (ms / 1000.0)
 
         # ---------------- end to end: pinned host clips -> H2D -> forward -> scores D2H ----------------
-        xh = [[t.pin_memory() for t in host_inputs(50)], [t.pin_memory() for t in host_inputs(60)]]
-        xd = [[torch.empty_like(t) for t in x], [torch.empty_like(t) for t in x]]
-        h2d_bytes = sum(t.numel() * t.element_size() for t in x)
+        # swin: the clips cross PCIe as fp16 (the drop-in accepts float16 'technical' tensors: the patch embedding rounds
+        # its operand to fp16 anyway, so the scores are bit-identical and the H2D feed -- the 8-GPU limiter of round 1 --
+        # halves); the other workloads ship the dtypes their datasets produce (uint8 frames, fp32 features)
+        e2e_half = args.workload == "swin" and not args.e2e_fp32
+        ship = (lambda t: t.half() if (e2e_half and t.dtype == torch.float32) else t)
+        xh = [[ship(t).pin_memory() for t in host_inputs(50)], [ship(t).pin_memory() for t in host_inputs(60)]]
+        xd = [[torch.empty_like(t, device=dev) for t in xh[0]], [torch.empty_like(t, device=dev) for t in xh[0]]]
+        h2d_bytes = sum(t.numel() * t.element_size() for t in xh[0])
         copy_stream = torch.cuda.Stream()
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -701,17 +729,23 @@ def run_ours(args):
             step_frac = wl["gflop_per_clip"] * 1e9 * value / world / 1e12 / pk["tflops"]
             if args.workload in ("swin", "fragment"):
                 # dominant kernel = the fused window attention; report the heaviest stage instance
-                top = next(r for r in rows if r[0].startswith("window_attn"))
+                top = max((r for r in rows if r[0].startswith("window_attn")), key=lambda r: r[1] / r[2])   # heaviest launch
                 stage = int(top[0][-1])
                 avg_ms = top[1] / top[2]
                 flops = ATTN_GFLOP_PER_CLIP_BLOCK[stage] * 1e9 * B
                 achieved = flops / (avg_ms * 1e-3) / 1e12
-                roof = {"kernel": f"window_attn2_kernel ({top[0]})", "bound": "tensor", "achieved": achieved,
+                variant = os.environ.get("KVQ_ATTN_VARIANT", "6")
+                kname = {"5": "window_attn2_kernel", "1": "window_attn_fast_kernel", "2": "window_attn_kernel"}.get(
+                    variant, "window_attn3_kernel")
+                traffic, traffic_src = ncu_traffic(kname) if stage == 0 else (None, "committed capture is of the stage-0 launch")
+                roof = {"kernel": f"{kname} ({top[0]})", "bound": "tensor", "achieved": achieved,
                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                        "traffic": args.traffic, "avg_launch_ms": avg_ms,
+                        "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": avg_ms,
                         "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
                         "algorithmic": f"{ATTN_GFLOP_PER_CLIP_BLOCK[stage]} GFLOP/clip/block (QK^T+PV) x {B} clips per launch",
-                        "step_tensor_frac": step_frac}
+                        "step_tensor_frac": step_frac,
+                        "breakdown_note": "breakdown = eager instrumented pass (CUDA events between launches); it sums to "
+                                          "more than ms_per_step, which is the CUDA-graph replay"}
             else:
                 # convolution workloads: ~100 conv-GEMM launches of very different shapes; the figure is for the whole
                 # step (algorithmic FLOPs of SURVEY 8d / device time of the step), not a single launch
@@ -741,6 +775,14 @@ def run_ours(args):
         else:
             cpu, score_delta = oracle_workload(args.workload, host_inputs(3), scores_gpu.cpu(), sd)
 
+    # ---------------- the other BASELINE configs, device-timed, short (N = 1 only) ----------------
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extras and args.workload == "swin":
+        del x, xd, xh
+        for m in modules:
+            m.use_cuda_graph = not args.no_graph
+        extra = run_extras(args, dev)
+
     if rank == 0:
         line = {"metric": wl["metric"], "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -752,12 +794,61 @@ def run_ours(args):
                            "launch": "eager" if args.no_graph else "CUDA graph replay per input buffer"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": int((world if world > 1 else 1) * scores_gpu.numel() * 4)},
+                        "d2h_bytes_per_step": int((world if world > 1 else 1) * scores_gpu.numel() * 4),
+                        "input_dtype": "f16" if e2e_half else "as produced by the dataset (f32 / u8)",
+                        "h2d_gbs_per_gpu": h2d_bytes * (e2e_value / world / B) / 1e9,
+                        "bound": "h2d" if (e2e_value < 0.9 * value and h2d_bytes * (e2e_value / world / B) / 1e9 > 30.0)
+                        else "device"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "score_delta_vs_oracle": score_delta, "breakdown": breakdown}
+        if extra is not None:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+EXTRA_WORKLOADS = ("slowfast", "simplevqa", "ksvqe_full", "fragment", "ksvqe")
+
+
+def run_extras(args, dev, steps=5):
+    """BASELINE configs 3 / 1 (GPU batch) / 4 / 5 and the literal KSVQE key at their per-GPU batch: device-resident
+    clips/s over `steps` CUDA-event-timed steps after 3 warm-ups, one entry per workload.  Same public-API steps as
+    `--workload <name>`, which remains the way to get a workload's full line (e2e, roofline, cpu_baseline)."""
+    import gc
+    import torch
+    from kvq_b200 import ops as kops
+    out = {"note": f"device-timed, inputs resident in HBM, {steps} steps after 3 warm-ups, 1 GPU; `--workload <name>` "
+                   "gives the full line of each", "workloads": []}
+    for name in EXTRA_WORKLOADS:
+        wl = WORKLOADS[name]
+        try:
+            host, wl_step, modules = build_workload(name, wl["batch"], dev, 0)
+            for m in modules:
+                m.use_cuda_graph = not args.no_graph and name != "ksvqe"     # ksvqe: host callback per stage, eager
+            xin = [t.to(dev) for t in host(3)]
+            with torch.no_grad():
+                for _ in range(3):
+                    wl_step(xin)
+                torch.cuda.synchronize()
+                n0 = kops.kernel_launches()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    wl_step(xin)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out["workloads"].append({"name": name, "metric": wl["metric"], "workload": wl["workload"],
+                                     "value": wl["batch"] / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms,
+                                     "steps": steps, "batch": wl["batch"],
+                                     "gpu_launches": int(kops.kernel_launches() - n0)})
+            del host, wl_step, modules, xin
+        except Exception as e:                                       # an extra must never take the headline line down
+            out["workloads"].append({"name": name, "error": f"{type(e).__name__}: {e}"[:300]})
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -773,9 +864,9 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=4, help="clips timed by the CPU baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of CUDA-graph replay")
-    ap.add_argument("--traffic", type=float, default=295.4e6,
-                    help="dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (stage-0 "
-                         "window_attn_fast_kernel at batch 8) from the ncu --set full capture in profiles/r01_summary.md")
+    ap.add_argument("--e2e-fp32", action="store_true", help="ship the swin clips as fp32 in the end-to-end leg (round-1 behaviour)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the short device-timed runs of the other BASELINE configs appended under `extra` (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

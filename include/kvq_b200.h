@@ -93,6 +93,13 @@ int kvq_swin3d_forward_hooked(const KvqSwinConfig* cfg, const void* const* weigh
                               int B, int T, int H, int W, float* feat_out, float* score_out, void* workspace,
                               size_t workspace_bytes, void* stream, kvq_stage_hook hook, void* hook_arg);
 
+/* Same forward for clips already stored as IEEE fp16 [B,3,T,H,W] (half the host->device and read traffic).  The patch
+ * embedding rounds its operand to fp16 in either case (swin_backbone.py:707-731 runs it in fp32; the stated 1e-3 score
+ * tolerance covers the rounding), so a round-to-nearest conversion on the host gives bit-identical results. */
+int kvq_swin3d_forward_x16(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const void* x_f16,
+                           int B, int T, int H, int W, float* feat_out, float* score_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- weight packing (once per load_state_dict) ---- */
 int kvq_cast_f16(const float* in, void* out_f16, size_t n, void* stream);
 /* fp32 [rows, K] -> fp16 [rows, 2*ceil64(K)] = [hi | 0 | lo | 0] with hi = fp16(w), lo = fp16(w - hi) */

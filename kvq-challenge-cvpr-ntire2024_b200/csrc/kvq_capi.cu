@@ -211,9 +211,27 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
                                    workspace_bytes, stream, nullptr, nullptr);
 }
 
+static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const void* x,
+                               int x_is_f16, int B, int T, int H, int W, float* feat_out, float* score_out,
+                               void* workspace, size_t workspace_bytes, void* stream, kvq_stage_hook hook, void* hook_arg);
+
 int kvq_swin3d_forward_hooked(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const float* x,
                               int B, int T, int H, int W, float* feat_out, float* score_out, void* workspace,
                               size_t workspace_bytes, void* stream, kvq_stage_hook hook, void* hook_arg) {
+  return swin3d_forward_impl(cfg, weights, num_weights, x, 0, B, T, H, W, feat_out, score_out, workspace, workspace_bytes,
+                             stream, hook, hook_arg);
+}
+
+int kvq_swin3d_forward_x16(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const void* x_f16,
+                           int B, int T, int H, int W, float* feat_out, float* score_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return swin3d_forward_impl(cfg, weights, num_weights, x_f16, 1, B, T, H, W, feat_out, score_out, workspace,
+                             workspace_bytes, stream, nullptr, nullptr);
+}
+
+static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const void* x,
+                               int x_is_f16, int B, int T, int H, int W, float* feat_out, float* score_out,
+                               void* workspace, size_t workspace_bytes, void* stream, kvq_stage_hook hook, void* hook_arg) {
   int rc = validate_cfg(cfg);
   if (rc != 0) return rc;
   Plan pl;
@@ -248,7 +266,7 @@ int kvq_swin3d_forward_hooked(const KvqSwinConfig* cfg, const void* const* weigh
   {
     {
       ProfScope ps(PK_EMBED_IM2COL, 0, st);
-      rc = launch_patch_im2col(x, a16, B, T, H, W, st);
+      rc = launch_patch_im2col(x, x_is_f16, a16, B, T, H, W, st);
     }
     if (rc != 0) return rc;
     GemmParams gp{};

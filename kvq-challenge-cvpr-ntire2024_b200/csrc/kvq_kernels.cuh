@@ -204,8 +204,8 @@ int launch_ln_rows(const float* x, __half* out, float* feat_cf, const float* gam
 // PatchMerging gather + LN(4C) (:533-555): out[(b,d,h2,w2), 4C]
 int launch_ln_merge(const float* x, __half* out, const float* gamma, const float* beta, float eps, int B, int D,
                     int H, int W, int C, cudaStream_t stream);
-// PatchEmbed3D im2col: x[B,3,T,H,W] fp32 -> A[B*D*Hs*Ws, 96] fp16, K index = c*32 + kt*16 + kh*4 + kw
-int launch_patch_im2col(const float* x, __half* out, int B, int T, int H, int W, cudaStream_t stream);
+// PatchEmbed3D im2col: x[B,3,T,H,W] fp32 (or fp16) -> A[B*D*Hs*Ws, 96] fp16, K index = c*32 + kt*16 + kh*4 + kw
+int launch_patch_im2col(const void* x, int x_is_f16, __half* out, int B, int T, int H, int W, cudaStream_t stream);
 // score[b] = mean_t rowscore[b*tokens + t]
 int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cudaStream_t stream);
 // Grid mini-patch sampling + normalisation (datasets/fusion_datasets.py:22-121, :1017-1020)

@@ -162,8 +162,11 @@ ln_merge_kernel(const float* __restrict__ x, __half* __restrict__ out, const flo
 
 // PatchEmbed3D im2col (:715-731).  One thread per (output token, c, kt, kh): copies the 4 kw taps (16 B in, 8 B out).
 // Zero padding when T/H/W are not multiples of (2,4,4).
+// TIn = float (the reference's input dtype) or __half (clips stored / shipped as fp16: the operand is rounded to fp16
+// here anyway, so a host-side round-to-nearest gives bit-identical operands at half the H2D and read traffic).
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-patch_im2col_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int T, int H, int W, int D, int Hs,
+patch_im2col_kernel(const TIn* __restrict__ x, __half* __restrict__ out, int B, int T, int H, int W, int D, int Hs,
                     int Ws, long long total) {
   pdl_launch_dependents();
   pdl_wait();
@@ -179,21 +182,34 @@ patch_im2col_kernel(const float* __restrict__ x, __half* __restrict__ out, int B
   const int c = kq >> 3, kt = (kq >> 2) & 1, kh = kq & 3;
   const long long tok = ((static_cast<long long>(b) * D + d) * Hs + hs) * Ws + ws;
   const int t = 2 * d + kt, h = 4 * hs + kh, w0 = 4 * ws;
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  uint2 h2 = make_uint2(0u, 0u);
   if (t < T && h < H) {
-    const float* src = x + (((static_cast<size_t>(b) * 3 + c) * T + t) * H + h) * W + w0;
-    if (w0 + 3 < W && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(src));
-      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-    } else {
+    const TIn* src = x + (((static_cast<size_t>(b) * 3 + c) * T + t) * H + h) * W + w0;
+    if constexpr (sizeof(TIn) == 4) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (w0 + 3 < W && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (w0 + k < W) v[k] = __ldg(src + k);
+        for (int k = 0; k < 4; ++k)
+          if (w0 + k < W) v[k] = __ldg(src + k);
+      }
+      h2.x = pack_half2(v[0], v[1]);
+      h2.y = pack_half2(v[2], v[3]);
+    } else {
+      if (w0 + 3 < W && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        h2 = __ldg(reinterpret_cast<const uint2*>(src));
+      } else {
+        unsigned short u[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (w0 + k < W) u[k] = __ldg(reinterpret_cast<const unsigned short*>(src) + k);
+        h2.x = u[0] | (static_cast<uint32_t>(u[1]) << 16);
+        h2.y = u[2] | (static_cast<uint32_t>(u[3]) << 16);
+      }
     }
   }
-  uint2 h2;
-  h2.x = pack_half2(v[0], v[1]);
-  h2.y = pack_half2(v[2], v[3]);
   *reinterpret_cast<uint2*>(out + tok * 96 + c * 32 + kt * 16 + kh * 4) = h2;
 }
 
@@ -495,14 +511,17 @@ int launch_ln_merge(const float* x, __half* out, const float* gamma, const float
   });
 }
 
-int launch_patch_im2col(const float* x, __half* out, int B, int T, int H, int W, cudaStream_t stream) {
+int launch_patch_im2col(const void* x, int x_is_f16, __half* out, int B, int T, int H, int W, cudaStream_t stream) {
   const int D = (T + 1) / 2, Hs = (H + 3) / 4, Ws = (W + 3) / 4;
   const long long total = static_cast<long long>(B) * D * Hs * Ws * 24;
   const long long grid = (total + 255) / 256;
   KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "im2col: grid too large");
   count_launch();
-  return launch_pdl(patch_im2col_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0, stream, x, out, B, T, H, W, D,
-                    Hs, Ws, total);
+  if (x_is_f16)
+    return launch_pdl(patch_im2col_kernel<__half>, dim3(static_cast<unsigned>(grid)), dim3(256), 0, stream,
+                      static_cast<const __half*>(x), out, B, T, H, W, D, Hs, Ws, total);
+  return launch_pdl(patch_im2col_kernel<float>, dim3(static_cast<unsigned>(grid)), dim3(256), 0, stream,
+                    static_cast<const float*>(x), out, B, T, H, W, D, Hs, Ws, total);
 }
 
 int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cudaStream_t stream) {

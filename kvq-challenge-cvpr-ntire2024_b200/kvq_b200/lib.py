@@ -39,6 +39,8 @@ PROTOTYPES = {
     "kvq_swin3d_workspace_bytes": (c_size_t, [POINTER(KvqSwinConfig), c_int, c_int, c_int, c_int]),
     "kvq_swin3d_forward": (c_int, [POINTER(KvqSwinConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
                                    c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_swin3d_forward_x16": (c_int, [POINTER(KvqSwinConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kvq_swin3d_forward_hooked": (c_int, [POINTER(KvqSwinConfig), POINTER(c_void_p), c_int, c_void_p, c_int, c_int, c_int,
                                           c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, STAGE_HOOK, c_void_p]),
     "kvq_pack_split_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

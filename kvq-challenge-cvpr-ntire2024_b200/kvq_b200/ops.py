@@ -301,8 +301,9 @@ class SwinWeights:
 
     def _launch(self, x, feat, score, ws):
         B, _, T, H, W = x.shape
-        rc = _l.load().kvq_swin3d_forward(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(x), B, T, H, W,
-                                          _p(feat), _p(score), _p(ws), ws.numel(), _stream())
+        fn = _l.load().kvq_swin3d_forward_x16 if x.dtype == torch.float16 else _l.load().kvq_swin3d_forward
+        rc = fn(ctypes.byref(self.cfg), self.ptrs, len(self.tensors), _p(x), B, T, H, W, _p(feat), _p(score), _p(ws),
+                ws.numel(), _stream())
         _l.check(rc, "swin3d_forward")
 
     def forward_hooked(self, x, stage_hook, want_feat=True, want_score=True):
@@ -334,14 +335,15 @@ class SwinWeights:
         return feat, score
 
     def forward(self, x, want_feat=False, want_score=True, score_out=None, graph=None):
-        """x f32 [B,3,T,H,W] on this device -> (feat [B,Cf,D,h,w] or None, score [B] or None).
+        """x f32 (or f16: clips shipped at half the bytes, identical operands after the patch embedding's fp16
+        rounding) [B,3,T,H,W] on this device -> (feat [B,Cf,D,h,w] or None, score [B] or None).
 
         graph=True (default: env KVQ_CUDA_GRAPH=1) replays the ~95 kernel launches of the forward from a CUDA graph
         captured per (input buffer, shape): the library enqueues everything on the current stream, allocates nothing
         and takes tensor maps by value, so the whole call is capturable.  Outputs of a graphed call live in buffers
         owned by the graph and are overwritten by the next replay for the same input buffer."""
-        if not x.is_cuda or x.dtype != torch.float32:
-            raise RuntimeError("kvq_b200: input clips must be float32 CUDA tensors (no CPU fallback exists)")
+        if not x.is_cuda or x.dtype not in (torch.float32, torch.float16):
+            raise RuntimeError("kvq_b200: input clips must be float32 / float16 CUDA tensors (no CPU fallback exists)")
         x = x.contiguous()
         B, _, T, H, W = x.shape
         ws, need = self.workspace(B, T, H, W)
@@ -349,7 +351,7 @@ class SwinWeights:
         if graph is None:
             graph = os.environ.get("KVQ_CUDA_GRAPH", "0") == "1"
         if graph and score_out is None:
-            key = (x.data_ptr(), tuple(x.shape), bool(want_feat), has_score, ws.data_ptr())
+            key = (x.data_ptr(), tuple(x.shape), x.dtype, bool(want_feat), has_score, ws.data_ptr())
             entry = self._graphs.get(key)
             if entry is None:
                 feat = torch.empty(self.feat_shape(B, T, H, W), dtype=torch.float32, device=x.device) if want_feat else None

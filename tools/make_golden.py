@@ -30,12 +30,16 @@ SWIN_CASES = [
     ("swin_m444_t16_96", (1, 3, 16, 96, 96), 17, 27, {"frag_biases": [0, 0, 0, 0], "window_size": (4, 4, 4)}),
     # swin_small (swin_backbone.py:1093-1095): depths [2,2,18,2]
     ("swin_small_t16_64", (1, 3, 16, 64, 64), 18, 28, {"frag_biases": [0, 0, 0, 0], "depths": [2, 2, 18, 2]}),
+    # BASELINE config 2 exactly: batch 8 clips of 32x224x224 (round 2: the batch-2 case above left batch 8 unpinned)
+    ("swin_b8_t32_224", (8, 3, 32, 224, 224), 19, 29, {}),
 ]
 
 
-def gen_swin(ref):
-    keys_written = False
+def gen_swin(ref, case=None):
+    keys_written = case is not None          # a single-case run leaves the key list alone
     for name, shape, wseed, xseed, kw in SWIN_CASES:
+        if case is not None and name != case:
+            continue
         fb = kw.get("frag_biases", [True, True, True, False])
         window = tuple(kw.get("window_size", (8, 7, 7)))
         depths = list(kw.get("depths", [2, 2, 6, 2]))
@@ -74,6 +78,7 @@ def gen_swin(ref):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
+    ap.add_argument("--case", default=None, help="with --only swin: regenerate just this fixture")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_import.load_reference()
@@ -85,7 +90,10 @@ def main():
         pass
     for k, fn in gens.items():
         if args.only in ("all", k):
-            fn(ref)
+            if k == "swin" and args.case:
+                fn(ref, args.case)
+            else:
+                fn(ref)
 
 
 if __name__ == "__main__":
