@@ -47,6 +47,10 @@ typedef struct KvqSwinConfig {
   int32_t split_weights;              /* bit 0 patch-embed, bit 1 PatchMerging reductions, bit 2 VQAHead fc_hid: the
                                          weight is passed as an fp16 pair [W_hi | W_lo] (kvq_pack_split_f16, row
                                          stride 2*ceil64(K)) so its rounding error drops from 2^-11 to 2^-22 */
+  int32_t resized_window[3];          /* adaptive_window_size (swin_backbone.py:53-61, :1049-1055): every block
+                                         partitions with this window (<= window per dim) instead of `window`, indexes
+                                         the bias tables with the token's own (d,h,w) and keeps the base shift
+                                         window/2.  0,0,0 = off */
 } KvqSwinConfig;
 
 /*
@@ -87,7 +91,9 @@ int kvq_swin3d_forward(const KvqSwinConfig* cfg, const void* const* weights, int
  * channels-last activation [rows, channels] (rows = B*D*h*w of the stage output) that the next stage reads, and may be
  * modified in place by work the hook enqueues on `stream` (KSVQE's cross-gating modulation after stages >= tuning_stage,
  * models/backbones/KSVQE_model.py:1436-1482).  The hook runs on the calling thread while the forward is being
- * enqueued (also under CUDA-graph capture); a non-zero return aborts the forward. */
+ * enqueued (also under CUDA-graph capture); a non-zero return aborts the forward.  It is also called once with
+ * stage = -1 on the patch-embedding output (feats[0] of SwinTransformer3D.forward :1058, for its `layer` / `multi`
+ * outputs). */
 typedef int (*kvq_stage_hook)(void* arg, int stage, float* tokens, int rows, int channels, void* stream);
 int kvq_swin3d_forward_hooked(const KvqSwinConfig* cfg, const void* const* weights, int num_weights, const float* x,
                               int B, int T, int H, int W, float* feat_out, float* score_out, void* workspace,

@@ -570,14 +570,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) window_attn_kernel(const AttnP
         const int th = hw / g.ww, tw = hw - th * g.ww;
         const int i = d * g.SL + hw;
         const int pd = wdi * g.wd + d, ph = whi * g.wh + th, pw = wwi * g.ww + tw;
-        int oh = ph + g.sh; if (oh >= g.Hp) oh -= g.Hp;
-        int ow = pw + g.sw; if (ow >= g.Wp) ow -= g.Wp;
-        const int rd = g.sd == 0 ? 0 : (pd >= g.Dp - g.wd) + (pd >= g.Dp - g.sd);
-        const int rh = g.sh == 0 ? 0 : (ph >= g.Hp - g.wh) + (ph >= g.Hp - g.sh);
-        const int rw = g.sw == 0 ? 0 : (pw >= g.Wp - g.ww) + (pw >= g.Wp - g.sw);
+        const int oh = (ph + g.sh) % g.Hp;
+        const int ow = (pw + g.sw) % g.Wp;
+        // compute_mask (:560-586) writes slice(-w), slice(-w, -s), slice(-s, None) in that order: the last one wins, which
+        // matters when s >= w (adaptive windows keep the base shift)
+        const int rd = g.sd == 0 ? 0 : (pd >= g.Dp - g.sd ? 2 : (pd >= g.Dp - g.wd ? 1 : 0));
+        const int rh = g.sh == 0 ? 0 : (ph >= g.Hp - g.sh ? 2 : (ph >= g.Hp - g.wh ? 1 : 0));
+        const int rw = g.sw == 0 ? 0 : (pw >= g.Wp - g.sw ? 2 : (pw >= g.Wp - g.ww ? 1 : 0));
         int fh = static_cast<int>(floorf(static_cast<float>(oh) * fscale_h)); if (fh > g.wh - 1) fh = g.wh - 1;
         int fw = static_cast<int>(floorf(static_cast<float>(ow) * fscale_w)); if (fw > g.ww - 1) fw = g.ww - 1;
-        const int brd = i / bhw, brh = (i / p.base_ww) % p.base_wh, brw = i % p.base_ww;
+        const int brd = p.rpi_geometric ? d : i / bhw, brh = p.rpi_geometric ? th : (i / p.base_ww) % p.base_wh,
+                  brw = p.rpi_geometric ? tw : i % p.base_ww;
         m.base = brd * s1 + brh * s2 + brw;
         m.pk = static_cast<uint32_t>(fh) | (static_cast<uint32_t>(fw) << 8) |
                (static_cast<uint32_t>(9 * rd + 3 * rh + rw) << 16) | (1u << 24);

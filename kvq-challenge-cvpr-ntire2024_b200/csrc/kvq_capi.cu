@@ -42,6 +42,12 @@ int validate_cfg(const KvqSwinConfig* cfg) {
               KVQ_ERR_BAD_SHAPE, "window (%d,%d,%d) exceeds (8,7,7)", cfg->window[0], cfg->window[1], cfg->window[2]);
   KVQ_REQUIRE(cfg->head_hidden == 0 || cfg->head_hidden == 64, KVQ_ERR_BAD_SHAPE, "head_hidden=%d (0 or 64)",
               cfg->head_hidden);
+  const int32_t* rw = cfg->resized_window;
+  KVQ_REQUIRE((rw[0] == 0 && rw[1] == 0 && rw[2] == 0) ||
+                  (rw[0] >= 1 && rw[0] <= cfg->window[0] && rw[1] >= 1 && rw[1] <= cfg->window[1] && rw[2] >= 1 &&
+                   rw[2] <= cfg->window[2]),
+              KVQ_ERR_BAD_SHAPE, "resized_window (%d,%d,%d) must be 0,0,0 or within window (%d,%d,%d)", rw[0], rw[1],
+              rw[2], cfg->window[0], cfg->window[1], cfg->window[2]);
   return KVQ_OK;
 }
 
@@ -56,7 +62,7 @@ int make_plan(const KvqSwinConfig* cfg, int B, int T, int H, int W, Plan* pl) {
   for (int s = 0; s < cfg->num_stages; ++s) {
     const int C = cfg->embed_dim << s;
     pl->st[s] = {D, Hh, Ww, C, cfg->num_heads[s]};
-    const WinGeom g = make_geom(D, Hh, Ww, cfg->window, zero);  // padded sizes do not depend on the shift
+    const WinGeom g = make_geom(D, Hh, Ww, cfg->resized_window[0] > 0 ? cfg->resized_window : cfg->window, zero);  // padded sizes do not depend on the shift
     const size_t rows_w = static_cast<size_t>(B) * g.nW * g.N;
     const size_t rows = static_cast<size_t>(B) * g.tokens;
     KVQ_REQUIRE(rows_w < (1ull << 31), KVQ_ERR_BAD_SHAPE, "stage %d has %zu window rows (int32 overflow)", s, rows_w);
@@ -86,7 +92,7 @@ int make_plan(const KvqSwinConfig* cfg, int B, int T, int H, int W, Plan* pl) {
 
 int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, const float* packed_tab, __half* out,
                   __half* img, int B, int C, int heads, const WinGeom& g, const int32_t base_win[3], int variant,
-                  cudaStream_t st, int stage = 0) {
+                  cudaStream_t st, int stage = 0, int rpi_geometric = 0) {
   const int rows_w = B * g.nW * g.N;
   GemmParams gp{};
   gp.M = rows_w; gp.N = 3 * C; gp.K = C;
@@ -112,6 +118,7 @@ int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, con
   ap.geom = g;
   ap.base_wd = base_win[0]; ap.base_wh = base_win[1]; ap.base_ww = base_win[2];
   ap.variant = variant;
+  ap.rpi_geometric = rpi_geometric;
   ProfScope ps(PK_ATTN, stage, st);
   return launch_window_attn(ap, st);
 }
@@ -282,15 +289,21 @@ static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weig
     if (rc != 0) return rc;
   }
 
+  if (hook != nullptr) {   // feats[0] of SwinTransformer3D.forward (:1058): the patch-embedding output
+    rc = hook(hook_arg, -1, xa, B * pl.D0 * pl.H0 * pl.W0, cfg->embed_dim, stream);
+    KVQ_REQUIRE(rc == 0, rc < 0 ? rc : KVQ_ERR_BAD_SHAPE, "stage hook failed after the patch embedding (code %d)", rc);
+  }
   float* xcur = xa;
   float* xnext = xb;
-  const int shift_full[3] = {cfg->window[0] / 2, cfg->window[1] / 2, cfg->window[2] / 2};
+  const int shift_full[3] = {cfg->window[0] / 2, cfg->window[1] / 2, cfg->window[2] / 2};   // the BASE window's shift (:633)
+  const bool adaptive = cfg->resized_window[0] > 0;
   const int shift_none[3] = {0, 0, 0};
   for (int s = 0; s < cfg->num_stages; ++s) {
     const StageDims& sd = pl.st[s];
     const int C = sd.C, M = B * sd.D * sd.H * sd.W;
     for (int j = 0; j < cfg->depths[s]; ++j) {
-      const WinGeom g = make_geom(sd.D, sd.H, sd.W, cfg->window, (j & 1) ? shift_full : shift_none);
+      const WinGeom g = make_geom(sd.D, sd.H, sd.W, adaptive ? cfg->resized_window : cfg->window,
+                                  (j & 1) ? shift_full : shift_none);
       const float* n1g = WF(); const float* n1b = WF();
       const __half* qkv_w = WH(); const float* qkv_b = WF(); const float* tab = WF();
       const __half* proj_w = WH(); const float* proj_b = WF();
@@ -304,7 +317,7 @@ static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weig
         rc = launch_ln_window(xcur, a16, n1g, n1b, eps, B, C, g, st);
       }
       if (rc != 0) return rc;
-      rc = run_attention(a16, qkv_w, qkv_b, tab, a16, img, B, C, sd.heads, g, cfg->window, 0, st, s);
+      rc = run_attention(a16, qkv_w, qkv_b, tab, a16, img, B, C, sd.heads, g, cfg->window, 0, st, s, adaptive ? 1 : 0);
       if (rc != 0) return rc;
       {
         GemmParams gp{};

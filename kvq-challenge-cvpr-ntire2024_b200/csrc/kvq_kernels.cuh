@@ -72,9 +72,10 @@ __host__ __device__ __forceinline__ int win_row_to_src(const WinGeom& g, int r) 
   const int win = r / g.N, i = r - win * g.N;
   const int wdi = win / (g.nwh * g.nww), whi = (win / g.nww) % g.nwh, wwi = win % g.nww;
   const int td = i / g.SL, th = (i / g.ww) % g.wh, tw = i % g.ww;
-  int od = wdi * g.wd + td + g.sd; if (od >= g.Dp) od -= g.Dp;
-  int oh = whi * g.wh + th + g.sh; if (oh >= g.Hp) oh -= g.Hp;
-  int ow = wwi * g.ww + tw + g.sw; if (ow >= g.Wp) ow -= g.Wp;
+  // torch.roll semantics: modulo (an adaptive window keeps the base shift, which can exceed a tiny padded grid)
+  const int od = (wdi * g.wd + td + g.sd) % g.Dp;
+  const int oh = (whi * g.wh + th + g.sh) % g.Hp;
+  const int ow = (wwi * g.ww + tw + g.sw) % g.Wp;
   if (od >= g.D || oh >= g.H || ow >= g.W) return -1;
   return (od * g.H + oh) * g.W + ow;
 }
@@ -266,6 +267,9 @@ struct AttnParams {
   WinGeom geom;
   int base_wd, base_wh, base_ww;  // un-clamped window the bias tables are indexed with
   int variant;              // debug: 1 swaps LBO/SBO of the MN-major V descriptor
+  int rpi_geometric;        // adaptive_window_size: bias index from the token's own (d,h,w) in the resized window
+                            // (relative_position_index.reshape(*base,*base)[:d,:h,:w,...], :264-271) instead of the
+                            // flat [:N,:N] slice the reference takes for clamped windows
 };
 // entries per head of the packed table for a base window (L rounded up to even)
 int attn_table_len(int bd, int bh, int bw);

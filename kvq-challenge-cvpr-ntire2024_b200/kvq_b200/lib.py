@@ -12,7 +12,8 @@ MAX_STAGES = 4
 class KvqSwinConfig(ctypes.Structure):
     _fields_ = [("embed_dim", c_int32), ("num_stages", c_int32), ("depths", c_int32 * MAX_STAGES),
                 ("num_heads", c_int32 * MAX_STAGES), ("window", c_int32 * 3), ("frag_bias", c_int32 * MAX_STAGES),
-                ("head_hidden", c_int32), ("ln_eps", c_float), ("split_weights", c_int32)]
+                ("head_hidden", c_int32), ("ln_eps", c_float), ("split_weights", c_int32),
+                ("resized_window", c_int32 * 3)]
 
 
 class KvqResNetConfig(ctypes.Structure):

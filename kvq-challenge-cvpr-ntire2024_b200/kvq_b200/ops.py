@@ -50,6 +50,19 @@ def pack_split_f16(w2d):
     return out
 
 
+class _DeviceView:
+    """A raw device pointer exposed through __cuda_array_interface__ so torch can alias it without a copy."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3}
+
+
+def device_view_f32(ptr, shape, device):
+    """fp32 tensor aliasing `ptr` (used inside stage hooks: valid only while the forward's workspace is alive)."""
+    return torch.as_tensor(_DeviceView(ptr, shape), device=device)
+
+
 def attn_table_len(window):
     return _l.load().kvq_attn_table_len(*[int(w) for w in window])
 
@@ -306,10 +319,20 @@ class SwinWeights:
                 ws.numel(), _stream())
         _l.check(rc, "swin3d_forward")
 
+    def set_resized_window(self, window):
+        """adaptive_window_size: partition with `window` (<= the base window per dim) from the next forward on; None
+        switches it off.  Captured graphs are per setting."""
+        rw = (0, 0, 0) if window is None else tuple(int(v) for v in window)
+        if tuple(self.cfg.resized_window) != rw:
+            self.cfg.resized_window = (ctypes.c_int32 * 3)(*rw)
+            self._graphs = {}
+            self._ws = None
+
     def forward_hooked(self, x, stage_hook, want_feat=True, want_score=True):
-        """Eager forward with `stage_hook(stage, tokens_ptr, rows, channels, stream_ptr) -> int` called after every
-        stage; tokens_ptr is the raw device pointer of the fp32 [rows, channels] stage output, which work enqueued
-        on the stream may modify in place (KSVQE's modulation).  Returns (feat or None, score or None)."""
+        """Eager forward with `stage_hook(stage, tokens_ptr, rows, channels, stream_ptr) -> int` called after the patch
+        embedding (stage -1) and after every stage; tokens_ptr is the raw device pointer of the fp32 [rows, channels]
+        output, which work enqueued on the stream may modify in place (KSVQE's modulation).  Returns (feat or None,
+        score or None)."""
         if not x.is_cuda or x.dtype != torch.float32:
             raise RuntimeError("kvq_b200: input clips must be float32 CUDA tensors (no CPU fallback exists)")
         x = x.contiguous()

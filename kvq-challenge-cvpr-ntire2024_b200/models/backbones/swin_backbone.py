@@ -177,14 +177,54 @@ class SwinTransformer3D(nn.Module):
             raise RuntimeError("kvq_b200: input clips must be CUDA tensors -- this path has no CPU fallback")
 
     def forward(self, batch, multi=False, layer=-1, adaptive_window_size=False):
-        """batch['technical'] f32 [B,3,T,H,W] -> [B, 8C, T/2, H/32, W/32]  (:1044-1080)."""
-        if multi or layer > -1 or adaptive_window_size:
-            raise NotImplementedError("kvq_b200: multi / layer / adaptive_window_size outputs are not on the B200 path")
+        """batch['technical'] f32 [B,3,T,H,W] -> [B, 8C, T/2, H/32, W/32]  (:1044-1080).
+
+        adaptive_window_size: every block partitions with window * input_size // base_x_size (get_adaptive_window_size
+        :53-61) -- a C-ABI configuration field, same kernels.  layer > -1 / multi return the un-normalised stage
+        outputs (feats[layer]) / all of them resized to the last grid and concatenated: the stage outputs are picked up
+        through the C-ABI stage hook; `multi` then uses ATen's trilinear resize on them (off the hot path)."""
         x = batch["technical"] if isinstance(batch, dict) else batch
         self._require_cuda(x)
         with torch.cuda.device(x.device):
-            feat, _ = self.packed().forward(x, want_feat=True, want_score=False)
-        return feat
+            wts = self.packed()
+            if adaptive_window_size:
+                rw = tuple((w * xi) // bx for w, xi, bx in zip(self.window_size, x.shape[2:], self.base_x_size))
+                if min(rw) < 1 or any(r > w for r, w in zip(rw, self.window_size)):
+                    raise RuntimeError(f"kvq_b200: adaptive window {rw} for input {tuple(x.shape[2:])} must lie within "
+                                       f"1..{self.window_size} (the reference's bias-table slice fails outside it too)")
+                wts.set_resized_window(rw)
+            else:
+                wts.set_resized_window(None)
+            if not (multi or layer > -1):
+                feat, _ = wts.forward(x, want_feat=True, want_score=False)
+                return feat
+            # feats[0] = patch embedding, feats[s + 1] = BasicLayer s (after its PatchMerging), channels-last tokens
+            B, _, T, H, W = x.shape
+            D, h, w = (T + 1) // 2, (H + 3) // 4, (W + 3) // 4
+            grids = [(D, h, w)]
+            for s_ in range(self.num_layers):
+                if s_ < self.num_layers - 1:
+                    h, w = (h + 1) // 2, (w + 1) // 2
+                grids.append((D, h, w))
+            feats = {}
+
+            def hook(stage, tokens_ptr, nrows, channels, stream_ptr):
+                idx = stage + 1
+                if multi or idx == layer:
+                    d_, h_, w_ = grids[idx]
+                    t = ops.device_view_f32(tokens_ptr, (B, d_, h_, w_, channels), x.device)
+                    feats[idx] = t.permute(0, 4, 1, 2, 3).contiguous()            # n c d h w, own storage
+                return 0
+
+            final, _ = wts.forward_hooked(x.float() if x.dtype != torch.float32 else x, hook, want_feat=True,
+                                          want_score=False)
+            if multi:
+                import torch.nn.functional as F
+                return torch.cat([F.interpolate(feats[i], size=final.shape[2:], mode="trilinear")
+                                  for i in range(self.num_layers)], 1)
+            if layer not in feats:
+                raise IndexError(f"layer={layer}: SwinTransformer3D has feats[0..{self.num_layers}]")
+            return feats[layer]
 
     def forward_with_head(self, x, head, want_feat=False, graph=None):
         """Fused backbone + VQAHead: one C-ABI call, score [B,1] (+ features when asked)."""

@@ -48,7 +48,7 @@ def clamp_window(dims, window, shift):
     return tuple(w), tuple(s)
 
 
-def token_tables(dims_p, window, shift, base_window=BASE_WINDOW):
+def token_tables(dims_p, window, shift, base_window=BASE_WINDOW, geometric_rpi=False):
     """Per-window-token index tables for a (padded) token grid.
 
     Returns dict of int64 tensors, each [nW, N] (windows ordered (d_win,h_win,w_win), tokens (d,h,w),
@@ -78,16 +78,23 @@ def token_tables(dims_p, window, shift, base_window=BASE_WINDOW):
     od, oh, ow = (pd + sd) % Dp, (ph + sh) % Hp, (pw + sw) % Wp
 
     def reg(p, size, win, s):
+        # compute_mask (:560-586) assigns slice(-win), slice(-win, -s), slice(-s, None) IN THAT ORDER: the last one wins,
+        # which only matters when s >= win (adaptive windows keep the base shift): then [size-s, size-win) is region 2 too
         if s == 0:
             return torch.zeros_like(p)
-        return (p >= size - win).long() + (p >= size - s).long()
+        return torch.where(p >= size - s, 2, (p >= size - win).long())
 
     region = 9 * reg(pd, Dp, wd, sd) + 3 * reg(ph, Hp, wh, sh) + reg(pw, Wp, ww, sw)
     # F.interpolate(nearest) of arange(frag) to size: src = floor(dst * frag / size)
     fh = torch.floor(oh.float() * (float(wh) / float(Hp))).long().clamp_(max=wh - 1)
     fw = torch.floor(ow.float() * (float(ww) / float(Wp))).long().clamp_(max=ww - 1)
     bd, bh, bw = base_window
-    rd, rh, rw = ti // (bh * bw), (ti // bw) % bh, ti % bw
+    if geometric_rpi:
+        # adaptive_window_size (:264-271): relative_position_index.reshape(*base, *base)[:d,:h,:w,:d,:h,:w] -- the token's
+        # own (d,h,w) inside the resized window indexes the base table
+        rd, rh, rw = td, th, tw
+    else:
+        rd, rh, rw = ti // (bh * bw), (ti // bw) % bh, ti % bw
     return dict(src=(od * Hp + oh) * Wp + ow, region=region, fh=fh, fw=fw,
                 rpi_d=rd, rpi_h=rh, rpi_w=rw, N=N, nW=nd * nh * nw_)
 
@@ -143,15 +150,16 @@ def window_attention(xw, p, num_heads, tabs, frag_bias, shifted, cast=_ident, ba
     return (cast(probs) @ cast(v)).permute(0, 1, 3, 2, 4).reshape(B, nW * N, C)
 
 
-def swin_block(x, p, num_heads, window, shift, frag_bias, cast=_ident):
-    """x: [B,D,H,W,C] fp32.  p(name) -> tensor for this block's parameters."""
+def swin_block(x, p, num_heads, window, shift, frag_bias, cast=_ident, resized_window=None):
+    """x: [B,D,H,W,C] fp32.  p(name) -> tensor for this block's parameters.  resized_window: adaptive_window_size
+    (:407-414) -- the block partitions with this window instead of its own and indexes the bias table geometrically."""
     B, D, H, W, C = x.shape
-    win, sh = clamp_window((D, H, W), window, shift)
+    win, sh = clamp_window((D, H, W), window if resized_window is None else resized_window, shift)
     shifted = any(s > 0 for s in sh)
     Dp = math.ceil(D / win[0]) * win[0]
     Hp = math.ceil(H / win[1]) * win[1]
     Wp = math.ceil(W / win[2]) * win[2]
-    tabs = token_tables((Dp, Hp, Wp), win, sh, base_window=tuple(window))
+    tabs = token_tables((Dp, Hp, Wp), win, sh, base_window=tuple(window), geometric_rpi=resized_window is not None)
     N, nW = tabs["N"], tabs["nW"]
     hd = C // num_heads
 
@@ -192,10 +200,16 @@ def patch_embed(x, sd, prefix="", patch=(2, 4, 4), cast=_ident):
     return y
 
 
+def adaptive_window(window, x_size, base_x_size=(32, 224, 224)):
+    """get_adaptive_window_size (:53-61): the window scales with the input clip relative to base_x_size."""
+    return tuple((w * xi) // bx for w, xi, bx in zip(window, x_size, base_x_size))
+
+
 def swin3d_forward(sd, x, prefix="", depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24),
                    window=BASE_WINDOW, frag_biases=(True, True, True, False), cast=_ident,
-                   return_stages=False):
-    """SwinTransformer3D.forward (:1044-1080) -> [B, 8C, D, H/32, W/32] fp32."""
+                   return_stages=False, multi=False, layer=-1, adaptive_window_size=False, base_x_size=(32, 224, 224)):
+    """SwinTransformer3D.forward (:1044-1080) -> [B, 8C, D, H/32, W/32] fp32 (or the `multi` / `layer` outputs)."""
+    resized = adaptive_window(window, tuple(x.shape[2:]), base_x_size) if adaptive_window_size else None
     x = patch_embed(x, sd, prefix, cast=cast)
     shift = tuple(i // 2 for i in window)
     stages = [x]
@@ -203,13 +217,17 @@ def swin3d_forward(sd, x, prefix="", depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 2
         for i in range(depth):
             base = f"{prefix}layers.{s}.blocks.{i}."
             x = swin_block(x, lambda n, b=base: sd[b + n], num_heads[s], window,
-                           (0, 0, 0) if i % 2 == 0 else shift, bool(frag_biases[s]), cast)
+                           (0, 0, 0) if i % 2 == 0 else shift, bool(frag_biases[s]), cast, resized_window=resized)
         if s < len(depths) - 1:
             base = f"{prefix}layers.{s}."
             x = patch_merge(x, lambda n, b=base: sd[b + n], cast)
         stages.append(x)
     x = layer_norm(x, sd[prefix + "norm.weight"], sd[prefix + "norm.bias"])
     x = x.permute(0, 4, 1, 2, 3).contiguous()
+    if multi:        # (:1069-1075) every earlier feature map resized to the last one's grid, concatenated on channels
+        return torch.cat([F.interpolate(f.permute(0, 4, 1, 2, 3), size=x.shape[2:], mode="trilinear") for f in stages[:-1]], 1)
+    if layer > -1:   # (:1076-1078) the un-normalised output of patch-embed (0) / stage layer-1
+        return stages[layer].permute(0, 4, 1, 2, 3).contiguous()
     return (x, stages) if return_stages else x
 
 

@@ -55,3 +55,20 @@ def test_state_dict_key_fixture_matches_synth_shapes():
     assert set(ours) == set(ref)
     for k, shp in ours.items():
         assert list(shp) == ref[k], k
+
+
+OPT_CASES = sorted(glob.glob(os.path.join(GOLDEN, "swinopt_*.npz")))
+
+
+@pytest.mark.parametrize("path", OPT_CASES, ids=[os.path.basename(p)[:-4] for p in OPT_CASES])
+def test_oracle_forward_options_match_reference_golden(path):
+    """adaptive_window_size / layer / multi of SwinTransformer3D.forward (:1044-1080): outputs of the REAL reference."""
+    import json
+    g = np.load(path)
+    kw = json.loads(str(g["kwargs"]))
+    sd = synth.synth_state_dict(synth.swin_shapes(frag_biases=[True, True, True, False]), int(g["wseed"]))
+    x = synth.clip_input(tuple(int(v) for v in g["shape"]), int(g["xseed"]))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    out = swin3d.swin3d_forward(sd, x, **kw).numpy()
+    assert out.shape == g["out"].shape
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=2e-4)

@@ -75,6 +75,30 @@ def gen_swin(ref, case=None):
             keys_written = True
 
 
+# forward options of SwinTransformer3D.forward (:1044-1080): (name, shape, wseed, xseed, forward kwargs)
+OPTION_CASES = [
+    ("swinopt_adaptive_t16_112", (1, 3, 16, 112, 112), 31, 41, {"adaptive_window_size": True}),   # window (4,3,3), shift (4,3,3)
+    ("swinopt_adaptive_t32_160", (1, 3, 32, 160, 160), 32, 42, {"adaptive_window_size": True}),   # window (8,5,5)
+    ("swinopt_layer2_t16_64", (1, 3, 16, 64, 64), 33, 43, {"layer": 2}),
+    ("swinopt_multi_t16_64", (1, 3, 16, 64, 64), 34, 44, {"multi": True}),
+]
+
+
+def gen_swin_options(ref):
+    for name, shape, wseed, xseed, kw in OPTION_CASES:
+        fb = [True, True, True, False]
+        m = ref.swin.SwinTransformer3D(pretrained=None, use_checkpoint=False, frag_biases=fb)
+        sd = synth.synth_state_dict(synth.swin_shapes(frag_biases=fb), wseed)
+        m.load_state_dict(sd, strict=False)
+        m.eval()
+        x = synth.clip_input(shape, xseed)
+        with torch.no_grad():
+            out = m({"technical": x}, **kw)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), out=out.numpy().astype(np.float32), shape=np.array(shape),
+                            wseed=wseed, xseed=xseed, kwargs=json.dumps(kw))
+        print(name, tuple(out.shape), "absmean", out.abs().mean().item())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
@@ -82,7 +106,7 @@ def main():
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_import.load_reference()
-    gens = {"swin": gen_swin}
+    gens = {"swin": gen_swin, "swinopt": gen_swin_options}
     try:
         from tools import make_golden_extra  # widened rows (fragments, simpleVQA, ...) live there
         gens.update(make_golden_extra.GENERATORS)
