@@ -366,6 +366,13 @@ size_t kvq_resize_view_workspace_bytes(int B, int T, int Hs, int Ws, int out_h, 
 int kvq_resize_view_u8(const uint8_t* frames, int layout, int B, int T, int Hs, int Ws, int out_h, int out_w, int crop_y,
                        int crop_x, int crop_h, int crop_w, float divisor, const float mean[3], const float std[3],
                        uint8_t* out_u8, float* out_f32, void* workspace, size_t workspace_bytes, void* stream);
+/* The same view with the NON-antialiased bilinear filter: what torchvision.transforms.Resize computes on tensors before
+ * 0.17 (antialias=None means off) -- the torch ~= 1.10 environment the reference's requirements.txt pins -- and with
+ * antialias=False today.  Bit-exact to F.interpolate(bilinear, align_corners=False, antialias=False) + torch.round.
+ * Two taps per axis, one fused kernel, no workspace. */
+int kvq_resize_view_bilinear_u8(const uint8_t* frames, int layout, int B, int T, int Hs, int Ws, int out_h, int out_w,
+                                int crop_y, int crop_x, int crop_h, int crop_w, float divisor, const float mean[3],
+                                const float std[3], uint8_t* out_u8, float* out_f32, void* stream);
 
 /* ---- measurement hooks (bench.py): kernels launched so far by this process, and optional CUDA-event timing of
  * every kernel of kvq_swin3d_forward grouped by (kind, stage).  Timing is OFF unless enabled. ---- */

@@ -497,6 +497,65 @@ resize_cols_kernel(const float* __restrict__ inter, const int32_t* __restrict__ 
   }
 }
 
+// ---- non-antialiased bilinear (torchvision Resize on tensors before 0.17, i.e. the torch ~= 1.10 environment the
+// reference pins: F.interpolate(bilinear, align_corners=False, antialias=False) on the float32 copy, torch.round, u8) ----
+// ATen's upsample_bilinear2d arithmetic, pinned bit for bit against torch (tools/make_golden_views.py, oracle/views.py):
+//   scale = float(in) / float(out);  src = max(fma(scale, i + 0.5, -0.5), 0);  i0 = min(int(src), in-1);  i1 = i0 + (i0 < in-1)
+//   l1 = clamp(src - i0, 0, 1);  l0 = 1 - l1;   W axis inside, H axis outside, each as fma(v0, l0, round(v1 * l1)).
+// Two taps per axis: one thread per output pixel reads its four source bytes; no intermediate, no tables.
+struct LinTap {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ LinTap linear_tap(int in_size, int out_size, int i) {
+  const float scale = __fdiv_rn(static_cast<float>(in_size), static_cast<float>(out_size));
+  float src = __fmaf_rn(scale, static_cast<float>(i) + 0.5f, -0.5f);
+  src = src < 0.0f ? 0.0f : src;
+  LinTap t;
+  t.i0 = static_cast<int>(src);
+  if (t.i0 > in_size - 1) t.i0 = in_size - 1;
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  float l1 = __fsub_rn(src, static_cast<float>(t.i0));
+  l1 = l1 < 0.0f ? 0.0f : (l1 > 1.0f ? 1.0f : l1);
+  t.l1 = l1;
+  t.l0 = __fsub_rn(1.0f, l1);
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+resize_bilinear_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out_u8, float* __restrict__ out_f32,
+                       int layout, int T, int Hs, int Ws, int oh, int ow, int cy, int cx, int ch, int cw, long long total,
+                       float divisor, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % cw);
+  const int oyc = static_cast<int>((idx / cw) % ch);
+  const long long p_out = idx / (static_cast<long long>(cw) * ch);   // (b*3 + c)*T + t
+  long long p_in = p_out;
+  const int t = static_cast<int>(p_out % T), c = static_cast<int>((p_out / T) % 3);
+  if (layout == 0) {
+    const long long b = p_out / (3 * T);
+    p_in = (b * T + t) * 3 + c;
+  }
+  const LinTap ty = linear_tap(Hs, oh, cy + oyc), tx = linear_tap(Ws, ow, cx + ox);
+  const uint8_t* r0 = frames + (p_in * Hs + ty.i0) * static_cast<long long>(Ws);
+  const uint8_t* r1 = frames + (p_in * Hs + ty.i1) * static_cast<long long>(Ws);
+  const float a = static_cast<float>(__ldg(r0 + tx.i0)), b_ = static_cast<float>(__ldg(r0 + tx.i1));
+  const float c_ = static_cast<float>(__ldg(r1 + tx.i0)), d = static_cast<float>(__ldg(r1 + tx.i1));
+  const float top = __fmaf_rn(a, tx.l0, __fmul_rn(b_, tx.l1));
+  const float bot = __fmaf_rn(c_, tx.l0, __fmul_rn(d, tx.l1));
+  const float v32 = __fmaf_rn(top, ty.l0, __fmul_rn(bot, ty.l1));
+  const float v = fminf(fmaxf(rintf(v32), 0.0f), 255.0f);            // torch.round (half to even) + uint8 cast
+  if (out_u8) out_u8[idx] = static_cast<uint8_t>(v);
+  if (out_f32) {
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+    const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    float x = v;
+    if (divisor != 1.0f) x = __fdiv_rn(x, divisor);
+    out_f32[idx] = __fdiv_rn(__fsub_rn(x, mean), sd);
+  }
+}
+
 struct ViewPlan {
   int oh, ow, cy, cx, ch, cw;
   int taps_x, taps_y, ry0, Hr;
@@ -590,6 +649,37 @@ int kvq_resize_aa_weights(int in_size, int out_size, int32_t* xmin, int32_t* xsi
     xsize[i] = n;
   }
   return KVQ_OK;
+}
+
+int kvq_resize_view_bilinear_u8(const uint8_t* frames, int layout, int B, int T, int Hs, int Ws, int out_h, int out_w,
+                                int crop_y, int crop_x, int crop_h, int crop_w, float divisor, const float mean[3],
+                                const float std[3], uint8_t* out_u8, float* out_f32, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  KVQ_REQUIRE(frames && (out_u8 || out_f32), KVQ_ERR_BAD_SHAPE, "resize_view_bilinear: NULL argument");
+  KVQ_REQUIRE(layout == 0 || layout == 1, KVQ_ERR_BAD_SHAPE, "resize_view_bilinear: layout %d (0 = [B,T,3,H,W], 1 = [B,3,T,H,W])",
+              layout);
+  KVQ_REQUIRE(B > 0 && T > 0 && Hs > 0 && Ws > 0 && out_h > 0 && out_w > 0, KVQ_ERR_BAD_SHAPE,
+              "resize_view_bilinear: frames %dx%dx3x%dx%d -> %dx%d", B, T, Hs, Ws, out_h, out_w);
+  KVQ_REQUIRE(!out_f32 || (mean && std && divisor > 0.0f), KVQ_ERR_BAD_SHAPE,
+              "resize_view_bilinear: the normalised view needs mean, std and a positive divisor");
+  if (crop_h <= 0 && crop_w <= 0) {
+    crop_y = crop_x = 0;
+    crop_h = out_h;
+    crop_w = out_w;
+  }
+  KVQ_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_h > 0 && crop_w > 0 && crop_y + crop_h <= out_h && crop_x + crop_w <= out_w,
+              KVQ_ERR_BAD_SHAPE, "resize_view_bilinear: crop window (%d,%d)+(%d,%d) leaves the %dx%d resized frame", crop_y,
+              crop_x, crop_h, crop_w, out_h, out_w);
+  const long long total = static_cast<long long>(B) * 3 * T * crop_h * crop_w;
+  const long long grid = (total + 255) / 256;
+  KVQ_REQUIRE(grid < (1ll << 31), KVQ_ERR_BAD_SHAPE, "resize_view_bilinear: grid too large");
+  const float m0 = mean ? mean[0] : 0.f, m1 = mean ? mean[1] : 0.f, m2 = mean ? mean[2] : 0.f;
+  const float s0 = std ? std[0] : 1.f, s1 = std ? std[1] : 1.f, s2 = std ? std[2] : 1.f;
+  resize_bilinear_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(frames, out_u8, out_f32, layout, T, Hs, Ws, out_h,
+                                                                       out_w, crop_y, crop_x, crop_h, crop_w, total, divisor,
+                                                                       m0, m1, m2, s0, s1, s2);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "resize_bilinear_kernel launch");
 }
 
 size_t kvq_resize_view_workspace_bytes(int B, int T, int Hs, int Ws, int out_h, int out_w, int crop_y, int crop_x,

@@ -6,7 +6,13 @@ Same names, argument meaning and results as datasets/fusion_datasets.py of the r
   UnifiedFrameSampler                               :612-660  frame indices (host arithmetic, numpy's global RNG)
 `video` is the reference's uint8 [3,T,H,W] CUDA tensor (or a batch [B,3,T,H,W]); the results equal the reference's byte
 for byte (`kvq_resize_view_u8` keeps ATen's order of roundings).  `*_normalised` additionally fuse the datasets'
-normalisation lines (:1017-1027, :902-905) and return the float32 model input directly.  There is no CPU fallback."""
+normalisation lines (:1017-1027, :902-905) and return the float32 model input directly.  There is no CPU fallback.
+
+Which filter `Resize` applies to a uint8 tensor depends on the torchvision the reference runs under (requirements.txt pins
+torch ~= 1.10 and leaves torchvision open): since torchvision 0.17 tensors are anti-aliased by default (`antialias=True`),
+before that they were not.  Every function here takes `antialias` (default: the module-level RESIZE_ANTIALIAS = True, the
+behaviour of a current install; set it to False, or pass the argument, to reproduce a checkpoint's pinned environment).
+Both filters are bit-exact against goldens of torchvision's own output (tests/golden/views_*.npz)."""
 import random
 
 import numpy as np
@@ -15,6 +21,11 @@ from kvq_b200 import ops
 
 IMAGENET_MEAN, IMAGENET_STD = ops.IMAGENET_MEAN, ops.IMAGENET_STD
 CLIP_MEAN, CLIP_STD = ops.CLIP_MEAN, ops.CLIP_STD
+RESIZE_ANTIALIAS = True      # torchvision >= 0.17 tensor default; False = torchvision < 0.17 (the torch 1.10 era)
+
+
+def _aa(antialias):
+    return RESIZE_ANTIALIAS if antialias is None else bool(antialias)
 
 
 def _batched(video):
@@ -35,12 +46,13 @@ def _resize_hw(size_h, size_w, src_h, src_w, arp):
     return size_h, size_w
 
 
-def get_resized_video(video, size_h=224, size_w=224, random_crop=False, arp=False, **kwargs):
+def get_resized_video(video, size_h=224, size_w=224, random_crop=False, arp=False, antialias=None, **kwargs):
     if random_crop:
         raise NotImplementedError("get_resized_video(random_crop=True) is a training augmentation (RandomResizedCrop)")
     v, squeeze = _batched(video)
     size_h, size_w = _resize_hw(size_h, size_w, v.shape[-2], v.shape[-1], arp)
-    out, _ = ops.resize_view_u8(v.contiguous(), size_h, size_w, layout="B3THW", want_u8=True, want_f32=False)
+    out, _ = ops.resize_view_u8(v.contiguous(), size_h, size_w, layout="B3THW", want_u8=True, want_f32=False,
+                                antialias=_aa(antialias))
     return out[0] if squeeze else out
 
 
@@ -50,7 +62,7 @@ def centre_crop_window(resize, crop):
     return lo, resize // 2 + crop // 2 - lo
 
 
-def get_resizecrop_video(video, resize=520, crop=448, phase="train", **kwargs):
+def get_resizecrop_video(video, resize=520, crop=448, phase="train", antialias=None, **kwargs):
     v, squeeze = _batched(video)
     if phase == "train":   # same draws as the reference (:308-310): random.randrange for rows, then columns
         y, x, n = random.randrange(resize - crop), random.randrange(resize - crop), crop
@@ -58,22 +70,25 @@ def get_resizecrop_video(video, resize=520, crop=448, phase="train", **kwargs):
         y, n = centre_crop_window(resize, crop)
         x = y
     out, _ = ops.resize_view_u8(v.contiguous(), resize, resize, crop=(y, x, n, n), layout="B3THW", want_u8=True,
-                                want_f32=False)
+                                want_f32=False, antialias=_aa(antialias))
     return out[0] if squeeze else out
 
 
 def resized_video_normalised(frames, size_h=224, size_w=224, mean=CLIP_MEAN, std=CLIP_STD, divisor=255.0,
-                             layout="BT3HW"):
+                             layout="BT3HW", antialias=None):
     """decoder-order frames u8 [B,T,3,H,W] -> the KSVQE `resize_video` input f32 [B,3,T,size_h,size_w]:
     get_resized_video + (v / 255 - clip_mean) / clip_std (:1021-1027) in one pass"""
-    return ops.resize_view_u8(frames, size_h, size_w, mean=mean, std=std, divisor=divisor, layout=layout)[1]
+    return ops.resize_view_u8(frames, size_h, size_w, mean=mean, std=std, divisor=divisor, layout=layout,
+                              antialias=_aa(antialias))[1]
 
 
-def resizecrop_video_normalised(frames, resize=520, crop=448, mean=IMAGENET_MEAN, std=IMAGENET_STD, layout="BT3HW"):
+def resizecrop_video_normalised(frames, resize=520, crop=448, mean=IMAGENET_MEAN, std=IMAGENET_STD, layout="BT3HW",
+                                antialias=None):
     """decoder-order frames u8 [B,T,3,H,W] -> the SimpleVQA input f32 [B,3,T,crop,crop]: get_resizecrop_video (test
     phase) + (v - mean) / std (:902-905) in one pass"""
     lo, n = centre_crop_window(resize, crop)
-    return ops.resize_view_u8(frames, resize, resize, crop=(lo, lo, n, n), mean=mean, std=std, layout=layout)[1]
+    return ops.resize_view_u8(frames, resize, resize, crop=(lo, lo, n, n), mean=mean, std=std, layout=layout,
+                              antialias=_aa(antialias))[1]
 
 
 class UnifiedFrameSampler:

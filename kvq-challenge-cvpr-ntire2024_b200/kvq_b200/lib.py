@@ -114,6 +114,8 @@ PROTOTYPES = {
     "kvq_resize_view_workspace_bytes": (c_size_t, [c_int] * 10),
     "kvq_resize_view_u8": (c_int, [c_void_p] + [c_int] * 11 + [c_float, POINTER(c_float), POINTER(c_float), c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kvq_resize_view_bilinear_u8": (c_int, [c_void_p] + [c_int] * 11 + [c_float, POINTER(c_float), POINTER(c_float), c_void_p,
+                                            c_void_p, c_void_p]),
     "kvq_launch_count": (ctypes.c_longlong, []),
     "kvq_profile_enable": (None, [c_int]),
     "kvq_profile_num_categories": (c_int, []),

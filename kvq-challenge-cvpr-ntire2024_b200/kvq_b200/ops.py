@@ -178,12 +178,13 @@ _VIEW_LAYOUTS = {"BT3HW": 0, "B3THW": 1}
 
 
 def resize_view_u8(frames, out_h, out_w, crop=None, mean=IMAGENET_MEAN, std=IMAGENET_STD, divisor=1.0, layout="BT3HW",
-                   want_u8=False, want_f32=True, workspace=None):
+                   want_u8=False, want_f32=True, workspace=None, antialias=True):
     """torchvision Resize((out_h, out_w)) on uint8 frames (get_resized_video / get_resizecrop_video,
     fusion_datasets.py:244-252, :299-316) + optional crop window + normalisation (:1017-1027, :902-905), byte- and
     float-exact to the reference.  frames u8 [B,T,3,Hs,Ws] (layout "BT3HW") or [B,3,T,Hs,Ws] ("B3THW"); crop =
     (y, x, h, w) on the resized frame or None -> (u8 [B,3,T,h,w] or None, f32 [B,3,T,h,w] = ((v / divisor) - mean[c]) /
-    std[c] or None)."""
+    std[c] or None).  antialias=True is torchvision's tensor default since 0.17 (ATen's anti-aliased filter); False is
+    what the torch ~= 1.10 environment pinned by the reference computes (plain two-tap bilinear) -- both bit-exact."""
     _need_cuda(frames)
     if frames.dtype != torch.uint8 or frames.dim() != 5:
         raise RuntimeError("resize_view_u8: frames must be a 5-D uint8 tensor")
@@ -197,6 +198,13 @@ def resize_view_u8(frames, out_h, out_w, crop=None, mean=IMAGENET_MEAN, std=IMAG
         raise RuntimeError(f"resize_view_u8: {C} colour channels (3 expected) for layout {layout}")
     cy, cx, ch, cw = (0, 0, out_h, out_w) if crop is None else (int(v) for v in crop)
     lib = _l.load()
+    if not antialias:
+        out_u8 = torch.empty((B, 3, T, ch, cw), dtype=torch.uint8, device=frames.device) if want_u8 else None
+        out_f32 = torch.empty((B, 3, T, ch, cw), dtype=torch.float32, device=frames.device) if want_f32 else None
+        _l.check(lib.kvq_resize_view_bilinear_u8(_p(frames), _VIEW_LAYOUTS[layout], B, T, Hs, Ws, out_h, out_w, cy, cx, ch,
+                                                 cw, float(divisor), _l.f3(mean), _l.f3(std), _p(out_u8), _p(out_f32),
+                                                 _stream()), "resize_view_bilinear_u8")
+        return out_u8, out_f32
     need = lib.kvq_resize_view_workspace_bytes(B, T, Hs, Ws, out_h, out_w, cy, cx, ch, cw)
     if need == 0:
         raise RuntimeError(f"kvq_b200.resize_view_u8: {_l.last_error()}")

@@ -46,7 +46,10 @@ def score_video(model, data, key_list, device=None):
             from datasets import views
             ro = data["resize_opts"]
             data["fragment"] = data["technical"]
-            data["resize_video"] = views.resized_video_normalised(frames, g(ro["size_h"]), g(ro["size_w"]))
+            aa = ro.get("antialias")                     # None -> datasets.views.RESIZE_ANTIALIAS (torchvision >= 0.17)
+            if torch.is_tensor(aa):
+                aa = bool(aa.reshape(-1)[0])
+            data["resize_video"] = views.resized_video_normalised(frames, g(ro["size_h"]), g(ro["size_w"]), antialias=aa)
     if "KSVQE" in key_list and device is not None:
         # nn.DataParallel scatters these in the reference (trainer.py:61); 'KSVQE' is not a key of the data dict, so
         # the clip reshape below never applies to them (the 96 frames of a video go through as one clip)

@@ -105,14 +105,47 @@ def interpolate_bilinear_aa(x, out_h, out_w):
     return np.ascontiguousarray(np.swapaxes(v, -1, -2))
 
 
-def resize_u8(video, out_h, out_w):
+def bilinear_taps(in_size, out_size):
+    """ATen upsample_bilinear2d source index / lambdas (align_corners=False), float32 as the x86 build computes them:
+    scale = float(in) / float(out); src = max(fma(scale, i + 0.5, -0.5), 0) -- the multiply-add is contracted, pinned
+    against torch in tools/make_golden_views.py"""
+    i = np.arange(out_size)
+    scale = np.float32(in_size) / np.float32(out_size)
+    src = (np.float64(scale) * (i.astype(np.float64) + 0.5) - 0.5).astype(np.float32)   # one rounding = fma
+    src = np.maximum(src, np.float32(0))
+    i0 = np.minimum(src.astype(np.int64), in_size - 1)
+    i1 = i0 + (i0 < in_size - 1)
+    l1 = np.clip(src - i0.astype(np.float32), 0, 1).astype(np.float32)
+    l0 = (np.float32(1) - l1).astype(np.float32)
+    return i0, i1, l0, l1
+
+
+def _fma_exact(a, b, c):
+    return (a.astype(np.longdouble) * b.astype(np.longdouble) + c.astype(np.longdouble)).astype(np.float32)
+
+
+def interpolate_bilinear(x, out_h, out_w):
+    """float32 [..., H, W] -> [..., out_h, out_w]: F.interpolate(mode="bilinear", align_corners=False, antialias=False)
+    on CPU, bit for bit: W axis inside, H axis outside, each fma(v0, l0, round(v1 * l1))."""
+    x = np.asarray(x, dtype=np.float32)
+    y0, y1, hy0, hy1 = bilinear_taps(x.shape[-2], out_h)
+    x0, x1, wx0, wx1 = bilinear_taps(x.shape[-1], out_w)
+    r = _fma_exact(x[..., x0], wx0, (x[..., x1] * wx1).astype(np.float32))
+    t0, t1 = r[..., y0, :], r[..., y1, :]
+    return _fma_exact(t0, hy0[:, None], (t1 * hy1[:, None]).astype(np.float32))
+
+
+def resize_u8(video, out_h, out_w, antialias=True):
+    if not antialias:
+        f = interpolate_bilinear(np.asarray(video).astype(np.float32), out_h, out_w)
+        return np.clip(np.rint(f), 0, 255).astype(np.uint8)
     """torchvision Resize((out_h, out_w)) on a uint8 array [..., H, W]: float32 interpolate, round half to even, cast."""
     return np.rint(interpolate_bilinear_aa(video.astype(F32), out_h, out_w)).astype(np.uint8)
 
 
-def resized_video(video, size_h=224, size_w=224, **_):
-    """fusion_datasets.py:244-252 (arp=False, random_crop=False): video u8 [3,T,H,W] -> u8 [3,T,size_h,size_w]."""
-    return resize_u8(video, size_h, size_w)
+def resized_video(video, size_h=224, size_w=224, antialias=True, **_):
+    """get_resized_video (fusion_datasets.py:244-252), arp=False: Resize((size_h, size_w)) on the [T,3,H,W] permutation."""
+    return resize_u8(video, size_h, size_w, antialias)
 
 
 def resize_hw(size_h, size_w, src_h, src_w, arp=False):
@@ -139,9 +172,9 @@ def centre_crop_window(resize, crop):
     return lo, resize // 2 + crop // 2 - lo
 
 
-def resizecrop_video(video, resize=520, crop=448, **_):
+def resizecrop_video(video, resize=520, crop=448, antialias=True, **_):
     """fusion_datasets.py:299-316, test phase: Resize((resize, resize)) then the centre crop."""
-    r = resize_u8(video, resize, resize)
+    r = resize_u8(video, resize, resize, antialias)
     lo, n = centre_crop_window(resize, crop)
     return r[..., lo:lo + n, lo:lo + n]
 

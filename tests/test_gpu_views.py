@@ -60,6 +60,47 @@ def test_views_match_reference_golden(path):
     np.testing.assert_array_equal(f32[0].cpu().numpy(), norm)
 
 
+NOAA_CASES = sorted(glob.glob(os.path.join(GOLDEN, "views_noaa_*.npz")))
+
+
+@pytest.mark.parametrize("path", NOAA_CASES, ids=[os.path.basename(p)[:-4] for p in NOAA_CASES])
+def test_views_without_antialias_match_torchvision_golden(path):
+    """antialias=False (kvq_resize_view_bilinear_u8): what torchvision < 0.17 -- the torch ~= 1.10 environment the
+    reference pins -- computes for Resize on a uint8 tensor.  Goldens: the reference functions' lines run with
+    Resize(..., antialias=False) (tools/make_golden_views.py).  Bit-exact, like the anti-aliased path."""
+    from datasets import views as V
+    g = np.load(path)
+    thwc = _golden_frames(g)
+    video = thwc.permute(3, 0, 1, 2).contiguous().cuda()
+    bt3hw = thwc.permute(0, 3, 1, 2).contiguous().unsqueeze(0).cuda()
+    if str(g["kind"]) == "resize":
+        out = V.get_resized_video(video, size_h=int(g["size_h"]), size_w=int(g["size_w"]), antialias=False)
+        norm = V.resized_video_normalised(bt3hw, int(g["size_h"]), int(g["size_w"]), antialias=False)[0]
+        aa = V.get_resized_video(video, size_h=int(g["size_h"]), size_w=int(g["size_w"]))
+    else:
+        out = V.get_resizecrop_video(video, resize=int(g["resize"]), crop=int(g["crop"]), phase="test", antialias=False)
+        norm = V.resizecrop_video_normalised(bt3hw, int(g["resize"]), int(g["crop"]), antialias=False)[0]
+        aa = V.get_resizecrop_video(video, resize=int(g["resize"]), crop=int(g["crop"]), phase="test")
+    out, norm = out.cpu().numpy(), norm.cpu().numpy()
+    np.testing.assert_array_equal(out, g["out"])
+    assert _sha(out) == str(g["out_sha256"])
+    np.testing.assert_array_equal(norm[:, :, ::7, ::5], g["norm_sample"])
+    assert _sha(norm) == str(g["norm_sha256"])
+    T, H, W = (int(v) for v in g["shape"])
+    if H > 2 * out.shape[-2]:                     # a real down-scale: the two filters must differ (the flag is live)
+        assert not np.array_equal(out, aa.cpu().numpy())
+    # module-level switch = per-call argument
+    V.RESIZE_ANTIALIAS = False
+    try:
+        if str(g["kind"]) == "resize":
+            again = V.get_resized_video(video, size_h=int(g["size_h"]), size_w=int(g["size_w"]))
+        else:
+            again = V.get_resizecrop_video(video, resize=int(g["resize"]), crop=int(g["crop"]), phase="test")
+    finally:
+        V.RESIZE_ANTIALIAS = True
+    np.testing.assert_array_equal(again.cpu().numpy(), out)
+
+
 @pytest.mark.parametrize("B,T,Hs,Ws,oh,ow,crop", [
     (2, 3, 135, 241, 112, 112, None),            # KSVQE resize_video geometry, odd source, unaligned row starts
     (1, 2, 540, 960, 112, 112, None),            # 8.6x / 4.8x down-scaling: tap windows of 19 / 11

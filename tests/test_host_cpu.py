@@ -245,11 +245,11 @@ def test_view_functions_host_logic_with_oracle_backed_kernel(monkeypatch):
     import views_cases
 
     def fake(frames, out_h, out_w, crop=None, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, divisor=1.0, layout="BT3HW",
-             want_u8=False, want_f32=True, workspace=None):
+             want_u8=False, want_f32=True, workspace=None, antialias=True):
         x = frames.numpy()
         if layout == "BT3HW":
             x = x.transpose(0, 2, 1, 3, 4)
-        r = O.resize_u8(x, out_h, out_w)
+        r = O.resize_u8(x, out_h, out_w, antialias)
         if crop is not None:
             y, x0, h, w = crop
             r = r[..., y:y + h, x0:x0 + w]

@@ -12,7 +12,9 @@ import torch
 from conftest import GOLDEN
 from oracle import views
 
-CASES = sorted(glob.glob(os.path.join(GOLDEN, "views_resize*.npz")))
+# anti-aliased goldens (torchvision >= 0.17 tensor default) and the views_noaa_* twins (antialias=False: torchvision
+# < 0.17, the torch ~= 1.10 environment the reference pins)
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "views_resize*.npz")) + glob.glob(os.path.join(GOLDEN, "views_noaa_*.npz")))
 
 
 def golden_frames(g):
@@ -23,10 +25,11 @@ def golden_frames(g):
 
 
 def golden_view(g, video):
+    aa = bool(int(g["antialias"])) if "antialias" in g else True
     if str(g["kind"]) == "resize":
-        out = views.resized_video(video, size_h=int(g["size_h"]), size_w=int(g["size_w"]))
+        out = views.resized_video(video, size_h=int(g["size_h"]), size_w=int(g["size_w"]), antialias=aa)
         return out, views.normalise(out, views.CLIP_MEAN, views.CLIP_STD, 255.0)
-    out = views.resizecrop_video(video, resize=int(g["resize"]), crop=int(g["crop"]))
+    out = views.resizecrop_video(video, resize=int(g["resize"]), crop=int(g["crop"]), antialias=aa)
     return out, views.normalise(out, views.IMAGENET_MEAN, views.IMAGENET_STD)
 
 

@@ -88,6 +88,38 @@ def main():
                             norm_sha256=np.array(sha(n)), norm_sample=n[:, :, ::7, ::5], kind=np.array(kind),
                             shape=np.array([T, H, W]), seed=seed, **{k: np.array(v) for k, v in kw.items()})
         print(name, tuple(out.shape), "mean", float(o.mean()), "float32 interpolate bit-exact, u8 exact, norm exact")
+    # ---- the same views under torchvision < 0.17 semantics (tensors are NOT anti-aliased: what the torch ~= 1.10
+    # environment pinned by the reference computes): the reference functions' own lines with Resize(..., antialias=False)
+    import torchvision
+    for name, T, H, W, kind, kw, seed in RESIZE_CASES:
+        video = seeded_frames(T, H, W, seed)
+        if kind == "resize":
+            oh, ow = kw["size_h"], kw["size_w"]
+            out = torchvision.transforms.Resize((oh, ow), antialias=False)(video.permute(1, 0, 2, 3)).permute(1, 0, 2, 3)
+            norm = ((out.permute(1, 2, 3, 0) / 255.0 - cmean) / cstd).permute(3, 0, 1, 2)
+            mine = views.resized_video(video.numpy(), antialias=False, **kw)
+            mine_norm = views.normalise(mine, views.CLIP_MEAN, views.CLIP_STD, 255.0)
+        else:
+            oh = ow = kw["resize"]
+            r = torchvision.transforms.Resize((oh, ow), antialias=False)(video.permute(1, 0, 2, 3)).permute(1, 0, 2, 3)
+            lo, n = views.centre_crop_window(kw["resize"], kw["crop"])
+            out = r[..., lo:lo + n, lo:lo + n]                                       # fusion_datasets.py:313-315
+            norm = ((out.permute(1, 2, 3, 0) - mean) / std).permute(3, 0, 1, 2)
+            mine = views.resizecrop_video(video.numpy(), antialias=False, **kw)
+            mine_norm = views.normalise(mine, views.IMAGENET_MEAN, views.IMAGENET_STD)
+        x = video.permute(1, 0, 2, 3).to(torch.float32)
+        f_ref = F.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False, antialias=False).numpy()
+        f_mine = views.interpolate_bilinear(x.numpy(), oh, ow)
+        assert np.array_equal(f_ref, f_mine), (name, int((f_ref != f_mine).sum()))
+        assert np.array_equal(mine, out.numpy()), name
+        assert np.array_equal(mine_norm, norm.contiguous().numpy()), name
+        o, n_ = out.contiguous().numpy(), norm.contiguous().numpy()
+        nm = name.replace("views_", "views_noaa_")
+        np.savez_compressed(os.path.join(GOLD, nm + ".npz"), out=o, out_sha256=np.array(sha(o)),
+                            norm_sha256=np.array(sha(n_)), norm_sample=n_[:, :, ::7, ::5], kind=np.array(kind),
+                            shape=np.array([T, H, W]), seed=seed, antialias=np.array(0),
+                            **{k: np.array(v) for k, v in kw.items()})
+        print(nm, tuple(out.shape), "mean", float(o.mean()), "plain bilinear: float32 interpolate bit-exact, u8 exact, norm exact")
     import random
     geo = {"arp_cases": np.array(ARP_CASES), "train_cases": np.array(TRAIN_CROP_CASES)}
     for i, (T, H, W, sh, sw, seed) in enumerate(ARP_CASES):
