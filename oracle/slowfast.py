@@ -168,12 +168,14 @@ def slowfast_forward_fp16(inputs, sd, prefix="feature_extraction."):
         return head_pools(slow, fast)
 
 
-def count_macs(T=32, H=256, W=256):
-    """Multiply-accumulates of the trunk per clip, from the conv shapes alone (no arithmetic)."""
+def count_macs(T=32, H=256, W=256, per_stage=False):
+    """Multiply-accumulates of the trunk per clip, from the conv shapes alone (no arithmetic).  per_stage=True returns
+    [stem (+ its lateral), res2, res3, res4, res5] with each stage's trailing lateral conv counted in the stage."""
     def out(n, k, s, p):
         return (n + 2 * p - k) // s + 1
 
     macs = 0
+    stages = []
     Ts, Tf = T // ALPHA, T
     h, w = out(H, 7, 2, 3), out(W, 7, 2, 3)
     macs += Ts * h * w * 64 * 3 * 49 + Tf * h * w * 8 * 3 * 5 * 49
@@ -181,6 +183,7 @@ def count_macs(T=32, H=256, W=256):
     cs, cf = 64, 8
     macs += Ts * h * w * (2 * cf) * cf * FUSE_KT
     cs += 2 * cf
+    stages.append(macs)
     for s in range(4):
         inner_s, inner_f = 64 << s, 8 << s
         for j in range(DEPTHS[s]):
@@ -197,4 +200,5 @@ def count_macs(T=32, H=256, W=256):
         if s < 3:
             macs += Ts * h * w * (2 * cf) * cf * FUSE_KT
             cs += 2 * cf
-    return macs
+        stages.append(macs - sum(stages))
+    return stages if per_stage else macs

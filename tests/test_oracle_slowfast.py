@@ -17,6 +17,24 @@ def test_mac_count_matches_published_figure():
     assert abs(2 * osf.count_macs(32, 224, 224) / 1e9 - 100.62) < 0.01
 
 
+def test_per_stage_macs_and_parameter_count_match_the_published_model():
+    """The strongest pins available offline for the absent pytorchvideo source (parity stays UNPINNED): the per-stage
+    multiply-accumulate counts SURVEY.md Appendix B derives from create_slowfast's depth-50 defaults (stem 4.35 G, res2
+    8.20 G, res3 12.75 G, res4 25.79 G, res5 14.62 G at 32x256x256) and the model zoo's parameter count for
+    slowfast_r50 (34.57 M with the 400-class head; the trunk the reference keeps -- blocks 0..4, SlowFast_features.py:
+    137-165 -- is that minus the 2304 x 400 + 400 projection)."""
+    st = [m / 1e9 for m in osf.count_macs(32, 256, 256, per_stage=True)]
+    for got, want in zip(st, (4.35, 8.20, 12.75, 25.79, 14.62)):
+        assert abs(got - want) < 0.006, (st,)
+    shapes = synth.slowfast_shapes()
+    n_params = sum(int(np.prod(v)) for k, v in shapes.items() if not k.endswith(("running_mean", "running_var")))
+    head = 2304 * 400 + 400
+    assert abs((n_params + head) / 1e6 - 34.57) < 0.01, (n_params + head) / 1e6
+    # hub layout: blocks.{0..4}.multipathway_blocks.{0,1}.*, fusion convs under multipathway_fusion (none after res5)
+    fus = sorted({k.split(".multipathway_fusion")[0] for k in shapes if "multipathway_fusion" in k})
+    assert len(fus) == 4
+
+
 def test_slow_frame_indices():
     assert osf.slow_frame_indices(32).tolist() == [0, 4, 8, 13, 17, 22, 26, 31]      # SURVEY.md section 8a, row S1
     x = torch.arange(2 * 3 * 32 * 4, dtype=torch.float32).view(2, 3, 32, 2, 2)
