@@ -13,7 +13,8 @@
 //     pass, P_c is written in place over S_c and O += P_c V_c is a TS-form MMA (K = 64: the 8 pad columns of P are 0).
 //   * the two temporal neighbours (d = 2k, 2k+1) of a key position sit in adjacent TMEM columns and share the GRPB
 //     gate fg = |dfh| + |dfw| (it does not depend on d), so the bias is ONE LDS.128 + FFMA2 + FADD2 per two logits:
-//     table entry {t0[e], t0[e-1], t1[e], t1[e-1]} with e = d_i - 2k, conflict-free strides (15, 201).
+//     table entry {t0[e], t0[e-1], t1[e], t1[e-1]} with e = d_i - 2k.  Query rows use the same (h,w,d) order, so a
+//     quarter-warp holds the 8 frames of one cell and its LDS.128 is conflict-free for any odd e-stride (169).
 //   * lazy row max (as in FlashAttention-4): P = exp2(v - m_ref) with m_ref the exact max of the row's FIRST chunk;
 //     later chunks run the fused pass against that m_ref and only when a logit exceeds it by more than 15 (P would
 //     leave fp16 range) is the chunk redone in two passes, m_ref raised and O, l rescaled.  The result is exact up to
@@ -373,7 +374,8 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       it.mw = g.sw != 0 && wwi == g.nww - 1;
       it.tail = x.it == 1;
       it.ri = it.tail ? 384 + (lane & 7) : s * 128 + q * 32 + lane;
-      const int d_i = it.ri / 49, hw_i = it.ri - d_i * 49, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
+      // query rows are (h,w,d) with d fastest, like the key slots: the tail tile is the 8 frames of the last cell
+      const int d_i = it.ri & 7, hw_i = it.ri >> 3, h_i = hw_i / 7, w_i = hw_i - h_i * 7;
       it.fval = (lane & 8) ? frag_coord(wwi * 7, lane & 7, g.sw, g.Wp, invW) : frag_coord(whi * 7, lane & 7, g.sh, g.Hp, invH);
       it.fh_i = __shfl_sync(0xffffffffu, it.fval, h_i);
       it.fw_i = __shfl_sync(0xffffffffu, it.fval, 8 + w_i);
@@ -546,7 +548,8 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       if (lane == 0) mbar_arrive(&bars.of[s]);
       if (!tail) {
         const float inv = 1.0f / l_run;
-        __half* dst = p.out + (static_cast<size_t>(item.win_g) * 392 + item.ri) * p.C + head * ATT_HD;
+        const int orow = p.rows_dfast ? item.ri : (item.ri & 7) * 49 + (item.ri >> 3);   // natural rows for the stand-alone op
+        __half* dst = p.out + (static_cast<size_t>(item.win_g) * 392 + orow) * p.C + head * ATT_HD;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 v;
@@ -578,7 +581,8 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
 #pragma unroll
           for (int i = 1; i < 4; ++i) L = fmaf(wq[i], scr[((i - 1) * 8 + lane) * 34 + 32], L);
           const float inv = 1.0f / L;
-          __half* dst = p.out + (static_cast<size_t>(item.win_g) * 392 + 384 + lane) * p.C + head * ATT_HD;
+          const int orow = p.rows_dfast ? 384 + lane : lane * 49 + 48;
+          __half* dst = p.out + (static_cast<size_t>(item.win_g) * 392 + orow) * p.C + head * ATT_HD;
 #pragma unroll
           for (int i0 = 0; i0 < 32; i0 += 8) {
             float v[8];

@@ -118,6 +118,7 @@ int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, con
   ap.geom = g;
   ap.base_wd = base_win[0]; ap.base_wh = base_win[1]; ap.base_ww = base_win[2];
   ap.variant = variant;
+  ap.rows_dfast = g.dfast;
   ap.rpi_geometric = rpi_geometric;
   ProfScope ps(PK_ATTN, stage, st);
   return launch_window_attn(ap, st);
@@ -302,8 +303,10 @@ static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weig
     const StageDims& sd = pl.st[s];
     const int C = sd.C, M = B * sd.D * sd.H * sd.W;
     for (int j = 0; j < cfg->depths[s]; ++j) {
-      const WinGeom g = make_geom(sd.D, sd.H, sd.W, adaptive ? cfg->resized_window : cfg->window,
-                                  (j & 1) ? shift_full : shift_none);
+      WinGeom g = make_geom(sd.D, sd.H, sd.W, adaptive ? cfg->resized_window : cfg->window,
+                            (j & 1) ? shift_full : shift_none);
+      // rows of a window travel d-fastest between LN1 and proj when the third-generation attention kernel runs
+      g.dfast = window_attn_pitch(g, cfg->window, 0) == ATT3_PITCH ? 1 : 0;
       const float* n1g = WF(); const float* n1b = WF();
       const __half* qkv_w = WH(); const float* qkv_b = WF(); const float* tab = WF();
       const __half* proj_w = WH(); const float* proj_b = WF();

@@ -574,7 +574,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kv_bytes = kv_rows * ATT_HD * 2;
         const size_t unit_bytes = static_cast<size_t>(ATT_IMG_BYTES) + 2 * kv_bytes;
         const int pos = i - slab * p.geom.SL;
-        const int kv_row = hwd ? (pos / 7) * ATT3_PITCH + (pos % 7) * 8 + slab : slab * pitch + pos;
+        // third generation: image rows are (h,w,d) d-fastest for Q, K and V alike.  With geom.dfast the GEMM rows already
+        // arrive in that order (row i -> image row i: consecutive tokens fill whole core-matrix lines); natural-order
+        // rows (the stand-alone op) are scattered to the same places
+        const int hwd_row = p.geom.dfast ? i : pos * 8 + slab;
+        const int kv_row = hwd ? hwd_row : slab * pitch + pos;
         constexpr int MYCH = MT == 2 ? NCHUNK : (NCHUNK + 1) / 2;
         if (n_blk != bias_nblk) {     // bias slice of this warp's chunks -> private smem, once per n-block
           __syncwarp();
@@ -611,7 +615,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             h[2 * j + 1] = pack_half2(v23.x, v23.y);
           }
           if (row_ok) {
-            const int rimg = which == 0 ? i : kv_row;
+            const int rimg = which == 0 ? (hwd ? hwd_row : i) : kv_row;
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.img) + (static_cast<size_t>(win_g) * p.heads + head) * unit_bytes +
                            (which == 0 ? 0 : ATT_IMG_BYTES + (which - 1) * kv_bytes);
 #pragma unroll
@@ -619,7 +623,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               st_global_v4(dst + att_img_offset(rimg, kc0 + j), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
             // the last token of a slab also zeroes the padded K/V key slots behind it (P is 0 there, but 0 * NaN
             // from uninitialised workspace would poison PV); the last token of the window zeroes all the rest
-            const bool pad_owner = hwd ? (slab == 7 && pos == 48) : (pos == p.geom.SL - 1);
+            const bool pad_owner = hwd ? (hwd_row == 391) : (pos == p.geom.SL - 1);
             if (which != 0 && pad_owner) {
               const int end = hwd ? kv_row + 9 : (i == ntok - 1) ? kv_rows : (slab + 1) * pitch;
               for (int rz = kv_row + 1; rz < end; ++rz) {

@@ -43,6 +43,11 @@ struct WinGeom {
   int SL;             // wh*ww     tokens per temporal slab of a window
   int nW;             // windows per clip
   int tokens;         // D*H*W
+  int dfast;          // order of the N rows inside a window: 0 = (d,h,w) with w fastest (window_partition :92-117),
+                      // 1 = (h,w,d) with d fastest -- the order the third-generation attention kernel keeps its keys
+                      // in; used by the fused forward so LN output rows, Q rows, key slots and attention output rows
+                      // all share one order (coalesced QKV-epilogue stores).  Only the order of intermediate rows
+                      // changes: proj scatters back through the same map
 };
 
 static inline WinGeom make_geom(int D, int H, int W, const int base_win[3], const int shift[3]) {
@@ -63,6 +68,7 @@ static inline WinGeom make_geom(int D, int H, int W, const int base_win[3], cons
   g.SL = g.wh * g.ww;
   g.nW = g.nwd * g.nwh * g.nww;
   g.tokens = D * H * W;
+  g.dfast = 0;
   return g;
 }
 
@@ -71,7 +77,17 @@ static inline WinGeom make_geom(int D, int H, int W, const int base_win[3], cons
 __host__ __device__ __forceinline__ int win_row_to_src(const WinGeom& g, int r) {
   const int win = r / g.N, i = r - win * g.N;
   const int wdi = win / (g.nwh * g.nww), whi = (win / g.nww) % g.nwh, wwi = win % g.nww;
-  const int td = i / g.SL, th = (i / g.ww) % g.wh, tw = i % g.ww;
+  int td, th, tw;
+  if (g.dfast) {
+    td = i % g.wd;
+    const int pos = i / g.wd;
+    th = pos / g.ww;
+    tw = pos - th * g.ww;
+  } else {
+    td = i / g.SL;
+    th = (i / g.ww) % g.wh;
+    tw = i % g.ww;
+  }
   // torch.roll semantics: modulo (an adaptive window keeps the base shift, which can exceed a tiny padded grid)
   const int od = (wdi * g.wd + td + g.sd) % g.Dp;
   const int oh = (whi * g.wh + th + g.sh) % g.Hp;
@@ -108,8 +124,10 @@ constexpr int ATT3_PITCH = 56;
 constexpr int ATT3_KV_ROWS = 400;
 constexpr int ATT3_KV_BYTES = ATT3_KV_ROWS * ATT_HD * 2;   // 25 600
 constexpr int ATT3_UNIT_BYTES = ATT_IMG_BYTES + 2 * ATT3_KV_BYTES;   // 76 800
-constexpr int ATT3_SH = 15, ATT3_SD = 201;                 // bank-conflict-free strides for LDS.128 (16 B entries)
-constexpr int ATT3_PAIR_LEN = 13 * ATT3_SD + 12 * ATT3_SH + 13;      // 2806 float4 per head
+// compact strides: a quarter-warp of the softmax threads holds the 8 temporal positions of ONE (h,w) cell (rows are
+// d-fastest), whose entries are SD apart: any odd SD is bank-conflict-free for LDS.128 (16 B entries)
+constexpr int ATT3_SH = 13, ATT3_SD = 169;
+constexpr int ATT3_PAIR_LEN = 14 * ATT3_SD;                          // 2366 float4 per head
 
 __host__ __device__ __forceinline__ int att_img_offset(int r, int chunk) {  // byte offset of a 16 B chunk
   return (r >> 3) * 512 + chunk * 128 + (r & 7) * 16;
@@ -267,6 +285,7 @@ struct AttnParams {
   WinGeom geom;
   int base_wd, base_wh, base_ww;  // un-clamped window the bias tables are indexed with
   int variant;              // debug: 1 swaps LBO/SBO of the MN-major V descriptor
+  int rows_dfast;           // third generation: geom.dfast rows in / out (fused forward); 0 = natural rows (stand-alone op)
   int rpi_geometric;        // adaptive_window_size: bias index from the token's own (d,h,w) in the resized window
                             // (relative_position_index.reshape(*base,*base)[:d,:h,:w,...], :264-271) instead of the
                             // flat [:N,:N] slice the reference takes for clamped windows

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_host_only_entry_points():
     from kvq_b200 import lib
     L = lib.load()
-    assert L.kvq_attn_table_len(8, 7, 7) == 2536 + 4336 + 2 * 2806   # compact + conflict-free fast + paired float4 layouts
+    assert L.kvq_attn_table_len(8, 7, 7) == 2536 + 4336 + 2 * 2366   # compact + conflict-free fast + paired float4 layouts
     assert L.kvq_attn_table_len(4, 4, 4) == 344
     cfg = lib.KvqSwinConfig()
     cfg.embed_dim, cfg.num_stages, cfg.head_hidden, cfg.ln_eps = 96, 4, 64, 1e-5
