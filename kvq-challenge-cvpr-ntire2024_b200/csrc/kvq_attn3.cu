@@ -24,7 +24,8 @@
 //     (key region bits, static); the second 8-half K chunk aliases the first (LBO = 0), hence the factor 1/2.
 //     -100 per differing dim instead of -100 once: exp(-100) and exp(-300) are both 0 next to an unmasked logit.
 //   * the 8 tail rows (384..391) are replicated into all lane groups (SBO = 0, as in the second generation); warp q
-//     takes the chunks c = q (mod 4) and writes zero P elsewhere; the four partial (m, l, O) are merged in smem.
+//     takes the temporal pair d = 2q, 2q+1 of every key position and writes zero P elsewhere, so all four warps work
+//     on every tail chunk; the four partial (m, l, O) are merged in smem.
 //   * the MMA issuers run warp-uniform code with uniform operands (TMEM base 0, descriptors from uniform offsets) and
 //     one elected lane: a per-lane `if (lane == 0)` issue path makes ptxas emit an R2UR waterfall of ~130 cycles per
 //     MMA (tools/ubench/mma_lat.cu: 27 cycles for a TS N=32 MMA, 75 for an SS N=64 one when issued uniformly).
@@ -401,6 +402,14 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
 
     Cursor cur = {0, 0, 0, 0};
     uint32_t j = 0;                            // chunk ordinal of this slot
+#ifdef A3_TIMING   // debug build: per-warp cycle accounting, printed by one CTA (tools/attn_profile.py)
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+    long long t_mark = t_begin;
+#define A3_LAP(k) do { const long long t_now = clock64(); tacc[k] += t_now - t_mark; t_mark = t_now; } while (0)
+#else
+#define A3_LAP(k)
+#endif
     mbar_wait(&bars.tab, 0);
     Item item;
     if (cur.n < n_units) item = open_item(cur);
@@ -417,12 +426,13 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       bool fresh = true;                       // no chunk of this row processed yet (warp-uniform)
 #pragma unroll 1
       for (int c = 0; c < NCHUNK3; ++c, ++j) {
-        const bool own = !tail || (c & 3) == q;
         const uint32_t tS = tB + (j & 1) * 64;
+        A3_LAP(7);                             // loop top
         mbar_wait(&bars.s[s][j & 1], (j >> 1) & 1);
+        A3_LAP(tail ? 1 : 0);                  // wait for S
         __syncwarp();
         tc_fence_after();
-        if (own) {
+        if (!tail) {
           uint32_t r[56], h[32];
           const uint32_t tb = item.trow0 - 16u * static_cast<uint32_t>(c * ATT3_SH);
           const float Ah = fabsf(item.fh_i - __shfl_sync(0xffffffffu, item.fval, c));
@@ -522,22 +532,75 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
           h[28] = h[29] = h[30] = h[31] = 0u;  // 8 zero pad slots complete the fourth K step
           tmem_st_x32(tS, h);                  // P_c in place over S_c
         } else {
-          uint32_t z[32];
+          // ---- tail tile: the 8 rows are replicated in every lane group; warp q takes the temporal pair d = 2q, 2q+1 of
+          // every key position (14 logits per chunk, all four warps busy on every chunk) and writes zero P elsewhere.
+          // Few enough values to keep in registers: always the exact two-pass form. ----
+          const uint32_t tb = item.trow0 - 16u * static_cast<uint32_t>(c * ATT3_SH + 2 * q * ATT3_SD);
+          const float Ah = fabsf(item.fh_i - __shfl_sync(0xffffffffu, item.fval, c));
+          uint32_t r2[7][2];
+          float4 e[7];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) z[i] = 0u;
-          tmem_st_x32(tS, z);
+          for (int wj = 0; wj < 7; ++wj) {
+            tmem_ld_x2(tS + 8 * wj + 2 * q, r2[wj]);
+            e[wj] = lds_f4(tb - 16u * wj);
+          }
+          tmem_wait_ld();
+          float2 v[7];
+          float gmax = -INFINITY;
+#pragma unroll
+          for (int wj = 0; wj < 7; ++wj) {
+            v[wj] = fadd2(ffma2(splat2(Ah + item.Aw[wj]), make_float2(e[wj].z, e[wj].w),
+                                make_float2(__uint_as_float(r2[wj][0]), __uint_as_float(r2[wj][1]))),
+                          make_float2(e[wj].x, e[wj].y));
+            gmax = fmax3(gmax, v[wj].x, v[wj].y);
+          }
+          if (__any_sync(0xffffffffu, fresh || gmax > m_ref + TAU)) {
+            const float m_new = fmaxf(m_ref, gmax);
+            if (!fresh) {
+              const float alpha = fast_exp2(m_ref - m_new);
+              mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
+              tc_fence_after();
+              uint32_t o[32];
+              tmem_ld_x32(tO, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x32(tO, o);
+              l_run *= alpha;
+            }
+            m_ref = m_new;
+          }
+          fresh = false;
+          const float2 negm2 = splat2(-m_ref);
+          float2 sum2 = make_float2(0.f, 0.f);
+          uint32_t h[32];
+#pragma unroll
+          for (int wj = 0; wj < 7; ++wj) {
+            const float2 x = fadd2(v[wj], negm2);
+            const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            sum2 = fadd2(sum2, pe);
+            const uint32_t ph = pack_half2(pe.x, pe.y);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) h[4 * wj + kk] = (kk == q) ? ph : 0u;
+          }
+          l_run += sum2.x + sum2.y;
+          h[28] = h[29] = h[30] = h[31] = 0u;
+          tmem_st_x32(tS, h);
         }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.p[s][j & 1]);
+        A3_LAP(tail ? 4 : 3);                  // chunk work
       }
       // every S MMA of this item has completed (its last chunk was visible): the next item's Qaug rows may go in, and
       // the rest of its set-up runs while the MMA issuer finishes PV of the last chunk
       if (next.n < n_units) nitem = open_item(next);
+      A3_LAP(5);                               // next item's set-up
 
       // ---- epilogue: O / l -> global ----
       mbar_wait(&bars.pv[s][(j - 1) & 1], ((j - 1) >> 1) & 1);
+      A3_LAP(2);                               // wait for the last PV
       __syncwarp();
       tc_fence_after();
       uint32_t o[32];
@@ -605,7 +668,14 @@ window_attn3_kernel(const AttnParams p, const float4* __restrict__ tabs, int uni
       }
       cur = next;
       item = nitem;
+      A3_LAP(6);                               // epilogue
     }
+#ifdef A3_TIMING
+    if (blockIdx.x == 5 && lane == 0)
+      printf("A3T warp %2d slot %d q %d: total %lld | S wait %lld tail %lld | pv wait %lld | chunk full %lld tail %lld | "
+             "set-up %lld | epilogue %lld | other %lld\n", warp, s, q, clock64() - t_begin, tacc[0], tacc[1], tacc[2], tacc[3],
+             tacc[4], tacc[5], tacc[6], tacc[7]);
+#endif
   }
 
   tc_fence_before();
