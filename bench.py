@@ -61,6 +61,28 @@ def ncu_traffic(kernel_substr, csv_name="r02_window_attn3_ncu_full.csv"):
     return tot, f"profiles/{csv_name} (one ncu --set full capture of the stage-0 launch at batch 8, not this run)"
 
 
+def init_nccl_quietly(dev, world):
+    """Create and warm up the NCCL communicator with file descriptor 1 pointed at stderr: NCCL prints its version banner
+    (and any NCCL_DEBUG lines) to stdout from C, and rank 0's stdout must stay ONE JSON line.  Nothing is silenced: the
+    lines arrive on stderr under whatever NCCL_DEBUG the caller set."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)
+        g_warm = torch.empty(world, device=dev)
+        dist.all_gather_into_tensor(g_warm, warm)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -435,8 +457,7 @@ def run_views(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dev, world)
     wl = WORKLOADS["views"]
     B = args.batch or wl["batch"]
     T, _, Hs, Ws = VIEW_SRC
@@ -572,6 +593,8 @@ def run_views(args):
                                "ms_per_step": (ms - ms_resize) / args.steps}]}
         print(json.dumps(line), flush=True)
     if world > 1:
+        sys.stdout.flush()
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
@@ -587,12 +610,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: NCCL's own log lines (init banner, ring / tree set-up, nranks) go to
-        # stderr instead of being silenced, so a driver that sets or reads NCCL_DEBUG can still count the ranks
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dev, world)
     L = lib.load()
     wl = WORKLOADS[args.workload]
     B = args.batch or wl["batch"]
@@ -808,6 +826,8 @@ def run_ours(args):
             line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
+        sys.stdout.flush()
+        os.dup2(2, 1)                 # NCCL's teardown lines (NCCL_DEBUG=INFO) must not follow the JSON line on stdout
         dist.destroy_process_group()
 
 
