@@ -53,24 +53,7 @@ struct Cfg {
   static_assert(TMEM_NEED <= 512 && SMEM <= 227 * 1024, "tile configuration exceeds the SM");
 };
 
-// exact-erf GELU (nn.GELU default, swin_backbone.py:72).  erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, below
-// fp32 round-off of the surrounding arithmetic), branch-free: 2 MUFU + ~10 FMA-pipe instructions.
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = fast_exp2(-1.4426950408889634f * ax * ax);
-  return copysignf(fmaf(-p, e, 1.0f), x);
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float hx = 0.5f * x;
-  return fmaf(hx, erf_as(x * 0.70710678118654752f), hx);
-}
+__device__ __forceinline__ float gelu_erf(float x) { return gelu_erf_fast(x); }
 
 // QuickGELU of OpenAI CLIP (models/backbones/clip/model.py: x * sigmoid(1.702 * x))
 __device__ __forceinline__ float2 quick_gelu2(float2 x) {
@@ -81,25 +64,7 @@ __device__ __forceinline__ float2 quick_gelu2(float2 x) {
   return fmul2(x, r);
 }
 
-// two GELUs per call on the packed fp32x2 pipe (same formula as gelu_erf)
-__device__ __forceinline__ float2 gelu_erf2(float2 x) {
-  const float2 z = fmul2(x, splat2(0.70710678118654752f));
-  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
-  const float2 den = ffma2(splat2(0.3275911f), az, splat2(1.0f));
-  float2 t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
-  float2 p = ffma2(splat2(1.061405429f), t, splat2(-1.453152027f));
-  p = ffma2(p, t, splat2(1.421413741f));
-  p = ffma2(p, t, splat2(-0.284496736f));
-  p = ffma2(p, t, splat2(0.254829592f));
-  p = fmul2(p, t);
-  const float2 q = fmul2(fmul2(az, az), splat2(-1.4426950408889634f));
-  const float2 e = make_float2(fast_exp2(q.x), fast_exp2(q.y));
-  const float2 er = ffma2(make_float2(-p.x, -p.y), e, splat2(1.0f));          // erf(|z|)
-  const float2 hx = fmul2(x, splat2(0.5f));
-  return ffma2(hx, make_float2(copysignf(er.x, x.x), copysignf(er.y, x.y)), hx);
-}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) { return make_float2(gelu_erf_fast(x.x), gelu_erf_fast(x.y)); }
 
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");

@@ -8,7 +8,7 @@ using namespace kvq;
 namespace kvq { void set_error(const char*, ...) {} int check_cuda(cudaError_t e, const char*) { return e != cudaSuccess; } bool pdl_enabled() { return false; } }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 1) mma_bench(long long* out, int N, int ts, int nmma, int rotate, int issuers) {
+__global__ void __launch_bounds__(128, 1) mma_bench(long long* out, int N, int ts, int nmma, int rotate, int issuers, int sw) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(128, 1) mma_bench(long long* out, int N, int t
     if (warp < issuers) {
       const uint32_t idesc = umma_idesc_f16(128, N, 0, 0);
       const uint32_t sbase = smem_u32(smem);
-      const uint64_t da = umma_smem_desc(sbase, 128, 256, UMMA_SW_NONE);
-      const uint64_t db = umma_smem_desc(sbase + 16384, 128, 256, UMMA_SW_NONE);
+      const uint64_t da = sw ? umma_smem_desc(sbase, 16, 1024, UMMA_SW_128) : umma_smem_desc(sbase, 128, 256, UMMA_SW_NONE);
+      const uint64_t db = sw ? umma_smem_desc(sbase + 16384, 16, 1024, UMMA_SW_128) : umma_smem_desc(sbase + 16384, 128, 256, UMMA_SW_NONE);
       const uint32_t dbase = warp * 128;
       if (elect_one()) { umma_f16_ss(dbase, da, db, idesc, 0); umma_commit(&bar[warp]); }
       mbar_wait(&bar[warp], 0);
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(128, 1) mma_bench(long long* out, int N, int t
         for (int i = 0; i < nmma; i += 16) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (ts) umma_f16_ts(dbase, 448 + 8 * (j & 3), db, idesc, 1);
-            else umma_f16_ss(dbase, da, db, idesc, 1);
+            if (ts) umma_f16_ts(dbase, 448 + 8 * (j & 3), db + (sw ? 2 * (j & 3) : 0), idesc, 1);
+            else umma_f16_ss(dbase, da + (sw ? 2 * (j & 3) : 0), db + (sw ? 2 * (j & 3) : 0), idesc, 1);
           }
         }
       }
@@ -110,18 +110,17 @@ int main() {
   cudaFuncSetAttribute(mma_bench<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(mma_bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int nmma = 256;
-  for (int mode : {2})
-  for (int issuers : {1, 3})
+  for (int sw : {0, 1})
+  for (int issuers : {1, 2})
     for (int ts : {0, 1})
-      for (int N : {16, 32, 64, 128, 208})
-        for (int rotate : {0}) {
-          if (rotate && N * rotate > 128) continue;
-          cudaMemset(out, 0, 64);
-          if (mode == 2) mma_bench<2><<<1, 128, 100 * 1024>>>(out, N, ts, nmma, rotate, issuers); else if (mode) mma_bench<1><<<1, 128, 100 * 1024>>>(out, N, ts, nmma, rotate, issuers); else mma_bench<0><<<1, 128, 100 * 1024>>>(out, N, ts, nmma, rotate, issuers);
-          cudaError_t e = cudaDeviceSynchronize();
-          long long h[8]; cudaMemcpy(h, out, 64, cudaMemcpyDeviceToHost);
-          printf("mode %d issuers %d %s N=%3d rotate=%d : issue %.1f clk/MMA, complete %.1f clk/MMA (ideal %.1f) [%s]\n", mode, issuers, ts ? "TS" : "SS", N, rotate,
-                 double(h[1 - 1]) / nmma, double(h[1]) / nmma, 128.0 * N / 256, cudaGetErrorString(e));
-        }
+      for (int N : {64, 96, 128, 256}) {
+        if (issuers * N > 512 - 64) continue;
+        cudaMemset(out, 0, 64);
+        mma_bench<2><<<1, 128, 100 * 1024>>>(out, N, ts, nmma, 0, issuers, sw);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[8]; cudaMemcpy(h, out, 64, cudaMemcpyDeviceToHost);
+        printf("%s issuers %d %s N=%3d : issue %.1f clk/MMA, complete %.1f clk/MMA (math %.1f) [%s]\n", sw ? "SW128 K-major" : "no-swizzle   ", issuers, ts ? "TS" : "SS", N,
+               double(h[0]) / nmma, double(h[1]) / nmma, 128.0 * N / 256, cudaGetErrorString(e));
+      }
   return 0;
 }
