@@ -61,6 +61,34 @@ def ncu_traffic(kernel_substr, csv_name="r02_window_attn3_ncu_full.csv"):
     return tot, f"profiles/{csv_name} (one ncu --set full capture of the stage-0 launch at batch 8, not this run)"
 
 
+def ncu_step_traffic(csv_name="r02_launches.csv"):
+    """DRAM bytes of ONE swin step (batch 8) summed over the committed ncu launch list in profiles/ (the
+    `--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` pass of an eager step): a step is the
+    launches from one patch_im2col_kernel to the next.  None when the file is missing."""
+    import csv
+    import io
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None
+    with open(path, newline="") as f:
+        lines = [ln for ln in f if ln.startswith('"')]
+    per = {}
+    order = []
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        if r["ID"] not in per:
+            per[r["ID"]] = {"name": r["Kernel Name"]}
+            order.append(r["ID"])
+        per[r["ID"]][r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+    starts = [i for i, k in enumerate(order) if "patch_im2col" in per[k]["name"]]
+    if not starts:
+        return None
+    ids = order[starts[0]:starts[1]] if len(starts) > 1 else order[starts[0]:]
+    rd = sum(per[k].get("dram__bytes_read.sum", 0.0) for k in ids)
+    wr = sum(per[k].get("dram__bytes_write.sum", 0.0) for k in ids)
+    return {"launches": len(ids), "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes_per_clip": (rd + wr) / 8,
+            "source": f"profiles/{csv_name} (ncu launch list of one eager step at batch 8, not this run)"}
+
+
 def init_nccl_quietly(dev, world):
     """Create and warm up the NCCL communicator with file descriptor 1 pointed at stderr: NCCL prints its version banner
     (and any NCCL_DEBUG lines) to stdout from C, and rank 0's stdout must stay ONE JSON line.  Nothing is silenced: the
@@ -765,6 +793,7 @@ def run_ours(args):
                         "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
                         "algorithmic": f"{ATTN_GFLOP_PER_CLIP_BLOCK[stage]} GFLOP/clip/block (QK^T+PV) x {B} clips per launch",
                         "step_tensor_frac": step_frac,
+                        "step_traffic": ncu_step_traffic() if args.workload == "swin" else None,
                         "breakdown_note": "breakdown = eager instrumented pass (CUDA events between launches); it sums to "
                                           "more than ms_per_step, which is the CUDA-graph replay"}
             else:
