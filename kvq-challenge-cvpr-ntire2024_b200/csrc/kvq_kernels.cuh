@@ -96,6 +96,21 @@ __host__ __device__ __forceinline__ int win_row_to_src(const WinGeom& g, int r) 
   return (od * g.H + oh) * g.W + ow;
 }
 
+// Inverse of win_row_to_src for grids without padding (Dp == D, Hp == H, Wp == W: then the map is a bijection):
+// flat original token index -> window-order row in [0, nW*N).
+__host__ __device__ __forceinline__ int src_to_win_row(const WinGeom& g, int t) {
+  const int ow = t % g.W, oh = (t / g.W) % g.H, od = t / (g.W * g.H);
+  const int pd = (od + g.Dp - g.sd % g.Dp) % g.Dp;   // position in the rolled grid: shifted[p] = x[(p + s) mod size]
+  const int ph = (oh + g.Hp - g.sh % g.Hp) % g.Hp;
+  const int pw = (ow + g.Wp - g.sw % g.Wp) % g.Wp;
+  const int wdi = pd / g.wd, td = pd - wdi * g.wd;
+  const int whi = ph / g.wh, th = ph - whi * g.wh;
+  const int wwi = pw / g.ww, tw = pw - wwi * g.ww;
+  const int win = (wdi * g.nwh + whi) * g.nww + wwi;
+  const int i = g.dfast ? (th * g.ww + tw) * g.wd + td : (td * g.wh + th) * g.ww + tw;
+  return win * g.N + i;
+}
+
 // ----------------------------------------------------------------------------------------------
 // attention operand images.  One (window, head) unit owns three 25 600 B images Q | K | V, each
 // 400 rows x 32 halfs in the UMMA no-swizzle core-matrix order
