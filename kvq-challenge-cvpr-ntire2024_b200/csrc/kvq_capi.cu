@@ -270,24 +270,36 @@ static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weig
   auto WF = [&]() { return static_cast<const float*>(weights[wi++]); };
   const float eps = cfg->ln_eps;
 
-  // ---- PatchEmbed3D: im2col -> GEMM (K = 96) with bias + LayerNorm epilogue ----
+  // ---- PatchEmbed3D: one implicit-GEMM kernel (kvq_embed.cu); KVQ_EMBED_EXPLICIT=1 keeps the round-1 path
+  //      im2col -> GEMM (K = 96) with bias + LayerNorm epilogue for comparison ----
   {
-    {
-      ProfScope ps(PK_EMBED_IM2COL, 0, st);
-      rc = launch_patch_im2col(x, x_is_f16, a16, B, T, H, W, st);
-    }
-    if (rc != 0) return rc;
-    GemmParams gp{};
-    gp.M = B * pl.D0 * pl.H0 * pl.W0; gp.N = 96; gp.K = 96;
+    static const bool explicit_embed = []() { const char* e = getenv("KVQ_EMBED_EXPLICIT"); return e && atoi(e) != 0; }();
     const __half* w = WH();
-    gp.bias = WF(); gp.gamma = WF(); gp.beta = WF(); gp.eps = eps;
-    gp.out = xa; gp.ldo = 96;
-    gp.split_b = cfg->split_weights & 1;
-    {
+    const float* pe_bias = WF();
+    const float* pe_gamma = WF();
+    const float* pe_beta = WF();
+    const int split = cfg->split_weights & 1;
+    if (cfg->embed_dim == 96 && !explicit_embed) {
       ProfScope ps(PK_EMBED_GEMM, 0, st);
-      rc = launch_gemm(EPI_LN_F32, a16, 96, w, gp.split_b ? 256 : 96, gp, st);
+      rc = launch_patch_embed(x, x_is_f16, w, split ? 256 : 96, split, pe_bias, pe_gamma, pe_beta, eps, xa, B, T, H, W, st);
+      if (rc != 0) return rc;
+    } else {
+      {
+        ProfScope ps(PK_EMBED_IM2COL, 0, st);
+        rc = launch_patch_im2col(x, x_is_f16, a16, B, T, H, W, st);
+      }
+      if (rc != 0) return rc;
+      GemmParams gp{};
+      gp.M = B * pl.D0 * pl.H0 * pl.W0; gp.N = 96; gp.K = 96;
+      gp.bias = pe_bias; gp.gamma = pe_gamma; gp.beta = pe_beta; gp.eps = eps;
+      gp.out = xa; gp.ldo = 96;
+      gp.split_b = split;
+      {
+        ProfScope ps(PK_EMBED_GEMM, 0, st);
+        rc = launch_gemm(EPI_LN_F32, a16, 96, w, gp.split_b ? 256 : 96, gp, st);
+      }
+      if (rc != 0) return rc;
     }
-    if (rc != 0) return rc;
   }
 
   if (hook != nullptr) {   // feats[0] of SwinTransformer3D.forward (:1058): the patch-embedding output

@@ -240,6 +240,11 @@ int launch_ln_merge(const float* x, __half* out, const float* gamma, const float
                     int H, int W, int C, cudaStream_t stream);
 // PatchEmbed3D im2col: x[B,3,T,H,W] fp32 (or fp16) -> A[B*D*Hs*Ws, 96] fp16, K index = c*32 + kt*16 + kh*4 + kw
 int launch_patch_im2col(const void* x, int x_is_f16, __half* out, int B, int T, int H, int W, cudaStream_t stream);
+// PatchEmbed3D in one kernel (kvq_embed.cu): clip [B,3,T,H,W] fp32 / fp16 -> LayerNorm(conv + bias) fp32 [tokens, 96];
+// w = patch_embed.proj.weight f16 [96, 96] (ldw 96) or its split pair [W_hi | W_lo] (ldw 256)
+int launch_patch_embed(const void* x, int x_is_f16, const __half* w, int ldw, int split, const float* bias,
+                       const float* gamma, const float* beta, float eps, float* out, int B, int T, int H, int W,
+                       cudaStream_t stream);
 // score[b] = mean_t rowscore[b*tokens + t]
 int launch_row_mean(const float* rowscore, float* score, int B, int tokens, cudaStream_t stream);
 // Grid mini-patch sampling + normalisation (datasets/fusion_datasets.py:22-121, :1017-1020)
