@@ -92,7 +92,7 @@ int make_plan(const KvqSwinConfig* cfg, int B, int T, int H, int W, Plan* pl) {
 
 int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, const float* packed_tab, __half* out,
                   __half* img, int B, int C, int heads, const WinGeom& g, const int32_t base_win[3], int variant,
-                  cudaStream_t st, int stage = 0, int rpi_geometric = 0) {
+                  cudaStream_t st, int stage = 0, int rpi_geometric = 0, bool qkv_done = false) {
   const int rows_w = B * g.nW * g.N;
   GemmParams gp{};
   gp.M = rows_w; gp.N = 3 * C; gp.K = C;
@@ -103,8 +103,8 @@ int run_attention(const __half* xw, const __half* qkv_w, const float* qkv_b, con
   gp.C = C;
   gp.heads = heads;
   gp.qscale = attn_qscale();  // head_dim^-0.5 (:191), folded with log2(e) for the exp2 softmax
-  int rc;
-  {
+  int rc = 0;
+  if (!qkv_done) {   // (the C = 96 stage of the fused forward writes the images from its LN1 + qkv kernel)
     ProfScope ps(PK_QKV_GEMM, stage, st);
     rc = launch_gemm(EPI_QKV_IMG, xw, C, qkv_w, C, gp, st);
   }
@@ -326,13 +326,20 @@ static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weig
       const __half* fc1_w = WH(); const float* fc1_b = WF();
       const __half* fc2_w = WH(); const float* fc2_b = WF();
 
-      // forward_part1 (:407-488)
-      {
+      // forward_part1 (:407-488).  C = 96 with full windows: LN1 + partition + qkv in one kernel (KVQ_LNQKV_SPLIT=1
+      // keeps the two-kernel form for comparison)
+      static const bool lnqkv_split = []() { const char* e = getenv("KVQ_LNQKV_SPLIT"); return e && atoi(e) != 0; }();
+      const bool fused_qkv = C == 96 && g.dfast && g.N == 392 && sd.heads == 3 && !lnqkv_split;
+      if (fused_qkv) {
+        ProfScope ps(PK_QKV_GEMM, s, st);
+        rc = launch_ln_qkv96(xcur, n1g, n1b, eps, qkv_w, qkv_b, img, B, sd.heads, attn_qscale(), g, st);
+      } else {
         ProfScope ps(PK_LN_WINDOW, s, st);
         rc = launch_ln_window(xcur, a16, n1g, n1b, eps, B, C, g, st);
       }
       if (rc != 0) return rc;
-      rc = run_attention(a16, qkv_w, qkv_b, tab, a16, img, B, C, sd.heads, g, cfg->window, 0, st, s, adaptive ? 1 : 0);
+      rc = run_attention(a16, qkv_w, qkv_b, tab, a16, img, B, C, sd.heads, g, cfg->window, 0, st, s, adaptive ? 1 : 0,
+                         fused_qkv);
       if (rc != 0) return rc;
       {
         GemmParams gp{};

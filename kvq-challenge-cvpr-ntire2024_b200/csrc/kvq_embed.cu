@@ -83,16 +83,16 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const TIn* __restric
     // ============================ producers ============================
     const int r = threadIdx.x & 127, gh = threadIdx.x >> 7;    // tile row, which 12 of the 24 (c, kt, kh) groups
     uint32_t n_t = 0;
+    const float r_Ws = 1.0f / Ws, r_Hs = 1.0f / Hs, r_D = 1.0f / D;
     const bool fast = (T % 2 == 0) && (H % 4 == 0) && (W % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_t) {
       const int buf = n_t & 1;
-      const long long tok = static_cast<long long>(tile) * PE_M + r;
+      const int tok = tile * PE_M + r;                     // < 2^31 (checked by the launcher)
       const bool live = tok < M;
-      const int ws = static_cast<int>(tok % Ws);
-      const long long bdh = tok / Ws;
-      const int hs = static_cast<int>(bdh % Hs);
-      const int d = static_cast<int>((bdh / Hs) % D);
-      const int b = static_cast<int>(bdh / (static_cast<long long>(Hs) * D));
+      // float-reciprocal divisions (fdiv_i): a generic integer division is a ~100-cycle dependent chain per thread
+      const int bdh = fdiv_i(tok, Ws, r_Ws), ws = tok - bdh * Ws;
+      const int bd = fdiv_i(bdh, Hs, r_Hs), hs = bdh - bd * Hs;
+      const int b = fdiv_i(bd, D, r_D), d = bd - b * D;
       const int w0 = 4 * ws;
       const bool wfull = w0 + 3 < W;
       uint2 v[12];

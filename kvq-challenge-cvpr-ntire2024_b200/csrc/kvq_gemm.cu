@@ -465,7 +465,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         bool ok = row_ok;
         if (p.remap) {
           const int rows_in = p.geom.nW * p.geom.N;
-          const int b = row / rows_in;
+          const int b = fdiv_i(row, rows_in, p.geom.r_rows);
           const int src = win_row_to_src(p.geom, row - b * rows_in);
           ok = ok && src >= 0;
           orow_idx = static_cast<long long>(b) * p.geom.tokens + src;
@@ -529,9 +529,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();                         // srow / tile are rewritten by the next tile
       } else if constexpr (EPI == EPI_QKV_IMG) {
         const int ntok = p.geom.N;
-        const int win_g = row / ntok;
+        const int win_g = fdiv_i(row, ntok, p.geom.r_N);   // (float-reciprocal division: kvq_kernels.cuh)
         const int i = row - win_g * ntok;
-        const int slab = i / p.geom.SL;
+        const int slab = fdiv_i(i, p.geom.SL, p.geom.r_SL);
         const int pitch = p.att_pitch;
         // pitch 50 / 52: slab-padded key slots d*pitch + h*7 + w; pitch 56 (third generation): h*56 + w*8 + d
         const bool hwd = pitch == ATT3_PITCH;

@@ -48,7 +48,19 @@ struct WinGeom {
                       // in; used by the fused forward so LN output rows, Q rows, key slots and attention output rows
                       // all share one order (coalesced QKV-epilogue stores).  Only the order of intermediate rows
                       // changes: proj scatters back through the same map
+  // reciprocals of the runtime divisors of the row maps (filled by make_geom): the maps run once per row inside
+  // latency-bound producer / epilogue code, where a generic 32-bit division is a ~100-cycle dependent chain
+  float r_N, r_wd, r_wh, r_ww, r_SL, r_nww, r_nhw, r_W, r_HW, r_rows, r_tokens;
 };
+
+// floor(n / d) for 0 <= n < 2^23, 0 < d < 2^23 with inv = 1.0f / d: the float estimate is off by at most one
+__host__ __device__ __forceinline__ int fdiv_i(int n, int d, float inv) {
+  int q = static_cast<int>(static_cast<float>(n) * inv);
+  const int r = n - q * d;
+  q += (r >= d) ? 1 : 0;
+  q -= (r < 0) ? 1 : 0;
+  return q;
+}
 
 static inline WinGeom make_geom(int D, int H, int W, const int base_win[3], const int shift[3]) {
   WinGeom g;
@@ -69,29 +81,40 @@ static inline WinGeom make_geom(int D, int H, int W, const int base_win[3], cons
   g.nW = g.nwd * g.nwh * g.nww;
   g.tokens = D * H * W;
   g.dfast = 0;
+  // torch.roll semantics: modulo (an adaptive window keeps the base shift, which can exceed a tiny padded grid)
+  g.sd %= g.Dp; g.sh %= g.Hp; g.sw %= g.Wp;
+  g.r_N = 1.0f / g.N; g.r_wd = 1.0f / g.wd; g.r_wh = 1.0f / g.wh; g.r_ww = 1.0f / g.ww; g.r_SL = 1.0f / g.SL;
+  g.r_nww = 1.0f / g.nww; g.r_nhw = 1.0f / (g.nwh * g.nww); g.r_W = 1.0f / W; g.r_HW = 1.0f / (H * W);
+  g.r_rows = 1.0f / (g.nW * g.N); g.r_tokens = 1.0f / g.tokens;
   return g;
 }
 
 // Window-order row r in [0, nW*N) of one clip  ->  flat original token index, or -1 for a padded slot.
 // shifted[p] = x[(p + s) mod size]  (torch.roll by -s, swin_backbone.py:430-435).
 __host__ __device__ __forceinline__ int win_row_to_src(const WinGeom& g, int r) {
-  const int win = r / g.N, i = r - win * g.N;
-  const int wdi = win / (g.nwh * g.nww), whi = (win / g.nww) % g.nwh, wwi = win % g.nww;
+  const int win = fdiv_i(r, g.N, g.r_N), i = r - win * g.N;
+  const int wdi = fdiv_i(win, g.nwh * g.nww, g.r_nhw);
+  const int rem = win - wdi * (g.nwh * g.nww);
+  const int whi = fdiv_i(rem, g.nww, g.r_nww), wwi = rem - whi * g.nww;
   int td, th, tw;
   if (g.dfast) {
-    td = i % g.wd;
-    const int pos = i / g.wd;
-    th = pos / g.ww;
+    const int pos = fdiv_i(i, g.wd, g.r_wd);
+    td = i - pos * g.wd;
+    th = fdiv_i(pos, g.ww, g.r_ww);
     tw = pos - th * g.ww;
   } else {
-    td = i / g.SL;
-    th = (i / g.ww) % g.wh;
-    tw = i % g.ww;
+    td = fdiv_i(i, g.SL, g.r_SL);
+    const int pos = i - td * g.SL;
+    th = fdiv_i(pos, g.ww, g.r_ww);
+    tw = pos - th * g.ww;
   }
-  // torch.roll semantics: modulo (an adaptive window keeps the base shift, which can exceed a tiny padded grid)
-  const int od = (wdi * g.wd + td + g.sd) % g.Dp;
-  const int oh = (whi * g.wh + th + g.sh) % g.Hp;
-  const int ow = (wwi * g.ww + tw + g.sw) % g.Wp;
+  // shifted[p] = x[(p + s) mod size]; make_geom keeps s < size, so one conditional subtraction is the modulo
+  int od = wdi * g.wd + td + g.sd;
+  int oh = whi * g.wh + th + g.sh;
+  int ow = wwi * g.ww + tw + g.sw;
+  od -= od >= g.Dp ? g.Dp : 0;
+  oh -= oh >= g.Hp ? g.Hp : 0;
+  ow -= ow >= g.Wp ? g.Wp : 0;
   if (od >= g.D || oh >= g.H || ow >= g.W) return -1;
   return (od * g.H + oh) * g.W + ow;
 }
@@ -99,13 +122,16 @@ __host__ __device__ __forceinline__ int win_row_to_src(const WinGeom& g, int r) 
 // Inverse of win_row_to_src for grids without padding (Dp == D, Hp == H, Wp == W: then the map is a bijection):
 // flat original token index -> window-order row in [0, nW*N).
 __host__ __device__ __forceinline__ int src_to_win_row(const WinGeom& g, int t) {
-  const int ow = t % g.W, oh = (t / g.W) % g.H, od = t / (g.W * g.H);
-  const int pd = (od + g.Dp - g.sd % g.Dp) % g.Dp;   // position in the rolled grid: shifted[p] = x[(p + s) mod size]
-  const int ph = (oh + g.Hp - g.sh % g.Hp) % g.Hp;
-  const int pw = (ow + g.Wp - g.sw % g.Wp) % g.Wp;
-  const int wdi = pd / g.wd, td = pd - wdi * g.wd;
-  const int whi = ph / g.wh, th = ph - whi * g.wh;
-  const int wwi = pw / g.ww, tw = pw - wwi * g.ww;
+  const int od = fdiv_i(t, g.H * g.W, g.r_HW);
+  const int rem = t - od * (g.H * g.W);
+  const int oh = fdiv_i(rem, g.W, g.r_W), ow = rem - oh * g.W;
+  int pd = od - g.sd, ph = oh - g.sh, pw = ow - g.sw;   // position in the rolled grid: shifted[p] = x[(p + s) mod size]
+  pd += pd < 0 ? g.Dp : 0;
+  ph += ph < 0 ? g.Hp : 0;
+  pw += pw < 0 ? g.Wp : 0;
+  const int wdi = fdiv_i(pd, g.wd, g.r_wd), td = pd - wdi * g.wd;
+  const int whi = fdiv_i(ph, g.wh, g.r_wh), th = ph - whi * g.wh;
+  const int wwi = fdiv_i(pw, g.ww, g.r_ww), tw = pw - wwi * g.ww;
   const int win = (wdi * g.nwh + whi) * g.nww + wwi;
   const int i = g.dfast ? (th * g.ww + tw) * g.wd + td : (td * g.wh + th) * g.ww + tw;
   return win * g.N + i;
@@ -240,6 +266,11 @@ int launch_ln_merge(const float* x, __half* out, const float* gamma, const float
                     int H, int W, int C, cudaStream_t stream);
 // PatchEmbed3D im2col: x[B,3,T,H,W] fp32 (or fp16) -> A[B*D*Hs*Ws, 96] fp16, K index = c*32 + kt*16 + kh*4 + kw
 int launch_patch_im2col(const void* x, int x_is_f16, __half* out, int B, int T, int H, int W, cudaStream_t stream);
+// LN1 + window partition + qkv Linear + attention-image scatter in one kernel for C = 96 (kvq_lnqkv.cu): x fp32
+// [B*tokens, 96] -> img (third-generation layout); needs g.dfast, the full (8,7,7) window and 3 heads
+int launch_ln_qkv96(const float* x, const float* gamma, const float* beta, float eps, const __half* qkv_w,
+                    const float* qkv_b, __half* img, int B, int heads, float qscale, const WinGeom& g,
+                    cudaStream_t stream);
 // PatchEmbed3D in one kernel (kvq_embed.cu): clip [B,3,T,H,W] fp32 / fp16 -> LayerNorm(conv + bias) fp32 [tokens, 96];
 // w = patch_embed.proj.weight f16 [96, 96] (ldw 96) or its split pair [W_hi | W_lo] (ldw 256)
 int launch_patch_embed(const void* x, int x_is_f16, const __half* w, int ldw, int split, const float* bias,

@@ -99,7 +99,7 @@ ln_window_kernel(const float* __restrict__ x, __half* __restrict__ out, const fl
   const bool live = row < rows;
   if (!live) row = rows - 1;
   const int rows_in = g.nW * g.N;
-  const int b = row / rows_in;
+  const int b = fdiv_i(row, rows_in, g.r_rows);
   const int src = win_row_to_src(g, row - b * rows_in);
   __half* orow = live ? out + static_cast<size_t>(row) * C : nullptr;
   const float* sp = x + (static_cast<size_t>(b) * g.tokens + (src < 0 ? 0 : src)) * C;
@@ -147,7 +147,7 @@ ln_window_scatter_kernel(const float* __restrict__ x, __half* __restrict__ out, 
   int row = (blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5)) * RPW + lane / LPR;
   const bool live = row < rows;
   if (!live) row = rows - 1;
-  const int b = row / g.tokens;
+  const int b = fdiv_i(row, g.tokens, g.r_tokens);
   const int dst = b * (g.nW * g.N) + src_to_win_row(g, row - b * g.tokens);
   const float* sp = x + static_cast<size_t>(row) * C;
   ln_row<LPR, MAXV>(&sp, 1, C, gamma, beta, eps, live ? out + static_cast<size_t>(dst) * C : nullptr, nullptr, 0, sub);
