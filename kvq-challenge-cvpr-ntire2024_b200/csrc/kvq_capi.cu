@@ -326,13 +326,16 @@ static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weig
       const __half* fc1_w = WH(); const float* fc1_b = WF();
       const __half* fc2_w = WH(); const float* fc2_b = WF();
 
-      // forward_part1 (:407-488).  C = 96 with full windows: LN1 + partition + qkv in one kernel (KVQ_LNQKV_SPLIT=1
-      // keeps the two-kernel form for comparison)
+      // forward_part1 (:407-488).  C = 96 with full windows: LN1 + partition + qkv in one kernel (KVQ_LNQKV_SPLIT=1 keeps
+      // the two-kernel form).  The kernel also exists for C = 192 / 384 with a TMA-streamed weight (KVQ_LNQKV_MAX_C=384),
+      // correct but measured slower than ln_window + the 128 x 192-tile GEMM there (r02: 0.228 vs 0.141 ms at stage 1,
+      // 0.608 vs 0.288 ms at stage 2: N = 96 MMAs and 12 KB weight slices), so it is used for the resident-weight case only
       static const bool lnqkv_split = []() { const char* e = getenv("KVQ_LNQKV_SPLIT"); return e && atoi(e) != 0; }();
-      const bool fused_qkv = C == 96 && g.dfast && g.N == 392 && sd.heads == 3 && !lnqkv_split;
+      static const int lnqkv_max_c = []() { const char* e = getenv("KVQ_LNQKV_MAX_C"); return e ? atoi(e) : 96; }();
+      const bool fused_qkv = ln_qkv_supported(C) && C <= lnqkv_max_c && g.dfast && g.N == 392 && sd.heads * 32 == C && !lnqkv_split;
       if (fused_qkv) {
         ProfScope ps(PK_QKV_GEMM, s, st);
-        rc = launch_ln_qkv96(xcur, n1g, n1b, eps, qkv_w, qkv_b, img, B, sd.heads, attn_qscale(), g, st);
+        rc = launch_ln_qkv(xcur, n1g, n1b, eps, qkv_w, qkv_b, img, B, C, sd.heads, attn_qscale(), g, st);
       } else {
         ProfScope ps(PK_LN_WINDOW, s, st);
         rc = launch_ln_window(xcur, a16, n1g, n1b, eps, B, C, g, st);

@@ -266,11 +266,12 @@ int launch_ln_merge(const float* x, __half* out, const float* gamma, const float
                     int H, int W, int C, cudaStream_t stream);
 // PatchEmbed3D im2col: x[B,3,T,H,W] fp32 (or fp16) -> A[B*D*Hs*Ws, 96] fp16, K index = c*32 + kt*16 + kh*4 + kw
 int launch_patch_im2col(const void* x, int x_is_f16, __half* out, int B, int T, int H, int W, cudaStream_t stream);
-// LN1 + window partition + qkv Linear + attention-image scatter in one kernel for C = 96 (kvq_lnqkv.cu): x fp32
-// [B*tokens, 96] -> img (third-generation layout); needs g.dfast, the full (8,7,7) window and 3 heads
-int launch_ln_qkv96(const float* x, const float* gamma, const float* beta, float eps, const __half* qkv_w,
-                    const float* qkv_b, __half* img, int B, int heads, float qscale, const WinGeom& g,
-                    cudaStream_t stream);
+// LN1 + window partition + qkv Linear + attention-image scatter in one kernel (kvq_lnqkv.cu), C = 96 / 192 / 384: x fp32
+// [B*tokens, C] -> img (third-generation layout); needs g.dfast, the full (8,7,7) window and head_dim 32
+bool ln_qkv_supported(int C);
+int launch_ln_qkv(const float* x, const float* gamma, const float* beta, float eps, const __half* qkv_w,
+                  const float* qkv_b, __half* img, int B, int C, int heads, float qscale, const WinGeom& g,
+                  cudaStream_t stream);
 // PatchEmbed3D in one kernel (kvq_embed.cu): clip [B,3,T,H,W] fp32 / fp16 -> LayerNorm(conv + bias) fp32 [tokens, 96];
 // w = patch_embed.proj.weight f16 [96, 96] (ldw 96) or its split pair [W_hi | W_lo] (ldw 256)
 int launch_patch_embed(const void* x, int x_is_f16, const __half* w, int ldw, int split, const float* bias,
