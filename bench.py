@@ -64,7 +64,7 @@ def ncu_traffic(kernel_substr, csv_name="r02_window_attn3_ncu_full.csv"):
 def ncu_step_traffic(csv_name="r02_launches.csv"):
     """DRAM bytes of ONE swin step (batch 8) summed over the committed ncu launch list in profiles/ (the
     `--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` pass of an eager step): a step is the
-    launches from one patch_im2col_kernel to the next.  None when the file is missing."""
+    launches from one patch_embed_kernel (patch_im2col_kernel on the explicit path) to the next.  None when the file is missing."""
     import csv
     import io
     path = os.path.join(ROOT, "profiles", csv_name)
@@ -79,7 +79,7 @@ def ncu_step_traffic(csv_name="r02_launches.csv"):
             per[r["ID"]] = {"name": r["Kernel Name"]}
             order.append(r["ID"])
         per[r["ID"]][r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
-    starts = [i for i, k in enumerate(order) if "patch_im2col" in per[k]["name"]]
+    starts = [i for i, k in enumerate(order) if "patch_embed" in per[k]["name"] or "patch_im2col" in per[k]["name"]]
     if not starts:
         return None
     ids = order[starts[0]:starts[1]] if len(starts) > 1 else order[starts[0]:]
