@@ -321,22 +321,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (ci + 1 < MYCH && c0 + c_step * CW < BN) tmem_ld_chunk<CW>(taddr + c0 + c_step * CW, r[(ci + 1) & 1]);
           const uint32_t* rc = r[ci & 1];
           uint32_t h[CW / 2];
+          // the activation switch sits OUTSIDE the element loop: with the branch inside, every float4 group was its own
+          // basic block and the GELU chains of only four elements overlapped (r02 ncu: the fc1 epilogue warps were
+          // stalled on dependencies 52 % of the time, the kernel epilogue-bound at 28 % tensor-pipe activity)
+          auto act_chunk = [&](auto act) {
 #pragma unroll
-          for (int j = 0; j < CW / 4; ++j) {
-            const float4 bb = *reinterpret_cast<const float4*>(stile + ci * CW + 4 * j);
-            float2 v01 = fadd2(make_float2(__uint_as_float(rc[4 * j]), __uint_as_float(rc[4 * j + 1])), make_float2(bb.x, bb.y));
-            float2 v23 = fadd2(make_float2(__uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3])), make_float2(bb.z, bb.w));
-            if constexpr (EPI == EPI_GELU_F16) {
-              if (p.quick_gelu) {
-                v01 = quick_gelu2(v01);
-                v23 = quick_gelu2(v23);
-              } else {
-                v01 = gelu_erf2(v01);
-                v23 = gelu_erf2(v23);
-              }
+            for (int j = 0; j < CW / 4; ++j) {
+              const float4 bb = *reinterpret_cast<const float4*>(stile + ci * CW + 4 * j);
+              const float2 v01 = act(fadd2(make_float2(__uint_as_float(rc[4 * j]), __uint_as_float(rc[4 * j + 1])), make_float2(bb.x, bb.y)));
+              const float2 v23 = act(fadd2(make_float2(__uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3])), make_float2(bb.z, bb.w)));
+              h[2 * j] = pack_half2(v01.x, v01.y);
+              h[2 * j + 1] = pack_half2(v23.x, v23.y);
             }
-            h[2 * j] = pack_half2(v01.x, v01.y);
-            h[2 * j + 1] = pack_half2(v23.x, v23.y);
+          };
+          if constexpr (EPI == EPI_GELU_F16) {
+            if (p.quick_gelu) act_chunk([](float2 v) { return quick_gelu2(v); });
+            else act_chunk([](float2 v) { return gelu_erf2(v); });
+          } else {
+            act_chunk([](float2 v) { return v; });
           }
           // transpose through the warp's smem tile (80 B row pitch: conflict-free both ways) so that every store
           // instruction writes whole 32 B sectors: 32/SEGS rows x (CW*2) contiguous bytes instead of 32 x 16 B
@@ -723,6 +725,12 @@ inline bool use_big_tiles(const GemmParams& p) {
 
 template <int EPI>
 int launch_bn(const __half* A, int lda, const __half* B, int ldb, const GemmParams& p, cudaStream_t stream) {
+  // KVQ_GEMM_BN256=1: 128 x 256 tiles where N allows and every SM still gets tiles (fc1 of stages 2-3)
+  static const int bn256 = []() { const char* e = getenv("KVQ_GEMM_BN256"); return e ? atoi(e) : 0; }();
+  if constexpr (EPI == EPI_GELU_F16) {
+    if (bn256 && p.N % 256 == 0 && ((p.M + BM - 1) / BM) * (p.N / 256) >= 4 * num_sms())
+      return launch_impl<256, EPI>(A, lda, B, ldb, p, stream);
+  }
   if (p.N % 192 == 0 && use_big_tiles(p)) return launch_impl<192, EPI, 2>(A, lda, B, ldb, p, stream);
   if (p.N % 192 == 0) return launch_impl<192, EPI>(A, lda, B, ldb, p, stream);
   if (p.N % 96 == 0) return launch_impl<96, EPI>(A, lda, B, ldb, p, stream);
