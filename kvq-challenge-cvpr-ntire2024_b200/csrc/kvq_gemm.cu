@@ -725,10 +725,11 @@ inline bool use_big_tiles(const GemmParams& p) {
 
 template <int EPI>
 int launch_bn(const __half* A, int lda, const __half* B, int ldb, const GemmParams& p, cudaStream_t stream) {
-  // KVQ_GEMM_BN256=1: 128 x 256 tiles where N allows and every SM still gets tiles (fc1 of stages 2-3)
-  static const int bn256 = []() { const char* e = getenv("KVQ_GEMM_BN256"); return e ? atoi(e) : 0; }();
+  // 128 x 256 tiles where N allows and every SM still gets a few tiles (fc1 of stages 2-3: 0.306 -> 0.286 ms at stage 2;
+  // KVQ_GEMM_BN256=0 goes back to 128 x 192)
+  static const int bn256 = []() { const char* e = getenv("KVQ_GEMM_BN256"); return e ? atoi(e) : 1; }();
   if constexpr (EPI == EPI_GELU_F16) {
-    if (bn256 && p.N % 256 == 0 && ((p.M + BM - 1) / BM) * (p.N / 256) >= 4 * num_sms())
+    if (bn256 && p.N % 256 == 0 && ((p.M + BM - 1) / BM) * (p.N / 256) >= 2 * num_sms())
       return launch_impl<256, EPI>(A, lda, B, ldb, p, stream);
   }
   if (p.N % 192 == 0 && use_big_tiles(p)) return launch_impl<192, EPI, 2>(A, lda, B, ldb, p, stream);
