@@ -39,15 +39,22 @@ constexpr int BIAS_BYTES = MAX_BIAS_N * 4;   // the whole bias vector, staged on
 // MT = 128-row sub-tiles per CTA tile: MT = 2 (256 x BLOCK_N tile, two MMAs per K step sharing the B tile) cuts
 // the operand bytes pulled from L2 per FLOP by 30 % -- the stage-2/3 GEMMs (K >= 384) are L2-bandwidth bound
 // with 128 x 192 tiles -- at the price of single-buffered accumulators.
-template <int BN, int MT = 1>
+// BSTAT ("B stationary", K <= 384): the CTA keeps its [BN x K] weight tile resident in shared memory for the whole kernel
+// and walks M tiles, so only the A operand streams through the ring.  The stage-2 GEMMs are bound by the L2 -> SM feed
+// (r02 ncu: 40 KB of operands per 560 cycles of MMAs at 128 x 192 tiles = 71 B/clk/SM against ~42 available when every SM
+// pulls; tensor pipe 44-46 % active, epilogue warps waiting for accumulators): this form moves 16 KB per K block.
+// It did not pay (see use_bstat) and is opt-in.
+constexpr int BSTAT_MAX_KB = 6;
+template <int BN, int MT = 1, bool BSTAT = false>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
-  static constexpr int STAGES = MT == 2 ? 3 : (BN >= 256 ? 3 : BN >= 192 ? 4 : BN >= 128 ? 5 : 6);
+  static constexpr int STAGE_BYTES = MT * A_BYTES + (BSTAT ? 0 : B_BYTES);
+  static constexpr int STAGES = BSTAT ? 4 : MT == 2 ? 3 : (BN >= 256 ? 3 : BN >= 192 ? 4 : BN >= 128 ? 5 : 6);
+  static constexpr int BRES_BYTES = BSTAT ? BSTAT_MAX_KB * B_BYTES : 0;
   static constexpr int ACC_STAGES = MT == 2 ? 1 : 2;
   static constexpr int CW = (BN % 64 == 0) ? 32 : 16;       // TMEM columns per epilogue chunk
   static constexpr int NCHUNK = BN / CW;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + BRES_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_BYTES;
   static constexpr int TMEM_NEED = ACC_STAGES * MT * BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_NEED <= 512 && SMEM <= 227 * 1024, "tile configuration exceeds the SM");
@@ -76,24 +83,26 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t* r) {
   else tmem_ld_x16(taddr, r);
 }
 
-template <int BN, int EPI, int MT>
+template <int BN, int EPI, int MT, bool BSTAT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  constexpr int STAGES = Cfg<BN, MT>::STAGES;
-  constexpr int ACC = Cfg<BN, MT>::ACC_STAGES;
-  constexpr int CW = Cfg<BN, MT>::CW;
-  constexpr int NCHUNK = Cfg<BN, MT>::NCHUNK;
-  uint8_t* staging = smem + STAGES * Cfg<BN, MT>::STAGE_BYTES;
+  constexpr int STAGES = Cfg<BN, MT, BSTAT>::STAGES;
+  constexpr int ACC = Cfg<BN, MT, BSTAT>::ACC_STAGES;
+  constexpr int CW = Cfg<BN, MT, BSTAT>::CW;
+  constexpr int NCHUNK = Cfg<BN, MT, BSTAT>::NCHUNK;
+  uint8_t* bres = smem + STAGES * Cfg<BN, MT, BSTAT>::STAGE_BYTES;     // BSTAT: the resident weight tile (K blocks of BN rows)
+  uint8_t* staging = bres + Cfg<BN, MT, BSTAT>::BRES_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bfull = bars + 2 * STAGES + 5;    // BSTAT: the weight tile has landed
   float* sbias = reinterpret_cast<float*>(bars + 32);
 
   const int warp = threadIdx.x >> 5;
@@ -107,6 +116,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int nkb = (p.K + BK - 1) / BK;   // narrow mode: p.K = 64 * (number of K blocks of 64 / csub taps)
   // split-weight mode: B holds [W_hi | W_lo] along K (each padded to 64); the K loop runs twice over A
   const int nkb_tot = p.split_b ? 2 * nkb : nkb;
+  // tile walk.  Default: tile = blockIdx.x + i * gridDim.x over (m, n) with n fastest.  BSTAT: the CTA owns ONE n block and
+  // walks every cpn-th m block of it (cpn = CTAs per n block), expressed as (first, stride) over the same tile index.
+  int tile_first = blockIdx.x, tile_stride = gridDim.x;
+  if constexpr (BSTAT) {
+    const int cpn = static_cast<int>(gridDim.x) / num_n;               // the launcher guarantees >= 1
+    const int nb = static_cast<int>(blockIdx.x) / cpn, rank = static_cast<int>(blockIdx.x) - nb * cpn;
+    tile_first = nb < num_n ? rank * num_n + nb : tiles;               // left-over CTAs idle
+    tile_stride = cpn * num_n;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -119,17 +137,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], (EPI == EPI_CONV_F16 && MT == 1) ? EPI_WARPS / 2 : EPI_WARPS);
     }
+    mbar_init(bfull, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg<BN, MT>::TMEM_COLS);
+    tmem_alloc(tmem_slot, Cfg<BN, MT, BSTAT>::TMEM_COLS);
     tmem_relinquish();
   }
   if constexpr (EPI == EPI_CONV_F16) {
     if (narrow) {
       // a K block whose tap count is not a multiple of 64 / csub leaves sub-tiles unloaded; their weights are zero, so
       // the smem behind them only has to be finite: clear the ring once (0 x NaN would poison the accumulator)
-      for (int i = threadIdx.x; i < STAGES * Cfg<BN, MT>::STAGE_BYTES / 16; i += GEMM_THREADS)
+      for (int i = threadIdx.x; i < STAGES * Cfg<BN, MT, BSTAT>::STAGE_BYTES / 16; i += GEMM_THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
       fence_proxy_async_smem();
     }
@@ -152,7 +171,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      if constexpr (BSTAT) {
+        if (tile_first < tiles) {
+          const int n_blk = tile_first % num_n;
+          mbar_expect_tx(bfull, static_cast<uint32_t>(nkb * Cfg<BN, MT, BSTAT>::B_BYTES));
+          for (int kb = 0; kb < nkb; ++kb) tma_load_2d(bres + kb * Cfg<BN, MT, BSTAT>::B_BYTES, &tmB, bfull, kb * BK, n_blk * BN);
+        }
+      }
+      for (int tile = tile_first; tile < tiles; tile += tile_stride) {
         const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
         int cw0 = 0, ch0 = 0, ct0 = 0, cb = 0, cblocks = 1;
         if constexpr (EPI == EPI_CONV_F16) {
@@ -171,7 +197,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int tap_w = 0, tap_h = 0, tap_t = 0, cblk = 0;
         for (int kb = 0; kb < nkb_tot; ++kb) {
           mbar_wait(&empty[stage], ph ^ 1);
-          uint8_t* sA = smem + stage * Cfg<BN, MT>::STAGE_BYTES;
+          uint8_t* sA = smem + stage * Cfg<BN, MT, BSTAT>::STAGE_BYTES;
           uint8_t* sB = sA + MT * A_BYTES;
           if (EPI == EPI_CONV_F16 && narrow) {
             // 64 / csub taps per K block, one [128 pixels x csub] sub-tile each; the weight image is one bulk copy
@@ -188,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (++stage == STAGES) { stage = 0; ph ^= 1; }
             continue;
           }
-          mbar_expect_tx(&full[stage], Cfg<BN, MT>::STAGE_BYTES);
+          mbar_expect_tx(&full[stage], Cfg<BN, MT, BSTAT>::STAGE_BYTES);
           if (EPI == EPI_CONV_F16 && conv_mode) {
             tma_load_5d(sA, &tmA, &full[stage], cblk * BK, cw0 + tap_w, ch0 + tap_h, ct0 + tap_t, cb);
             if (++cblk == cblocks) {
@@ -198,7 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             tma_load_2d(sA, &tmA, &full[stage], (kb >= nkb ? kb - nkb : kb) * BK, m_blk * TM);
           }
-          tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if constexpr (!BSTAT) tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
       }
@@ -208,14 +234,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
       int stage = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      if constexpr (BSTAT) {
+        if (tile_first < tiles) mbar_wait(bfull, 0);
+      }
+      for (int tile = tile_first; tile < tiles; tile += tile_stride) {
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * MT * BN);
         for (int kb = 0; kb < nkb_tot; ++kb) {
           mbar_wait(&full[stage], ph);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * Cfg<BN, MT>::STAGE_BYTES);
+          const uint32_t sA = smem_u32(smem + stage * Cfg<BN, MT, BSTAT>::STAGE_BYTES);
           if (EPI == EPI_CONV_F16 && narrow) {
             // four K = 16 steps per block; where they live depends on the sub-tile width (see GemmParams::conv)
             const uint32_t sBa = sA + A_BYTES;
@@ -239,7 +268,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (++stage == STAGES) { stage = 0; ph ^= 1; }
             continue;
           }
-          const uint64_t db = umma_smem_desc(sA + MT * A_BYTES, 16, 1024, UMMA_SW_128);
+          const uint64_t db = BSTAT ? umma_smem_desc(smem_u32(bres) + kb * Cfg<BN, MT, BSTAT>::B_BYTES, 16, 1024, UMMA_SW_128)
+                                    : umma_smem_desc(sA + MT * A_BYTES, 16, 1024, UMMA_SW_128);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const uint64_t da = umma_smem_desc(sA + mt * A_BYTES, 16, 1024, UMMA_SW_128);
@@ -278,7 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t aph = 0;
     int bias_nblk = -1;
     uint32_t nstore = 0;          // conv epilogue: TMA stores issued by this warp (selects the smem box)
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < tiles; tile += tile_stride) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       if constexpr (kTileSplit) {
         if (as != half) {                     // the other warp set owns this tile / accumulator stage
@@ -684,15 +714,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg<BN, MT>::TMEM_COLS);
+    tmem_dealloc(tmem_base, Cfg<BN, MT, BSTAT>::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI, int MT = 1>
+template <int BN, int EPI, int MT = 1, bool BSTAT = false>
 int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    KVQ_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::SMEM));
+    KVQ_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MT, BSTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT, BSTAT>::SMEM));
     attr_set = true;
   }
   CUtensorMap tmA, tmB;
@@ -710,9 +740,10 @@ int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmPa
     if (rc != 0) return rc;
   }
   const int tiles = ((p.M + BM * MT - 1) / (BM * MT)) * (p.N / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if constexpr (BSTAT) grid = (num_sms() / (p.N / BN)) * (p.N / BN);   // a whole number of CTAs per n block
   count_launch();
-  return launch_pdl(gemm_kernel<BN, EPI, MT>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, MT>::SMEM, stream, tmA, tmB, tmC,
+  return launch_pdl(gemm_kernel<BN, EPI, MT, BSTAT>, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, MT, BSTAT>::SMEM, stream, tmA, tmB, tmC,
                     p);
 }
 
@@ -721,6 +752,18 @@ int launch_impl(const __half* A, int lda, const __half* B, int ldb, const GemmPa
 inline bool use_big_tiles(const GemmParams& p) {
   static const int mode = []() { const char* e = getenv("KVQ_GEMM_BIG_TILES"); return e ? atoi(e) : 0; }();
   return mode != 0 && p.K >= 384 && (p.M + 255) / 256 * (p.N / 192) >= num_sms();
+}
+
+// B-stationary form (see Cfg): K <= 384, N a multiple of 128 with at most one n block per SM, enough m tiles that every
+// CTA of an n block gets a few.  Opt-in (KVQ_GEMM_BSTAT=1): measured SLOWER than the 128 x 192 ring form on the stage-2
+// GEMMs (qkv 0.223 vs 0.187 ms, fc1 0.336 vs 0.306 ms per step) -- the N = 128 MMA costs 107 cycles for 64 of math, and
+// the smaller operand stream does not make up for it.
+inline bool use_bstat(const GemmParams& p) {
+  static const int mode = []() { const char* e = getenv("KVQ_GEMM_BSTAT"); return e ? atoi(e) : 0; }();
+  if (mode == 0 || p.split_b || p.K > 64 * BSTAT_MAX_KB || p.K % 64 != 0 || p.N % 128 != 0) return false;
+  const int num_n = p.N / 128, num_m = (p.M + BM - 1) / BM;
+  if (num_n > num_sms()) return false;
+  return num_m >= 4 * (num_sms() / num_n);
 }
 
 template <int EPI>
@@ -732,6 +775,7 @@ int launch_bn(const __half* A, int lda, const __half* B, int ldb, const GemmPara
     if (bn256 && p.N % 256 == 0 && ((p.M + BM - 1) / BM) * (p.N / 256) >= 2 * num_sms())
       return launch_impl<256, EPI>(A, lda, B, ldb, p, stream);
   }
+  if (use_bstat(p)) return launch_impl<128, EPI, 1, true>(A, lda, B, ldb, p, stream);
   if (p.N % 192 == 0 && use_big_tiles(p)) return launch_impl<192, EPI, 2>(A, lda, B, ldb, p, stream);
   if (p.N % 192 == 0) return launch_impl<192, EPI>(A, lda, B, ldb, p, stream);
   if (p.N % 96 == 0) return launch_impl<96, EPI>(A, lda, B, ldb, p, stream);
@@ -913,6 +957,7 @@ int launch_gemm(int epi, const __half* A, int lda, const __half* B, int ldb, con
     case EPI_QKV_IMG:
       KVQ_REQUIRE(p.N == 3 * p.C && p.C % 32 == 0 && p.bias != nullptr, KVQ_ERR_BAD_SHAPE,
                   "gemm(qkv): N=%d C=%d (need N == 3C, C %% 32 == 0, bias)", p.N, p.C);
+      if (use_bstat(p)) return launch_impl<128, EPI_QKV_IMG, 1, true>(A, lda, B, ldb, p, stream);
       if (p.N % 192 == 0 && use_big_tiles(p)) return launch_impl<192, EPI_QKV_IMG, 2>(A, lda, B, ldb, p, stream);
       if (p.N % 192 == 0) return launch_impl<192, EPI_QKV_IMG>(A, lda, B, ldb, p, stream);
       if (p.N % 96 == 0) return launch_impl<96, EPI_QKV_IMG>(A, lda, B, ldb, p, stream);
