@@ -167,8 +167,8 @@ WORKLOADS = {
                    "gflop_per_clip": 175.53 + 100.62 + 65.0},
     "ksvqe": {"workload": "literal KSVQE key (config/Kwai_KSVQE_test.yml): CLIP ViT-B/16 on 4 key frames + QRS + CONTRIQUE "
                           "ResNet-50 on 784 patches + Swin3D-GRPB with the cross-gating modulation + VQAHead; views fragment "
-                          "32x3x288x288 + resize_video 32x3x112x112, batch 8 per GPU (eager launches: the modulation runs "
-                          "in a host callback)",
+                          "32x3x288x288 + resize_video 32x3x112x112, batch 8 per GPU (whole step captured in one CUDA graph, "
+                          "the modulation is enqueued from the stage hook during capture)",
               "metric": "clips/sec KSVQE (CLIP + QRS + CONTRIQUE + CDM + Swin3D) 32x288x288", "batch": 8,
               "gflop_per_clip": 175.53 + 170.0},
     "views": {"workload": "KSVQE view pipeline (SURVEY 8f-3): decoder-order uint8 frames [B,32,3,1080,1920] -> "
@@ -877,7 +877,7 @@ def run_extras(args, dev, steps=5):
         try:
             host, wl_step, modules = build_workload(name, wl["batch"], dev, 0)
             for m in modules:
-                m.use_cuda_graph = not args.no_graph and name != "ksvqe"     # ksvqe: host callback per stage, eager
+                m.use_cuda_graph = not args.no_graph
             xin = [t.to(dev) for t in host(3)]
             with torch.no_grad():
                 for _ in range(3):

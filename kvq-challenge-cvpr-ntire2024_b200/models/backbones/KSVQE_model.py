@@ -15,6 +15,7 @@ There is no CPU / eager fallback.  The one value computed with torch ops (on the
 import collections
 import ctypes
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -144,6 +145,8 @@ class KSVQE(SwinTransformer3D):
         self.distortion_self = nn.ModuleList([_SelfAttn(c) for _ in range(n_mod)])
         self._extra = None
         self._extra_key = None
+        self._grp_cache = {}
+        self._graphs = {}
 
     # ---- packed device weights of everything around the Swin stages ----
     def _pack_extras(self, dev):
@@ -257,7 +260,13 @@ class KSVQE(SwinTransformer3D):
             self._keep = []
             # key frames t = 0, T/4-1, T/2-1, 3T/4-1 and the frame -> key-frame group map (obtain_keyframes :1352-1376)
             kt = [0, T // 4 - 1, T // 2 - 1, T * 3 // 4 - 1]
-            key_frames = revideo.to(dev, torch.float32)[:, :, kt].permute(0, 2, 1, 3, 4).reshape(B * 4, 3, *revideo.shape[-2:])
+            kkey = ("kt", T, str(dev))                                              # device index tensors are cached: a graph
+            kt_idx = self._grp_cache.get(kkey)                                      # capture cannot copy them from the host
+            if kt_idx is None:
+                kt_idx = torch.tensor(kt, device=dev)
+                self._grp_cache[kkey] = kt_idx
+            key_frames = revideo.to(dev, torch.float32).index_select(2, kt_idx).permute(0, 2, 1, 3, 4).reshape(
+                B * 4, 3, *revideo.shape[-2:])
             cls_attn, tokens = ex["clip"].forward(key_frames.contiguous())
             x_sel, _ = ops.qrs_select_gather(fragment.to(torch.float32), cls_attn)
             z = ex["contrique"].forward(x_sel)                                     # [B, T/2, 49, 128]
@@ -270,7 +279,11 @@ class KSVQE(SwinTransformer3D):
             _l.check(_l.load().kvq_blend_f16_f32(ops._p(ad), ops._p(z), 0.2, 0.8, ops._p(dist16), ops._p(dist32), rows * 128,
                                                  stream), "blend")
             # CLIP patch tokens of every 2nd frame, through the frame's key-frame group (extend_fullcls_attn :1378-1386)
-            grp = torch.tensor([(t >= kt[1]) + (t >= kt[2]) + (t >= kt[3]) for t in range(0, T, 2)], device=dev)
+            gkey = (T, str(dev))                                                    # cached: no H2D copy inside a graph capture
+            grp = self._grp_cache.get(gkey)
+            if grp is None:
+                grp = torch.tensor([(t >= kt[1]) + (t >= kt[2]) + (t >= kt[3]) for t in range(0, T, 2)], device=dev)
+                self._grp_cache[gkey] = grp
             pat = tokens.view(B, 4, 50, 768)[:, :, 1:]                              # [B,4,49,768]
             clip16 = ops.cast_f16(pat[:, grp].reshape(rows, 768).contiguous())
 
@@ -296,6 +309,35 @@ class KSVQE(SwinTransformer3D):
         return feat, loss
 
     def forward_with_head(self, x, head, want_feat=False, graph=None):
-        feat, score, loss = self._run(x, head, want_feat=want_feat)
+        """graph=True (env KVQ_CUDA_GRAPH=1): the whole step -- CLIP, QRS, CONTRIQUE, the Swin stages with the modulation
+        launched from the stage hook, head, loss: ~180 launches per clip batch -- is captured once per set of input
+        buffers and replayed.  The hook is a host callback that only ENQUEUES work on the capturing stream, so it is
+        captured like everything else; inputs must already be CUDA tensors (a capture cannot copy from pageable memory)."""
+        if graph is None:
+            graph = os.environ.get("KVQ_CUDA_GRAPH", "0") == "1"
+        on_dev = all(torch.is_tensor(x[k]) and x[k].is_cuda for k in ("fragment", "resize_video", "dis_label"))
+        if graph and on_dev and x["fragment"].dtype == torch.float32 and x["resize_video"].dtype == torch.float32:
+            key = (x["fragment"].data_ptr(), tuple(x["fragment"].shape), x["resize_video"].data_ptr(),
+                   tuple(x["resize_video"].shape), x["dis_label"].data_ptr(), bool(want_feat), id(head),
+                   self._state_key(list(self.buffers())))
+            ent = self._graphs.get(key)
+            if ent is None:
+                for _ in range(2):                       # packs the weights, fills the caches, warms the allocator
+                    self._run(x, head, want_feat=want_feat)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = int(_l.load().kvq_launch_count())
+                with torch.cuda.graph(g):
+                    out = self._run(x, head, want_feat=want_feat)
+                nodes = int(_l.load().kvq_launch_count()) - n0      # library kernels inside one replay (torch ops excluded)
+                if len(self._graphs) >= 4:
+                    self._graphs.pop(next(iter(self._graphs)))
+                ent = (g, out, nodes)
+                self._graphs[key] = ent
+            g, (feat, score, loss), nodes = ent
+            g.replay()
+            ops.GRAPH_KERNEL_LAUNCHES += nodes
+        else:
+            feat, score, loss = self._run(x, head, want_feat=want_feat)
         self.last_dis_contra_loss = loss
         return feat, score.reshape(-1, 1)

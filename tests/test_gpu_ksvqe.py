@@ -90,3 +90,33 @@ def test_trainer_flow_with_the_ksvqe_yaml(tmp_path):
     lines = (tmp_path / "output.txt").read_text().strip().split("\n")
     assert [l.split(",")[0] for l in lines] == ["synthetic_0000", "synthetic_0001"]
     assert all(np.isfinite(s) for _, s in res) and abs(res[0][1] - res[1][1]) > 0
+
+
+def test_ksvqe_whole_step_cuda_graph_matches_eager():
+    """The whole KSVQE step captured in one CUDA graph (the modulation is enqueued from the stage hook DURING capture)
+    replays to the same scores / features as eager launches, also after the input buffers were refilled in place."""
+    g = np.load(os.path.join(GOLDEN, "ksvqe_b2_t32_288.npz"))
+    B, T = int(g["B"]), int(g["T"])
+    net = _network(g)
+    gen = torch.Generator().manual_seed(int(g["xseed"]))
+    x = {"fragment": torch.randn((B, 3, T, 288, 288), generator=gen).cuda(),
+         "resize_video": torch.randn((B, 3, T, 112, 112), generator=gen).cuda(),
+         "dis_label": torch.from_numpy(np.asarray(g["labels"])).long().cuda()}
+    with torch.no_grad():
+        net.use_cuda_graph = False
+        s0, f0, l0 = net(inputs=x, reduce_scores=True, return_pooled_feats=True)
+        s0, f0, l0 = s0.clone(), f0["KSVQE"].clone(), l0.clone()
+        net.use_cuda_graph = True
+        s1, f1, l1 = net(inputs=x, reduce_scores=True, return_pooled_feats=True)      # capture + first replay
+        torch.cuda.synchronize()
+        assert torch.equal(s1, s0) and torch.equal(f1["KSVQE"], f0) and torch.allclose(l1, l0)
+        # new clip contents in the SAME buffers: the replay must see them
+        x["fragment"].copy_(torch.randn((B, 3, T, 288, 288), generator=gen))
+        x["resize_video"].copy_(torch.randn((B, 3, T, 112, 112), generator=gen))
+        s2, f2, _ = net(inputs=x, reduce_scores=True, return_pooled_feats=True)
+        s2, f2 = s2.clone(), f2["KSVQE"].clone()
+        net.use_cuda_graph = False
+        s3, f3, _ = net(inputs=x, reduce_scores=True, return_pooled_feats=True)
+        torch.cuda.synchronize()
+    assert not torch.equal(s2, s0)
+    assert torch.equal(s2, s3) and torch.equal(f2, f3["KSVQE"])
