@@ -344,24 +344,39 @@ static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weig
       rc = run_attention(a16, qkv_w, qkv_b, tab, a16, img, B, C, sd.heads, g, cfg->window, 0, st, s, adaptive ? 1 : 0,
                          fused_qkv);
       if (rc != 0) return rc;
-      {
-        GemmParams gp{};
-        gp.M = B * g.nW * g.N; gp.N = C; gp.K = C;
-        gp.bias = proj_b; gp.out = xcur; gp.ldo = C; gp.resid = xcur; gp.remap = 1; gp.geom = g;
+      // proj + window_reverse + shortcut (:322-324, :472-488, :509) and norm2 (:490).  C = 96: one kernel that also writes
+      // the fp16 norm2 output (into the free PatchMerging buffer: a16 is still being read as the proj operand);
+      // KVQ_PROJLN_SPLIT=1 keeps proj GEMM + ln_rows.  The kernel exists for C = 192 too (KVQ_PROJLN_MAX_C=192) but measured
+      // slower there than the two kernels (0.225 vs 0.142 ms per step at stage 1; stage 0: 0.230 vs 0.283 ms).
+      static const bool projln_split = []() { const char* e = getenv("KVQ_PROJLN_SPLIT"); return e && atoi(e) != 0; }();
+      const __half* mlp_in = a16;
+      static const int projln_max_c = []() { const char* e = getenv("KVQ_PROJLN_MAX_C"); return e ? atoi(e) : 96; }();
+      if (proj_ln_supported(C) && C <= projln_max_c && !projln_split) {
+        __half* a2 = reinterpret_cast<__half*>(xnext);
         ProfScope ps(PK_PROJ_GEMM, s, st);
-        rc = launch_gemm(EPI_RESID_F32, a16, C, proj_w, C, gp, st);
+        rc = launch_proj_ln(a16, proj_w, proj_b, n2g, n2b, eps, xcur, a2, B, C, g, st);
+        if (rc != 0) return rc;
+        mlp_in = a2;
+      } else {
+        {
+          GemmParams gp{};
+          gp.M = B * g.nW * g.N; gp.N = C; gp.K = C;
+          gp.bias = proj_b; gp.out = xcur; gp.ldo = C; gp.resid = xcur; gp.remap = 1; gp.geom = g;
+          ProfScope ps(PK_PROJ_GEMM, s, st);
+          rc = launch_gemm(EPI_RESID_F32, a16, C, proj_w, C, gp, st);
+          if (rc != 0) return rc;
+        }
+        // forward_part2 (:490-491)
+        {
+          ProfScope ps(PK_LN_ROWS, s, st);
+          rc = launch_ln_rows(xcur, a16, nullptr, n2g, n2b, eps, M, C, sd.D * sd.H * sd.W, st);
+        }
         if (rc != 0) return rc;
       }
-      // forward_part2 (:490-491)
-      {
-        ProfScope ps(PK_LN_ROWS, s, st);
-        rc = launch_ln_rows(xcur, a16, nullptr, n2g, n2b, eps, M, C, sd.D * sd.H * sd.W, st);
-      }
-      if (rc != 0) return rc;
       static const bool fuse_mlp = []() { const char* e = getenv("KVQ_FUSED_MLP"); return e == nullptr || atoi(e) != 0; }();
       if (fuse_mlp && fused_mlp_supported(C)) {
         ProfScope ps(PK_FUSED_MLP, s, st);
-        rc = launch_fused_mlp(a16, fc1_w, fc1_b, fc2_w, fc2_b, xcur, M, C, st);
+        rc = launch_fused_mlp(mlp_in, fc1_w, fc1_b, fc2_w, fc2_b, xcur, M, C, st);
         if (rc != 0) return rc;
       } else {
         {
@@ -369,7 +384,7 @@ static int swin3d_forward_impl(const KvqSwinConfig* cfg, const void* const* weig
           gp.M = M; gp.N = 4 * C; gp.K = C;
           gp.bias = fc1_b; gp.out = hid; gp.ldo = 4 * C;
           ProfScope ps(PK_FC1_GEMM, s, st);
-          rc = launch_gemm(EPI_GELU_F16, a16, C, fc1_w, C, gp, st);
+          rc = launch_gemm(EPI_GELU_F16, mlp_in, C, fc1_w, C, gp, st);
           if (rc != 0) return rc;
         }
         {

@@ -272,6 +272,11 @@ bool ln_qkv_supported(int C);
 int launch_ln_qkv(const float* x, const float* gamma, const float* beta, float eps, const __half* qkv_w,
                   const float* qkv_b, __half* img, int B, int C, int heads, float qscale, const WinGeom& g,
                   cudaStream_t stream);
+// proj Linear + window_reverse + shortcut + norm2 in one kernel (kvq_projln.cu), C = 96 / 192: x += attn_out W^T + b scattered
+// back to token order, a2 = LayerNorm(x) fp16 [tokens, C] (must not alias attn_out)
+bool proj_ln_supported(int C);
+int launch_proj_ln(const __half* attn_out, const __half* w, const float* bias, const float* gamma, const float* beta,
+                   float eps, float* x, __half* a2, int B, int C, const WinGeom& g, cudaStream_t stream);
 // PatchEmbed3D in one kernel (kvq_embed.cu): clip [B,3,T,H,W] fp32 / fp16 -> LayerNorm(conv + bias) fp32 [tokens, 96];
 // w = patch_embed.proj.weight f16 [96, 96] (ldw 96) or its split pair [W_hi | W_lo] (ldw 256)
 int launch_patch_embed(const void* x, int x_is_f16, const __half* w, int ldw, int split, const float* bias,

@@ -17,6 +17,10 @@ from tools import synth  # noqa: E402
 
 GEOMS = [("s0", 8, 16, 56, 56, 96, 3), ("s1", 8, 16, 28, 28, 192, 6), ("s2", 8, 16, 14, 14, 384, 12),
          ("s3", 8, 16, 7, 7, 768, 24)]
+if os.environ.get("ATTN_BENCH_BATCHES"):     # e.g. "s2:8,16,32": the same stage geometry at several batch sizes
+    _tag, _bs = os.environ["ATTN_BENCH_BATCHES"].split(":")
+    _g = next(g for g in GEOMS if g[0] == _tag)
+    GEOMS = [(f"{_tag}_b{b}", int(b)) + _g[2:] for b in _bs.split(",")]
 
 
 def main():
