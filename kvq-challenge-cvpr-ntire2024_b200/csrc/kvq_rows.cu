@@ -167,9 +167,8 @@ ln_merge_kernel(const float* __restrict__ x, __half* __restrict__ out, const flo
   const bool live = row < rows;
   if (!live) row = rows - 1;
   const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
-  const int w2 = row % W2;
-  const int h2 = (row / W2) % H2;
-  const int bd = row / (W2 * H2);  // b*D + d
+  const int t2 = fdiv_i(row, W2, 1.0f / W2), w2 = row - t2 * W2;      // (float-reciprocal divisions: kvq_kernels.cuh)
+  const int bd = fdiv_i(t2, H2, 1.0f / H2), h2 = t2 - bd * H2;       // bd = b*D + d
   const float* seg[4];
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
