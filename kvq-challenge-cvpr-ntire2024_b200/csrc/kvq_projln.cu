@@ -133,7 +133,7 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int sub = lane & 7, rsel = lane >> 3;
     const int rows_in = g.nW * g.N;
     constexpr int NCH = Cfg::NCH;
-    constexpr int PF = NCH < 3 ? NCH : 3;                  // chunks whose residual is prefetched before the accumulator wait
+    constexpr int PF = NCH < 3 ? NCH : 3;                  // residual chunks in flight (the first PF are fetched before the accumulator wait)
     const float* sgam = spar + C;
     const float* sbet = spar + 2 * C;
     uint32_t n_t = 0;
@@ -186,21 +186,24 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const long long off = srow[rr];
           if (off >= 0) {
             float4 v = *reinterpret_cast<const float4*>(stile + rr * 36 + 4 * sub);
-            float4 rv;
-            if (ci < PF) rv = pre[ci < PF ? ci : 0][it];
-            else rv = *reinterpret_cast<const float4*>(x + off + ci * 32 + 4 * sub);
+            const float4 rv = pre[ci % PF][it];
             v.x += bb.x + rv.x; v.y += bb.y + rv.y; v.z += bb.z + rv.z; v.w += bb.w + rv.w;
             *reinterpret_cast<float4*>(x + off + ci * 32 + 4 * sub) = v;
             s1[it] += (v.x + v.y) + (v.z + v.w);
             s2[it] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            // the slot is free: fetch the residual of chunk ci + PF into it (PF chunks stay in flight); when the whole
+            // row fits the PF slots (C = 96) keep the new value there instead, so norm2 below needs no re-read
+            if (ci + PF < NCH) pre[ci % PF][it] = *reinterpret_cast<const float4*>(x + off + (ci + PF) * 32 + 4 * sub);
+            else if (NCH <= PF) pre[ci][it] = v;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[buf]);            // the accumulator is free: the rest works on global memory
-      // row statistics (8 lanes share a row), then norm2 over the rows this thread just wrote (same-thread read after
-      // write through global memory: L1 / L2 hits)
+      // row statistics (8 lanes share a row), then norm2 over the rows this thread just wrote: from registers when the row
+      // fits (C = 96), else re-read through global memory (same-thread read after write: L1 / L2 hits, but one L2 round
+      // trip per chunk -- the reason the C = 192 instantiation is slower than proj GEMM + ln_rows)
       float mean[8], rstd[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -220,7 +223,9 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int it = 0; it < 8; ++it) {
           const long long off = srow[it * 4 + rsel];
           if (off >= 0) {
-            const float4 v = *reinterpret_cast<const float4*>(x + off + ci * 32 + 4 * sub);
+            float4 v;
+            if constexpr (NCH <= PF) v = pre[ci][it];
+            else v = *reinterpret_cast<const float4*>(x + off + ci * 32 + 4 * sub);
             const float m = mean[it], rs = rstd[it];
             uint2 hv;
             hv.x = pack_half2((v.x - m) * rs * gm.x + bt.x, (v.y - m) * rs * gm.y + bt.y);
