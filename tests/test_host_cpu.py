@@ -6,6 +6,8 @@ import json
 import os
 import re
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -297,3 +299,34 @@ def test_bench_reference_arm_contract():
     assert "workload" in d["config"] and "model" not in d["config"]
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_float_reciprocal_division_is_exact_on_the_ranges_the_kernels_use():
+    """fdiv_i (csrc/kvq_kernels.cuh): floor(n / d) from a float32 reciprocal estimate plus one correction step.  The row maps
+    call it with quotients far below 2^21 and either n < 2^24 or a divisor >= 256; this emulates the float32 arithmetic
+    and checks it against integer division on those ranges (rows up to 2^31 / rows-per-clip, token grids, windows)."""
+    rng = np.random.default_rng(3)
+
+    def fdiv(n, d):
+        inv = np.float32(1.0) / d.astype(np.float32)
+        q = (n.astype(np.float32) * inv).astype(np.int64)          # C++ float -> int conversion truncates
+        r = n - q * d
+        q = q + (r >= d) - (r < 0)
+        return q
+
+    cases = []
+    # small divisors (window sizes, lanes) with n < 2^22
+    cases.append((rng.integers(0, 1 << 22, 200000), rng.integers(1, 400, 200000)))
+    # rows / rows-per-clip and tokens / tokens-per-clip: n up to 2^31 - 1, divisor >= 392
+    cases.append((rng.integers(0, (1 << 31) - 1, 200000), rng.integers(392, 1 << 20, 200000)))
+    # exact multiples and off-by-one neighbours (where a float estimate is most likely to land on the wrong side)
+    d = rng.integers(1, 5000, 100000)
+    k = rng.integers(0, 4000, 100000)
+    for delta in (-1, 0, 1):
+        n = np.maximum(k * d + delta, 0)
+        cases.append((n, d))
+    for n, d in cases:
+        n = n.astype(np.int64)
+        d = d.astype(np.int64)
+        keep = (n // d) < (1 << 21)
+        assert np.array_equal(fdiv(n[keep], d[keep]), n[keep] // d[keep])
