@@ -53,7 +53,10 @@ struct WinGeom {
   float r_N, r_wd, r_wh, r_ww, r_SL, r_nww, r_nhw, r_W, r_HW, r_rows, r_tokens;
 };
 
-// floor(n / d) for 0 <= n < 2^23, 0 < d < 2^23 with inv = 1.0f / d: the float estimate is off by at most one
+// floor(n / d) with inv = 1.0f / d: the float estimate is off by at most one (corrected below) as long as the quotient
+// stays below 2^21 and either n < 2^24 or d >= 256 (float(n) rounds n by up to 128 beyond 2^24).  Every call site
+// divides rows / tokens (< 2^31) by rows or tokens per clip, or a window-sized index by a window dimension
+// (tests/test_host_cpu.py emulates the float arithmetic on those ranges).
 __host__ __device__ __forceinline__ int fdiv_i(int n, int d, float inv) {
   int q = static_cast<int>(static_cast<float>(n) * inv);
   const int r = n - q * d;
