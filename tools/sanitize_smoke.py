@@ -1,5 +1,6 @@
-"""compute-sanitizer target: one small forward that exercises every kernel family (generic + both fast attention
-generations, fused MLP, all GEMM epilogues, LN/gather kernels, fragment gather).
+"""compute-sanitizer target: one small forward that exercises every kernel family of the default path (generic + third-
+generation attention, patch-embed / LN1+qkv / proj+norm2 / fused-MLP kernels, the GEMM epilogues, LN / gather kernels,
+fragment gather), with fp32 and fp16 clips.
     compute-sanitizer --tool memcheck  python tools/sanitize_smoke.py
     compute-sanitizer --tool racecheck python tools/sanitize_smoke.py"""
 import os
@@ -17,9 +18,11 @@ sd = synth.swin_network_state_dict(3)
 wts = ops.SwinWeights(sd, dev, prefix="swin_tiny_grpb_backbone.", head_prefix="swin_tiny_grpb_head.")
 # 16 x 112 x 112: stage 0/1 run full (8,7,7) windows (fast kernels), stages 2/3 clamp the window (generic kernel)
 x = synth.clip_input((1, 3, 16, 112, 112), 4).to(dev)
-for variant in ("5", "1"):
-    os.environ["KVQ_ATTN_VARIANT"] = variant          # read once per process: second value only documents intent
-    feat, score = wts.forward(x, want_feat=True)
+# default kernel paths (third-generation attention, patch_embed / ln_qkv / proj_ln / fused MLP kernels); the older paths are
+# selected by environment, read once per process: run the tool again under KVQ_ATTN_VARIANT=5, KVQ_EMBED_EXPLICIT=1, ...
+feat, score = wts.forward(x, want_feat=True)
+x16 = x.half()
+feat16, score16 = wts.forward(x16, want_feat=True)
 torch.cuda.synchronize()
 frames = torch.randint(0, 256, (1, 8, 3, 80, 72), dtype=torch.uint8, device=dev)
 offs = torch.zeros((1, 2, 2, 2, 1), dtype=torch.int32, device=dev)
