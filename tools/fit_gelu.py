@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """Coefficients of gelu_erf_fast (csrc/kvq_common.cuh) and its error against the exact erf GELU.
 
-0.5*erfc(t) = 2^(t*Q(t) - 1) with Q of degree 6: weighted least squares of log2(erfc(t)) over t in [0, 4], re-weighted
+0.5*erfc(t) = 2^(t*Q(t) - 1) with Q of degree DEG - 1: weighted least squares of log2(erfc(t)) over t in [0, 4], re-weighted
 towards the minimax solution of |t * (2^P(t) - erfc(t))| (the GELU's absolute error is |x| * |0.5 erfc error|).
 The second half evaluates the kernel's fp32 Horner scheme (fma emulated in float64, rounded to fp32 after every step).
 """
 import numpy as np
 from scipy.special import erf, erfc
 
-T, DEG = 4.0, 7
+T, DEG = 4.0, 5          # P(t) = t * Q(t) of degree 5 (Q of degree 4); DEG = 7 was the first version (5.1e-7)
 
 
 def fit():
@@ -27,8 +27,8 @@ def gelu_kernel(x, c):
     c32 = [np.float32(v) for v in c]
     x = x.astype(np.float32)
     t = np.minimum(np.abs(x) * np.float32(0.70710678118654752), np.float32(T)).astype(np.float32)
-    q = np.full_like(t, c32[6])
-    for k in range(5, -1, -1):
+    q = np.full_like(t, c32[-1])
+    for k in range(len(c32) - 2, -1, -1):
         q = (q.astype(np.float64) * t + np.float64(c32[k])).astype(np.float32)
     p = (q.astype(np.float64) * t - 1.0).astype(np.float32)
     e = np.exp2(p.astype(np.float64)).astype(np.float32)
@@ -37,7 +37,7 @@ def gelu_kernel(x, c):
 
 if __name__ == "__main__":
     c = fit()
-    print("c1..c7 =", [float(np.float32(v)) for v in c])
+    print(f"c1..c{DEG} =", [float(np.float32(v)) for v in c])
     x = np.linspace(-8, 8, 400001)
     exact = 0.5 * x * (1 + erf(x / np.sqrt(2)))
     got = gelu_kernel(x, c).astype(np.float64)
