@@ -23,7 +23,7 @@
 //   warp 3       : idle (fills the warpgroup)
 //   warps 4..11  : GELU per chunk (H -> G), nothing else; lane 0 polls the barriers for its warp
 //   warps 12..15 : residual epilogue per tile (x += O + b2), concurrent with the GELU of the next tile
-// r02 (batch 8, 32x224x224): 196 -> 142 us per stage-0 launch, 138 -> 107 us per stage-1 launch.
+// r02 (batch 8, 32x224x224): 196 -> 132 us per stage-0 launch, 138 -> 101 us per stage-1 launch.
 #include "kvq_common.cuh"
 #include "kvq_kernels.cuh"
 
