@@ -133,6 +133,14 @@ int kvq_ln_window(const float* x, void* out_f16, const float* gamma, const float
                   int H, int W, int C, const int32_t window[3], const int32_t shift[3], void* stream);
 /* rows of the window-ordered matrix for a geometry: B*nW*N */
 int64_t kvq_window_rows(int B, int D, int H, int W, const int32_t window[3], const int32_t shift[3]);
+/* Host-only: the row maps the kernels use for one clip (roll by -shift + window_partition, swin_backbone.py:92-117,
+ * :430-435), computed by the same inline functions the device code calls (float-reciprocal divisions included).
+ * row_to_src [nW*N]: window-order row -> flat token index (d*H + h)*W + w, or -1 for a padded slot;
+ * src_to_row [D*H*W] (may be NULL; filled only when the grid needs no padding): the inverse.
+ * d_fastest = 0: rows of a window in (d,h,w) order (window_partition); 1: (h,w,d), the order of the fused forward.
+ * Returns nW*N, or a negative error code. */
+int64_t kvq_window_row_map(int D, int H, int W, const int32_t window[3], const int32_t shift[3], int d_fastest,
+                           int32_t* row_to_src, int32_t* src_to_row);
 /* scratch bytes for kvq_window_attention */
 size_t kvq_window_attention_workspace_bytes(int B, int D, int H, int W, int C, const int32_t window[3],
                                             const int32_t shift[3]);

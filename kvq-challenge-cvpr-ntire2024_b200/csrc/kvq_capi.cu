@@ -900,6 +900,18 @@ int64_t kvq_window_rows(int B, int D, int H, int W, const int32_t window[3], con
   return static_cast<int64_t>(B) * g.nW * g.N;
 }
 
+int64_t kvq_window_row_map(int D, int H, int W, const int32_t window[3], const int32_t shift[3], int d_fastest,
+                           int32_t* row_to_src, int32_t* src_to_row) {
+  KVQ_REQUIRE(D > 0 && H > 0 && W > 0 && window && shift && row_to_src, KVQ_ERR_BAD_SHAPE, "window_row_map: bad arguments");
+  WinGeom g = make_geom(D, H, W, window, shift);
+  g.dfast = d_fastest ? 1 : 0;
+  const int rows = g.nW * g.N;
+  for (int r = 0; r < rows; ++r) row_to_src[r] = win_row_to_src(g, r);
+  if (src_to_row != nullptr && g.Dp == g.D && g.Hp == g.H && g.Wp == g.W)
+    for (int t = 0; t < g.tokens; ++t) src_to_row[t] = src_to_win_row(g, t);
+  return rows;
+}
+
 int kvq_ln_window(const float* x, void* out_f16, const float* gamma, const float* beta, float eps, int B, int D,
                   int H, int W, int C, const int32_t window[3], const int32_t shift[3], void* stream) {
   const WinGeom g = make_geom(D, H, W, window, shift);

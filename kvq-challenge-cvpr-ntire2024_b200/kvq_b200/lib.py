@@ -54,6 +54,7 @@ PROTOTYPES = {
     "kvq_ln_window": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
                               POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "kvq_window_rows": (c_int64, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32)]),
+    "kvq_window_row_map": (c_int64, [c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "kvq_window_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int32),
                                                         POINTER(c_int32)]),
     "kvq_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

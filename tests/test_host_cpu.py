@@ -330,3 +330,41 @@ def test_float_reciprocal_division_is_exact_on_the_ranges_the_kernels_use():
         d = d.astype(np.int64)
         keep = (n // d) < (1 << 21)
         assert np.array_equal(fdiv(n[keep], d[keep]), n[keep] // d[keep])
+
+
+@pytest.mark.parametrize("dims,window,shift", [
+    ((16, 56, 56), (8, 7, 7), (0, 0, 0)), ((16, 56, 56), (8, 7, 7), (4, 3, 3)), ((16, 14, 14), (8, 7, 7), (4, 3, 3)),
+    ((9, 25, 19), (8, 7, 7), (4, 3, 3)), ((4, 24, 32), (8, 7, 7), (4, 3, 3)), ((48, 7, 7), (8, 7, 7), (4, 3, 3)),
+    ((8, 16, 16), (4, 4, 4), (2, 2, 2))])
+def test_window_row_maps_match_the_oracle_tables(dims, window, shift):
+    """kvq_window_row_map runs, on the host, the same inline row-map functions the kernels call (float-reciprocal divisions
+    included): roll(-shift) + window_partition against the oracle's token table, the d-fastest order against its
+    definition, and src_to_win_row as the inverse on grids without padding."""
+    import ctypes as C
+    from kvq_b200 import lib
+    from oracle import swin3d
+    L = lib.load()
+    D, H, W = dims
+    cw, cs = swin3d.clamp_window(dims, window, shift)
+    Dp, Hp, Wp = [-(-n // w) * w for n, w in zip(dims, cw)]
+    tabs = swin3d.token_tables((Dp, Hp, Wp), cw, cs)
+    src = tabs["src"].numpy()                                   # [nW, N] indices into the PADDED grid
+    pd, ph, pw = src // (Hp * Wp), (src // Wp) % Hp, src % Wp
+    expect = np.where((pd < D) & (ph < H) & (pw < W), (pd * H + ph) * W + pw, -1).reshape(-1)
+    rows = expect.size
+    i3 = lambda v: (C.c_int32 * 3)(*v)
+    for dfast in (0, 1):
+        r2s = np.full(rows, -7, dtype=np.int32)
+        s2r = np.full(D * H * W, -7, dtype=np.int32)
+        n = L.kvq_window_row_map(D, H, W, i3(window), i3(shift), dfast, r2s.ctypes.data, s2r.ctypes.data)
+        assert n == rows
+        if dfast == 0:
+            assert np.array_equal(r2s, expect)
+        else:                                                   # row (h, w, d) of a window <-> row (d, h, w)
+            wd, wh, ww = cw
+            e = expect.reshape(-1, wd, wh * ww).transpose(0, 2, 1).reshape(-1)
+            assert np.array_equal(r2s, e)
+        if (Dp, Hp, Wp) == (D, H, W):
+            assert np.array_equal(s2r[r2s], np.arange(rows))    # bijection, and src_to_win_row is its inverse
+        else:
+            assert (s2r == -7).all() and (r2s == -1).any()
