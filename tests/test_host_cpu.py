@@ -368,3 +368,27 @@ def test_window_row_maps_match_the_oracle_tables(dims, window, shift):
             assert np.array_equal(s2r[r2s], np.arange(rows))    # bijection, and src_to_win_row is its inverse
         else:
             assert (s2r == -7).all() and (r2s == -1).any()
+
+
+def test_gelu_polynomial_of_the_kernels_is_within_its_stated_error():
+    """gelu_erf_fast (csrc/kvq_common.cuh): the coefficients in the source are the ones tools/fit_gelu.py derives, and the
+    float32 evaluation order of the kernel stays within 1e-6 of the exact erf GELU over [-8, 8] (stated: 9.2e-7)."""
+    import importlib.util
+    from scipy.special import erf
+    spec = importlib.util.spec_from_file_location("fit_gelu", os.path.join(ROOT, "tools", "fit_gelu.py"))
+    fg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fg)
+    src = open(os.path.join(PKG, "csrc", "kvq_common.cuh")).read()
+    body = src[src.index("float gelu_erf_fast(float x)"):]
+    body = body[:body.index("}\n")]
+    horner = [ln for ln in body.splitlines() if "q = fmaf(" in ln]
+    consts = [float(v) for ln in horner for v in re.findall(r"(-?\d\.\d+(?:e[+-]\d+)?)f", ln)]
+    # source order: c5, c4, c3, c2, c1 (Horner from the highest coefficient)
+    coeffs = consts[::-1]
+    assert len(coeffs) == 5
+    fitted = [float(np.float32(v)) for v in fg.fit()]
+    assert np.allclose(coeffs, fitted, rtol=2e-4, atol=1e-7), (coeffs, fitted)
+    x = np.linspace(-8, 8, 200001)
+    exact = 0.5 * x * (1 + erf(x / np.sqrt(2)))
+    got = fg.gelu_kernel(x, np.array(coeffs)).astype(np.float64)
+    assert np.abs(got - exact).max() < 1e-6
